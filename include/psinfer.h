@@ -1,0 +1,198 @@
+/* psinfer.h -- C ABI of the B200-native pictorial-structures inference library (libpsinfer.so).
+ *
+ * The reference (leonid-pishchulin/partapp) has no plugin/FFI layer; the seam is cut at the call
+ *
+ *   object_detect::computeRootPosteriorRot(part_app, log_part_detections, root_part_posterior,
+ *                                          rootpart_idx, joints, flip, bIsSparse, imgidx,
+ *                                          best_part_hyp, bSaveMarginals)
+ *   -- declared src/libs/libPictStruct/objectdetect.h:269-274,
+ *      defined  src/libs/libPictStruct/objectdetect_findrot.cpp:470-727,
+ *      called   objectdetect_findrot.cpp:992, objectdetect_roi.cpp:262
+ *
+ * with computeRotJointMarginal (objectdetect.h:277-282, findrot.cpp:292-456) as the finer test seam.
+ * Every entry point below names the reference interface it replaces.  Conventions kept from the
+ * reference: grids are contiguous C-order fp32 [rotation][y][x]; unaries are log-domain with
+ * LOG_ZERO = -1e6 (libBoostMath/boost_math.h:23) marking unevaluated cells; joints arrive 0-based and
+ * already flipped; geometry is double precision; ExpParam rotation/scale ranges are *floats*.
+ * Conventions that differ: no assert/abort, no stdout -- every call returns an int status and the
+ * message is available from ps_last_error(); no exceptions cross the ABI.
+ *
+ * Threading: one ps_ctx per (host thread, GPU).  A ctx is not thread-safe; distinct ctxs are fully
+ * independent (images shard across GPUs/ctxs with no collective).
+ *
+ * There is no CPU fallback: ps_create fails with PS_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef PSINFER_H_
+#define PSINFER_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_MAX_PARTS 64
+#define PS_HYP_VEC 7 /* PartHyp::toVect(): scaleidx, scale, rotidx, rot_deg, x, y, score (objectdetect.h:139-160) */
+
+enum ps_status {
+  PS_OK = 0,
+  PS_ERR_INVALID = 1,     /* bad argument / violated precondition (an assert in the reference) */
+  PS_ERR_CUDA = 2,        /* CUDA runtime failure, or no usable device */
+  PS_ERR_STATE = 3,       /* call order violated (e.g. ps_infer before ps_set_joints) */
+  PS_ERR_UNSUPPORTED = 4  /* valid in the reference but not implemented here; never silently approximated */
+};
+
+enum ps_mem_kind { PS_MEM_HOST = 0, PS_MEM_DEVICE = 1 };
+
+/* Joint::POS_GAUSSIAN / ROT_GAUSSIAN, objectdetect.h:55 */
+enum ps_joint_type { PS_JOINT_POS_GAUSSIAN = 1, PS_JOINT_ROT_GAUSSIAN = 2 };
+
+/* flags for ps_infer */
+enum ps_infer_flags {
+  PS_INFER_SPARSE = 1,        /* bIsSparse of computeRootPosteriorRot (findrot.cpp:740 passes true) */
+  PS_INFER_LOCAL_MAX = 2,     /* also extract <=K local maxima per part (findLocalMax, aux.cpp:193-261) */
+  PS_INFER_ROOT_HYPS = 4,     /* also extract <=1000 local maxima of the root posterior (findrot.cpp:1037-1038) */
+  PS_INFER_KEEP_UNARIES = 8   /* restore the unaries after the call (what findrot.cpp:847,1001 does around it) */
+};
+
+/* The ExpParam / PartConfig fields the path reads:
+ * ExpParam.proto:189-195 (scale/rotation ranges), :229 strip_border_detections, :282 roi_save_num_samples;
+ * PartConfig.part[i].{is_detect,is_upright,is_root}. */
+typedef struct ps_config {
+  int device;                 /* CUDA device ordinal */
+  int num_parts;              /* part_conf.part_size() */
+  int num_rotation_steps;     /* ExpParam.num_rotation_steps */
+  float min_part_rotation;    /* degrees */
+  float max_part_rotation;
+  int num_scale_steps;        /* ExpParam.num_scale_steps */
+  float min_object_scale;
+  float max_object_scale;
+  int height, width;          /* image (= state grid) size */
+  int root_idx;               /* 0-based root part; -1: the unique part with is_detect && is_root (findrot.cpp:783-788) */
+  unsigned char is_detect[PS_MAX_PARTS];
+  unsigned char is_upright[PS_MAX_PARTS];
+  unsigned char is_root[PS_MAX_PARTS];
+  float strip_border_detections;
+  int roi_save_num_samples;   /* K of findLocalMax; ExpParam default 1000 */
+  int keep_all_scales;        /* 1: keep the marginals of every scale resident (bSaveMarginals use); 0: last scale only */
+} ps_config;
+
+/* object_detect::Joint (objectdetect.h:54-86) after loadJoints (aux.cpp:54-141): 0-based ids, flipped. */
+typedef struct ps_joint {
+  int type;                   /* ps_joint_type; only ROT_GAUSSIAN is on this path (findrot.cpp:766) */
+  int child_idx, parent_idx;
+  double offset_c[2];         /* parent_pos - child_pos, pixels */
+  double offset_p[2];         /* child_pos - parent_pos, pixels */
+  double C[4];                /* 2x2 covariance, row-major */
+  double rot_mean, rot_sigma; /* radians */
+} ps_joint;
+
+typedef struct ps_ctx ps_ctx;
+
+/* ---- lifetime --------------------------------------------------------------------------------- */
+
+/* Allocates every tree level (unaries, beliefs, root messages, scratch) in HBM once. */
+int ps_create(const ps_config *cfg, ps_ctx **out);
+void ps_destroy(ps_ctx *ctx);
+/* Message of the last failing call on this ctx (ctx == NULL: of the last failing ps_create). */
+const char *ps_last_error(const ps_ctx *ctx);
+/* Run the ctx's work on an existing CUDA stream (a cudaStream_t passed as void*); NULL = the ctx's own stream. */
+int ps_set_stream(ps_ctx *ctx, void *cuda_stream);
+int ps_synchronize(ps_ctx *ctx);
+
+/* ---- model ------------------------------------------------------------------------------------ */
+
+/* Replaces the `std::vector<Joint> joints` argument of computeRootPosteriorRot (objectdetect.h:269-274).
+ * Validates the topology the reference asserts (root with chains: findrot.cpp:207-210) and precomputes, per
+ * joint x direction x scale, the shift tables, Gaussian taps, eigen-frames and scatter maps. */
+int ps_set_joints(ps_ctx *ctx, const ps_joint *joints, int num_joints);
+
+/* loadJoints' flip branch (aux.cpp:102-119) as a pure function on one joint: C <- T C T, offsets x-negated,
+ * rot_mean negated. */
+void ps_flip_joint(ps_joint *joint);
+
+/* partapp_aux.hpp:45-58,123-129,86-92,94-100 */
+double ps_rot_from_index(const ps_config *cfg, int rotidx);
+double ps_scale_from_index(const ps_config *cfg, int scaleidx);
+int ps_index_from_rot(const ps_config *cfg, double rot_deg);
+
+/* ---- unaries: `log_part_detections[part][scale]` ------------------------------------------------ */
+
+/* Copies one [R][H][W] grid into the resident unary of (part, scale).  raw_scores != 0: `src` holds
+ * classifier scores as loadScoreGrid returns them (partapp.cpp:830-903) and the device applies
+ * clip_scores_fill + computeLogGrid (findrot.cpp:834-845; aux.hpp:42-59; op.hpp:154-167). */
+int ps_set_unary(ps_ctx *ctx, int part, int scale, const float *src, int mem_kind, int raw_scores);
+/* Reads the resident (possibly masked) unary back. */
+int ps_get_unary(ps_ctx *ctx, int part, int scale, float *dst, int mem_kind);
+
+/* addExtraUnary (icps.cpp:526-548) for grids that are a broadcast of a small table:
+ *   table_kind 0: table[R]     (getRotScoreGrid, icps.cpp:228-281)   unary += weight * table[r]
+ *   table_kind 1: table[H][W]  (getPosScoreGrid, icps.cpp:366-423)   unary += weight * table[y][x]
+ *   table_kind 2: table[H][W]  (setTorsoPosPrior, icps.cpp:183-190)  unary += table[y][x]
+ * applied to every scale of `part`. */
+int ps_add_unary_table(ps_ctx *ctx, int part, const float *table, int table_kind, float weight);
+
+/* Host builders of those tables (same arithmetic as the reference, which builds them on the CPU). */
+void ps_rot_score_table(const ps_config *cfg, double mu, double var, float *table /*[R]*/);
+void ps_pos_score_table(int height, int width, double mu_x, double mu_y, double var_x, double var_y,
+                        double root_x, double root_y, float *table /*[H][W]*/);
+void ps_torso_prior_table(int height, int width, double mu_x, double mu_y, double var_x, double var_y,
+                          float weight, float *table /*[H][W]*/);
+
+/* ---- inference -------------------------------------------------------------------------------- */
+
+/* computeRootPosteriorRot (findrot.cpp:470-727) on the resident unaries: upright masking, border strip,
+ * upward pass, downward pass (computePartMarginals, :124-286), per-part argmax, root rotation-marginal.
+ * The unaries are masked in place exactly as the reference mutates its argument unless
+ * PS_INFER_KEEP_UNARIES is set. Asynchronous on the ctx stream; getters synchronise. */
+int ps_infer(ps_ctx *ctx, int flags);
+
+/* getMaxStates (findrot.cpp:73-110): use_pairwise:false shortcut -- argmax (+ local maxima) of the
+ * unaries at scale 0. */
+int ps_max_states(ps_ctx *ctx, int flags);
+
+/* best_part_hyp[p][0].toVect() for every part -> out[P][7] (the `best_conf` of findrot.cpp:1005-1011).
+ * Describes the LAST scale, like the reference (best_part_hyp is refilled per scale, :257-259). */
+int ps_get_best_conf(ps_ctx *ctx, float *out);
+
+/* best_part_hyp[part]: the argmax record followed by <=K local maxima (findrot.cpp:277-283), rows of 7.
+ * Needs PS_INFER_LOCAL_MAX.  Local maxima are ordered by the reference scan order (rotation, x, y) when
+ * there are <=K of them, by descending score otherwise (ties: scan order; the reference's std::sort
+ * leaves that unspecified).  *count receives the number of rows written (<= cap). */
+int ps_get_part_hyps(ps_ctx *ctx, int part, float *out, int cap, int *count);
+
+/* log_part_posterior[part] of `scale` -> dst[R][H][W] (what bSaveMarginals dumps as log_prob_grid,
+ * findrot.cpp:239-253).  scale must be the last one unless keep_all_scales was set. */
+int ps_get_marginal(ps_ctx *ctx, int part, int scale, float *dst, int mem_kind);
+
+/* root_part_posterior -> dst[S][H][W] (findrot.cpp:714-726). */
+int ps_get_root_posterior(ps_ctx *ctx, float *dst, int mem_kind);
+
+/* findLocalMax(root_part_posterior, hypothesis_list, 1000) (findrot.cpp:1037-1038; aux.cpp:266-290):
+ * rows of (scaleidx, x, y, score); needs PS_INFER_ROOT_HYPS. */
+int ps_get_root_hyps(ps_ctx *ctx, float *out, int cap, int *count);
+
+/* ---- test seam --------------------------------------------------------------------------------- */
+
+/* computeRotJointMarginal (findrot.cpp:292-456) on caller buffers: one message
+ * log_prob_parent = MSG(log_prob_child; offset_in, offset_out, C, rot_mean, rot_sigma, scale, sparse).
+ * Upward calls pass (offset_c, offset_p, +rot_mean, sparse); downward (offset_p, offset_c, -rot_mean, 0). */
+int ps_message(ps_ctx *ctx, const float *log_prob_child, float *log_prob_parent, int mem_kind,
+               const double offset_in[2], const double offset_out[2], const double C[4],
+               double rot_mean, double rot_sigma, double scale, int sparse);
+
+/* findLocalMax core (aux.cpp:193-261) on a caller grid [D0][H][W] (H, W may differ from the ctx's):
+ * rows of (dim0, x, y, score). */
+int ps_find_local_max(ps_ctx *ctx, const float *grid, int mem_kind, int d0, int height, int width,
+                      int max_n, float *out, int *count);
+
+/* Number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches). */
+long long ps_launch_count(const ps_ctx *ctx);
+
+/* Library identification: "psinfer <version> sm_100a". */
+const char *ps_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSINFER_H_ */

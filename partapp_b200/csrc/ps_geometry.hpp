@@ -1,0 +1,323 @@
+// ps_geometry.hpp -- host-side, double-precision parameter math of one message.
+//
+// The reference evaluates all geometry of computeRotJointMarginal on the CPU in double precision
+// (libBoostMath/homogeneous_coord.{h,cpp}, boost_math.cpp, libPartApp/partapp_aux.hpp) and only the
+// grid sweeps are hot.  We keep that split: everything here runs once per (joint, direction, scale)
+// when ps_set_joints is called and is turned into small device tables (integer shift tables, fp32
+// taps, 2x3 affine rows); the kernels never redo this math in a different precision.
+//
+// Expression order follows the reference so the tables are identical to what its loops would see:
+// 3x3 products are "t = 0; t += a(i,k)*b(k,j)" (uBLAS prod), map_point is
+// M00*x + M01*y + M02 (homogeneous_coord.h:79-80), round is floor(v+0.5) (boost_math.hpp:35).
+// This translation unit is compiled by the host compiler (nvcc -Xcompiler -ffp-contract=off),
+// so no FMA contraction happens here.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace psg {
+
+constexpr float kLogZero = -1e6f;  // LOG_ZERO, libBoostMath/boost_math.h:23
+
+struct M3 {
+  double a[3][3];
+  static M3 zero() {
+    M3 r;
+    for (auto &row : r.a)
+      for (double &v : row) v = 0.0;
+    return r;
+  }
+  static M3 eye() {
+    M3 r = zero();
+    r.a[0][0] = r.a[1][1] = r.a[2][2] = 1.0;
+    return r;
+  }
+};
+
+inline M3 mul(const M3 &x, const M3 &y) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double t = 0.0;
+      for (int k = 0; k < 3; ++k) t += x.a[i][k] * y.a[k][j];
+      r.a[i][j] = t;
+    }
+  return r;
+}
+
+inline void mul(const M3 &x, const double v[3], double out[3]) {
+  for (int i = 0; i < 3; ++i) {
+    double t = 0.0;
+    for (int k = 0; k < 3; ++k) t += x.a[i][k] * v[k];
+    out[i] = t;
+  }
+}
+
+// hc::get_rotation_matrix / get_scaling_matrix / get_translation_matrix / get_homogeneous_matrix
+// (homogeneous_coord.cpp:81-93, :71-78, :95-103, :38-47)
+inline M3 rotation(double rad) {
+  M3 r = M3::zero();
+  double ca = std::cos(rad), sa = std::sin(rad);
+  r.a[0][0] = ca; r.a[0][1] = -sa; r.a[1][0] = sa; r.a[1][1] = ca; r.a[2][2] = 1;
+  return r;
+}
+inline M3 scaling(double s) {
+  M3 r = M3::eye();
+  r.a[0][0] = s; r.a[1][1] = s;
+  return r;
+}
+inline M3 translation(double dx, double dy) {
+  M3 r = M3::eye();
+  r.a[0][2] = dx; r.a[1][2] = dy;
+  return r;
+}
+inline M3 homogeneous(const double R[2][2], double dx, double dy) {
+  M3 r = M3::zero();
+  r.a[0][0] = R[0][0]; r.a[0][1] = R[0][1]; r.a[1][0] = R[1][0]; r.a[1][1] = R[1][1];
+  r.a[0][2] = dx; r.a[1][2] = dy; r.a[2][2] = 1;
+  return r;
+}
+
+// hc::inverse (homogeneous_coord.cpp:49-69): analytic affine inverse
+inline M3 inverse(const M3 &T) {
+  M3 inv;
+  double D = T.a[0][0] * T.a[1][1] - T.a[1][0] * T.a[0][1];
+  inv.a[0][0] = T.a[1][1] / D;
+  inv.a[0][1] = -T.a[0][1] / D;
+  inv.a[1][0] = -T.a[1][0] / D;
+  inv.a[1][1] = T.a[0][0] / D;
+  for (int i = 0; i < 2; ++i) {
+    double t = 0.0;
+    for (int k = 0; k < 2; ++k) t += inv.a[i][k] * T.a[k][2];
+    inv.a[i][2] = -t;
+  }
+  inv.a[2][0] = 0; inv.a[2][1] = 0; inv.a[2][2] = 1;
+  return inv;
+}
+
+// hc::map_point (homogeneous_coord.h:72-81)
+inline void map_point(const M3 &M, double x, double y, double &ox, double &oy) {
+  ox = M.a[0][0] * x + M.a[0][1] * y + M.a[0][2];
+  oy = M.a[1][0] * x + M.a[1][1] * y + M.a[1][2];
+}
+
+// hc::get_transformed_bbox (homogeneous_coord.cpp:139-156)
+inline void transformed_bbox(const M3 &T21, int w, int h, double &minx, double &miny, double &maxx,
+                             double &maxy) {
+  const double pts[4][3] = {{0, 0, 1}, {double(w - 1), 0, 1}, {0, double(h - 1), 1},
+                            {double(w - 1), double(h - 1), 1}};
+  for (int i = 0; i < 4; ++i) {
+    double c[3];
+    mul(T21, pts[i], c);
+    if (i == 0) {
+      minx = maxx = c[0];
+      miny = maxy = c[1];
+    } else {
+      minx = std::fmin(minx, c[0]); maxx = std::fmax(maxx, c[0]);
+      miny = std::fmin(miny, c[1]); maxy = std::fmax(maxy, c[1]);
+    }
+  }
+}
+
+// boost_math::eig2d (boost_math.cpp:40-99): smallest eigenvalue first, V = [v1 v2], v2 = (-v1y, v1x)
+inline void eig2d(const double M[2][2], double V[2][2], double E[2]) {
+  double m11 = M[0][0], m12 = M[0][1], m22 = M[1][1];
+  double e1, e2, v11, v21;
+  if (m12 != 0) {
+    double sqrtD = std::sqrt((m11 - m22) * (m11 - m22) + 4 * m12 * m12);
+    e1 = 0.5 * (m11 + m22 - sqrtD);
+    e2 = 0.5 * (m11 + m22 + sqrtD);
+    v11 = 0.5 * (m11 - m22 - sqrtD) / m12;
+    v21 = 1;
+  } else if (m11 < m22) {
+    e1 = m11; e2 = m22; v11 = 1; v21 = 0;
+  } else {
+    e1 = m22; e2 = m11; v11 = 0; v21 = 1;
+  }
+  double nrm = std::sqrt(v11 * v11 + v21 * v21);
+  v11 /= nrm;
+  v21 /= nrm;
+  V[0][0] = v11; V[1][0] = v21; V[0][1] = -v21; V[1][1] = v11;
+  E[0] = e1; E[1] = e2;
+}
+
+// boost_math::get_gaussian_filter (boost_math.cpp:104-117), unnormalised (peak tap = 1)
+inline std::vector<double> gaussian_taps(double sigma) {
+  int k = (int)std::floor(3 * sigma + 0.5);
+  std::vector<double> f(2 * k + 1);
+  f[k] = 1.0;
+  for (int i = 1; i <= k; ++i) {
+    f[k + i] = std::exp(-i * i / (2 * sigma * sigma));
+    f[k - i] = f[k + i];
+  }
+  return f;
+}
+
+inline std::vector<float> to_float(const std::vector<double> &d) {
+  std::vector<float> f(d.size());
+  for (size_t i = 0; i < d.size(); ++i) f[i] = (float)d[i];
+  return f;
+}
+
+// partapp_aux.hpp:45-58 / :25-43
+inline double value_from_index(double lo, double hi, double steps, int idx) {
+  if (lo == hi) return lo;
+  double step = (hi - lo) / steps;
+  return lo + step * (0.5 + idx);
+}
+inline int index_from_value(double lo, double hi, double steps, double val) {
+  if (lo == hi) return 0;
+  if (!(val >= lo && val < hi)) return -1;
+  double step = (hi - lo) / steps;
+  return (int)(unsigned)std::floor((val - lo) / step);
+}
+
+struct Grid {
+  int R, H, W;
+  float min_rot, max_rot;  // degrees, ExpParam floats
+};
+
+inline double rot_deg(const Grid &g, int r) { return value_from_index(g.min_rot, g.max_rot, g.R, r); }
+
+// Everything one computeRotJointMarginal call (findrot.cpp:292-456) derives from its scalar arguments.
+struct MessagePlan {
+  // rotation axis (:319-326, :377-420)
+  int rot_shift = 0;            // rot_mean_idx: slice r is written to r + rot_shift, no wrap
+  int rot_mode = 0;             // 0: rot_sigma == 0 (copy), 1: circular filter, 2: rot_sigma < 0 (all zero)
+  std::vector<float> rot_taps;  // tail-clipped (:385-390), fp32
+
+  // nearest-neighbour translations (:345-359 in, :438-448 out): source index per destination index, -1 = out of bounds
+  std::vector<int> xin, yin;    // [R][W], [R][H]
+  std::vector<int> xout, yout;
+
+  // spatial filter (:423-429 -> multi_array_filter.hpp:375-388)
+  bool diag = true;
+  std::vector<float> fx, fy;    // taps along x / y of the (possibly rotated) frame
+  // general covariance only (multi_array_filter.hpp:335-369):
+  int EH = 0, EW = 0;           // size of the eigen-frame grid, transform.hpp:298-299
+  double T31[6];                // image -> eigen-frame (TM_DIRECT forward scatter), rows 0,1 of the 3x3
+  double T13[6];                // eigen-frame -> image (TM_BILINEAR gather into the eigen-frame)
+  double T34[6];                // image -> eigen-frame coordinates for the bilinear read-back
+  std::string error;            // non-empty: the reference would have hit an assert
+};
+
+inline void rows01(const M3 &m, double out[6]) {
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) out[i * 3 + j] = m.a[i][j];
+}
+
+// Source-index tables of transform_grid_fixed_size(..., Trans(tx,ty), TM_NEAREST)
+// (transform.hpp:194-216): src = floor(T13 * dst + 0.5) with T13 = inverse(T21) * I.
+inline void nearest_tables(const M3 &T21, int W, int H, int *xt, int *yt) {
+  M3 T13 = mul(inverse(T21), M3::eye());
+  for (int x3 = 0; x3 < W; ++x3) {
+    double x1, y1;
+    map_point(T13, (double)x3, 0.0, x1, y1);
+    int ix = (int)std::floor(x1 + 0.5);
+    xt[x3] = (ix >= 0 && ix < W) ? ix : -1;
+  }
+  for (int y3 = 0; y3 < H; ++y3) {
+    double x1, y1;
+    map_point(T13, 0.0, (double)y3, x1, y1);
+    int iy = (int)std::floor(y1 + 0.5);
+    yt[y3] = (iy >= 0 && iy < H) ? iy : -1;
+  }
+}
+
+inline MessagePlan plan_message(const Grid &g, const double off_in[2], const double off_out[2],
+                                const double C[4], double rot_mean, double rot_sigma, double scale) {
+  MessagePlan p;
+  const int R = g.R, H = g.H, W = g.W;
+
+  // findrot.cpp:319-326 -- the range and the division are float arithmetic (float ExpParam fields, uint32 count)
+  double rot_step = (g.max_rot - g.min_rot) / (float)g.R;
+  rot_step *= M_PI / 180.0;
+  if (!(rot_step > 0)) {
+    p.error = "rot_step_size must be > 0 (findrot.cpp:321)";
+    return p;
+  }
+  double rot_sigma_idx = rot_sigma / rot_step;
+  p.rot_shift = (int)std::floor(-rot_mean / rot_step + 0.5);
+
+  if (rot_sigma > 0) {
+    p.rot_mode = 1;
+    std::vector<double> f = gaussian_taps(rot_sigma_idx);
+    int first = 0, len = (int)f.size();
+    if (len >= R) {  // clip kernel tails, :385-390
+      int c = len / 2;
+      len = (R % 2 == 1) ? R - 2 : R - 1;
+      first = c - len / 2;
+    }
+    if (len < 1 || len > 1000) {
+      p.error = "rotation filter length out of range (findrot.cpp:402)";
+      return p;
+    }
+    p.rot_taps.resize(len);
+    for (int i = 0; i < len; ++i) p.rot_taps[i] = (float)f[first + i];
+  } else if (rot_sigma == 0) {
+    p.rot_mode = 0;
+  } else {
+    p.rot_mode = 2;
+  }
+
+  // per-rotation translations
+  p.xin.resize((size_t)R * W); p.yin.resize((size_t)R * H);
+  p.xout.resize((size_t)R * W); p.yout.resize((size_t)R * H);
+  const double vin[3] = {off_in[0], off_in[1], 0}, vout[3] = {off_out[0], off_out[1], 0};
+  for (int r = 0; r < R; ++r) {
+    float alpha = rot_deg(g, r) * M_PI / 180.0;  // narrowed to float, :348 / :439
+    M3 Tg = mul(rotation(alpha), scaling(scale));
+    double t[3], u[3];
+    mul(Tg, vin, t);
+    mul(Tg, vout, u);
+    nearest_tables(translation(t[0], t[1]), W, H, &p.xin[(size_t)r * W], &p.yin[(size_t)r * H]);
+    nearest_tables(translation(-u[0], -u[1]), W, H, &p.xout[(size_t)r * W], &p.yout[(size_t)r * H]);
+  }
+
+  // spatial covariance, :423 scaleC = square(scale)*C
+  double s2 = scale * scale;
+  double Cs[2][2] = {{s2 * C[0], s2 * C[1]}, {s2 * C[2], s2 * C[3]}};
+  p.diag = (Cs[0][1] == 0 && Cs[1][0] == 0);
+  double var_x, var_y;
+  if (p.diag) {
+    var_x = Cs[0][0];
+    var_y = Cs[1][1];
+  } else {
+    double V[2][2], E[2];
+    eig2d(Cs, V, E);
+    var_x = E[0];
+    var_y = E[1];
+    double Vt[2][2] = {{V[0][0], V[1][0]}, {V[0][1], V[1][1]}};
+    M3 T21 = homogeneous(Vt, 0, 0);
+    double minx, miny, maxx, maxy;
+    transformed_bbox(T21, W, H, minx, miny, maxx, maxy);
+    p.EW = (int)std::ceil(maxx - minx);
+    p.EH = (int)std::ceil(maxy - miny);
+    if (p.EW < 1 || p.EH < 1) {
+      p.error = "degenerate eigen-frame grid";
+      return p;
+    }
+    M3 T23 = translation(minx, miny), T32 = translation(-minx, -miny);
+    rows01(mul(T32, T21), p.T31);
+    rows01(mul(inverse(T21), T23), p.T13);
+    M3 T43 = mul(homogeneous(V, -0.0, -0.0), T23);
+    rows01(mul(inverse(T43), M3::eye()), p.T34);
+  }
+  if (!(var_x > 0 && var_y > 0)) {
+    p.error = "covariance must be positive definite (multi_array_filter.hpp:219)";
+    return p;
+  }
+  std::vector<double> fx = gaussian_taps(std::sqrt(var_x)), fy = gaussian_taps(std::sqrt(var_y));
+  if (fx.size() >= 1000 || fy.size() >= 1000) {
+    p.error = "spatial filter longer than F_SIZE (multi_array_filter.hpp:238-244)";
+    return p;
+  }
+  p.fx = to_float(fx);
+  p.fy = to_float(fy);
+  return p;
+}
+
+}  // namespace psg

@@ -1,0 +1,1054 @@
+// psinfer.cu -- context, schedule and C ABI of libpsinfer.so (see include/psinfer.h).
+//
+// Replaces object_detect::computeRootPosteriorRot / computePartMarginals / computeRotJointMarginal
+// (reference src/libs/libPictStruct/objectdetect_findrot.cpp:470-727, :124-286, :292-456) with a schedule of
+// sm_100a kernels over grids that stay resident in HBM.  No CPU fallback exists: every entry point that
+// computes needs a CUDA device.
+#include "../../include/psinfer.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ps_geometry.hpp"
+#include "ps_kernels.cuh"
+
+namespace {
+
+using psk::Affine;
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <typename T>
+  T *as() const { return (T *)p; }
+};
+
+// Device-side image of one psg::MessagePlan.
+struct DevPlan {
+  psg::MessagePlan host;
+  DevBuf ints;    // xin | yin | xout | yout
+  DevBuf floats;  // rot taps | fx | fy
+  DevBuf map;     // int2 [EH][EW], built on first sparse use
+  DevBuf mats;    // T31 | T13 (doubles) for the map builder
+  bool map_ready = false;
+  int EP = 0;     // eigen-frame row pitch
+  const int *xin() const { return ints.as<int>(); }
+  const int *yin(int R, int W) const { return ints.as<int>() + (size_t)R * W; }
+  const int *xout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * (W + H); }
+  const int *yout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * (2 * W + H); }
+  const float *rot_taps() const { return floats.as<float>(); }
+  const float *fx() const { return floats.as<float>() + host.rot_taps.size(); }
+  const float *fy() const { return floats.as<float>() + host.rot_taps.size() + host.fx.size(); }
+};
+
+struct Node {
+  int parent = -1;
+  int joint = -1;               // joint connecting this node to its parent
+  std::vector<int> children;    // in joint-list order (get_incoming_joints, findrot.cpp:59-71)
+  std::vector<int> child_joints;
+};
+
+}  // namespace
+
+struct ps_ctx {
+  ps_config cfg{};
+  int R = 0, S = 0, H = 0, W = 0, P = 0, root = -1;
+  size_t HW = 0, N = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  // resident grids
+  DevBuf unary;         // [P][S][N]
+  DevBuf unary_backup;  // lazily, for PS_INFER_KEEP_UNARIES
+  DevBuf post;          // [keep_all ? S : 1][P][N]
+  DevBuf rootmsg;       // [n_root_children][N]: upward messages into the root, then fr_j
+  DevBuf tmp[2];        // [N] down-pass inputs (unary + from_root)
+  DevBuf bufB;          // [N] rotation-filtered / diag y-pass output
+  DevBuf bufU, bufV;    // eigen-frame scratch [R][EHmax][EPmax] (>= N)
+  DevBuf root_post;     // [S][HW]
+  DevBuf maxes;         // int [P + kMaxRootChildren + 4] encoded maxima
+  DevBuf upright_mask;  // uchar [R]
+  DevBuf valid_rots;    // int [R]
+  int n_valid_rots = 0;
+  DevBuf argmax_keys;   // u64 [P]
+  DevBuf cand;          // Cand [N] local-max candidates
+  DevBuf counters;      // unsigned [8]
+  size_t scratch_elems = 0;
+
+  // model
+  bool joints_set = false;
+  std::vector<ps_joint> joints;
+  std::vector<Node> nodes;
+  // plans[(joint*2 + dir) * S + scale], dir 0 = upward, 1 = downward
+  std::vector<std::unique_ptr<DevPlan>> plans;
+  std::map<std::string, std::unique_ptr<DevPlan>> adhoc_plans;  // ps_message cache
+
+  // results
+  bool have_result = false;
+  int result_scale = -1;
+  std::vector<float> best_conf;               // [P][7]
+  std::vector<std::vector<float>> part_hyps;  // per part rows of 7
+  std::vector<float> root_hyps;               // rows of 4
+  bool have_local_max = false, have_root_hyps = false;
+
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  float *U(int p, int s) const { return unary.as<float>() + ((size_t)p * S + s) * N; }
+  float *POST(int p, int s) const {
+    return post.as<float>() + ((size_t)(cfg.keep_all_scales ? s : 0) * P + p) * N;
+  }
+  int *MAXP(int i) const { return maxes.as<int>() + i; }
+};
+
+#define PS_CUDA(ctx, call)                                                                          \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return (ctx)->fail(PS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define PS_LAUNCH_CHECK(ctx)                                                                        \
+  do {                                                                                              \
+    ++(ctx)->launches;                                                                              \
+    cudaError_t e_ = cudaGetLastError();                                                            \
+    if (e_ != cudaSuccess) return (ctx)->fail(PS_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+psg::Grid grid_of(const ps_ctx *c) {
+  psg::Grid g;
+  g.R = c->R; g.H = c->H; g.W = c->W;
+  g.min_rot = c->cfg.min_part_rotation;
+  g.max_rot = c->cfg.max_part_rotation;
+  return g;
+}
+
+double scale_of(const ps_config &cfg, int s) {
+  return psg::value_from_index(cfg.min_object_scale, cfg.max_object_scale, cfg.num_scale_steps, s);
+}
+
+int upload_plan(ps_ctx *c, DevPlan &dp) {
+  const psg::MessagePlan &h = dp.host;
+  std::vector<int> ints;
+  ints.insert(ints.end(), h.xin.begin(), h.xin.end());
+  ints.insert(ints.end(), h.yin.begin(), h.yin.end());
+  ints.insert(ints.end(), h.xout.begin(), h.xout.end());
+  ints.insert(ints.end(), h.yout.begin(), h.yout.end());
+  std::vector<float> fl;
+  fl.insert(fl.end(), h.rot_taps.begin(), h.rot_taps.end());
+  fl.insert(fl.end(), h.fx.begin(), h.fx.end());
+  fl.insert(fl.end(), h.fy.begin(), h.fy.end());
+  PS_CUDA(c, dp.ints.alloc(ints.size() * sizeof(int)));
+  PS_CUDA(c, dp.floats.alloc(fl.size() * sizeof(float)));
+  PS_CUDA(c, cudaMemcpyAsync(dp.ints.p, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  PS_CUDA(c, cudaMemcpyAsync(dp.floats.p, fl.data(), fl.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+  if (!h.diag) {
+    dp.EP = (h.EW + 7) & ~7;
+    double m[12];
+    memcpy(m, h.T31, sizeof h.T31);
+    memcpy(m + 6, h.T13, sizeof h.T13);
+    PS_CUDA(c, dp.mats.alloc(sizeof m));
+    PS_CUDA(c, cudaMemcpy(dp.mats.p, m, sizeof m, cudaMemcpyHostToDevice));
+  }
+  return PS_OK;
+}
+
+size_t plan_scratch_elems(const ps_ctx *c, const DevPlan &dp) {
+  if (dp.host.diag) return c->N;
+  return std::max(c->N, (size_t)c->R * dp.host.EH * dp.EP);
+}
+
+int ensure_scratch(ps_ctx *c, size_t elems) {
+  if (elems <= c->scratch_elems) return PS_OK;
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  PS_CUDA(c, c->bufU.alloc(elems * sizeof(float)));
+  PS_CUDA(c, c->bufV.alloc(elems * sizeof(float)));
+  c->scratch_elems = elems;
+  return PS_OK;
+}
+
+int ensure_direct_map(ps_ctx *c, DevPlan &dp) {
+  if (dp.map_ready) return PS_OK;
+  const psg::MessagePlan &h = dp.host;
+  PS_CUDA(c, dp.map.alloc((size_t)h.EH * h.EW * sizeof(int2)));
+  int *ovf = c->counters.as<int>() + 7;
+  PS_CUDA(c, cudaMemsetAsync(ovf, 0, sizeof(int), c->stream));
+  dim3 b(32, 8), g(cdiv(h.EW, 32), cdiv(h.EH, 8));
+  psk::k_build_direct_map<<<g, b, 0, c->stream>>>(dp.map.as<int2>(), h.EH, h.EW, c->H, c->W, dp.mats.as<double>(),
+                                                  dp.mats.as<double>() + 6, ovf);
+  PS_LAUNCH_CHECK(c);
+  int hovf = 0;
+  PS_CUDA(c, cudaMemcpyAsync(&hovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (hovf)
+    return c->fail(PS_ERR_UNSUPPORTED,
+                   "TM_DIRECT scatter map: an eigen-frame cell has more than two pre-images (transform.hpp:167-192)");
+  dp.map_ready = true;
+  return PS_OK;
+}
+
+// Where the value of one message goes (the addGrid2 calls around computeRotJointMarginal).
+struct Sink {
+  float *out0 = nullptr;
+  const float *acc0 = nullptr;
+  const float *add0 = nullptr;
+  float *out1 = nullptr;
+  const float *add1 = nullptr;
+  int *max0 = nullptr;
+  int *max1 = nullptr;
+};
+
+// One computeRotJointMarginal (findrot.cpp:292-456) on device buffers.  `in_max` holds enc(max(in)).
+int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool sparse, const Sink &sink) {
+  const psg::MessagePlan &h = dp.host;
+  const int R = c->R, H = c->H, W = c->W;
+  int rc = ensure_scratch(c, plan_scratch_elems(c, dp));
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+
+  // stage 1: shift + exp + rotation filter -> bufB
+  {
+    psk::RotArgs a;
+    a.in = in; a.out = c->bufB.as<float>();
+    a.xin = dp.xin(); a.yin = dp.yin(R, W);
+    a.taps = dp.rot_taps(); a.max_enc = in_max;
+    a.R = R; a.H = H; a.W = W;
+    a.shift = h.rot_shift; a.mode = h.rot_mode; a.len = (int)h.rot_taps.size();
+    size_t smem = (size_t)R * psk::kRotThreads * sizeof(float);
+    psk::k_rotconv<<<cdiv(c->HW, psk::kRotThreads), psk::kRotThreads, smem, st>>>(a);
+    PS_LAUNCH_CHECK(c);
+  }
+
+  psk::EpiArgs e{};
+  const float *filtered = nullptr;
+  auto conv_rows = [&](const float *src, float *dst, int rows, int cols, int pitch, size_t plane, const float *taps,
+                       int len) -> int {
+    constexpr int T = 8;
+    psk::ConvArgs a{src, dst, taps, len, rows, cols, pitch, plane};
+    int n = (len - 1) / 2;
+    int G = (cols + T - 1) / T;
+    int span_groups = (G * T + 2 * n + T - 1) / T + 1;
+    int S = span_groups;
+    while (S % 8 != 4) ++S;  // conflict-free transposed staging
+    int TY = 4;
+    size_t smem = (size_t)TY * T * S * sizeof(float);
+    psk::k_conv_rows<T><<<dim3(cdiv(rows, TY), R), 256, smem, st>>>(a, TY, S);
+    PS_LAUNCH_CHECK(c);
+    return PS_OK;
+  };
+  auto conv_cols = [&](const float *src, float *dst, int rows, int cols, int pitch, size_t plane, const float *taps,
+                       int len) -> int {
+    constexpr int T = 8;
+    psk::ConvArgs a{src, dst, taps, len, rows, cols, pitch, plane};
+    psk::k_conv_cols<T><<<dim3(cdiv(cols, 128), cdiv(rows, T), R), 128, 0, st>>>(a);
+    PS_LAUNCH_CHECK(c);
+    return PS_OK;
+  };
+
+  if (h.diag) {
+    // gaussFilterDiag2d on the image grid: x then y
+    rc = conv_rows(c->bufB.as<float>(), c->bufU.as<float>(), H, W, W, c->HW, dp.fx(), (int)h.fx.size());
+    if (rc) return rc;
+    rc = conv_cols(c->bufU.as<float>(), c->bufB.as<float>(), H, W, W, c->HW, dp.fy(), (int)h.fy.size());
+    if (rc) return rc;
+    filtered = c->bufB.as<float>();
+    e.general = 0;
+  } else {
+    // gaussFilter2dOffset: rotate into the eigen-frame, filter there, bilinear read-back in the epilogue
+    const int EH = h.EH, EW = h.EW, EP = dp.EP;
+    const size_t eplane = (size_t)EH * EP;
+    if (sparse) {
+      rc = ensure_direct_map(c, dp);
+      if (rc) return rc;
+      psk::k_warp_direct<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(),
+                                                                 dp.map.as<int2>(), R, c->HW, EH, EW, EP);
+    } else {
+      Affine T13;
+      memcpy(T13.m, h.T13, sizeof T13.m);
+      psk::k_warp_bilinear<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(), T13, R,
+                                                                   H, W, EH, EW, EP);
+    }
+    PS_LAUNCH_CHECK(c);
+    rc = conv_rows(c->bufU.as<float>(), c->bufV.as<float>(), EH, EW, EP, eplane, dp.fx(), (int)h.fx.size());
+    if (rc) return rc;
+    rc = conv_cols(c->bufV.as<float>(), c->bufU.as<float>(), EH, EW, EP, eplane, dp.fy(), (int)h.fy.size());
+    if (rc) return rc;
+    filtered = c->bufU.as<float>();
+    e.general = 1;
+    memcpy(e.T34.m, h.T34, sizeof e.T34.m);
+    e.EH = EH; e.EW = EW; e.EP = EP;
+  }
+
+  // stage 3: log, +M, shift, combine
+  e.src = filtered;
+  e.xout = dp.xout(R, H, W); e.yout = dp.yout(R, H, W);
+  e.max_enc = in_max;
+  e.R = R; e.H = H; e.W = W;
+  e.out0 = sink.out0; e.acc0 = sink.acc0; e.add0 = sink.add0;
+  e.out1 = sink.out1; e.add1 = sink.add1;
+  e.max0 = sink.max0; e.max1 = sink.max1;
+  psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e);
+  PS_LAUNCH_CHECK(c);
+  return PS_OK;
+}
+
+int reset_max(ps_ctx *c, int *slot) {
+  psk::k_set_int<<<1, 32, 0, c->stream>>>(slot, 1, PS_ENC_NEG_INF);
+  PS_LAUNCH_CHECK(c);
+  return PS_OK;
+}
+
+int grid_max(ps_ctx *c, const float *g, size_t n, int *slot) {
+  int rc = reset_max(c, slot);
+  if (rc) return rc;
+  psk::k_grid_max<<<std::min(cdiv(n, 256 * 8), 148u * 8), 256, 0, c->stream>>>(g, n, slot);
+  PS_LAUNCH_CHECK(c);
+  return PS_OK;
+}
+
+int validate_config(const ps_config *cfg, std::string &why) {
+  char buf[256];
+#define BAD(...)                         \
+  do {                                   \
+    snprintf(buf, sizeof buf, __VA_ARGS__); \
+    why = buf;                           \
+    return PS_ERR_INVALID;               \
+  } while (0)
+  if (cfg->num_parts < 1 || cfg->num_parts > PS_MAX_PARTS) BAD("num_parts %d out of [1,%d]", cfg->num_parts, PS_MAX_PARTS);
+  if (cfg->num_rotation_steps < 1 || cfg->num_rotation_steps > 512) BAD("num_rotation_steps %d out of [1,512]", cfg->num_rotation_steps);
+  if (cfg->num_scale_steps < 1) BAD("num_scale_steps %d < 1", cfg->num_scale_steps);
+  if (cfg->height < 1 || cfg->width < 1) BAD("grid %dx%d is empty", cfg->height, cfg->width);
+  if ((size_t)cfg->num_rotation_steps * cfg->height * cfg->width >= (size_t)1 << 31)
+    BAD("R*H*W does not fit the reference's int flat index (findrot.cpp:266)");
+  if (cfg->min_part_rotation == cfg->max_part_rotation && cfg->num_rotation_steps != 1)
+    BAD("min_part_rotation == max_part_rotation needs num_rotation_steps == 1 (partapp_aux.hpp:29-31)");
+  if (cfg->min_object_scale == cfg->max_object_scale && cfg->num_scale_steps != 1)
+    BAD("min_object_scale == max_object_scale needs num_scale_steps == 1 (partapp_aux.hpp:29-31)");
+  if (cfg->strip_border_detections >= 0.5f) BAD("strip_border_detections must be < 0.5 (findrot.cpp:529)");
+  if (cfg->roi_save_num_samples < 0) BAD("roi_save_num_samples < 0");
+#undef BAD
+  return PS_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *ps_version(void) { return "psinfer 0.1 sm_100a"; }
+
+const char *ps_last_error(const ps_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+long long ps_launch_count(const ps_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+double ps_rot_from_index(const ps_config *cfg, int idx) {
+  return psg::value_from_index(cfg->min_part_rotation, cfg->max_part_rotation, cfg->num_rotation_steps, idx);
+}
+double ps_scale_from_index(const ps_config *cfg, int idx) { return scale_of(*cfg, idx); }
+int ps_index_from_rot(const ps_config *cfg, double rot) {
+  return psg::index_from_value(cfg->min_part_rotation, cfg->max_part_rotation, cfg->num_rotation_steps, rot);
+}
+
+void ps_flip_joint(ps_joint *j) {
+  // C <- T*(C*T), T = diag(-1, 1); offsets <- T*offset; rot_mean <- -rot_mean (aux.cpp:102-119)
+  const double T[2][2] = {{-1, 0}, {0, 1}};
+  double C[2][2] = {{j->C[0], j->C[1]}, {j->C[2], j->C[3]}}, CT[2][2], R[2][2];
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 2; ++k) {
+      double t = 0;
+      for (int l = 0; l < 2; ++l) t += C[i][l] * T[l][k];
+      CT[i][k] = t;
+    }
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 2; ++k) {
+      double t = 0;
+      for (int l = 0; l < 2; ++l) t += T[i][l] * CT[l][k];
+      R[i][k] = t;
+    }
+  double op[2], oc[2];
+  for (int i = 0; i < 2; ++i) {
+    double t = 0, u = 0;
+    for (int l = 0; l < 2; ++l) {
+      t += T[i][l] * j->offset_p[l];
+      u += T[i][l] * j->offset_c[l];
+    }
+    op[i] = t;
+    oc[i] = u;
+  }
+  j->C[0] = R[0][0]; j->C[1] = R[0][1]; j->C[2] = R[1][0]; j->C[3] = R[1][1];
+  j->offset_p[0] = op[0]; j->offset_p[1] = op[1];
+  j->offset_c[0] = oc[0]; j->offset_c[1] = oc[1];
+  if (j->type == PS_JOINT_ROT_GAUSSIAN) j->rot_mean = -j->rot_mean;
+}
+
+// ---- conditioning tables: host arithmetic of objectdetect_icps.cpp (float/double mix kept) ---------
+static inline float sqf(float t) { return t * t; }  // pow(float,int) / square<float> of the C++98 reference build
+
+void ps_rot_score_table(const ps_config *cfg, double mu_d, double var_d, float *table) {
+  float mu = (float)mu_d, var = (float)var_d;  // icps.cpp:245-246
+  for (int r = 0; r < cfg->num_rotation_steps; ++r) {
+    float rot = (float)(ps_rot_from_index(cfg, r) / 180 * M_PI);
+    float score = (float)std::exp(-0.5 * sqf(rot - mu) / var);
+    if (score < 1e-4) score = (float)1e-4;
+    score = logf(score);
+    table[r] = score;
+  }
+}
+
+void ps_pos_score_table(int H, int W, double mu_x_d, double mu_y_d, double var_x_d, double var_y_d, double root_x,
+                        double root_y, float *table) {
+  float var_weight = 1.0f;
+  float mu_x = (float)mu_x_d, mu_y = (float)mu_y_d;
+  float var_x = (float)(var_x_d * var_weight), var_y = (float)(var_y_d * var_weight);
+  for (int iy = 0; iy < H; ++iy)
+    for (int ix = 0; ix < W; ++ix) {
+      float ix_rel = (float)(ix - root_x), iy_rel = (float)(iy - root_y);
+      float sx = (float)std::exp(-0.5 * sqf(ix_rel - mu_x) / var_x);
+      float sy = (float)std::exp(-0.5 * sqf(iy_rel - mu_y) / var_y);
+      float score = sx * sy;
+      if (score < 1e-4) score = (float)1e-4;
+      table[(size_t)iy * W + ix] = logf(score);
+    }
+}
+
+void ps_torso_prior_table(int H, int W, double mu_x_d, double mu_y_d, double var_x_d, double var_y_d, float weight,
+                          float *table) {
+  float mu_x = (float)mu_x_d, mu_y = (float)mu_y_d, var_x = (float)var_x_d, var_y = (float)var_y_d;
+  float img_c_x = (float)(0.5 * W), img_c_y = (float)(0.5 * H);
+  float var_weight = 1.0f * 1.0f;
+  var_x *= var_weight;
+  var_y *= var_weight;
+  for (int iy = 0; iy < H; ++iy)
+    for (int ix = 0; ix < W; ++ix) {
+      float ix_rel = img_c_x - ix, iy_rel = img_c_y - iy;
+      float sx = (float)std::exp(-0.5 * sqf(ix_rel - mu_x) / var_x);
+      float sy = (float)std::exp(-0.5 * sqf(iy_rel - mu_y) / var_y);
+      float score = weight * sx * sy;
+      if (score < 1e-4) score = (float)1e-4;
+      table[(size_t)iy * W + ix] = logf(score);
+    }
+}
+
+// ---- lifetime -------------------------------------------------------------------------------------
+
+int ps_create(const ps_config *cfg, ps_ctx **out) {
+  if (!cfg || !out) {
+    g_create_error = "ps_create: null argument";
+    return PS_ERR_INVALID;
+  }
+  *out = nullptr;
+  std::string why;
+  if (validate_config(cfg, why)) {
+    g_create_error = "ps_create: " + why;
+    return PS_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("ps_create: no CUDA device (") + cudaGetErrorString(e) +
+                     "); libpsinfer has no CPU fallback";
+    return PS_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "ps_create: device ordinal out of range";
+    return PS_ERR_INVALID;
+  }
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("ps_create: cudaSetDevice: ") + cudaGetErrorString(e);
+    return PS_ERR_CUDA;
+  }
+  std::unique_ptr<ps_ctx> c(new ps_ctx);
+  c->cfg = *cfg;
+  c->R = cfg->num_rotation_steps; c->S = cfg->num_scale_steps;
+  c->H = cfg->height; c->W = cfg->width; c->P = cfg->num_parts;
+  c->HW = (size_t)c->H * c->W;
+  c->N = c->HW * c->R;
+  c->root = cfg->root_idx;
+  if (c->root < 0) {
+    for (int p = 0; p < c->P; ++p)
+      if (cfg->is_detect[p] && cfg->is_root[p]) {
+        if (c->root >= 0) {
+          g_create_error = "ps_create: more than one root part (findrot.cpp:786)";
+          return PS_ERR_INVALID;
+        }
+        c->root = p;
+      }
+  }
+  if (c->root < 0 || c->root >= c->P) {
+    g_create_error = "ps_create: root part not found (findrot.cpp:831)";
+    return PS_ERR_INVALID;
+  }
+  c->cfg.root_idx = c->root;
+
+  auto cu = [&](cudaError_t err, const char *what) -> bool {
+    if (err == cudaSuccess) return true;
+    g_create_error = std::string("ps_create: ") + what + ": " + cudaGetErrorString(err);
+    return false;
+  };
+  if (!cu(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return PS_ERR_CUDA;
+  c->stream = c->own_stream;
+  const size_t G = c->N * sizeof(float);
+  if (!cu(c->unary.alloc(G * c->P * c->S), "alloc unaries")) return PS_ERR_CUDA;
+  if (!cu(c->post.alloc(G * c->P * (cfg->keep_all_scales ? c->S : 1)), "alloc beliefs")) return PS_ERR_CUDA;
+  if (!cu(c->tmp[0].alloc(G), "alloc tmp") || !cu(c->tmp[1].alloc(G), "alloc tmp")) return PS_ERR_CUDA;
+  if (!cu(c->bufB.alloc(G), "alloc scratch")) return PS_ERR_CUDA;
+  if (!cu(c->bufU.alloc(G), "alloc scratch") || !cu(c->bufV.alloc(G), "alloc scratch")) return PS_ERR_CUDA;
+  c->scratch_elems = c->N;
+  if (!cu(c->root_post.alloc(c->HW * c->S * sizeof(float)), "alloc root posterior")) return PS_ERR_CUDA;
+  if (!cu(c->maxes.alloc((c->P + psk::kMaxRootChildren + 4) * sizeof(int)), "alloc maxima")) return PS_ERR_CUDA;
+  if (!cu(c->argmax_keys.alloc(c->P * sizeof(unsigned long long)), "alloc argmax")) return PS_ERR_CUDA;
+  if (!cu(c->counters.alloc(8 * sizeof(unsigned)), "alloc counters")) return PS_ERR_CUDA;
+  // non-detect parts have all-zero unaries in the reference (findrot.cpp:794 resize, never loaded)
+  if (!cu(cudaMemsetAsync(c->unary.p, 0, c->unary.bytes, c->stream), "memset")) return PS_ERR_CUDA;
+
+  // upright mask (findrot.cpp:512-515) and valid root rotations (:694-712)
+  std::vector<unsigned char> mask(c->R);
+  for (int r = 0; r < c->R; ++r) mask[r] = !(std::fabs(ps_rot_from_index(cfg, r)) < 15.0);
+  if (!cu(c->upright_mask.alloc(c->R), "alloc mask")) return PS_ERR_CUDA;
+  if (!cu(cudaMemcpy(c->upright_mask.p, mask.data(), c->R, cudaMemcpyHostToDevice), "copy mask")) return PS_ERR_CUDA;
+  std::vector<int> valid;
+  if (cfg->is_upright[c->root]) {
+    int k1 = ps_index_from_rot(cfg, -1e-6), k2 = ps_index_from_rot(cfg, 1e-6);
+    if (k1 < 0 || k2 < 0) {
+      g_create_error = "ps_create: upright root needs 0 degrees inside the rotation range (partapp_aux.hpp:35-38)";
+      return PS_ERR_INVALID;
+    }
+    valid.push_back(k1);
+    if (k2 != k1) valid.push_back(k2);
+  } else {
+    for (int r = 0; r < c->R; ++r) valid.push_back(r);
+  }
+  c->n_valid_rots = (int)valid.size();
+  if (!cu(c->valid_rots.alloc(valid.size() * sizeof(int)), "alloc rots")) return PS_ERR_CUDA;
+  if (!cu(cudaMemcpy(c->valid_rots.p, valid.data(), valid.size() * sizeof(int), cudaMemcpyHostToDevice), "copy rots"))
+    return PS_ERR_CUDA;
+  if (!cu(cudaStreamSynchronize(c->stream), "sync")) return PS_ERR_CUDA;
+  *out = c.release();
+  return PS_OK;
+}
+
+void ps_destroy(ps_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int ps_set_stream(ps_ctx *c, void *s) {
+  if (!c) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return PS_OK;
+}
+
+int ps_synchronize(ps_ctx *c) {
+  if (!c) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+// ---- model ----------------------------------------------------------------------------------------
+
+int ps_set_joints(ps_ctx *c, const ps_joint *joints, int nj) {
+  if (!c || !joints) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  if (nj != c->P - 1) return c->fail(PS_ERR_INVALID, "need num_parts-1 = %d joints, got %d (aux.cpp:129)", c->P - 1, nj);
+  std::vector<Node> nodes(c->P);
+  for (int j = 0; j < nj; ++j) {
+    const ps_joint &q = joints[j];
+    if (q.type != PS_JOINT_ROT_GAUSSIAN)
+      return c->fail(PS_ERR_UNSUPPORTED, "joint %d: only ROT_GAUSSIAN joints are on this path (findrot.cpp:766)", j);
+    if (q.child_idx < 0 || q.child_idx >= c->P || q.parent_idx < 0 || q.parent_idx >= c->P || q.child_idx == q.parent_idx)
+      return c->fail(PS_ERR_INVALID, "joint %d: part index out of range (aux.cpp:126-127)", j);
+    if (nodes[q.child_idx].parent >= 0) return c->fail(PS_ERR_INVALID, "part %d has two parents", q.child_idx);
+    nodes[q.child_idx].parent = q.parent_idx;
+    nodes[q.child_idx].joint = j;
+    nodes[q.parent_idx].children.push_back(q.child_idx);
+    nodes[q.parent_idx].child_joints.push_back(j);
+  }
+  if (nodes[c->root].parent >= 0) return c->fail(PS_ERR_INVALID, "root part %d has a parent", c->root);
+  for (int p = 0; p < c->P; ++p) {
+    // every part must reach the root (a tree); non-root parts may have at most one child (findrot.cpp:207-210)
+    int q = p, steps = 0;
+    while (q != c->root && q >= 0 && steps <= c->P) {
+      q = nodes[q].parent;
+      ++steps;
+    }
+    if (q != c->root) return c->fail(PS_ERR_INVALID, "part %d is not connected to the root", p);
+    if (p != c->root && nodes[p].children.size() > 1)
+      return c->fail(PS_ERR_INVALID, "part %d has %zu children; only the root may branch (findrot.cpp:210)", p,
+                     nodes[p].children.size());
+  }
+  if ((int)nodes[c->root].children.size() > psk::kMaxRootChildren)
+    return c->fail(PS_ERR_UNSUPPORTED, "root has more than %d children", psk::kMaxRootChildren);
+
+  psg::Grid g = grid_of(c);
+  std::vector<std::unique_ptr<DevPlan>> plans((size_t)nj * 2 * c->S);
+  size_t need = c->N;
+  for (int j = 0; j < nj; ++j)
+    for (int dir = 0; dir < 2; ++dir)
+      for (int s = 0; s < c->S; ++s) {
+        const ps_joint &q = joints[j];
+        std::unique_ptr<DevPlan> dp(new DevPlan);
+        // upward: (offset_c, offset_p, +rot_mean) findrot.cpp:630-635; downward: (offset_p, offset_c, -rot_mean) :174-179
+        dp->host = dir == 0 ? psg::plan_message(g, q.offset_c, q.offset_p, q.C, q.rot_mean, q.rot_sigma, scale_of(c->cfg, s))
+                            : psg::plan_message(g, q.offset_p, q.offset_c, q.C, -q.rot_mean, q.rot_sigma, scale_of(c->cfg, s));
+        if (!dp->host.error.empty()) return c->fail(PS_ERR_INVALID, "joint %d: %s", j, dp->host.error.c_str());
+        int rc = upload_plan(c, *dp);
+        if (rc) return rc;
+        need = std::max(need, plan_scratch_elems(c, *dp));
+        plans[((size_t)j * 2 + dir) * c->S + s] = std::move(dp);
+      }
+  int rc = ensure_scratch(c, need);
+  if (rc) return rc;
+  size_t nroot = nodes[c->root].children.size();
+  if (c->rootmsg.bytes < nroot * c->N * sizeof(float)) PS_CUDA(c, c->rootmsg.alloc(nroot * c->N * sizeof(float)));
+  c->plans = std::move(plans);
+  c->nodes = std::move(nodes);
+  c->joints.assign(joints, joints + nj);
+  c->joints_set = true;
+  c->have_result = false;
+  return PS_OK;
+}
+
+// ---- unaries --------------------------------------------------------------------------------------
+
+int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind, int raw) {
+  if (!c || !src) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  float *dst = c->U(part, scale);
+  PS_CUDA(c, cudaMemcpyAsync(dst, src, c->N * sizeof(float),
+                             mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  if (raw) {
+    psk::k_prepare_unary<<<std::min(cdiv(c->N, 256 * 4), 148u * 16), 256, 0, c->stream>>>(dst, c->N);
+    PS_LAUNCH_CHECK(c);
+  }
+  return PS_OK;
+}
+
+int ps_get_unary(ps_ctx *c, int part, int scale, float *dst, int mem_kind) {
+  if (!c || !dst) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  PS_CUDA(c, cudaMemcpyAsync(dst, c->U(part, scale), c->N * sizeof(float),
+                             mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+int ps_add_unary_table(ps_ctx *c, int part, const float *table, int kind, float weight) {
+  if (!c || !table) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P) return c->fail(PS_ERR_INVALID, "part out of range");
+  if (kind < 0 || kind > 2) return c->fail(PS_ERR_INVALID, "table_kind must be 0, 1 or 2");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  size_t n = kind == 0 ? (size_t)c->R : c->HW;
+  DevBuf d;
+  PS_CUDA(c, d.alloc(n * sizeof(float)));
+  PS_CUDA(c, cudaMemcpyAsync(d.p, table, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  for (int s = 0; s < c->S; ++s) {
+    psk::k_add_table<<<dim3(std::min(cdiv(c->HW, 256), 1024u), c->R), 256, 0, c->stream>>>(c->U(part, s), c->R, c->HW,
+                                                                                       d.as<float>(), kind, weight);
+    PS_LAUNCH_CHECK(c);
+  }
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+// ---- readout helpers ------------------------------------------------------------------------------
+
+namespace {
+
+void fill_hyp(const ps_config &cfg, float *row, int scaleidx, int rotidx, int x, int y, float score) {
+  // PartHyp ctor (objectdetect.h:91-97): m_scale, m_rot are floats; toVect :139-160
+  row[0] = (float)scaleidx;
+  row[1] = (float)ps_scale_from_index(&cfg, scaleidx);
+  row[2] = (float)rotidx;
+  row[3] = (float)ps_rot_from_index(&cfg, rotidx);
+  row[4] = (float)x;
+  row[5] = (float)y;
+  row[6] = score;
+}
+
+// findLocalMax (aux.cpp:193-261) of a device grid [D0][H][W]: returns (d0,x,y,score) rows.
+int local_max_device(ps_ctx *c, const float *g, int D0, int H, int W, int max_n, std::vector<float> &rows) {
+  size_t n = (size_t)D0 * H * W;
+  if (c->cand.bytes < n * sizeof(psk::Cand)) {
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PS_CUDA(c, c->cand.alloc(n * sizeof(psk::Cand)));
+  }
+  unsigned *cnt = c->counters.as<unsigned>();
+  PS_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned), c->stream));
+  psk::k_local_max<<<dim3(cdiv(W, 256), H, D0), 256, 0, c->stream>>>(g, D0, H, W, c->cand.as<psk::Cand>(), (unsigned)n, cnt);
+  PS_LAUNCH_CHECK(c);
+  unsigned hcnt = 0;
+  PS_CUDA(c, cudaMemcpyAsync(&hcnt, cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<psk::Cand> cand(hcnt);
+  if (hcnt)
+    PS_CUDA(c, cudaMemcpy(cand.data(), c->cand.p, hcnt * sizeof(psk::Cand), cudaMemcpyDeviceToHost));
+  // reference order: scan order when everything is kept, descending score otherwise (ties: scan order)
+  std::sort(cand.begin(), cand.end(), [](const psk::Cand &a, const psk::Cand &b) { return a.key < b.key; });
+  if ((int)hcnt > max_n) {
+    std::stable_sort(cand.begin(), cand.end(), [](const psk::Cand &a, const psk::Cand &b) { return a.score > b.score; });
+    cand.resize(max_n);
+  }
+  rows.resize(cand.size() * 4);
+  for (size_t i = 0; i < cand.size(); ++i) {
+    unsigned key = cand[i].key;
+    int y = key % H;
+    int x = (key / H) % W;
+    int d0 = key / ((unsigned)H * W);
+    rows[4 * i + 0] = (float)d0;
+    rows[4 * i + 1] = (float)x;
+    rows[4 * i + 2] = (float)y;
+    rows[4 * i + 3] = cand[i].score;
+  }
+  return PS_OK;
+}
+
+// argmax + optional local maxima of grids g[p] for all parts (findrot.cpp:255-285 / :88-109)
+int readout_parts(ps_ctx *c, const std::vector<const float *> &grids, int scaleidx, bool local_max) {
+  const int P = c->P;
+  PS_CUDA(c, cudaMemsetAsync(c->argmax_keys.p, 0, P * sizeof(unsigned long long), c->stream));
+  for (int p = 0; p < P; ++p) {
+    psk::k_argmax<<<std::min(cdiv(c->N, 256 * 8), 148u * 8), 256, 0, c->stream>>>(
+        grids[p], c->N, c->argmax_keys.as<unsigned long long>() + p);
+    PS_LAUNCH_CHECK(c);
+  }
+  std::vector<unsigned long long> keys(P);
+  PS_CUDA(c, cudaMemcpyAsync(keys.data(), c->argmax_keys.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->best_conf.assign((size_t)P * PS_HYP_VEC, 0.f);
+  c->part_hyps.assign(P, std::vector<float>());
+  for (int p = 0; p < P; ++p) {
+    if (keys[p] == 0) return c->fail(PS_ERR_INVALID, "part %d: no finite maximum (findrot.cpp:273 assert)", p);
+    unsigned idx = ~(unsigned)(keys[p] & 0xffffffffu);
+    float val = psk::dec_f((int)((unsigned)(keys[p] >> 32) ^ 0x80000000u));
+    int rot = idx / (unsigned)c->HW, rem = idx % (unsigned)c->HW;
+    int y = rem / c->W, x = rem % c->W;
+    fill_hyp(c->cfg, &c->best_conf[(size_t)p * PS_HYP_VEC], scaleidx, rot, x, y, val);
+    c->part_hyps[p].assign(c->best_conf.begin() + (size_t)p * PS_HYP_VEC,
+                           c->best_conf.begin() + (size_t)(p + 1) * PS_HYP_VEC);
+  }
+  if (local_max)
+    for (int p = 0; p < P; ++p) {
+      std::vector<float> rows;
+      int rc = local_max_device(c, grids[p], c->R, c->H, c->W, c->cfg.roi_save_num_samples, rows);
+      if (rc) return rc;
+      for (size_t i = 0; i < rows.size() / 4; ++i) {
+        float h[PS_HYP_VEC];
+        // findLocalMax wrapper tags scaleidx 0 (aux.cpp:305)
+        fill_hyp(c->cfg, h, 0, (int)rows[4 * i], (int)rows[4 * i + 1], (int)rows[4 * i + 2], rows[4 * i + 3]);
+        c->part_hyps[p].insert(c->part_hyps[p].end(), h, h + PS_HYP_VEC);
+      }
+    }
+  c->have_local_max = local_max;
+  return PS_OK;
+}
+
+}  // namespace
+
+// ---- inference ------------------------------------------------------------------------------------
+
+int ps_infer(ps_ctx *c, int flags) {
+  if (!c) return PS_ERR_INVALID;
+  if (!c->joints_set) return c->fail(PS_ERR_STATE, "ps_infer before ps_set_joints");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  const int P = c->P, S = c->S, R = c->R, root = c->root;
+  const size_t N = c->N;
+  const bool sparse = flags & PS_INFER_SPARSE;
+  cudaStream_t st = c->stream;
+  c->have_result = false;
+  int rc;
+
+  if (flags & PS_INFER_KEEP_UNARIES) {
+    if (c->unary_backup.bytes < c->unary.bytes) PS_CUDA(c, c->unary_backup.alloc(c->unary.bytes));
+    PS_CUDA(c, cudaMemcpyAsync(c->unary_backup.p, c->unary.p, c->unary.bytes, cudaMemcpyDeviceToDevice, st));
+  }
+
+  const Node &rn = c->nodes[root];
+  const int nrc = (int)rn.children.size();
+
+  for (int s = 0; s < S; ++s) {
+    // upright masking of this scale (findrot.cpp:509-523)
+    for (int p = 0; p < P; ++p)
+      if (c->cfg.is_upright[p]) {
+        psk::k_mask_slices<<<dim3(std::min(cdiv(c->HW, 256), 512u), R), 256, 0, st>>>(c->U(p, s), R, c->HW,
+                                                                                 c->upright_mask.as<unsigned char>());
+        PS_LAUNCH_CHECK(c);
+      }
+    // border strip of the root, all scales, every iteration (findrot.cpp:528-551; idempotent)
+    if (c->cfg.strip_border_detections > 0) {
+      int sw = (int)(c->cfg.strip_border_detections * c->W);
+      if (sw > 0)
+        for (int s2 = 0; s2 < S; ++s2) {
+          psk::k_strip_border<<<cdiv((size_t)R * c->H, 8), dim3(32, 8), 0, st>>>(c->U(root, s2), R * c->H, c->W, sw);
+          PS_LAUNCH_CHECK(c);
+        }
+    }
+
+    // ---------------- upward pass (findrot.cpp:582-658) ----------------
+    // Every root child heads a chain; chains are independent, so they are walked one after another.
+    // `belief[p]` is the grid MSG_up reads for part p, `bmax[p]` its encoded maximum.
+    std::vector<const float *> belief(P, nullptr);
+    for (int ci = 0; ci < nrc; ++ci) {
+      // collect the chain root-child -> ... -> leaf
+      std::vector<int> chain;
+      for (int q = rn.children[ci]; q >= 0; q = c->nodes[q].children.empty() ? -1 : c->nodes[q].children[0])
+        chain.push_back(q);
+      const int leaf = chain.back();
+      // leaf belief: 0 + unary (is_detect) or all zeros
+      if (c->cfg.is_detect[leaf]) {
+        belief[leaf] = c->U(leaf, s);
+      } else {
+        psk::k_fill<<<std::min(cdiv(N, 1024), 2048u), 256, 0, st>>>(c->POST(leaf, s), N, 0.0f);
+        PS_LAUNCH_CHECK(c);
+        belief[leaf] = c->POST(leaf, s);
+      }
+      if ((rc = grid_max(c, belief[leaf], N, c->MAXP(leaf)))) return rc;
+      for (int k = (int)chain.size() - 1; k >= 0; --k) {
+        const int child = chain[k];
+        const int parent = c->nodes[child].parent;
+        DevPlan &dp = *c->plans[((size_t)c->nodes[child].joint * 2 + 0) * S + s];
+        Sink sink;
+        if (parent == root) {
+          sink.out0 = c->rootmsg.as<float>() + (size_t)ci * N;  // combined later, in joint order
+        } else {
+          sink.out0 = c->POST(parent, s);
+          if (c->cfg.is_detect[parent]) sink.add0 = c->U(parent, s);  // :652-654
+          sink.max0 = c->MAXP(parent);
+          if ((rc = reset_max(c, sink.max0))) return rc;
+          belief[parent] = sink.out0;
+        }
+        if ((rc = run_message(c, dp, belief[child], c->MAXP(child), sparse, sink))) return rc;
+      }
+    }
+    // root: post = sum of messages (joint order) + unary; fr_j = sum_{i != j} + unary (:637-654, :169)
+    {
+      psk::RootArgs a{};
+      a.n = nrc;
+      for (int j = 0; j < nrc; ++j) {
+        a.m[j] = c->rootmsg.as<float>() + (size_t)j * N;
+        a.fr_max[j] = c->MAXP(P + j);
+        if ((rc = reset_max(c, a.fr_max[j]))) return rc;
+      }
+      if (!c->cfg.is_detect[root])
+        return c->fail(PS_ERR_INVALID, "root part must have is_detect set (findrot.cpp:785)");
+      a.unary = c->U(root, s);
+      a.post = c->POST(root, s);
+      a.N = N;
+      if (nrc > 0) {
+        psk::k_root_combine<<<cdiv(N, 256), 256, 0, st>>>(a);
+        PS_LAUNCH_CHECK(c);
+      } else {
+        PS_CUDA(c, cudaMemcpyAsync(a.post, a.unary, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+    }
+
+    // ---------------- downward pass (computePartMarginals, findrot.cpp:158-236) ----------------
+    for (int ci = 0; ci < nrc; ++ci) {
+      const float *in = c->rootmsg.as<float>() + (size_t)ci * N;
+      const int *in_max = c->MAXP(P + ci);
+      int tsel = 0;
+      for (int q = rn.children[ci]; q >= 0;) {
+        const Node &nq = c->nodes[q];
+        DevPlan &dp = *c->plans[((size_t)nq.joint * 2 + 1) * S + s];
+        Sink sink;
+        // post[q] += from_root[q] (:201).  For a leaf, post[q] is still "0 + unary" held in the unary itself.
+        sink.out0 = c->POST(q, s);
+        sink.acc0 = belief[q];
+        int next = nq.children.empty() ? -1 : nq.children[0];
+        if (next >= 0) {
+          // tmp = unary[q] + from_root[q] (:221-222), input of the next message
+          sink.out1 = c->tmp[tsel].as<float>();
+          sink.add1 = c->U(q, s);
+          sink.max1 = c->MAXP(P + psk::kMaxRootChildren + tsel);
+          if ((rc = reset_max(c, sink.max1))) return rc;
+        }
+        if ((rc = run_message(c, dp, in, in_max, false, sink))) return rc;
+        if (next >= 0) {
+          in = sink.out1;
+          in_max = sink.max1;
+          tsel ^= 1;
+        }
+        q = next;
+      }
+    }
+
+    // root rotation-marginal of this scale (findrot.cpp:694-726)
+    psk::k_root_marginal<<<cdiv(c->HW, 256), 256, 0, st>>>(c->POST(root, s), c->HW, c->valid_rots.as<int>(),
+                                                          c->n_valid_rots, c->root_post.as<float>() + (size_t)s * c->HW);
+    PS_LAUNCH_CHECK(c);
+  }
+
+  // per-part readout: the reference redoes it for every scale and keeps the last (findrot.cpp:257-259)
+  std::vector<const float *> grids(P);
+  for (int p = 0; p < P; ++p) grids[p] = c->POST(p, S - 1);
+  if ((rc = readout_parts(c, grids, S - 1, flags & PS_INFER_LOCAL_MAX))) return rc;
+  c->result_scale = S - 1;
+
+  c->have_root_hyps = false;
+  if (flags & PS_INFER_ROOT_HYPS) {
+    if ((rc = local_max_device(c, c->root_post.as<float>(), S, c->H, c->W, 1000, c->root_hyps))) return rc;
+    c->have_root_hyps = true;
+  }
+  if (flags & PS_INFER_KEEP_UNARIES)
+    PS_CUDA(c, cudaMemcpyAsync(c->unary.p, c->unary_backup.p, c->unary.bytes, cudaMemcpyDeviceToDevice, st));
+  c->have_result = true;
+  return PS_OK;
+}
+
+int ps_max_states(ps_ctx *c, int flags) {
+  if (!c) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  std::vector<const float *> grids(c->P);
+  for (int p = 0; p < c->P; ++p) grids[p] = c->U(p, 0);
+  int rc = readout_parts(c, grids, 0, flags & PS_INFER_LOCAL_MAX);
+  if (rc) return rc;
+  c->have_result = true;
+  c->have_root_hyps = false;
+  c->result_scale = -2;  // marginals are not available after getMaxStates
+  return PS_OK;
+}
+
+int ps_get_best_conf(ps_ctx *c, float *out) {
+  if (!c || !out) return PS_ERR_INVALID;
+  if (!c->have_result) return c->fail(PS_ERR_STATE, "no result: call ps_infer first");
+  memcpy(out, c->best_conf.data(), c->best_conf.size() * sizeof(float));
+  return PS_OK;
+}
+
+int ps_get_part_hyps(ps_ctx *c, int part, float *out, int cap, int *count) {
+  if (!c || !out || !count) return PS_ERR_INVALID;
+  if (!c->have_result) return c->fail(PS_ERR_STATE, "no result: call ps_infer first");
+  if (part < 0 || part >= c->P) return c->fail(PS_ERR_INVALID, "part out of range");
+  int n = std::min((int)(c->part_hyps[part].size() / PS_HYP_VEC), cap);
+  memcpy(out, c->part_hyps[part].data(), (size_t)n * PS_HYP_VEC * sizeof(float));
+  *count = n;
+  return PS_OK;
+}
+
+int ps_get_marginal(ps_ctx *c, int part, int scale, float *dst, int mem_kind) {
+  if (!c || !dst) return PS_ERR_INVALID;
+  if (!c->have_result || c->result_scale < 0) return c->fail(PS_ERR_STATE, "no marginals: call ps_infer first");
+  if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  if (!c->cfg.keep_all_scales && scale != c->S - 1)
+    return c->fail(PS_ERR_STATE, "only the last scale is resident; create the ctx with keep_all_scales");
+  PS_CUDA(c, cudaMemcpyAsync(dst, c->POST(part, scale), c->N * sizeof(float),
+                             mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+int ps_get_root_posterior(ps_ctx *c, float *dst, int mem_kind) {
+  if (!c || !dst) return PS_ERR_INVALID;
+  if (!c->have_result || c->result_scale < 0) return c->fail(PS_ERR_STATE, "no root posterior: call ps_infer first");
+  PS_CUDA(c, cudaMemcpyAsync(dst, c->root_post.p, c->HW * c->S * sizeof(float),
+                             mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+int ps_get_root_hyps(ps_ctx *c, float *out, int cap, int *count) {
+  if (!c || !out || !count) return PS_ERR_INVALID;
+  if (!c->have_result || !c->have_root_hyps) return c->fail(PS_ERR_STATE, "no root hypotheses: ps_infer with PS_INFER_ROOT_HYPS");
+  int n = std::min((int)(c->root_hyps.size() / 4), cap);
+  memcpy(out, c->root_hyps.data(), (size_t)n * 4 * sizeof(float));
+  *count = n;
+  return PS_OK;
+}
+
+// ---- test seams -----------------------------------------------------------------------------------
+
+int ps_message(ps_ctx *c, const float *child, float *parent, int mem_kind, const double off_in[2],
+               const double off_out[2], const double C[4], double rot_mean, double rot_sigma, double scale, int sparse) {
+  if (!c || !child || !parent || !off_in || !off_out || !C) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  double keyv[11] = {off_in[0], off_in[1], off_out[0], off_out[1], C[0], C[1], C[2], C[3], rot_mean, rot_sigma, scale};
+  std::string key((const char *)keyv, sizeof keyv);
+  auto it = c->adhoc_plans.find(key);
+  if (it == c->adhoc_plans.end()) {
+    std::unique_ptr<DevPlan> dp(new DevPlan);
+    dp->host = psg::plan_message(grid_of(c), off_in, off_out, C, rot_mean, rot_sigma, scale);
+    if (!dp->host.error.empty()) return c->fail(PS_ERR_INVALID, "%s", dp->host.error.c_str());
+    int rc = upload_plan(c, *dp);
+    if (rc) return rc;
+    if (c->adhoc_plans.size() > 64) c->adhoc_plans.clear();
+    it = c->adhoc_plans.emplace(key, std::move(dp)).first;
+  }
+  DevPlan &dp = *it->second;
+  const float *din = child;
+  float *dout = parent;
+  if (mem_kind == PS_MEM_HOST) {
+    PS_CUDA(c, cudaMemcpyAsync(c->tmp[0].p, child, c->N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    din = c->tmp[0].as<float>();
+    dout = c->tmp[1].as<float>();
+  }
+  int *mx = c->MAXP(c->P + psk::kMaxRootChildren + 2);
+  int rc = grid_max(c, din, c->N, mx);
+  if (rc) return rc;
+  Sink sink;
+  sink.out0 = dout;
+  if ((rc = run_message(c, dp, din, mx, sparse != 0, sink))) return rc;
+  if (mem_kind == PS_MEM_HOST)
+    PS_CUDA(c, cudaMemcpyAsync(parent, dout, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+int ps_find_local_max(ps_ctx *c, const float *grid, int mem_kind, int d0, int h, int w, int max_n, float *out,
+                      int *count) {
+  if (!c || !grid || !out || !count || d0 < 1 || h < 1 || w < 1 || max_n < 0) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  size_t n = (size_t)d0 * h * w;
+  DevBuf tmp;
+  const float *dg = grid;
+  if (mem_kind == PS_MEM_HOST) {
+    PS_CUDA(c, tmp.alloc(n * sizeof(float)));
+    PS_CUDA(c, cudaMemcpyAsync(tmp.p, grid, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    dg = tmp.as<float>();
+  }
+  std::vector<float> rows;
+  int rc = local_max_device(c, dg, d0, h, w, max_n, rows);
+  if (rc) return rc;
+  memcpy(out, rows.data(), rows.size() * sizeof(float));
+  *count = (int)(rows.size() / 4);
+  return PS_OK;
+}
+
+}  // extern "C"
