@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- PS-inference images/sec on N B200s (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W                      # our arm (CUDA path through the C ABI)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                          # N > 1: images shard across ranks, no collective
+    python bench.py --impl reference --steps K --warmup W               # reference arm: the CPU oracle on all host threads
+
+A "step" is one pass of the hot path (unary prep a4 -> upward pass -> downward pass -> argmax readout, SURVEY.md
+section 8a) over a batch of synthetic LSP-shape images (BASELINE.json configs[1]: 10-part tree, 24 rotations x 1
+scale, 600x400 grid, generic full-covariance spatial model).  `value` times it with the classifier-score grids
+already resident in HBM; `e2e` times the same work through the host-buffer API (pinned host grids in, best_conf out).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(R=24, S=1, H=600, W=400, P=10)
+METRIC = "ps_inference_images_per_sec"
+UNIT = "images/s"
+
+
+def workload_config(parallelism, extra=None):
+    cfg = {"workload": "configs[1]: synthetic LSP-shape image, 10-part tree (root 4), R=24 x S=1, 600x400 grid, "
+                       "generic full-covariance joints (sigma 4-16 px), stride-4 sparse unaries",
+           "R": WORKLOAD["R"], "S": WORKLOAD["S"], "H": WORKLOAD["H"], "W": WORKLOAD["W"], "P": WORKLOAD["P"],
+           "parallelism": parallelism,
+           "l2_policy": "inputs larger than L2: ~0.75 GB of grids touched per image vs 126 MB L2; distinct images per step"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def algorithmic_bytes_per_image():
+    """B_img = S*G*(6J + 3P + 1), G = 4*R*H*W (SURVEY.md section 8d / BASELINE.md section 3)."""
+    w = WORKLOAD
+    G = 4 * w["R"] * w["H"] * w["W"]
+    J = w["P"] - 1
+    return w["S"] * G * (6 * J + 3 * w["P"] + 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["reasons"] = sorted(reasons)
+            out["samples"] = len(sm)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def make_inputs(n_images, first_index):
+    from partapp_b200 import ExpParam, synth
+    w = WORKLOAD
+    ep = ExpParam(num_rotation_steps=w["R"], num_scale_steps=w["S"])
+    pc = synth.part_conf(w["P"])
+    joints = synth.make_joints(w["P"], seed=7)
+    raws = [synth.raw_scores(ep, w["H"], w["W"], w["P"], first_index + i) for i in range(n_images)]
+    return ep, pc, joints, raws
+
+
+def run_ours(args):
+    import torch
+    from partapp_b200 import PsContext, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if rank == 0:
+            sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE=%d; launch with torch.distributed.run\n" % (args.gpus, world))
+        if world == 1 and args.gpus > 1:
+            sys.exit(2)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: partapp_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    w = WORKLOAD
+    B = args.images  # images per rank per step
+    # contiguous image-index shards per rank, like the reference's --first/--numimgs (main.cpp:155-192)
+    ep, pc, joints, raws = make_inputs(B, first_index=rank * B)
+    P, N = w["P"], w["R"] * w["H"] * w["W"]
+
+    n_ctx = args.streams
+    streams = [torch.cuda.Stream() for _ in range(n_ctx)]
+    ctxs = []
+    for i in range(n_ctx):
+        c = PsContext(ep, pc, w["H"], w["W"], device=local_rank)
+        c.set_stream(streams[i].cuda_stream)
+        c.set_joints(joints)
+        ctxs.append(c)
+
+    # resident inputs: raw classifier-score grids of B images in HBM, and the same in pinned host memory
+    dev_raw = [torch.from_numpy(r.reshape(P, N)).cuda() for r in raws]
+    pin_raw = [torch.from_numpy(r.reshape(P, N)).pin_memory() for r in raws]
+    results = np.zeros((B, P, 7), np.float32)
+
+    def step(device_resident):
+        # software pipeline over ctxs: enqueue image i on ctx i % n_ctx; results are read (host sync) one image late
+        pending = []
+        for i in range(B):
+            c = ctxs[i % n_ctx]
+            if len(pending) >= n_ctx:
+                j, cj = pending.pop(0)
+                results[j] = cj.best_conf()
+            src = dev_raw[i] if device_resident else pin_raw[i]
+            for p in range(P):
+                ptr = src[p].data_ptr()
+                if device_resident:
+                    c.set_unary_device(p, 0, ptr, raw_scores=True)
+                else:
+                    c.set_unary_pinned(p, 0, ptr, raw_scores=True)
+            c.infer_async(sparse=True)
+            pending.append((i, c))
+        for j, cj in pending:
+            results[j] = cj.best_conf()
+
+    def timed(n_steps, device_resident):
+        main = torch.cuda.current_stream()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for s in streams:
+            s.wait_event(e0)
+        for _ in range(n_steps):
+            step(device_resident)
+        for s in streams:
+            main.wait_stream(s)
+        e1.record(main)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput ----
+    if args.ncu:
+        for _ in range(args.warmup):
+            step(True)
+        timed(args.steps, True)
+        for c in ctxs:
+            c.close()
+        return
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    launches0 = sum(c.launch_count() for c in ctxs)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed(args.steps, True)
+    clocks = sampler.stop() if sampler else None
+    launches = sum(c.launch_count() for c in ctxs) - launches0
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the host-buffer API ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        step(False)
+    ms_e2e = timed(e2e_steps, False)
+    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+
+    out = None
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        # ---- instrumented pass: CUDA events around every launch of one ctx, for the per-kernel roofline ----
+        c = ctxs[0]
+        c.profile_enable(True)
+        for i in range(min(B, 2)):
+            for p in range(P):
+                c.set_unary_device(p, 0, dev_raw[i][p].data_ptr(), raw_scores=True)
+            c.infer_async(sparse=True)
+            c.best_conf()
+        prof = c.profile_read()
+        c.profile_enable(False)
+        n_img_prof = min(B, 2)
+        tot_ms = sum(v[0] for v in prof.values())
+        dom = max(prof.items(), key=lambda kv: kv[1][0])
+        G = 4.0 * N
+        # algorithmic bytes per launch of each kernel class (DESIGN.md "Kernels"): one read + one write of the grid
+        # the launch covers; for conv passes of a full-covariance message that grid is the eigen-frame grid, whose
+        # size we do not know here, so the image-grid figure (a lower bound) is used.
+        alg_per_launch = {"conv_rows": 2 * G, "conv_cols": 2 * G, "rotconv": 2 * G, "epilogue": 3 * G,
+                          "warp_direct": 2 * G, "warp_bilinear": 2 * G, "prepare_unary": 2 * G, "grid_max": G,
+                          "root_combine": 12 * G, "argmax": G, "root_marginal": G}
+        dom_ms_per_launch = dom[1][0] / dom[1][1]
+        dom_bytes = alg_per_launch.get(dom[0], 2 * G)
+        achieved = dom_bytes / (dom_ms_per_launch * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": round(dom_ms_per_launch, 4),
+                    "share_of_step": round(dom[1][0] / tot_ms, 3),
+                    "how": "CUDA events around every launch on the ctx stream (instrumented pass over %d images)" % n_img_prof,
+                    "kernel_ms_per_image": {k: round(v[0] / n_img_prof, 4) for k, v in sorted(prof.items())},
+                    "whole_image": {"algorithmic_bytes": algorithmic_bytes_per_image(),
+                                    "achieved_GBps": round(algorithmic_bytes_per_image() * value / world / 1e9, 1),
+                                    "frac": round(algorithmic_bytes_per_image() * value / world / 1e9 / peak, 4)},
+                    "note": "parity mode is bound by the fp32 pipe (separately rounded mul+add per tap), not by HBM; "
+                            "see DESIGN.md"}
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline = run_cpu_sample(ep, pc, joints, raws[0], threads=1)
+        out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": workload_config("images sharded over %d GPU(s), %d images/GPU/step, %d stream(s)/GPU, no collective"
+                                         % (world, B, n_ctx)),
+               "clocks": clocks,
+               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(B * P * N * 4),
+                       "d2h_bytes_per_step": int(B * P * 7 * 4), "steps": e2e_steps,
+                       "ms_per_step": round(ms_e2e / e2e_steps, 3)},
+               "gpu_launches": int(launches),
+               "roofline": roofline,
+               "cpu_baseline": cpu_baseline}
+    for c in ctxs:
+        c.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_cpu_sample(ep, pc, joints, raw, threads=1):
+    """Times the CPU oracle (the only runnable statement of the reference path) on one full image, one thread."""
+    import oracle
+    un = oracle.prepare_unary(raw)
+    t0 = time.perf_counter()
+    oracle.infer(ep, pc, joints, un, sparse=True, want_marginals=False)
+    dt = time.perf_counter() - t0
+    return {"value": round(1.0 / dt, 5), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "1 full image of the same workload (18 messages + readout) on 1 thread: %.1f s" % dt}
+
+
+def run_reference(args):
+    """Reference arm: the CPU oracle (kind "port": the reference itself cannot be compiled here), using
+    every host thread the way the reference scales -- independent images per process/thread (main.cpp:155-192).
+    Each step is a bounded sample: every thread runs `m` of the 18 messages of its own image at full size."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle
+    from partapp_b200 import synth
+    oracle.build()
+    w = WORKLOAD
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, args.ref_threads or cores))
+    ep, pc, joints, _ = make_inputs(0, 0)
+    J = len(joints)
+    n_msgs_per_image = 2 * J
+    # one sparse unary grid per thread (images are independent)
+    un = [oracle.prepare_unary(synth.raw_scores(ep, w["H"], w["W"], 1, 100 + t)[0, 0]) for t in range(min(threads, 8))]
+
+    def work(t, step_idx):
+        j = joints[(step_idx + t) % J]
+        g = un[t % len(un)]
+        up = oracle.message(ep, g, j.offset_c, j.offset_p, j.C, j.rot_mean, j.rot_sigma, 1.0, True)
+        oracle.message(ep, up, j.offset_p, j.offset_c, j.C, -j.rot_mean, j.rot_sigma, 1.0, False)
+        return 2
+
+    pool = ThreadPoolExecutor(threads)
+    warm = min(args.warmup, 1)
+    for s in range(warm):
+        list(pool.map(lambda t: work(t, s), range(threads)))
+    steps = args.steps
+    t0 = time.perf_counter()
+    msgs = 0
+    done_steps = 0
+    budget = args.ref_budget_s
+    for s in range(steps):
+        msgs += sum(pool.map(lambda t: work(t, s), range(threads)))
+        done_steps += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    dt = time.perf_counter() - t0
+    value = (msgs / float(n_msgs_per_image)) / dt
+    sample = ("each step: %d threads x 2 full-size messages (1 upward sparse + 1 downward) of the 18 per image, "
+              "scaled by 18; %d of %d requested steps inside a %.0f s budget" % (threads, done_steps, steps, budget))
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus,
+           "steps": done_steps, "warmup": warm, "ms_per_step": round(dt / done_steps * 1e3, 1),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config("CPU: one image per host thread, %d threads" % threads),
+           "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=4, help="images per GPU per step")
+    ap.add_argument("--streams", type=int, default=2, help="contexts/streams per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true",
+                    help="profiling run under ncu: honour a short warmup, skip e2e / instrumented pass / CPU baseline "
+                         "(numbers printed by such a run are not bench values)")
+    ap.add_argument("--ref-threads", type=int, default=0)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

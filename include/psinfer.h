@@ -189,6 +189,12 @@ int ps_find_local_max(ps_ctx *ctx, const float *grid, int mem_kind, int d0, int 
 /* Number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches). */
 long long ps_launch_count(const ps_ctx *ctx);
 
+/* Device timing per kernel class: with profiling on, every launch on the ctx stream is bracketed by CUDA events.
+ * ps_profile_read synchronises, returns (name, total ms, launches) per class seen since the last read and resets.
+ * The reference has no counterpart (its only timer, get_runtime(), findrot.cpp:52-57, is commented out at :987-998). */
+int ps_profile_enable(ps_ctx *ctx, int on);
+int ps_profile_read(ps_ctx *ctx, int cap, const char **names, double *total_ms, long long *launches, int *count);
+
 /* Library identification: "psinfer <version> sm_100a". */
 const char *ps_version(void);
 

@@ -79,6 +79,13 @@ struct ps_ctx {
   std::string err;
   long long launches = 0;
 
+  // optional per-kernel-class device timing (ps_profile_enable)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int klass; size_t e0, e1; };
+  std::vector<Span> spans;
+
   // resident grids
   DevBuf unary;         // [P][S][N]
   DevBuf unary_backup;  // lazily, for PS_INFER_KEEP_UNARIES
@@ -105,8 +112,14 @@ struct ps_ctx {
   std::vector<std::unique_ptr<DevPlan>> plans;
   std::map<std::string, std::unique_ptr<DevPlan>> adhoc_plans;  // ps_message cache
 
-  // results
+  // results.  ps_infer / ps_max_states only enqueue device work; the host part of the readout (decode of the
+  // argmax keys, local-maximum selection) runs in finish_result() when a getter needs it.
   bool have_result = false;
+  bool result_pending = false;
+  int pending_flags = 0;
+  int pending_scaleidx = 0;
+  std::vector<const float *> pending_grids;
+  unsigned long long *host_keys = nullptr;  // pinned [P]
   int result_scale = -1;
   std::vector<float> best_conf;               // [P][7]
   std::vector<std::vector<float>> part_hyps;  // per part rows of 7
@@ -135,8 +148,35 @@ struct ps_ctx {
     if (e_ != cudaSuccess) return (ctx)->fail(PS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
-#define PS_LAUNCH_CHECK(ctx)                                                                        \
+// kernel classes for ps_profile_read / DESIGN.md
+enum KClass {
+  KC_PREP = 0, KC_MAX, KC_MASK, KC_ROTCONV, KC_WARP_DIRECT, KC_WARP_BILINEAR, KC_CONV_ROWS, KC_CONV_COLS,
+  KC_EPILOGUE, KC_ROOT_COMBINE, KC_ROOT_MARGINAL, KC_ARGMAX, KC_LOCAL_MAX, KC_MISC, KC_COUNT
+};
+static const char *const kClassNames[KC_COUNT] = {
+    "prepare_unary", "grid_max", "mask", "rotconv", "warp_direct", "warp_bilinear", "conv_rows", "conv_cols",
+    "epilogue", "root_combine", "root_marginal", "argmax", "local_max", "misc"};
+
+static size_t prof_event(ps_ctx *c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  cudaEventRecord(c->ev_pool[c->ev_used], c->stream);
+  return c->ev_used++;
+}
+
+// Launch a kernel of class `klass` on the ctx stream; with profiling on, bracket it with CUDA events.
+#define PS_LAUNCH(ctx, klass, ...)                                                                  \
   do {                                                                                              \
+    size_t e0_ = 0;                                                                                 \
+    if ((ctx)->profiling) e0_ = prof_event(ctx);                                                    \
+    __VA_ARGS__;                                                                                    \
+    if ((ctx)->profiling) {                                                                         \
+      size_t e1_ = prof_event(ctx);                                                                 \
+      (ctx)->spans.push_back({(klass), e0_, e1_});                                                  \
+    }                                                                                               \
     ++(ctx)->launches;                                                                              \
     cudaError_t e_ = cudaGetLastError();                                                            \
     if (e_ != cudaSuccess) return (ctx)->fail(PS_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e_)); \
@@ -206,9 +246,8 @@ int ensure_direct_map(ps_ctx *c, DevPlan &dp) {
   int *ovf = c->counters.as<int>() + 7;
   PS_CUDA(c, cudaMemsetAsync(ovf, 0, sizeof(int), c->stream));
   dim3 b(32, 8), g(cdiv(h.EW, 32), cdiv(h.EH, 8));
-  psk::k_build_direct_map<<<g, b, 0, c->stream>>>(dp.map.as<int2>(), h.EH, h.EW, c->H, c->W, dp.mats.as<double>(),
-                                                  dp.mats.as<double>() + 6, ovf);
-  PS_LAUNCH_CHECK(c);
+  PS_LAUNCH(c, KC_MISC, psk::k_build_direct_map<<<g, b, 0, c->stream>>>(dp.map.as<int2>(), h.EH, h.EW, c->H, c->W, dp.mats.as<double>(),
+                                                  dp.mats.as<double>() + 6, ovf));
   int hovf = 0;
   PS_CUDA(c, cudaMemcpyAsync(&hovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -247,8 +286,7 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     a.R = R; a.H = H; a.W = W;
     a.shift = h.rot_shift; a.mode = h.rot_mode; a.len = (int)h.rot_taps.size();
     size_t smem = (size_t)R * psk::kRotThreads * sizeof(float);
-    psk::k_rotconv<<<cdiv(c->HW, psk::kRotThreads), psk::kRotThreads, smem, st>>>(a);
-    PS_LAUNCH_CHECK(c);
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv<<<cdiv(c->HW, psk::kRotThreads), psk::kRotThreads, smem, st>>>(a));
   }
 
   psk::EpiArgs e{};
@@ -264,16 +302,14 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     while (S % 8 != 4) ++S;  // conflict-free transposed staging
     int TY = 4;
     size_t smem = (size_t)TY * T * S * sizeof(float);
-    psk::k_conv_rows<T><<<dim3(cdiv(rows, TY), R), 256, smem, st>>>(a, TY, S);
-    PS_LAUNCH_CHECK(c);
+    PS_LAUNCH(c, KC_CONV_ROWS, psk::k_conv_rows<T><<<dim3(cdiv(rows, TY), R), 256, smem, st>>>(a, TY, S));
     return PS_OK;
   };
   auto conv_cols = [&](const float *src, float *dst, int rows, int cols, int pitch, size_t plane, const float *taps,
                        int len) -> int {
     constexpr int T = 8;
     psk::ConvArgs a{src, dst, taps, len, rows, cols, pitch, plane};
-    psk::k_conv_cols<T><<<dim3(cdiv(cols, 128), cdiv(rows, T), R), 128, 0, st>>>(a);
-    PS_LAUNCH_CHECK(c);
+    PS_LAUNCH(c, KC_CONV_COLS, psk::k_conv_cols<T><<<dim3(cdiv(cols, 128), cdiv(rows, T), R), 128, 0, st>>>(a));
     return PS_OK;
   };
 
@@ -292,15 +328,16 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     if (sparse) {
       rc = ensure_direct_map(c, dp);
       if (rc) return rc;
-      psk::k_warp_direct<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(),
-                                                                 dp.map.as<int2>(), R, c->HW, EH, EW, EP);
+      PS_LAUNCH(c, KC_WARP_DIRECT,
+                psk::k_warp_direct<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(),
+                                                                           dp.map.as<int2>(), R, c->HW, EH, EW, EP));
     } else {
       Affine T13;
       memcpy(T13.m, h.T13, sizeof T13.m);
-      psk::k_warp_bilinear<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(), T13, R,
-                                                                   H, W, EH, EW, EP);
+      PS_LAUNCH(c, KC_WARP_BILINEAR,
+                psk::k_warp_bilinear<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(),
+                                                                             T13, R, H, W, EH, EW, EP));
     }
-    PS_LAUNCH_CHECK(c);
     rc = conv_rows(c->bufU.as<float>(), c->bufV.as<float>(), EH, EW, EP, eplane, dp.fx(), (int)h.fx.size());
     if (rc) return rc;
     rc = conv_cols(c->bufV.as<float>(), c->bufU.as<float>(), EH, EW, EP, eplane, dp.fy(), (int)h.fy.size());
@@ -319,22 +356,19 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
   e.out0 = sink.out0; e.acc0 = sink.acc0; e.add0 = sink.add0;
   e.out1 = sink.out1; e.add1 = sink.add1;
   e.max0 = sink.max0; e.max1 = sink.max1;
-  psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e);
-  PS_LAUNCH_CHECK(c);
+  PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e));
   return PS_OK;
 }
 
 int reset_max(ps_ctx *c, int *slot) {
-  psk::k_set_int<<<1, 32, 0, c->stream>>>(slot, 1, PS_ENC_NEG_INF);
-  PS_LAUNCH_CHECK(c);
+  PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(slot, 1, PS_ENC_NEG_INF));
   return PS_OK;
 }
 
 int grid_max(ps_ctx *c, const float *g, size_t n, int *slot) {
   int rc = reset_max(c, slot);
   if (rc) return rc;
-  psk::k_grid_max<<<std::min(cdiv(n, 256 * 8), 148u * 8), 256, 0, c->stream>>>(g, n, slot);
-  PS_LAUNCH_CHECK(c);
+  PS_LAUNCH(c, KC_MAX, psk::k_grid_max<<<std::min(cdiv(n, 256 * 8), 148u * 8), 256, 0, c->stream>>>(g, n, slot));
   return PS_OK;
 }
 
@@ -372,6 +406,40 @@ const char *ps_version(void) { return "psinfer 0.1 sm_100a"; }
 const char *ps_last_error(const ps_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 long long ps_launch_count(const ps_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ps_profile_enable(ps_ctx *c, int on) {
+  if (!c) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->profiling = on != 0;
+  c->spans.clear();
+  c->ev_used = 0;
+  return PS_OK;
+}
+
+int ps_profile_read(ps_ctx *c, int cap, const char **names, double *total_ms, long long *launches, int *count) {
+  if (!c || !names || !total_ms || !launches || !count) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  double ms[KC_COUNT] = {0};
+  long long n[KC_COUNT] = {0};
+  for (const ps_ctx::Span &sp : c->spans) {
+    float t = 0;
+    PS_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[sp.e0], c->ev_pool[sp.e1]));
+    ms[sp.klass] += t;
+    ++n[sp.klass];
+  }
+  int k = 0;
+  for (int i = 0; i < KC_COUNT && k < cap; ++i)
+    if (n[i]) {
+      names[k] = kClassNames[i];
+      total_ms[k] = ms[i];
+      launches[k] = n[i];
+      ++k;
+    }
+  *count = k;
+  c->spans.clear();
+  c->ev_used = 0;
+  return PS_OK;
+}
 
 double ps_rot_from_index(const ps_config *cfg, int idx) {
   return psg::value_from_index(cfg->min_part_rotation, cfg->max_part_rotation, cfg->num_rotation_steps, idx);
@@ -531,6 +599,7 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   if (!cu(c->maxes.alloc((c->P + psk::kMaxRootChildren + 4) * sizeof(int)), "alloc maxima")) return PS_ERR_CUDA;
   if (!cu(c->argmax_keys.alloc(c->P * sizeof(unsigned long long)), "alloc argmax")) return PS_ERR_CUDA;
   if (!cu(c->counters.alloc(8 * sizeof(unsigned)), "alloc counters")) return PS_ERR_CUDA;
+  if (!cu(cudaMallocHost((void **)&c->host_keys, c->P * sizeof(unsigned long long)), "alloc pinned keys")) return PS_ERR_CUDA;
   // non-detect parts have all-zero unaries in the reference (findrot.cpp:794 resize, never loaded)
   if (!cu(cudaMemsetAsync(c->unary.p, 0, c->unary.bytes, c->stream), "memset")) return PS_ERR_CUDA;
 
@@ -565,6 +634,8 @@ void ps_destroy(ps_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->host_keys) cudaFreeHost(ctx->host_keys);
   delete ctx;
 }
 
@@ -642,6 +713,7 @@ int ps_set_joints(ps_ctx *c, const ps_joint *joints, int nj) {
   c->joints.assign(joints, joints + nj);
   c->joints_set = true;
   c->have_result = false;
+  c->result_pending = false;
   return PS_OK;
 }
 
@@ -655,8 +727,7 @@ int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind,
   PS_CUDA(c, cudaMemcpyAsync(dst, src, c->N * sizeof(float),
                              mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   if (raw) {
-    psk::k_prepare_unary<<<std::min(cdiv(c->N, 256 * 4), 148u * 16), 256, 0, c->stream>>>(dst, c->N);
-    PS_LAUNCH_CHECK(c);
+    PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N, 256 * 4), 148u * 16), 256, 0, c->stream>>>(dst, c->N));
   }
   return PS_OK;
 }
@@ -680,9 +751,8 @@ int ps_add_unary_table(ps_ctx *c, int part, const float *table, int kind, float 
   PS_CUDA(c, d.alloc(n * sizeof(float)));
   PS_CUDA(c, cudaMemcpyAsync(d.p, table, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   for (int s = 0; s < c->S; ++s) {
-    psk::k_add_table<<<dim3(std::min(cdiv(c->HW, 256), 1024u), c->R), 256, 0, c->stream>>>(c->U(part, s), c->R, c->HW,
-                                                                                       d.as<float>(), kind, weight);
-    PS_LAUNCH_CHECK(c);
+    PS_LAUNCH(c, KC_MISC, psk::k_add_table<<<dim3(std::min(cdiv(c->HW, 256), 1024u), c->R), 256, 0, c->stream>>>(c->U(part, s), c->R, c->HW,
+                                                                                       d.as<float>(), kind, weight));
   }
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
   return PS_OK;
@@ -712,8 +782,7 @@ int local_max_device(ps_ctx *c, const float *g, int D0, int H, int W, int max_n,
   }
   unsigned *cnt = c->counters.as<unsigned>();
   PS_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned), c->stream));
-  psk::k_local_max<<<dim3(cdiv(W, 256), H, D0), 256, 0, c->stream>>>(g, D0, H, W, c->cand.as<psk::Cand>(), (unsigned)n, cnt);
-  PS_LAUNCH_CHECK(c);
+  PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_local_max<<<dim3(cdiv(W, 256), H, D0), 256, 0, c->stream>>>(g, D0, H, W, c->cand.as<psk::Cand>(), (unsigned)n, cnt));
   unsigned hcnt = 0;
   PS_CUDA(c, cudaMemcpyAsync(&hcnt, cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -740,35 +809,50 @@ int local_max_device(ps_ctx *c, const float *g, int D0, int H, int W, int max_n,
   return PS_OK;
 }
 
-// argmax + optional local maxima of grids g[p] for all parts (findrot.cpp:255-285 / :88-109)
-int readout_parts(ps_ctx *c, const std::vector<const float *> &grids, int scaleidx, bool local_max) {
+// argmax of grids g[p] for all parts (findrot.cpp:261-277 / :93-98): device part, asynchronous
+int enqueue_readout(ps_ctx *c, const std::vector<const float *> &grids, int scaleidx, int flags) {
   const int P = c->P;
   PS_CUDA(c, cudaMemsetAsync(c->argmax_keys.p, 0, P * sizeof(unsigned long long), c->stream));
-  for (int p = 0; p < P; ++p) {
-    psk::k_argmax<<<std::min(cdiv(c->N, 256 * 8), 148u * 8), 256, 0, c->stream>>>(
-        grids[p], c->N, c->argmax_keys.as<unsigned long long>() + p);
-    PS_LAUNCH_CHECK(c);
-  }
-  std::vector<unsigned long long> keys(P);
-  PS_CUDA(c, cudaMemcpyAsync(keys.data(), c->argmax_keys.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+  for (int p = 0; p < P; ++p)
+    PS_LAUNCH(c, KC_ARGMAX,
+              psk::k_argmax<<<std::min(cdiv(c->N, 256 * 8), 148u * 8), 256, 0, c->stream>>>(
+                  grids[p], c->N, c->argmax_keys.as<unsigned long long>() + p));
+  PS_CUDA(c, cudaMemcpyAsync(c->host_keys, c->argmax_keys.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              c->stream));
+  c->pending_grids = grids;
+  c->pending_scaleidx = scaleidx;
+  c->pending_flags = flags;
+  c->result_pending = true;
+  c->have_result = false;
+  return PS_OK;
+}
+
+// host part of the readout: decode argmax keys, then (optionally) local maxima (findrot.cpp:277-283, :1037-1038)
+int finish_result(ps_ctx *c) {
+  if (!c->result_pending) return c->have_result ? PS_OK : c->fail(PS_ERR_STATE, "no result: call ps_infer first");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->result_pending = false;
+  const int P = c->P;
+  const int scaleidx = c->pending_scaleidx;
   c->best_conf.assign((size_t)P * PS_HYP_VEC, 0.f);
   c->part_hyps.assign(P, std::vector<float>());
   for (int p = 0; p < P; ++p) {
-    if (keys[p] == 0) return c->fail(PS_ERR_INVALID, "part %d: no finite maximum (findrot.cpp:273 assert)", p);
-    unsigned idx = ~(unsigned)(keys[p] & 0xffffffffu);
-    float val = psk::dec_f((int)((unsigned)(keys[p] >> 32) ^ 0x80000000u));
+    unsigned long long key = c->host_keys[p];
+    if (key == 0) return c->fail(PS_ERR_INVALID, "part %d: no finite maximum (findrot.cpp:273 assert)", p);
+    unsigned idx = ~(unsigned)(key & 0xffffffffu);
+    float val = psk::dec_f((int)((unsigned)(key >> 32) ^ 0x80000000u));
     int rot = idx / (unsigned)c->HW, rem = idx % (unsigned)c->HW;
     int y = rem / c->W, x = rem % c->W;
     fill_hyp(c->cfg, &c->best_conf[(size_t)p * PS_HYP_VEC], scaleidx, rot, x, y, val);
     c->part_hyps[p].assign(c->best_conf.begin() + (size_t)p * PS_HYP_VEC,
                            c->best_conf.begin() + (size_t)(p + 1) * PS_HYP_VEC);
   }
+  const bool local_max = c->pending_flags & PS_INFER_LOCAL_MAX;
   if (local_max)
     for (int p = 0; p < P; ++p) {
       std::vector<float> rows;
-      int rc = local_max_device(c, grids[p], c->R, c->H, c->W, c->cfg.roi_save_num_samples, rows);
+      int rc = local_max_device(c, c->pending_grids[p], c->R, c->H, c->W, c->cfg.roi_save_num_samples, rows);
       if (rc) return rc;
       for (size_t i = 0; i < rows.size() / 4; ++i) {
         float h[PS_HYP_VEC];
@@ -778,6 +862,13 @@ int readout_parts(ps_ctx *c, const std::vector<const float *> &grids, int scalei
       }
     }
   c->have_local_max = local_max;
+  c->have_root_hyps = false;
+  if (c->pending_flags & PS_INFER_ROOT_HYPS) {
+    int rc = local_max_device(c, c->root_post.as<float>(), c->S, c->H, c->W, 1000, c->root_hyps);
+    if (rc) return rc;
+    c->have_root_hyps = true;
+  }
+  c->have_result = true;
   return PS_OK;
 }
 
@@ -808,17 +899,15 @@ int ps_infer(ps_ctx *c, int flags) {
     // upright masking of this scale (findrot.cpp:509-523)
     for (int p = 0; p < P; ++p)
       if (c->cfg.is_upright[p]) {
-        psk::k_mask_slices<<<dim3(std::min(cdiv(c->HW, 256), 512u), R), 256, 0, st>>>(c->U(p, s), R, c->HW,
-                                                                                 c->upright_mask.as<unsigned char>());
-        PS_LAUNCH_CHECK(c);
+        PS_LAUNCH(c, KC_MASK, psk::k_mask_slices<<<dim3(std::min(cdiv(c->HW, 256), 512u), R), 256, 0, st>>>(c->U(p, s), R, c->HW,
+                                                                                 c->upright_mask.as<unsigned char>()));
       }
     // border strip of the root, all scales, every iteration (findrot.cpp:528-551; idempotent)
     if (c->cfg.strip_border_detections > 0) {
       int sw = (int)(c->cfg.strip_border_detections * c->W);
       if (sw > 0)
         for (int s2 = 0; s2 < S; ++s2) {
-          psk::k_strip_border<<<cdiv((size_t)R * c->H, 8), dim3(32, 8), 0, st>>>(c->U(root, s2), R * c->H, c->W, sw);
-          PS_LAUNCH_CHECK(c);
+          PS_LAUNCH(c, KC_MASK, psk::k_strip_border<<<cdiv((size_t)R * c->H, 8), dim3(32, 8), 0, st>>>(c->U(root, s2), R * c->H, c->W, sw));
         }
     }
 
@@ -836,8 +925,7 @@ int ps_infer(ps_ctx *c, int flags) {
       if (c->cfg.is_detect[leaf]) {
         belief[leaf] = c->U(leaf, s);
       } else {
-        psk::k_fill<<<std::min(cdiv(N, 1024), 2048u), 256, 0, st>>>(c->POST(leaf, s), N, 0.0f);
-        PS_LAUNCH_CHECK(c);
+        PS_LAUNCH(c, KC_MISC, psk::k_fill<<<std::min(cdiv(N, 1024), 2048u), 256, 0, st>>>(c->POST(leaf, s), N, 0.0f));
         belief[leaf] = c->POST(leaf, s);
       }
       if ((rc = grid_max(c, belief[leaf], N, c->MAXP(leaf)))) return rc;
@@ -873,8 +961,7 @@ int ps_infer(ps_ctx *c, int flags) {
       a.post = c->POST(root, s);
       a.N = N;
       if (nrc > 0) {
-        psk::k_root_combine<<<cdiv(N, 256), 256, 0, st>>>(a);
-        PS_LAUNCH_CHECK(c);
+        PS_LAUNCH(c, KC_ROOT_COMBINE, psk::k_root_combine<<<cdiv(N, 256), 256, 0, st>>>(a));
       } else {
         PS_CUDA(c, cudaMemcpyAsync(a.post, a.unary, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
       }
@@ -911,25 +998,21 @@ int ps_infer(ps_ctx *c, int flags) {
     }
 
     // root rotation-marginal of this scale (findrot.cpp:694-726)
-    psk::k_root_marginal<<<cdiv(c->HW, 256), 256, 0, st>>>(c->POST(root, s), c->HW, c->valid_rots.as<int>(),
-                                                          c->n_valid_rots, c->root_post.as<float>() + (size_t)s * c->HW);
-    PS_LAUNCH_CHECK(c);
+    PS_LAUNCH(c, KC_ROOT_MARGINAL, psk::k_root_marginal<<<cdiv(c->HW, 256), 256, 0, st>>>(c->POST(root, s), c->HW, c->valid_rots.as<int>(),
+                                                          c->n_valid_rots, c->root_post.as<float>() + (size_t)s * c->HW));
   }
 
   // per-part readout: the reference redoes it for every scale and keeps the last (findrot.cpp:257-259)
   std::vector<const float *> grids(P);
   for (int p = 0; p < P; ++p) grids[p] = c->POST(p, S - 1);
-  if ((rc = readout_parts(c, grids, S - 1, flags & PS_INFER_LOCAL_MAX))) return rc;
+  if ((rc = enqueue_readout(c, grids, S - 1, flags))) return rc;
   c->result_scale = S - 1;
-
-  c->have_root_hyps = false;
-  if (flags & PS_INFER_ROOT_HYPS) {
-    if ((rc = local_max_device(c, c->root_post.as<float>(), S, c->H, c->W, 1000, c->root_hyps))) return rc;
-    c->have_root_hyps = true;
-  }
-  if (flags & PS_INFER_KEEP_UNARIES)
+  if (flags & PS_INFER_KEEP_UNARIES) {
+    if (flags & (PS_INFER_LOCAL_MAX | PS_INFER_ROOT_HYPS)) {
+      if ((rc = finish_result(c))) return rc;  // local maxima read the beliefs, not the unaries, but keep order simple
+    }
     PS_CUDA(c, cudaMemcpyAsync(c->unary.p, c->unary_backup.p, c->unary.bytes, cudaMemcpyDeviceToDevice, st));
-  c->have_result = true;
+  }
   return PS_OK;
 }
 
@@ -938,24 +1021,22 @@ int ps_max_states(ps_ctx *c, int flags) {
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   std::vector<const float *> grids(c->P);
   for (int p = 0; p < c->P; ++p) grids[p] = c->U(p, 0);
-  int rc = readout_parts(c, grids, 0, flags & PS_INFER_LOCAL_MAX);
+  int rc = enqueue_readout(c, grids, 0, flags & PS_INFER_LOCAL_MAX);
   if (rc) return rc;
-  c->have_result = true;
-  c->have_root_hyps = false;
   c->result_scale = -2;  // marginals are not available after getMaxStates
   return PS_OK;
 }
 
 int ps_get_best_conf(ps_ctx *c, float *out) {
   if (!c || !out) return PS_ERR_INVALID;
-  if (!c->have_result) return c->fail(PS_ERR_STATE, "no result: call ps_infer first");
+  if (int rc = finish_result(c)) return rc;
   memcpy(out, c->best_conf.data(), c->best_conf.size() * sizeof(float));
   return PS_OK;
 }
 
 int ps_get_part_hyps(ps_ctx *c, int part, float *out, int cap, int *count) {
   if (!c || !out || !count) return PS_ERR_INVALID;
-  if (!c->have_result) return c->fail(PS_ERR_STATE, "no result: call ps_infer first");
+  if (int rc = finish_result(c)) return rc;
   if (part < 0 || part >= c->P) return c->fail(PS_ERR_INVALID, "part out of range");
   int n = std::min((int)(c->part_hyps[part].size() / PS_HYP_VEC), cap);
   memcpy(out, c->part_hyps[part].data(), (size_t)n * PS_HYP_VEC * sizeof(float));
@@ -965,7 +1046,8 @@ int ps_get_part_hyps(ps_ctx *c, int part, float *out, int cap, int *count) {
 
 int ps_get_marginal(ps_ctx *c, int part, int scale, float *dst, int mem_kind) {
   if (!c || !dst) return PS_ERR_INVALID;
-  if (!c->have_result || c->result_scale < 0) return c->fail(PS_ERR_STATE, "no marginals: call ps_infer first");
+  if (int rc = finish_result(c)) return rc;
+  if (c->result_scale < 0) return c->fail(PS_ERR_STATE, "no marginals: call ps_infer first");
   if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
   if (!c->cfg.keep_all_scales && scale != c->S - 1)
     return c->fail(PS_ERR_STATE, "only the last scale is resident; create the ctx with keep_all_scales");
@@ -977,7 +1059,8 @@ int ps_get_marginal(ps_ctx *c, int part, int scale, float *dst, int mem_kind) {
 
 int ps_get_root_posterior(ps_ctx *c, float *dst, int mem_kind) {
   if (!c || !dst) return PS_ERR_INVALID;
-  if (!c->have_result || c->result_scale < 0) return c->fail(PS_ERR_STATE, "no root posterior: call ps_infer first");
+  if (int rc = finish_result(c)) return rc;
+  if (c->result_scale < 0) return c->fail(PS_ERR_STATE, "no root posterior: call ps_infer first");
   PS_CUDA(c, cudaMemcpyAsync(dst, c->root_post.p, c->HW * c->S * sizeof(float),
                              mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -986,7 +1069,8 @@ int ps_get_root_posterior(ps_ctx *c, float *dst, int mem_kind) {
 
 int ps_get_root_hyps(ps_ctx *c, float *out, int cap, int *count) {
   if (!c || !out || !count) return PS_ERR_INVALID;
-  if (!c->have_result || !c->have_root_hyps) return c->fail(PS_ERR_STATE, "no root hypotheses: ps_infer with PS_INFER_ROOT_HYPS");
+  if (int rc = finish_result(c)) return rc;
+  if (!c->have_root_hyps) return c->fail(PS_ERR_STATE, "no root hypotheses: ps_infer with PS_INFER_ROOT_HYPS");
   int n = std::min((int)(c->root_hyps.size() / 4), cap);
   memcpy(out, c->root_hyps.data(), (size_t)n * 4 * sizeof(float));
   *count = n;

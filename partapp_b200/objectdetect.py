@@ -207,6 +207,8 @@ class PsContext:
                 (capi.PS_INFER_ROOT_HYPS if root_hyps else 0) | (capi.PS_INFER_KEEP_UNARIES if keep_unaries else 0)
         self._check(self.lib.ps_infer(self.h, flags))
 
+    infer_async = infer  # ps_infer only enqueues device work; getters synchronise
+
     def max_states(self, local_max=False):
         self._check(self.lib.ps_max_states(self.h, capi.PS_INFER_LOCAL_MAX if local_max else 0))
 
@@ -241,6 +243,19 @@ class PsContext:
 
     def launch_count(self):
         return int(self.lib.ps_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.ps_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{kernel class: (total device ms, launches)} since the last read."""
+        cap = 32
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        cnt = (C.c_longlong * cap)()
+        n = C.c_int()
+        self._check(self.lib.ps_profile_read(self.h, cap, names, ms, cnt, C.byref(n)))
+        return {names[i].decode(): (ms[i], int(cnt[i])) for i in range(n.value)}
 
     # -- seams -------------------------------------------------------------------------------------
     def message(self, log_prob_child, offset_in, offset_out, Cm, rot_mean, rot_sigma, scale, sparse):
