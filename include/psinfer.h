@@ -186,6 +186,12 @@ int ps_message(ps_ctx *ctx, const float *log_prob_child, float *log_prob_parent,
 int ps_find_local_max(ps_ctx *ctx, const float *grid, int mem_kind, int d0, int height, int width,
                       int max_n, float *out, int *count);
 
+/* Exhaustive check of the device exp/log used on the path: for every fp32 bit pattern in
+ * [first_bits, first_bits + count) compares the table-driven fast evaluation with CUDA's fp64 libm narrowed to fp32
+ * (the reference calls the double libm routines on floats: multi_array_op.hpp:165,177).
+ * out = {exp mismatches, exp inputs tested, log mismatches, log inputs tested}. */
+int ps_selftest_math(ps_ctx *ctx, unsigned first_bits, unsigned long long count, unsigned long long out[4]);
+
 /* Number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches). */
 long long ps_launch_count(const ps_ctx *ctx);
 

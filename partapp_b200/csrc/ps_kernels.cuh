@@ -41,14 +41,115 @@ __host__ __device__ inline float dec_f(int i) {
 }
 #define PS_ENC_NEG_INF ((int)0x807fffff) /* enc_f(-inf) = 0xff800000 ^ 0x7fffffff */
 
-// (float)exp((double)x).  Below -104 the double result is < 2^-150 and narrows to +0 exactly.
-__device__ __forceinline__ float exp_f64(float x) {
-  if (x < -104.0f) return 0.0f;
+// ---- exp / log of the reference: fp64 libm routine, narrowed to fp32 -------------------------------------------
+// Reference semantics: (float)exp((double)x), (float)log((double)x) (multi_array_op.hpp:165,177).
+// *_slow call CUDA's fp64 libm.  *_fast use a short table-driven fp64 evaluation (relative error < 2^-50) and fall
+// back to *_slow whenever the fp64 result lies within kGuard units (of 2^-29 fp32 ulp) of an fp32 rounding boundary,
+// so fast == slow for every input (checked exhaustively by ps_selftest_math / tests/test_gpu_math.py).
+// Tables are filled by the host at ps_create (ps_math_tables_init).
+__device__ double2 d_log_tab[129];   // .x = 1/F_j, .y = log(F_j) - (j >= 54 ? ln2 : 0),  F_j = 1 + j/128
+__device__ double d_eln2_tab[289];   // RN(e*ln2) for e = -160 .. 128
+__device__ double d_exp_tab[64];     // 2^(j/64)
+constexpr int kGuard = 64;
+
+__device__ __forceinline__ float exp_slow(float x) {
+  if (x < -104.0f) return 0.0f;  // the double result is < 2^-150 and narrows to +0 exactly
   return (float)exp((double)x);
 }
-// computeLogGrid cell (multi_array_op.hpp:162-165)
-__device__ __forceinline__ float log_f64(float d) {
+__device__ __forceinline__ float log_slow(float d) {  // computeLogGrid cell (multi_array_op.hpp:162-165)
   return d == 0.0f ? kLogZero : (float)log((double)d);
+}
+
+__device__ __forceinline__ bool near_f32_boundary(double v) {
+  // bits below the fp32 mantissa: 29 of them; the round-to-nearest boundary is the pattern 0x10000000
+  int lo = __double2loint(v) & 0x1fffffff;
+  return abs(lo - 0x10000000) <= kGuard;
+}
+
+__device__ __forceinline__ float exp_fast(float x) {
+  if (x < -104.0f) return 0.0f;
+  if (!(x > -87.0f && x < 88.0f)) return (float)exp((double)x);  // fp32-subnormal results, overflow, NaN
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  const double xd = (double)x;
+  const double t = __fma_rn(xd, 92.332482616893656877, MAGIC);  // 64/ln2
+  const int k = __double2loint(t);
+  const double kd = t - MAGIC;
+  // ln2/64 = hi + lo; hi = 0x1.62e42fe8p-7 carries 30 significant bits, so kd*hi is exact for |k| < 2^22
+  double r = __fma_rn(kd, -0x1.62e42fe800000p-7, xd);
+  r = __fma_rn(kd, -0x1.e8e7bcd5e4f1ep-37, r);
+  double p = __fma_rn(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+  p = __fma_rn(r, p, 1.6666666666666665741e-01);
+  p = __fma_rn(r, p, 0.5);
+  p = __fma_rn(r, p, 1.0);
+  p = __fma_rn(r, p, 1.0);
+  double res = d_exp_tab[k & 63] * p;
+  res = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+  if (near_f32_boundary(res)) return (float)exp((double)x);
+  return (float)res;
+}
+
+__device__ __forceinline__ float log_fast(float d) {
+  if (d == 0.0f) return kLogZero;
+  const unsigned ib = __float_as_uint(d);
+  if (ib - 0x00800000u >= 0x7f000000u) return (float)log((double)d);  // subnormal, inf, NaN, negative
+  const unsigned mant = ib & 0x7fffffu;
+  const int j = (int)((mant + 0x8000u) >> 16);                 // nearest multiple of 1/128: 0..128
+  const double m = __hiloint2double((int)(0x3ff00000u | (mant >> 3)), (int)(mant << 29));
+  const double F = __hiloint2double((int)(0x3ff00000u + ((unsigned)j << 13)), 0);
+  const double2 t = d_log_tab[j];
+  const double r = (m - F) * t.x;
+  const int e2 = (int)(ib >> 23) - 127 + (j >= 54 ? 1 : 0);
+  double p = __fma_rn(r, -1.6666666666666665741e-01, 0.2);
+  p = __fma_rn(r, p, -0.25);
+  p = __fma_rn(r, p, 3.3333333333333331483e-01);
+  p = __fma_rn(r, p, -0.5);
+  p = __fma_rn(r * r, p, r);
+  const double res = d_eln2_tab[e2 + 160] + (t.y + p);
+  if (near_f32_boundary(res)) return (float)log((double)d);
+  return (float)res;
+}
+
+#ifndef PS_SLOW_MATH
+__device__ __forceinline__ float exp_f64(float x) { return exp_fast(x); }
+__device__ __forceinline__ float log_f64(float d) { return log_fast(d); }
+#else
+__device__ __forceinline__ float exp_f64(float x) { return exp_slow(x); }
+__device__ __forceinline__ float log_f64(float d) { return log_slow(d); }
+#endif
+
+// Exhaustive self-test: every fp32 bit pattern in [first, first + count).
+// out[0]: exp mismatches, out[1]: exp inputs taking the fast path, out[2]: log mismatches, out[3]: log fast path.
+__global__ void k_selftest_math(unsigned first, unsigned long long count, unsigned long long *out) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long bad_e = 0, fast_e = 0, bad_l = 0, fast_l = 0;
+  for (; i < count; i += stride) {
+    const float x = __uint_as_float(first + (unsigned)i);
+    if (x == x) {
+      if (fabsf(x) <= 104.0f) {
+        float a = exp_fast(x), b = exp_slow(x);
+        if (__float_as_uint(a) != __float_as_uint(b)) ++bad_e;
+        ++fast_e;
+      }
+      if (x >= 0.0f && x < INFINITY) {
+        float a = log_fast(x), b = log_slow(x);
+        if (__float_as_uint(a) != __float_as_uint(b)) ++bad_l;
+        ++fast_l;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    bad_e += __shfl_xor_sync(0xffffffffu, bad_e, o);
+    fast_e += __shfl_xor_sync(0xffffffffu, fast_e, o);
+    bad_l += __shfl_xor_sync(0xffffffffu, bad_l, o);
+    fast_l += __shfl_xor_sync(0xffffffffu, fast_l, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 0, bad_e);
+    atomicAdd(out + 1, fast_e);
+    atomicAdd(out + 2, bad_l);
+    atomicAdd(out + 3, fast_l);
+  }
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -85,23 +186,45 @@ __global__ void k_set_int(int *p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
-// clip_scores_fill (objectdetect_aux.hpp:42-59) + computeLogGrid (multi_array_op.hpp:154-167)
-__global__ void k_prepare_unary(float *__restrict__ p, size_t n) {
+// clip_scores_fill (objectdetect_aux.hpp:42-59) + computeLogGrid (multi_array_op.hpp:154-167) of one cell
+__device__ __forceinline__ float prepare_cell(float v) {
+  if (v < 0.0f) v = (float)0.0001;
+  return log_f64(v);
+}
+// In place over n floats (n4 = n / 4 handled as float4, the tail scalar); also folds max(result) into *dst if given,
+// which is the getMinMax a leaf's upward message would otherwise spend a pass on.
+__global__ void __launch_bounds__(256) k_prepare_unary(float *__restrict__ p, size_t n, int *dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    float v = p[i];
-    if (v < 0.0f) v = (float)0.0001;
-    p[i] = log_f64(v);
+  const size_t n4 = ((uintptr_t)p % 16 == 0) ? n / 4 : 0;
+  float m = -INFINITY;
+  float4 *p4 = reinterpret_cast<float4 *>(p);
+  for (size_t j = i; j < n4; j += stride) {
+    float4 v = p4[j];
+    v.x = prepare_cell(v.x); v.y = prepare_cell(v.y); v.z = prepare_cell(v.z); v.w = prepare_cell(v.w);
+    p4[j] = v;
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
   }
+  for (size_t j = n4 * 4 + i; j < n; j += stride) {
+    float v = prepare_cell(p[j]);
+    p[j] = v;
+    m = fmaxf(m, v);
+  }
+  if (dst) block_max_to(m, dst);
 }
 
 // getMinMax (multi_array_op.hpp:61-77), max only
-__global__ void k_grid_max(const float *__restrict__ p, size_t n, int *dst) {
+__global__ void __launch_bounds__(256) k_grid_max(const float *__restrict__ p, size_t n, int *dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = ((uintptr_t)p % 16 == 0) ? n / 4 : 0;
   float m = -INFINITY;
-  for (; i < n; i += stride) m = fmaxf(m, p[i]);
+  const float4 *p4 = reinterpret_cast<const float4 *>(p);
+  for (size_t j = i; j < n4; j += stride) {
+    float4 v = __ldg(p4 + j);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (size_t j = n4 * 4 + i; j < n; j += stride) m = fmaxf(m, p[j]);
   block_max_to(m, dst);
 }
 
@@ -256,14 +379,24 @@ __global__ void k_warp_direct(const float *__restrict__ in, float *__restrict__ 
     return;
   }
   int2 m = map[(size_t)iy * EW + ix];
-  for (int r = 0; r < R; ++r) {
-    const float *s = in + (size_t)r * HW;
-    float v = 0.0f;
-    if (m.x >= 0) {
-      v = __ldg(&s[m.x]);
-      if (v == 0.0f && m.y >= 0) v = __ldg(&s[m.y]);
+  if (m.x < 0) {
+    for (int r = 0; r < R; ++r) out[r * eplane + o] = 0.0f;
+    return;
+  }
+  constexpr int UB = 8;  // slices in flight per thread
+  for (int r0 = 0; r0 < R; r0 += UB) {
+    float v[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u)
+      if (r0 + u < R) v[u] = __ldg(in + (size_t)(r0 + u) * HW + m.x);
+    if (m.y >= 0) {
+#pragma unroll
+      for (int u = 0; u < UB; ++u)
+        if (r0 + u < R && v[u] == 0.0f) v[u] = __ldg(in + (size_t)(r0 + u) * HW + m.y);
     }
-    out[r * eplane + o] = v;
+#pragma unroll
+    for (int u = 0; u < UB; ++u)
+      if (r0 + u < R) out[(r0 + u) * eplane + o] = v[u];
   }
 }
 
@@ -311,7 +444,45 @@ __global__ void k_warp_bilinear(const float *__restrict__ in, float *__restrict_
   }
   double x1, y1;
   affine_map(T13, (double)ix, (double)iy, x1, y1);
-  for (int r = 0; r < R; ++r) out[r * eplane + o] = bilinear_at(in + r * HW, H, W, W, x1, y1);
+  // the sample position is shared by all R slices: resolve the case and the weights once (transform.hpp:196-238)
+  const double fx = floor(x1), fy = floor(y1);
+  const int sx = (int)fx, sy = (int)fy;
+  int mode = 0;  // 0: default (0), 1: exact hit, 2: four-point blend
+  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+  if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
+    const float fa = (float)__dsub_rn(x1, (double)sx), fb = (float)__dsub_rn(y1, (double)sy);
+    const float eps10 = 10 * 1.1920928955078125e-07f;
+    if (fa < eps10 && fb < eps10) mode = 1;
+    else if (sx < W - 1 && sy < H - 1) {
+      mode = 2;
+      const float omb = __fsub_rn(1.0f, fb), oma = __fsub_rn(1.0f, fa);
+      w00 = __fmul_rn(omb, oma); w01 = __fmul_rn(omb, fa); w10 = __fmul_rn(fb, oma); w11 = __fmul_rn(fb, fa);
+    }
+  }
+  const float *p = in + (size_t)sy * W + sx;
+  if (mode == 0) {
+    for (int r = 0; r < R; ++r) out[r * eplane + o] = 0.0f;
+  } else if (mode == 1) {
+    for (int r = 0; r < R; ++r) out[r * eplane + o] = __ldg(p + r * HW);
+  } else {
+    constexpr int UB = 4;
+    for (int r0 = 0; r0 < R; r0 += UB) {
+      float q[UB][4];
+#pragma unroll
+      for (int u = 0; u < UB; ++u)
+        if (r0 + u < R) {
+          const float *s = p + (size_t)(r0 + u) * HW;
+          q[u][0] = __ldg(s); q[u][1] = __ldg(s + 1); q[u][2] = __ldg(s + W); q[u][3] = __ldg(s + W + 1);
+        }
+#pragma unroll
+      for (int u = 0; u < UB; ++u)
+        if (r0 + u < R) {
+          float t0 = __fmul_rn(w00, q[u][0]), t1 = __fmul_rn(w01, q[u][1]);
+          float t2 = __fmul_rn(w10, q[u][2]), t3 = __fmul_rn(w11, q[u][3]);
+          out[(r0 + u) * eplane + o] = __fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3);
+        }
+    }
+  }
 }
 
 // ---- message stage 2b: separable Gaussian, zero padded, unnormalised taps -------------------------------
@@ -426,6 +597,362 @@ __global__ void __launch_bounds__(256) k_conv_rows(ConvArgs a, int TY, int S) {
   }
 }
 
+
+// =====================================================================================================
+// v2 kernels: packed fp32x2 arithmetic.
+//
+// Measured on B200 (profiles/r01_fp32_pipe_microbench.txt): FFMA2/FADD2 retire two lanes per instruction but
+// occupy the fp32 pipe for two cycles, so they do not raise the arithmetic ceiling (18.0e12 separately rounded
+// multiply+add pairs per second) -- they halve the ISSUE slots per tap-output, which leaves the other half of
+// the issue bandwidth for loads and address arithmetic.  The scalar kernels above were issue-bound.
+//
+// Parity: a tap-output is still acc = RN(acc + RN(x*f)).  ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+// even with --fmad=false, so the multiply is spelled fma.rn.f32x2(x, f, -0.0) with the -0.0 pair passed as a
+// kernel argument (x*f + -0 == RN(x*f) for every x*f, including +-0, inf, NaN; ptxas cannot fold a run-time
+// addend), followed by add.rn.f32x2.  SASS: FFMA2 + FADD2 (checked by tests/test_build_sass.py).
+// =====================================================================================================
+typedef unsigned long long u64;
+#define PS_NEGZERO2 0x8000000080000000ull
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// RN(x.lo*f), RN(x.hi*f)
+__device__ __forceinline__ u64 mul2_rn(u64 x, float f, u64 negzero2) {
+  u64 r, ff = pk2(f, f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(ff), "l"(negzero2));
+  return r;
+}
+__device__ __forceinline__ u64 add2_rn(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// ---- stage 1 v2: shift + exp + circular rotation filter, register resident ------------------------------------
+// One thread owns two consecutive flat pixels; its 2 x R exponentiated values live in registers as R packed pairs.
+// L is the compile-time (zero-padded, centred) tap count: padding taps are exactly 0, so they add +0.
+template <int R, int L>
+__global__ void __launch_bounds__(128) k_rotconv2(RotArgs a, u64 nz) {
+  __shared__ float s_taps[L];
+  const int tid = threadIdx.x;
+  const int npad = (L - 1) / 2, n = (a.len - 1) / 2;
+  if (tid < L) {
+    int k = tid - (npad - n);
+    s_taps[tid] = (a.mode == 1 && k >= 0 && k < a.len) ? a.taps[k] : 0.0f;
+  }
+  __syncthreads();
+  const size_t HW = (size_t)a.H * a.W;
+  const size_t p0 = ((size_t)blockIdx.x * blockDim.x + tid) * 2;
+  if (p0 >= HW) return;
+  const bool has1 = p0 + 1 < HW;
+  const int y0 = (int)(p0 / a.W), x0 = (int)(p0 % a.W);
+  int y1 = y0, x1 = x0 + 1;
+  if (x1 == a.W) { x1 = 0; y1 = y0 + 1; }
+  const float negM = -dec_f(*a.max_enc);
+
+  u64 v[R];
+#pragma unroll
+  for (int ro = 0; ro < R; ++ro) {
+    int r = ro - a.shift;
+    float e0 = kLogZero, e1 = kLogZero;
+    if (r >= 0 && r < R) {
+      const float *s = a.in + (size_t)r * HW;
+      int ys = a.yin[r * a.H + y0], xs = a.xin[r * a.W + x0];
+      if ((ys | xs) >= 0) e0 = __ldg(&s[(size_t)ys * a.W + xs]);
+      if (has1) {
+        ys = a.yin[r * a.H + y1]; xs = a.xin[r * a.W + x1];
+        if ((ys | xs) >= 0) e1 = __ldg(&s[(size_t)ys * a.W + xs]);
+      }
+    }
+    v[ro] = pk2(exp_f64(__fadd_rn(e0, negM)), exp_f64(__fadd_rn(e1, negM)));
+  }
+  const bool vec = (HW & 1) == 0;
+  if (a.mode == 1) {
+    float tp[L];
+#pragma unroll
+    for (int k = 0; k < L; ++k) tp[k] = s_taps[k];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      u64 acc = pk2(0.0f, 0.0f);
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        const int src = ((i + k - npad) % R + R) % R;
+        acc = add2_rn(acc, mul2_rn(v[src], tp[k], nz));
+      }
+      float lo, hi;
+      upk2(acc, lo, hi);
+      float *o = a.out + (size_t)i * HW + p0;
+      if (vec) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+      else { o[0] = lo; if (has1) o[1] = hi; }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float lo = 0.0f, hi = 0.0f;
+      if (a.mode == 0) upk2(v[i], lo, hi);
+      float *o = a.out + (size_t)i * HW + p0;
+      if (vec) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+      else { o[0] = lo; if (has1) o[1] = hi; }
+    }
+  }
+}
+
+
+// ---- stage 1 v3: block-cooperative shift + exp, then rotation filter from shared memory ---------------------------
+// k_rotconv2 gave every thread 2 pixels x R rotations of serial work (gather, fp64 exp, filter): only ~25 warps per
+// SM existed and the kernel was latency-bound.  Here a block owns PX consecutive pixels: phase 1 spreads the R*PX
+// gather+exp cells over all threads (coalesced along pixels); phase 2 gives each thread one pixel PAIR and a run of
+// OUT consecutive output rotations, sliding a register window over the (circular) rotation axis.
+template <int R, int L, int PX, int OUT>
+__global__ void __launch_bounds__(256) k_rotconv3(RotArgs a, u64 nz) {
+  static_assert(R % OUT == 0 && PX % 2 == 0, "tiling");
+  __shared__ __align__(8) float s_e[R][PX];
+  __shared__ float s_taps[L];
+  const int tid = threadIdx.x;
+  const int npad = (L - 1) / 2, n = (a.len - 1) / 2;
+  if (tid < L) {
+    int k = tid - (npad - n);
+    s_taps[tid] = (a.mode == 1 && k >= 0 && k < a.len) ? a.taps[k] : 0.0f;
+  }
+  const size_t HW = (size_t)a.H * a.W;
+  const size_t base = (size_t)blockIdx.x * PX;
+  const float negM = -dec_f(*a.max_enc);
+  // phase 1: A[ro][px] = exp(shifted child - M).  256 % PX == 0, so a thread keeps one pixel and walks rotations.
+  static_assert(256 % PX == 0, "a thread must stay on one pixel");
+  {
+    const int px = tid % PX;
+    const unsigned p = (unsigned)base + px;
+    const bool okp = p < (unsigned)HW;
+    const int y = okp ? (int)(p / (unsigned)a.W) : 0, x = okp ? (int)(p % (unsigned)a.W) : 0;
+    constexpr int STEP = 256 / PX, NIT = (R + STEP - 1) / STEP;
+    // Three batched rounds (tables, data, exp) instead of NIT dependent load chains.
+    int off[NIT];
+#pragma unroll
+    for (int c = 0; c < NIT; ++c) {
+      const int ro = tid / PX + c * STEP;
+      const int r = ro - a.shift;
+      off[c] = -1;
+      if (okp && ro < R && r >= 0 && r < R) {
+        const int ys = a.yin[r * a.H + y], xs = a.xin[r * a.W + x];
+        if ((ys | xs) >= 0) off[c] = ys * a.W + xs;
+      }
+    }
+    float v[NIT];
+#pragma unroll
+    for (int c = 0; c < NIT; ++c) {
+      const int ro = tid / PX + c * STEP;
+      const int r = ro - a.shift;
+      v[c] = off[c] >= 0 ? __ldg(&a.in[(size_t)r * HW + (unsigned)off[c]]) : kLogZero;
+    }
+#pragma unroll
+    for (int c = 0; c < NIT; ++c) {
+      const int ro = tid / PX + c * STEP;
+      if (ro < R) s_e[ro][px] = okp ? exp_f64(__fadd_rn(v[c], negM)) : 0.0f;
+    }
+  }
+  __syncthreads();
+  // phase 2
+  constexpr int NPAIR = PX / 2, NRUN = R / OUT;
+  const bool vec = (HW & 1) == 0;
+  for (int it = tid; it < NPAIR * NRUN; it += 256) {
+    const int pp = it % NPAIR, run = it / NPAIR;
+    const size_t p0 = base + 2 * pp;
+    if (p0 >= HW) continue;
+    const bool has1 = p0 + 1 < HW;
+    const int i0 = run * OUT;
+    const u64 *col = reinterpret_cast<const u64 *>(&s_e[0][0]) + pp;  // row stride PX/2 in u64 units
+    float lo[OUT], hi[OUT];
+    if (a.mode == 1) {
+      // inputs (i0 - npad + m) mod R for m in [0, OUT + L - 1)
+      u64 w[OUT + L - 1];
+#pragma unroll
+      for (int m = 0; m < OUT + L - 1; ++m) {
+        int src = (i0 - npad + m) % R;
+        if (src < 0) src += R;
+        w[m] = col[src * (PX / 2)];
+      }
+      u64 acc[OUT];
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) acc[o] = pk2(0.0f, 0.0f);
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        const float f = s_taps[k];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) acc[o] = add2_rn(acc[o], mul2_rn(w[o + k], f, nz));
+      }
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) upk2(acc[o], lo[o], hi[o]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) {
+        lo[o] = hi[o] = 0.0f;
+        if (a.mode == 0) upk2(col[(i0 + o) * (PX / 2)], lo[o], hi[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+      float *dst = a.out + (size_t)(i0 + o) * HW + p0;
+      if (vec) *reinterpret_cast<float2 *>(dst) = make_float2(lo[o], hi[o]);
+      else { dst[0] = lo[o]; if (has1) dst[1] = hi[o]; }
+    }
+  }
+}
+
+// ---- stage 2b v2: Gaussian along y, two adjacent columns per thread, row tile staged in shared memory -----------
+// Block = 8 warps; warp w produces rows [y0 + w*T, y0 + w*T + T) of a 64-column strip.  The strip's
+// (8T + 2n) input rows are staged once (coalesced float2 rows), so each input element is read from L2
+// (8T+2n)/(8T) times instead of (len+T-1)/T times.  Requires an even pitch (8-byte aligned pairs).
+template <int T>
+__global__ void __launch_bounds__(256) k_conv_cols2(ConvArgs a, u64 nz) {
+  extern __shared__ float2 s_rows[];  // [8T + 2n][32]
+  __shared__ float s_taps[1000];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < a.len; i += 256) s_taps[i] = a.taps[i];
+  const int n = (a.len - 1) / 2;
+  const int x = (blockIdx.x * 32 + lane) * 2;
+  const int y0 = blockIdx.y * (8 * T);
+  const float *src = a.in + (size_t)blockIdx.z * a.plane;
+  float *dst = a.out + (size_t)blockIdx.z * a.plane;
+  const int nrows = 8 * T + 2 * n;
+  const bool in0 = x < a.cols, in1 = x + 1 < a.cols;
+  for (int rr = w; rr < nrows; rr += 8) {
+    int yy = y0 - n + rr;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (in0 && yy >= 0 && yy < a.rows) {
+      v = __ldg(reinterpret_cast<const float2 *>(src + (size_t)yy * a.pitch + x));
+      if (!in1) v.y = 0.0f;
+    }
+    s_rows[rr * 32 + lane] = v;
+  }
+  __syncthreads();
+  const u64 *win = reinterpret_cast<const u64 *>(s_rows) + (w * T) * 32 + lane;
+  u64 acc[T], d[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
+#pragma unroll
+  for (int j = 0; j < T - 1; ++j) d[j] = win[j * 32];
+  int kk = 0;
+  for (; kk + T <= a.len; kk += T) {
+#pragma unroll
+    for (int u = 0; u < T; ++u) {
+      d[(u + T - 1) % T] = win[(kk + u + T - 1) * 32];
+      const float f = s_taps[kk + u];
+#pragma unroll
+      for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < T; ++u) {
+    if (kk + u < a.len) {
+      d[(u + T - 1) % T] = win[(kk + u + T - 1) * 32];
+      const float f = s_taps[kk + u];
+#pragma unroll
+      for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+    }
+  }
+  if (!in0) return;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    int y = y0 + w * T + t;
+    if (y < a.rows) {
+      float lo, hi;
+      upk2(acc[t], lo, hi);
+      float *o = dst + (size_t)y * a.pitch + x;
+      if (in1) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+      else o[0] = lo;
+    }
+  }
+}
+
+// ---- stage 2b v2: Gaussian along x, two adjacent rows per thread -------------------------------------------------
+// A block stages PAIRS row pairs (+halo) as float2 (row 2q, row 2q+1) in the "transposed by T" layout
+// (element i at (i % T) * S + i / T); a thread owns T consecutive outputs of both rows of a pair.
+template <int T>
+__global__ void __launch_bounds__(256) k_conv_rows2(ConvArgs a, u64 nz, int PAIRS, int S) {
+  extern __shared__ float2 s_pairs[];  // [PAIRS][T*S]
+  __shared__ float s_taps[1000];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.len; i += 256) s_taps[i] = a.taps[i];
+  const int n = (a.len - 1) / 2;
+  const int y0 = blockIdx.x * (2 * PAIRS);
+  const float *src = a.in + (size_t)blockIdx.y * a.plane;
+  float *dst = a.out + (size_t)blockIdx.y * a.plane;
+  const int G = (a.cols + T - 1) / T;
+  const int span = G * T + 2 * n;
+  const int rowsz = T * S;
+  for (int pr = 0; pr < PAIRS; ++pr) {
+    const int ya = y0 + 2 * pr, yb = ya + 1;
+    const float *ra = src + (size_t)ya * a.pitch, *rb = src + (size_t)yb * a.pitch;
+    for (int i = tid; i < span; i += 256) {
+      int x = i - n;
+      bool okx = x >= 0 && x < a.cols;
+      float va = (okx && ya < a.rows) ? __ldg(ra + x) : 0.0f;
+      float vb = (okx && yb < a.rows) ? __ldg(rb + x) : 0.0f;
+      s_pairs[pr * rowsz + (i % T) * S + i / T] = make_float2(va, vb);
+    }
+  }
+  __syncthreads();
+  const int items = PAIRS * G;
+  for (int it = tid; it < items; it += 256) {
+    const int pr = it / G, g = it % G;
+    const int ya = y0 + 2 * pr;
+    if (ya >= a.rows) continue;
+    const u64 *tile = reinterpret_cast<const u64 *>(s_pairs) + pr * rowsz + g;
+    u64 acc[T], d[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < T - 1; ++j) d[j] = tile[j * S];
+    int kk = 0;
+    for (; kk + T <= a.len; kk += T) {
+#pragma unroll
+      for (int u = 0; u < T; ++u) {
+        d[(u + T - 1) % T] = tile[((u + T - 1) % T) * S + (kk + u + T - 1) / T];
+        const float f = s_taps[kk + u];
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < T; ++u) {
+      if (kk + u < a.len) {
+        d[(u + T - 1) % T] = tile[((u + T - 1) % T) * S + (kk + u + T - 1) / T];
+        const float f = s_taps[kk + u];
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+      }
+    }
+    float lo[T], hi[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
+    float *oa = dst + (size_t)ya * a.pitch + g * T;
+    const bool full = g * T + T <= a.cols;
+    const bool al = (a.pitch & 3) == 0;
+    if (full && al) {
+#pragma unroll
+      for (int t = 0; t < T; t += 4) *reinterpret_cast<float4 *>(oa + t) = make_float4(lo[t], lo[t + 1], lo[t + 2], lo[t + 3]);
+      if (ya + 1 < a.rows) {
+        float *ob = oa + a.pitch;
+#pragma unroll
+        for (int t = 0; t < T; t += 4) *reinterpret_cast<float4 *>(ob + t) = make_float4(hi[t], hi[t + 1], hi[t + 2], hi[t + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        if (g * T + t < a.cols) {
+          oa[t] = lo[t];
+          if (ya + 1 < a.rows) oa[a.pitch + t] = hi[t];
+        }
+    }
+  }
+}
+
 // ---- message stage 3: read back, log, +M, shift to the parent frame, combine ------------------------------
 // findrot.cpp:431-448 plus the addGrid2 calls that consume the message (findrot.cpp:637-654, :201, :221-222).
 struct EpiArgs {
@@ -487,6 +1014,114 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
   }
 }
 
+
+// ---- message stage 3 v2: four consecutive cells per thread -------------------------------------------------------
+// Same arithmetic as k_epilogue.  The per-row quantities (destination row -> source row, T34 row products, slice
+// bases) are computed once per thread, table / accumulator / output traffic is 128-bit, and the block maximum is
+// taken once over the four cells.  ncu r01a: k_epilogue spent 269 warp-instructions per cell, most of them
+// parameter and address arithmetic.
+template <bool GENERAL>
+__global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4) */) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  if (it < XG * a.H) {
+    const int y = it / XG, x0 = (it - y * XG) * 4;
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t cell0 = (size_t)r * HW + (size_t)y * a.W + x0;
+    const float M = dec_f(*a.max_enc);
+    const int ys = a.yout[r * a.H + y];
+    const int nx = min(4, a.W - x0);
+    const bool vec = (a.W & 3) == 0;  // rows and slices are then 16-byte aligned
+    int xs[4];
+    if (vec) {
+      int4 t = *reinterpret_cast<const int4 *>(a.xout + r * a.W + x0);
+      xs[0] = t.x; xs[1] = t.y; xs[2] = t.z; xs[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xs[j] = j < nx ? a.xout[r * a.W + x0 + j] : -1;
+    }
+    float v[4];
+    double ty1 = 0.0, ty4 = 0.0;
+    const float *srcr;
+    if (GENERAL) {
+      ty1 = __dmul_rn(a.T34.m[1], (double)ys);
+      ty4 = __dmul_rn(a.T34.m[4], (double)ys);
+      srcr = a.src + (size_t)r * a.EH * a.EP;
+    } else {
+      srcr = a.src + (size_t)r * HW + (size_t)(ys < 0 ? 0 : ys) * a.W;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = kLogZero;
+      if ((xs[j] | ys) >= 0) {
+        float d;
+        if (GENERAL) {
+          const double xd = (double)xs[j];
+          const double x1 = __dadd_rn(__dadd_rn(__dmul_rn(a.T34.m[0], xd), ty1), a.T34.m[2]);
+          const double y1 = __dadd_rn(__dadd_rn(__dmul_rn(a.T34.m[3], xd), ty4), a.T34.m[5]);
+          d = bilinear_at(srcr, a.EH, a.EW, a.EP, x1, y1);
+        } else {
+          d = __ldg(srcr + xs[j]);
+        }
+        v[j] = __fadd_rn(log_f64(d), M);
+      }
+    }
+    if (a.out0) {
+      float o[4] = {v[0], v[1], v[2], v[3]};
+      if (a.acc0) {
+        if (vec) {
+          float4 t = *reinterpret_cast<const float4 *>(a.acc0 + cell0);
+          o[0] = __fadd_rn(t.x, o[0]); o[1] = __fadd_rn(t.y, o[1]); o[2] = __fadd_rn(t.z, o[2]); o[3] = __fadd_rn(t.w, o[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nx) o[j] = __fadd_rn(a.acc0[cell0 + j], o[j]);
+        }
+      }
+      if (a.add0) {
+        if (vec) {
+          float4 t = *reinterpret_cast<const float4 *>(a.add0 + cell0);
+          o[0] = __fadd_rn(o[0], t.x); o[1] = __fadd_rn(o[1], t.y); o[2] = __fadd_rn(o[2], t.z); o[3] = __fadd_rn(o[3], t.w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (j < nx) o[j] = __fadd_rn(o[j], a.add0[cell0 + j]);
+        }
+      }
+      if (vec) *reinterpret_cast<float4 *>(a.out0 + cell0) = make_float4(o[0], o[1], o[2], o[3]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < nx) a.out0[cell0 + j] = o[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < nx) m0 = fmaxf(m0, o[j]);
+    }
+    if (a.out1) {
+      float o[4];
+      if (vec) {
+        float4 t = *reinterpret_cast<const float4 *>(a.add1 + cell0);
+        o[0] = __fadd_rn(t.x, v[0]); o[1] = __fadd_rn(t.y, v[1]); o[2] = __fadd_rn(t.z, v[2]); o[3] = __fadd_rn(t.w, v[3]);
+        *reinterpret_cast<float4 *>(a.out1 + cell0) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = -INFINITY;
+          if (j < nx) {
+            o[j] = __fadd_rn(a.add1[cell0 + j], v[j]);
+            a.out1[cell0 + j] = o[j];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < nx) m1 = fmaxf(m1, o[j]);
+    }
+  }
+  if (a.max0) block_max_to(m0, a.max0);
+  if (a.max1) {
+    __syncthreads();
+    block_max_to(m1, a.max1);
+  }
+}
+
 // ---- root: combine the stored upward messages (findrot.cpp:637-654 and :169) -----------------------------
 //   post[root]  = (((m_0 + m_1) + ...) + m_{n-1}) + unary[root]
 //   fr_j        = (sum over i != j, ascending, starting from 0) + unary[root]     (written over m_j)
@@ -500,36 +1135,66 @@ struct RootArgs {
   size_t N;
 };
 
-__global__ void __launch_bounds__(256) k_root_combine(RootArgs a) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float mv[kMaxRootChildren];
-  float frv[kMaxRootChildren];
+template <int NC>
+__device__ __forceinline__ void root_combine_cell(const float *mv, float u, float &post, float *fr) {
+  float tot = 0.0f;
 #pragma unroll
-  for (int j = 0; j < kMaxRootChildren; ++j) frv[j] = -INFINITY;
-  if (i < a.N) {
-    float u = a.unary[i];
-    float tot = 0.0f;
+  for (int j = 0; j < NC; ++j) tot = __fadd_rn(tot, mv[j]);
+  post = __fadd_rn(tot, u);
 #pragma unroll
-    for (int j = 0; j < kMaxRootChildren; ++j)
-      if (j < a.n) {
-        mv[j] = a.m[j][i];
-        tot = __fadd_rn(tot, mv[j]);
-      }
-    a.post[i] = __fadd_rn(tot, u);
+  for (int j = 0; j < NC; ++j) {
+    float s = 0.0f;
 #pragma unroll
-    for (int j = 0; j < kMaxRootChildren; ++j)
-      if (j < a.n) {
-        float s = 0.0f;
-#pragma unroll
-        for (int k = 0; k < kMaxRootChildren; ++k)
-          if (k < a.n && k != j) s = __fadd_rn(s, mv[k]);
-        s = __fadd_rn(s, u);
-        frv[j] = s;
-        a.m[j][i] = s;
-      }
+    for (int k = 0; k < NC; ++k)
+      if (k != j) s = __fadd_rn(s, mv[k]);
+    fr[j] = __fadd_rn(s, u);
   }
-  for (int j = 0; j < a.n; ++j) {
-    block_max_to(frv[j], a.fr_max[j]);
+}
+
+// NC = number of root children (compile time, so the sums stay in registers); NV = 4: float4 path
+// (N % 4 == 0, 16-byte aligned grids), NV = 1: scalar path.
+template <int NC, int NV>
+__global__ void __launch_bounds__(256) k_root_combine(RootArgs a) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * NV;
+  float frmax[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) frmax[j] = -INFINITY;
+  if (i < a.N) {
+    float u[NV], mv[NV][NC], post[NV], fr[NV][NC];
+    if (NV == 4) {
+      float4 t = *reinterpret_cast<const float4 *>(a.unary + i);
+      u[0] = t.x; u[1 % NV] = t.y; u[2 % NV] = t.z; u[3 % NV] = t.w;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        float4 q = *reinterpret_cast<const float4 *>(a.m[j] + i);
+        mv[0][j] = q.x; mv[1 % NV][j] = q.y; mv[2 % NV][j] = q.z; mv[3 % NV][j] = q.w;
+      }
+    } else {
+      u[0] = a.unary[i];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) mv[0][j] = a.m[j][i];
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) root_combine_cell<NC>(mv[v], u[v], post[v], fr[v]);
+    if (NV == 4) {
+      *reinterpret_cast<float4 *>(a.post + i) = make_float4(post[0], post[1 % NV], post[2 % NV], post[3 % NV]);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        *reinterpret_cast<float4 *>(a.m[j] + i) = make_float4(fr[0][j], fr[1 % NV][j], fr[2 % NV][j], fr[3 % NV][j]);
+        frmax[j] = fmaxf(fmaxf(fr[0][j], fr[1 % NV][j]), fmaxf(fr[2 % NV][j], fr[3 % NV][j]));
+      }
+    } else {
+      a.post[i] = post[0];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        a.m[j][i] = fr[0][j];
+        frmax[j] = fr[0][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    block_max_to(frmax[j], a.fr_max[j]);
     __syncthreads();
   }
 }
@@ -558,13 +1223,25 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, unsigned idx) 
 __global__ void __launch_bounds__(256) k_argmax(const float *__restrict__ g, size_t n, unsigned long long *dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  unsigned long long best = 0;
-  for (; i < n; i += stride) {
-    float v = g[i];
-    if (v != v) continue;  // NaN never wins a '>' comparison
-    unsigned long long k = argmax_key(v, (unsigned)i);
-    best = k > best ? k : best;
+  const size_t n4 = ((uintptr_t)g % 16 == 0) ? n / 4 : 0;
+  // running (value, first index) per thread; a strictly greater value replaces, so the earliest index of the
+  // thread's maximum is kept as long as the thread visits indices in ascending order
+  float bv = -INFINITY;
+  unsigned bi = 0xffffffffu;
+  const float4 *g4 = reinterpret_cast<const float4 *>(g);
+  for (size_t j = i; j < n4; j += stride) {
+    float4 v = __ldg(g4 + j);
+    unsigned b = (unsigned)(j * 4);
+    if (v.x > bv) { bv = v.x; bi = b; }
+    if (v.y > bv) { bv = v.y; bi = b + 1; }
+    if (v.z > bv) { bv = v.z; bi = b + 2; }
+    if (v.w > bv) { bv = v.w; bi = b + 3; }
   }
+  for (size_t j = n4 * 4 + i; j < n; j += stride) {
+    float v = g[j];
+    if (v > bv) { bv = v; bi = (unsigned)j; }
+  }
+  unsigned long long best = bi == 0xffffffffu ? 0ull : argmax_key(bv, bi);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);

@@ -47,15 +47,15 @@ struct DevBuf {
 // Device-side image of one psg::MessagePlan.
 struct DevPlan {
   psg::MessagePlan host;
-  DevBuf ints;    // xin | yin | xout | yout
+  DevBuf ints;    // xin | xout | yin | yout  (xout stays 16-byte aligned whenever W % 4 == 0)
   DevBuf floats;  // rot taps | fx | fy
   DevBuf map;     // int2 [EH][EW], built on first sparse use
   DevBuf mats;    // T31 | T13 (doubles) for the map builder
   bool map_ready = false;
   int EP = 0;     // eigen-frame row pitch
   const int *xin() const { return ints.as<int>(); }
-  const int *yin(int R, int W) const { return ints.as<int>() + (size_t)R * W; }
-  const int *xout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * (W + H); }
+  const int *xout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * W; }
+  const int *yin(int R, int W) const { return ints.as<int>() + (size_t)R * 2 * W; }
   const int *yout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * (2 * W + H); }
   const float *rot_taps() const { return floats.as<float>(); }
   const float *fx() const { return floats.as<float>() + host.rot_taps.size(); }
@@ -202,8 +202,8 @@ int upload_plan(ps_ctx *c, DevPlan &dp) {
   const psg::MessagePlan &h = dp.host;
   std::vector<int> ints;
   ints.insert(ints.end(), h.xin.begin(), h.xin.end());
-  ints.insert(ints.end(), h.yin.begin(), h.yin.end());
   ints.insert(ints.end(), h.xout.begin(), h.xout.end());
+  ints.insert(ints.end(), h.yin.begin(), h.yin.end());
   ints.insert(ints.end(), h.yout.begin(), h.yout.end());
   std::vector<float> fl;
   fl.insert(fl.end(), h.rot_taps.begin(), h.rot_taps.end());
@@ -258,6 +258,106 @@ int ensure_direct_map(ps_ctx *c, DevPlan &dp) {
   return PS_OK;
 }
 
+
+constexpr size_t kSmemBudget = 96 * 1024;  // per block, leaves room for 2 blocks per SM
+
+template <int Rr, int L, int OUT>
+int launch_rotconv_t(ps_ctx *c, const psk::RotArgs &a) {
+  constexpr int PX = 128;
+  PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv3<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(a, PS_NEGZERO2));
+  return PS_OK;
+}
+
+// Block-cooperative rotation filter for the common rotation counts, generic shared-memory kernel otherwise.
+int launch_rotconv(ps_ctx *c, const psk::RotArgs &a) {
+  const int len = a.mode == 1 ? a.len : 1;
+#define ROT_CASE(Rr, L, OUT) \
+  if (a.R == Rr && len <= L) return launch_rotconv_t<Rr, L, OUT>(c, a)
+  ROT_CASE(8, 7, 4);
+  ROT_CASE(12, 11, 6);
+  ROT_CASE(24, 7, 6);
+  ROT_CASE(24, 15, 6);
+  ROT_CASE(24, 23, 6);
+  ROT_CASE(48, 7, 8);
+  ROT_CASE(48, 15, 8);
+  ROT_CASE(48, 23, 8);
+  ROT_CASE(48, 47, 8);
+#undef ROT_CASE
+  size_t smem = (size_t)a.R * psk::kRotThreads * sizeof(float);
+  if (smem > 48 * 1024)
+    PS_CUDA(c, cudaFuncSetAttribute(psk::k_rotconv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv<<<cdiv(c->HW, psk::kRotThreads), psk::kRotThreads, smem, c->stream>>>(a));
+  return PS_OK;
+}
+
+int launch_conv_rows(ps_ctx *c, const psk::ConvArgs &a, int slices) {
+  constexpr int T = 8;
+  const int n = (a.len - 1) / 2;
+  const int G = (a.cols + T - 1) / T;
+  {
+    // v2: row pairs, packed arithmetic
+    int S = (G * T + 2 * n + T - 1) / T + 1;
+    while (S % 16 != 2) ++S;
+    const size_t pair_bytes = (size_t)T * S * sizeof(float2);
+    int best = 0;
+    double best_eff = 0;
+    for (int pairs = 1; pairs <= 32 && pairs * pair_bytes <= kSmemBudget / 2; ++pairs) {
+      int items = pairs * G;
+      double eff = (double)items / (((items + 255) / 256) * 256);
+      if (eff >= best_eff - 1e-9) { best_eff = eff; best = pairs; }
+    }
+    if (best > 0) {
+      size_t smem = best * pair_bytes;
+      PS_LAUNCH(c, KC_CONV_ROWS,
+                psk::k_conv_rows2<T><<<dim3(cdiv(a.rows, 2 * best), slices), 256, smem, c->stream>>>(a, PS_NEGZERO2, best, S));
+      return PS_OK;
+    }
+  }
+  // v1 fallback (very long filters)
+  int S = (G * T + 2 * n + T - 1) / T + 1;
+  while (S % 8 != 4) ++S;
+  size_t row_bytes = (size_t)T * S * sizeof(float);
+  if (row_bytes > kSmemBudget)
+    return c->fail(PS_ERR_UNSUPPORTED, "row filter of %d taps over %d columns exceeds the shared-memory tile", a.len, a.cols);
+  int TY = (int)std::max<size_t>(1, std::min<size_t>(4, kSmemBudget / row_bytes));
+  PS_LAUNCH(c, KC_CONV_ROWS,
+            psk::k_conv_rows<T><<<dim3(cdiv(a.rows, TY), slices), 256, TY * row_bytes, c->stream>>>(a, TY, S));
+  return PS_OK;
+}
+
+int launch_conv_cols(ps_ctx *c, const psk::ConvArgs &a, int slices) {
+  constexpr int T = 8;
+  const int n = (a.len - 1) / 2;
+  const size_t smem = (size_t)(8 * T + 2 * n) * 32 * sizeof(float2);
+  const bool aligned = (a.pitch % 2 == 0) && (a.plane % 2 == 0) && ((uintptr_t)a.in % 8 == 0) && ((uintptr_t)a.out % 8 == 0);
+  if (aligned && smem <= kSmemBudget) {
+    PS_LAUNCH(c, KC_CONV_COLS,
+              psk::k_conv_cols2<T><<<dim3(cdiv(a.cols, 64), cdiv(a.rows, 8 * T), slices), 256, smem, c->stream>>>(a, PS_NEGZERO2));
+    return PS_OK;
+  }
+  PS_LAUNCH(c, KC_CONV_COLS, psk::k_conv_cols<T><<<dim3(cdiv(a.cols, 128), cdiv(a.rows, T), slices), 128, 0, c->stream>>>(a));
+  return PS_OK;
+}
+
+template <int NC>
+int launch_root_combine_t(ps_ctx *c, const psk::RootArgs &a) {
+  if (a.N % 4 == 0)
+    PS_LAUNCH(c, KC_ROOT_COMBINE, psk::k_root_combine<NC, 4><<<cdiv(a.N / 4, 256), 256, 0, c->stream>>>(a));
+  else
+    PS_LAUNCH(c, KC_ROOT_COMBINE, psk::k_root_combine<NC, 1><<<cdiv(a.N, 256), 256, 0, c->stream>>>(a));
+  return PS_OK;
+}
+
+int launch_root_combine(ps_ctx *c, const psk::RootArgs &a) {
+  switch (a.n) {
+#define RC_CASE(NC) case NC: return launch_root_combine_t<NC>(c, a)
+    RC_CASE(1); RC_CASE(2); RC_CASE(3); RC_CASE(4); RC_CASE(5); RC_CASE(6); RC_CASE(7); RC_CASE(8);
+    RC_CASE(9); RC_CASE(10); RC_CASE(11); RC_CASE(12); RC_CASE(13); RC_CASE(14); RC_CASE(15); RC_CASE(16);
+#undef RC_CASE
+  }
+  return c->fail(PS_ERR_UNSUPPORTED, "root with %d children", a.n);
+}
+
 // Where the value of one message goes (the addGrid2 calls around computeRotJointMarginal).
 struct Sink {
   float *out0 = nullptr;
@@ -285,32 +385,19 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     a.taps = dp.rot_taps(); a.max_enc = in_max;
     a.R = R; a.H = H; a.W = W;
     a.shift = h.rot_shift; a.mode = h.rot_mode; a.len = (int)h.rot_taps.size();
-    size_t smem = (size_t)R * psk::kRotThreads * sizeof(float);
-    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv<<<cdiv(c->HW, psk::kRotThreads), psk::kRotThreads, smem, st>>>(a));
+    int rc2 = launch_rotconv(c, a);
+    if (rc2) return rc2;
   }
 
   psk::EpiArgs e{};
   const float *filtered = nullptr;
   auto conv_rows = [&](const float *src, float *dst, int rows, int cols, int pitch, size_t plane, const float *taps,
                        int len) -> int {
-    constexpr int T = 8;
-    psk::ConvArgs a{src, dst, taps, len, rows, cols, pitch, plane};
-    int n = (len - 1) / 2;
-    int G = (cols + T - 1) / T;
-    int span_groups = (G * T + 2 * n + T - 1) / T + 1;
-    int S = span_groups;
-    while (S % 8 != 4) ++S;  // conflict-free transposed staging
-    int TY = 4;
-    size_t smem = (size_t)TY * T * S * sizeof(float);
-    PS_LAUNCH(c, KC_CONV_ROWS, psk::k_conv_rows<T><<<dim3(cdiv(rows, TY), R), 256, smem, st>>>(a, TY, S));
-    return PS_OK;
+    return launch_conv_rows(c, psk::ConvArgs{src, dst, taps, len, rows, cols, pitch, plane}, R);
   };
   auto conv_cols = [&](const float *src, float *dst, int rows, int cols, int pitch, size_t plane, const float *taps,
                        int len) -> int {
-    constexpr int T = 8;
-    psk::ConvArgs a{src, dst, taps, len, rows, cols, pitch, plane};
-    PS_LAUNCH(c, KC_CONV_COLS, psk::k_conv_cols<T><<<dim3(cdiv(cols, 128), cdiv(rows, T), R), 128, 0, st>>>(a));
-    return PS_OK;
+    return launch_conv_cols(c, psk::ConvArgs{src, dst, taps, len, rows, cols, pitch, plane}, R);
   };
 
   if (h.diag) {
@@ -356,7 +443,19 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
   e.out0 = sink.out0; e.acc0 = sink.acc0; e.add0 = sink.add0;
   e.out1 = sink.out1; e.add1 = sink.add1;
   e.max0 = sink.max0; e.max1 = sink.max1;
-  PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e));
+  {
+    const int XG = (W + 3) / 4;
+    // the 128-bit paths need 16-byte aligned caller buffers (cudaMalloc'd grids always are)
+    const bool al = ((uintptr_t)e.out0 % 16 == 0) && ((uintptr_t)e.acc0 % 16 == 0) && ((uintptr_t)e.add0 % 16 == 0) &&
+                    ((uintptr_t)e.out1 % 16 == 0) && ((uintptr_t)e.add1 % 16 == 0) && ((uintptr_t)e.xout % 16 == 0);
+    if (!al) {
+      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e));
+    } else if (e.general) {
+      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue2<true><<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
+    } else {
+      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue2<false><<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
+    }
+  }
   return PS_OK;
 }
 
@@ -368,7 +467,25 @@ int reset_max(ps_ctx *c, int *slot) {
 int grid_max(ps_ctx *c, const float *g, size_t n, int *slot) {
   int rc = reset_max(c, slot);
   if (rc) return rc;
-  PS_LAUNCH(c, KC_MAX, psk::k_grid_max<<<std::min(cdiv(n, 256 * 8), 148u * 8), 256, 0, c->stream>>>(g, n, slot));
+  PS_LAUNCH(c, KC_MAX, psk::k_grid_max<<<std::min(cdiv(n / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(g, n, slot));
+  return PS_OK;
+}
+
+// Fills the device tables of exp_fast / log_fast (ps_kernels.cuh) with host-libm doubles.
+int math_tables_init(ps_ctx *c) {
+  double2 lt[129];
+  for (int j = 0; j <= 128; ++j) {
+    double F = 1.0 + j / 128.0;
+    lt[j].x = 1.0 / F;
+    lt[j].y = j == 128 ? 0.0 : (j >= 54 ? std::log(F * 0.5) : std::log(F));
+  }
+  double et[289];
+  for (int e = -160; e <= 128; ++e) et[e + 160] = e * 0.693147180559945309417232121458;
+  double xt[64];
+  for (int j = 0; j < 64; ++j) xt[j] = std::exp2(j / 64.0);
+  PS_CUDA(c, cudaMemcpyToSymbol(psk::d_log_tab, lt, sizeof lt));
+  PS_CUDA(c, cudaMemcpyToSymbol(psk::d_eln2_tab, et, sizeof et));
+  PS_CUDA(c, cudaMemcpyToSymbol(psk::d_exp_tab, xt, sizeof xt));
   return PS_OK;
 }
 
@@ -600,6 +717,10 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   if (!cu(c->argmax_keys.alloc(c->P * sizeof(unsigned long long)), "alloc argmax")) return PS_ERR_CUDA;
   if (!cu(c->counters.alloc(8 * sizeof(unsigned)), "alloc counters")) return PS_ERR_CUDA;
   if (!cu(cudaMallocHost((void **)&c->host_keys, c->P * sizeof(unsigned long long)), "alloc pinned keys")) return PS_ERR_CUDA;
+  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_conv_rows2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_conv_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr"))
+    return PS_ERR_CUDA;
   // non-detect parts have all-zero unaries in the reference (findrot.cpp:794 resize, never loaded)
   if (!cu(cudaMemsetAsync(c->unary.p, 0, c->unary.bytes, c->stream), "memset")) return PS_ERR_CUDA;
 
@@ -625,6 +746,10 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   if (!cu(cudaMemcpy(c->valid_rots.p, valid.data(), valid.size() * sizeof(int), cudaMemcpyHostToDevice), "copy rots"))
     return PS_ERR_CUDA;
   if (!cu(cudaStreamSynchronize(c->stream), "sync")) return PS_ERR_CUDA;
+  if (math_tables_init(c.get())) {
+    g_create_error = "ps_create: " + c->err;
+    return PS_ERR_CUDA;
+  }
   *out = c.release();
   return PS_OK;
 }
@@ -727,7 +852,7 @@ int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind,
   PS_CUDA(c, cudaMemcpyAsync(dst, src, c->N * sizeof(float),
                              mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   if (raw) {
-    PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N, 256 * 4), 148u * 16), 256, 0, c->stream>>>(dst, c->N));
+    PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(dst, c->N, nullptr));
   }
   return PS_OK;
 }
@@ -815,7 +940,7 @@ int enqueue_readout(ps_ctx *c, const std::vector<const float *> &grids, int scal
   PS_CUDA(c, cudaMemsetAsync(c->argmax_keys.p, 0, P * sizeof(unsigned long long), c->stream));
   for (int p = 0; p < P; ++p)
     PS_LAUNCH(c, KC_ARGMAX,
-              psk::k_argmax<<<std::min(cdiv(c->N, 256 * 8), 148u * 8), 256, 0, c->stream>>>(
+              psk::k_argmax<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(
                   grids[p], c->N, c->argmax_keys.as<unsigned long long>() + p));
   PS_CUDA(c, cudaMemcpyAsync(c->host_keys, c->argmax_keys.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              c->stream));
@@ -961,7 +1086,7 @@ int ps_infer(ps_ctx *c, int flags) {
       a.post = c->POST(root, s);
       a.N = N;
       if (nrc > 0) {
-        PS_LAUNCH(c, KC_ROOT_COMBINE, psk::k_root_combine<<<cdiv(N, 256), 256, 0, st>>>(a));
+        if ((rc = launch_root_combine(c, a))) return rc;
       } else {
         PS_CUDA(c, cudaMemcpyAsync(a.post, a.unary, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
       }
@@ -1111,6 +1236,18 @@ int ps_message(ps_ctx *c, const float *child, float *parent, int mem_kind, const
   if ((rc = run_message(c, dp, din, mx, sparse != 0, sink))) return rc;
   if (mem_kind == PS_MEM_HOST)
     PS_CUDA(c, cudaMemcpyAsync(parent, dout, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+int ps_selftest_math(ps_ctx *c, unsigned first_bits, unsigned long long count, unsigned long long out[4]) {
+  if (!c || !out) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  DevBuf d;
+  PS_CUDA(c, d.alloc(4 * sizeof(unsigned long long)));
+  PS_CUDA(c, cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), c->stream));
+  PS_LAUNCH(c, KC_MISC, psk::k_selftest_math<<<148 * 16, 256, 0, c->stream>>>(first_bits, count, d.as<unsigned long long>()));
+  PS_CUDA(c, cudaMemcpyAsync(out, d.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
   return PS_OK;
 }

@@ -241,6 +241,12 @@ class PsContext:
         self._check(self.lib.ps_get_root_hyps(self.h, out.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return out[:n.value].copy()
 
+    def selftest_math(self, first_bits, count):
+        """(exp mismatches, exp tested, log mismatches, log tested) over fp32 bit patterns [first, first+count)."""
+        out = (C.c_ulonglong * 4)()
+        self._check(self.lib.ps_selftest_math(self.h, first_bits, count, out))
+        return tuple(int(v) for v in out)
+
     def launch_count(self):
         return int(self.lib.ps_launch_count(self.h))
 
