@@ -192,6 +192,10 @@ struct MessagePlan {
   // nearest-neighbour translations (:345-359 in, :438-448 out): source index per destination index, -1 = out of bounds
   std::vector<int> xin, yin;    // [R][W], [R][H]
   std::vector<int> xout, yout;
+  // When every table row is a pure shift (src = dst + d, out of range -> -1) the kernels use the per-rotation
+  // shifts instead of table look-ups; a row that is not (a rounding tie of x3 - t at .5) keeps the tables.
+  bool in_pure = false, out_pure = false;
+  std::vector<int> in_shift, out_shift;  // [R][2] = (dx, dy)
 
   // spatial filter (:423-429 -> multi_array_filter.hpp:375-388)
   bool diag = true;
@@ -225,6 +229,24 @@ inline void nearest_tables(const M3 &T21, int W, int H, int *xt, int *yt) {
     int iy = (int)std::floor(y1 + 0.5);
     yt[y3] = (iy >= 0 && iy < H) ? iy : -1;
   }
+}
+
+// d such that t[i] == (0 <= i + d < n ? i + d : -1) for all i, if one exists.
+inline bool pure_shift(const int *t, int n, int &d) {
+  int found = 0;
+  d = 2 * n;  // everything out of range
+  for (int i = 0; i < n; ++i)
+    if (t[i] >= 0) {
+      d = t[i] - i;
+      found = 1;
+      break;
+    }
+  if (!found) return true;
+  for (int i = 0; i < n; ++i) {
+    int e = i + d;
+    if (t[i] != ((e >= 0 && e < n) ? e : -1)) return false;
+  }
+  return true;
 }
 
 inline MessagePlan plan_message(const Grid &g, const double off_in[2], const double off_out[2],
@@ -275,6 +297,15 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
     mul(Tg, vout, u);
     nearest_tables(translation(t[0], t[1]), W, H, &p.xin[(size_t)r * W], &p.yin[(size_t)r * H]);
     nearest_tables(translation(-u[0], -u[1]), W, H, &p.xout[(size_t)r * W], &p.yout[(size_t)r * H]);
+  }
+
+  p.in_shift.resize(2 * R); p.out_shift.resize(2 * R);
+  p.in_pure = p.out_pure = true;
+  for (int r = 0; r < R; ++r) {
+    p.in_pure = p.in_pure && pure_shift(&p.xin[(size_t)r * W], W, p.in_shift[2 * r]) &&
+                pure_shift(&p.yin[(size_t)r * H], H, p.in_shift[2 * r + 1]);
+    p.out_pure = p.out_pure && pure_shift(&p.xout[(size_t)r * W], W, p.out_shift[2 * r]) &&
+                 pure_shift(&p.yout[(size_t)r * H], H, p.out_shift[2 * r + 1]);
   }
 
   // spatial covariance, :423 scaleC = square(scale)*C

@@ -275,6 +275,7 @@ struct RotArgs {
   float *out;           // [R][H][W] rotation-filtered probabilities
   const int *xin;       // [R][W] source x or -1
   const int *yin;       // [R][H] source y or -1
+  const int *shift_xy;  // [R][2] (dx, dy) when every table row is a pure shift, else null
   const float *taps;    // [len]
   const int *max_enc;   // encoded max of `in`
   int R, H, W;
@@ -483,6 +484,106 @@ __global__ void k_warp_bilinear(const float *__restrict__ in, float *__restrict_
         }
     }
   }
+}
+
+
+// ---- resampling v2: one thread = one destination cell x a group of RG slices ----------------------------------
+// The source position of a cell is the same for every rotation slice, so its fp64 coordinate math, case analysis and
+// fp32 weights are done once per thread and reused for RG slices; RG < R keeps enough threads in flight (v1 looped
+// over all R slices per thread and was latency-bound).
+
+// Bilinear sample set-up shared by the slices (multi_array_transform.hpp:196-238, default value 0).
+struct BilinearTap {
+  int mode;      // 0: default, 1: exact hit, 2: four-point blend
+  int off;       // iy * pitch + ix
+  float w00, w01, w10, w11;
+};
+__device__ __forceinline__ BilinearTap bilinear_setup(int h, int w, int pitch, double x1, double y1) {
+  BilinearTap t;
+  t.mode = 0; t.off = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.0f;
+  const double fx = floor(x1), fy = floor(y1);
+  const int ix = (int)fx, iy = (int)fy;
+  if (ix >= 0 && ix < w && iy >= 0 && iy < h) {
+    const float a = (float)__dsub_rn(x1, fx), b = (float)__dsub_rn(y1, fy);
+    const float eps10 = 10 * 1.1920928955078125e-07f;
+    t.off = iy * pitch + ix;
+    if (a < eps10 && b < eps10) t.mode = 1;
+    else if (ix < w - 1 && iy < h - 1) {
+      t.mode = 2;
+      const float omb = __fsub_rn(1.0f, b), oma = __fsub_rn(1.0f, a);
+      t.w00 = __fmul_rn(omb, oma); t.w01 = __fmul_rn(omb, a); t.w10 = __fmul_rn(b, oma); t.w11 = __fmul_rn(b, a);
+    }
+  }
+  return t;
+}
+
+// dst[r][cell] = bilinear(src[r]) for r in the thread's slice group.  Used both ways: image -> eigen-frame
+// (TM_BILINEAR of gaussFilter2dOffset, filter.hpp:359) and eigen-frame -> image (filter.hpp:367-368).
+template <int RG>
+__global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restrict__ src, float *__restrict__ dst, Affine T,
+                                                           int R, int sh, int sw, int spitch, size_t splane, int dh,
+                                                           int dw, int dpitch, size_t dplane) {
+  // 2-D tiles: a tile's rotated footprint in the source stays compact, so the four taps of neighbouring cells
+  // hit the same L1 lines
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+  const int r0 = blockIdx.z * RG;
+  if (ix >= dpitch || iy >= dh) return;
+  float *o = dst + (size_t)r0 * dplane + (size_t)iy * dpitch + ix;
+  BilinearTap t;
+  t.mode = 0;
+  if (ix < dw) {
+    double x1, y1;
+    affine_map(T, (double)ix, (double)iy, x1, y1);
+    t = bilinear_setup(sh, sw, spitch, x1, y1);
+  }
+  const float *p = src + (size_t)r0 * splane + t.off;
+  if (t.mode == 2) {
+    float q[RG][4];
+#pragma unroll
+    for (int u = 0; u < RG; ++u)
+      if (r0 + u < R) {
+        const float *s = p + (size_t)u * splane;
+        q[u][0] = __ldg(s); q[u][1] = __ldg(s + 1); q[u][2] = __ldg(s + spitch); q[u][3] = __ldg(s + spitch + 1);
+      }
+#pragma unroll
+    for (int u = 0; u < RG; ++u)
+      if (r0 + u < R) {
+        float t0 = __fmul_rn(t.w00, q[u][0]), t1 = __fmul_rn(t.w01, q[u][1]);
+        float t2 = __fmul_rn(t.w10, q[u][2]), t3 = __fmul_rn(t.w11, q[u][3]);
+        o[(size_t)u * dplane] = __fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3);
+      }
+  } else {
+#pragma unroll
+    for (int u = 0; u < RG; ++u)
+      if (r0 + u < R) o[(size_t)u * dplane] = t.mode == 1 ? __ldg(p + (size_t)u * splane) : 0.0f;
+  }
+}
+
+// TM_DIRECT as a gather through the winner map, RG slices per thread.
+template <int RG>
+__global__ void __launch_bounds__(256) k_warp_direct2(const float *__restrict__ in, float *__restrict__ out,
+                                                      const int2 *__restrict__ map, int R, size_t HW, int EH, int EW,
+                                                      int EP) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+  const int r0 = blockIdx.z * RG;
+  if (ix >= EP || iy >= EH) return;
+  const size_t eplane = (size_t)EH * EP;
+  float *o = out + (size_t)r0 * eplane + (size_t)iy * EP + ix;
+  int2 m = make_int2(-1, -1);
+  if (ix < EW) m = map[(size_t)iy * EW + ix];
+  float v[RG];
+#pragma unroll
+  for (int u = 0; u < RG; ++u) v[u] = (m.x >= 0 && r0 + u < R) ? __ldg(in + (size_t)(r0 + u) * HW + m.x) : 0.0f;
+  if (m.y >= 0) {
+#pragma unroll
+    for (int u = 0; u < RG; ++u)
+      if (r0 + u < R && v[u] == 0.0f) v[u] = __ldg(in + (size_t)(r0 + u) * HW + m.y);
+  }
+#pragma unroll
+  for (int u = 0; u < RG; ++u)
+    if (r0 + u < R) o[(size_t)u * eplane] = v[u];
 }
 
 // ---- message stage 2b: separable Gaussian, zero padded, unnormalised taps -------------------------------
@@ -739,8 +840,13 @@ __global__ void __launch_bounds__(256) k_rotconv3(RotArgs a, u64 nz) {
       const int r = ro - a.shift;
       off[c] = -1;
       if (okp && ro < R && r >= 0 && r < R) {
-        const int ys = a.yin[r * a.H + y], xs = a.xin[r * a.W + x];
-        if ((ys | xs) >= 0) off[c] = ys * a.W + xs;
+        if (a.shift_xy) {
+          const int xs = x + a.shift_xy[2 * r], ys = y + a.shift_xy[2 * r + 1];
+          if ((unsigned)xs < (unsigned)a.W && (unsigned)ys < (unsigned)a.H) off[c] = ys * a.W + xs;
+        } else {
+          const int ys = a.yin[r * a.H + y], xs = a.xin[r * a.W + x];
+          if ((ys | xs) >= 0) off[c] = ys * a.W + xs;
+        }
       }
     }
     float v[NIT];
@@ -809,7 +915,7 @@ __global__ void __launch_bounds__(256) k_rotconv3(RotArgs a, u64 nz) {
 // (8T + 2n) input rows are staged once (coalesced float2 rows), so each input element is read from L2
 // (8T+2n)/(8T) times instead of (len+T-1)/T times.  Requires an even pitch (8-byte aligned pairs).
 template <int T>
-__global__ void __launch_bounds__(256) k_conv_cols2(ConvArgs a, u64 nz) {
+__global__ void __launch_bounds__(256, 4) k_conv_cols2(ConvArgs a, u64 nz) {
   extern __shared__ float2 s_rows[];  // [8T + 2n][32]
   __shared__ float s_taps[1000];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -874,7 +980,7 @@ __global__ void __launch_bounds__(256) k_conv_cols2(ConvArgs a, u64 nz) {
 // A block stages PAIRS row pairs (+halo) as float2 (row 2q, row 2q+1) in the "transposed by T" layout
 // (element i at (i % T) * S + i / T); a thread owns T consecutive outputs of both rows of a pair.
 template <int T>
-__global__ void __launch_bounds__(256) k_conv_rows2(ConvArgs a, u64 nz, int PAIRS, int S) {
+__global__ void __launch_bounds__(256, 4) k_conv_rows2(ConvArgs a, u64 nz, int PAIRS, int S) {
   extern __shared__ float2 s_pairs[];  // [PAIRS][T*S]
   __shared__ float s_taps[1000];
   const int tid = threadIdx.x;
@@ -961,6 +1067,7 @@ struct EpiArgs {
   Affine T34;
   int EH, EW, EP;
   const int *xout, *yout;  // [R][W], [R][H]
+  const int *shift_xy;  // [R][2] (dx, dy) when every table row is a pure shift, else null
   const int *max_enc;   // M of the message input
   int R, H, W;
   // out0 = (acc0 ? acc0 + v : v) (+ add0);  out1 = add1 + v
@@ -1030,11 +1137,19 @@ __global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4
     const size_t HW = (size_t)a.H * a.W;
     const size_t cell0 = (size_t)r * HW + (size_t)y * a.W + x0;
     const float M = dec_f(*a.max_enc);
-    const int ys = a.yout[r * a.H + y];
     const int nx = min(4, a.W - x0);
     const bool vec = (a.W & 3) == 0;  // rows and slices are then 16-byte aligned
-    int xs[4];
-    if (vec) {
+    int xs[4], ys;
+    if (a.shift_xy) {
+      const int dx = a.shift_xy[2 * r];
+      ys = y + a.shift_xy[2 * r + 1];
+      if ((unsigned)ys >= (unsigned)a.H) ys = -1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xs[j] = x0 + j + dx;
+        if ((unsigned)xs[j] >= (unsigned)a.W || j >= nx) xs[j] = -1;
+      }
+    } else if (ys = a.yout[r * a.H + y], vec) {
       int4 t = *reinterpret_cast<const int4 *>(a.xout + r * a.W + x0);
       xs[0] = t.x; xs[1] = t.y; xs[2] = t.z; xs[3] = t.w;
     } else {

@@ -47,7 +47,7 @@ struct DevBuf {
 // Device-side image of one psg::MessagePlan.
 struct DevPlan {
   psg::MessagePlan host;
-  DevBuf ints;    // xin | xout | yin | yout  (xout stays 16-byte aligned whenever W % 4 == 0)
+  DevBuf ints;    // xin | xout | yin | yout | in_shift | out_shift (xout stays 16-byte aligned whenever W % 4 == 0)
   DevBuf floats;  // rot taps | fx | fy
   DevBuf map;     // int2 [EH][EW], built on first sparse use
   DevBuf mats;    // T31 | T13 (doubles) for the map builder
@@ -57,6 +57,8 @@ struct DevPlan {
   const int *xout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * W; }
   const int *yin(int R, int W) const { return ints.as<int>() + (size_t)R * 2 * W; }
   const int *yout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * (2 * W + H); }
+  const int *in_shift(int R, int H, int W) const { return host.in_pure ? ints.as<int>() + (size_t)R * 2 * (W + H) : nullptr; }
+  const int *out_shift(int R, int H, int W) const { return host.out_pure ? ints.as<int>() + (size_t)R * 2 * (W + H) + 2 * R : nullptr; }
   const float *rot_taps() const { return floats.as<float>(); }
   const float *fx() const { return floats.as<float>() + host.rot_taps.size(); }
   const float *fy() const { return floats.as<float>() + host.rot_taps.size() + host.fx.size(); }
@@ -151,11 +153,11 @@ struct ps_ctx {
 // kernel classes for ps_profile_read / DESIGN.md
 enum KClass {
   KC_PREP = 0, KC_MAX, KC_MASK, KC_ROTCONV, KC_WARP_DIRECT, KC_WARP_BILINEAR, KC_CONV_ROWS, KC_CONV_COLS,
-  KC_EPILOGUE, KC_ROOT_COMBINE, KC_ROOT_MARGINAL, KC_ARGMAX, KC_LOCAL_MAX, KC_MISC, KC_COUNT
+  KC_WARP_BACK, KC_EPILOGUE, KC_ROOT_COMBINE, KC_ROOT_MARGINAL, KC_ARGMAX, KC_LOCAL_MAX, KC_MISC, KC_COUNT
 };
 static const char *const kClassNames[KC_COUNT] = {
     "prepare_unary", "grid_max", "mask", "rotconv", "warp_direct", "warp_bilinear", "conv_rows", "conv_cols",
-    "epilogue", "root_combine", "root_marginal", "argmax", "local_max", "misc"};
+    "warp_back", "epilogue", "root_combine", "root_marginal", "argmax", "local_max", "misc"};
 
 static size_t prof_event(ps_ctx *c) {
   if (c->ev_used == c->ev_pool.size()) {
@@ -205,6 +207,8 @@ int upload_plan(ps_ctx *c, DevPlan &dp) {
   ints.insert(ints.end(), h.xout.begin(), h.xout.end());
   ints.insert(ints.end(), h.yin.begin(), h.yin.end());
   ints.insert(ints.end(), h.yout.begin(), h.yout.end());
+  ints.insert(ints.end(), h.in_shift.begin(), h.in_shift.end());
+  ints.insert(ints.end(), h.out_shift.begin(), h.out_shift.end());
   std::vector<float> fl;
   fl.insert(fl.end(), h.rot_taps.begin(), h.rot_taps.end());
   fl.insert(fl.end(), h.fx.begin(), h.fx.end());
@@ -301,7 +305,7 @@ int launch_conv_rows(ps_ctx *c, const psk::ConvArgs &a, int slices) {
     const size_t pair_bytes = (size_t)T * S * sizeof(float2);
     int best = 0;
     double best_eff = 0;
-    for (int pairs = 1; pairs <= 32 && pairs * pair_bytes <= kSmemBudget / 2; ++pairs) {
+    for (int pairs = 1; pairs <= 32 && pairs * pair_bytes <= 40 * 1024; ++pairs) {
       int items = pairs * G;
       double eff = (double)items / (((items + 255) / 256) * 256);
       if (eff >= best_eff - 1e-9) { best_eff = eff; best = pairs; }
@@ -382,6 +386,7 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     psk::RotArgs a;
     a.in = in; a.out = c->bufB.as<float>();
     a.xin = dp.xin(); a.yin = dp.yin(R, W);
+    a.shift_xy = dp.in_shift(R, H, W);
     a.taps = dp.rot_taps(); a.max_enc = in_max;
     a.R = R; a.H = H; a.W = W;
     a.shift = h.rot_shift; a.mode = h.rot_mode; a.len = (int)h.rot_taps.size();
@@ -412,32 +417,39 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     // gaussFilter2dOffset: rotate into the eigen-frame, filter there, bilinear read-back in the epilogue
     const int EH = h.EH, EW = h.EW, EP = dp.EP;
     const size_t eplane = (size_t)EH * EP;
+    constexpr int RG = 6;
     if (sparse) {
       rc = ensure_direct_map(c, dp);
       if (rc) return rc;
       PS_LAUNCH(c, KC_WARP_DIRECT,
-                psk::k_warp_direct<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(),
-                                                                           dp.map.as<int2>(), R, c->HW, EH, EW, EP));
+                psk::k_warp_direct2<RG><<<dim3(cdiv(EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                    c->bufB.as<float>(), c->bufU.as<float>(), dp.map.as<int2>(), R, c->HW, EH, EW, EP));
     } else {
       Affine T13;
       memcpy(T13.m, h.T13, sizeof T13.m);
       PS_LAUNCH(c, KC_WARP_BILINEAR,
-                psk::k_warp_bilinear<<<dim3(cdiv(EP, 128), EH), 128, 0, st>>>(c->bufB.as<float>(), c->bufU.as<float>(),
-                                                                             T13, R, H, W, EH, EW, EP));
+                psk::k_resample_bilinear<RG><<<dim3(cdiv(EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                    c->bufB.as<float>(), c->bufU.as<float>(), T13, R, H, W, W, c->HW, EH, EW, EP, eplane));
     }
     rc = conv_rows(c->bufU.as<float>(), c->bufV.as<float>(), EH, EW, EP, eplane, dp.fx(), (int)h.fx.size());
     if (rc) return rc;
     rc = conv_cols(c->bufV.as<float>(), c->bufU.as<float>(), EH, EW, EP, eplane, dp.fy(), (int)h.fy.size());
     if (rc) return rc;
-    filtered = c->bufU.as<float>();
-    e.general = 1;
-    memcpy(e.T34.m, h.T34, sizeof e.T34.m);
-    e.EH = EH; e.EW = EW; e.EP = EP;
+    // bilinear read-back into the image frame (filter.hpp:367-368); the sample position does not depend on the
+    // rotation slice, so it is resolved once per pixel here instead of once per cell inside the epilogue
+    Affine T34;
+    memcpy(T34.m, h.T34, sizeof T34.m);
+    PS_LAUNCH(c, KC_WARP_BACK,
+              psk::k_resample_bilinear<RG><<<dim3(cdiv(W, 16), cdiv(H, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                  c->bufU.as<float>(), c->bufB.as<float>(), T34, R, EH, EW, EP, eplane, H, W, W, c->HW));
+    filtered = c->bufB.as<float>();
+    e.general = 0;
   }
 
   // stage 3: log, +M, shift, combine
   e.src = filtered;
   e.xout = dp.xout(R, H, W); e.yout = dp.yout(R, H, W);
+  e.shift_xy = dp.out_shift(R, H, W);
   e.max_enc = in_max;
   e.R = R; e.H = H; e.W = W;
   e.out0 = sink.out0; e.acc0 = sink.acc0; e.add0 = sink.add0;
