@@ -1,0 +1,107 @@
+"""CPU checks of the build: the C-ABI library exists, loads without a GPU, exports every symbol include/psinfer.h
+declares, fails loudly (no CPU fallback), and its Gaussian kernels keep both roundings of a tap (FFMA2 + FADD2)."""
+import ctypes
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "psinfer.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ps_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(pslib):
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(pslib, s), "libpsinfer.so does not export %s" % s
+
+
+def test_ctypes_prototypes_cover_header():
+    from partapp_b200 import capi
+    assert sorted(capi.PROTOTYPES) == declared_symbols()
+
+
+def test_version_and_pure_host_entry_points(pslib):
+    from partapp_b200 import capi
+    assert b"sm_100a" in pslib.ps_version()
+    cfg = capi.ps_config()
+    cfg.num_rotation_steps, cfg.min_part_rotation, cfg.max_part_rotation = 24, -180.0, 180.0
+    cfg.num_scale_steps, cfg.min_object_scale, cfg.max_object_scale = 5, 0.8, 1.2
+    assert pslib.ps_rot_from_index(ctypes.byref(cfg), 0) == -172.5
+    assert abs(pslib.ps_scale_from_index(ctypes.byref(cfg), 2) - 1.0) < 1e-7
+    assert pslib.ps_index_from_rot(ctypes.byref(cfg), 0.5) == 12
+    j = capi.ps_joint()
+    j.type = capi.PS_JOINT_ROT_GAUSSIAN
+    j.offset_c[0], j.offset_c[1], j.rot_mean = 3.0, 4.0, 0.25
+    j.C[0], j.C[1], j.C[2], j.C[3] = 2.0, 0.5, 0.5, 1.0
+    pslib.ps_flip_joint(ctypes.byref(j))
+    assert (j.offset_c[0], j.offset_c[1], j.rot_mean) == (-3.0, 4.0, -0.25)
+    assert (j.C[0], j.C[1], j.C[2], j.C[3]) == (2.0, -0.5, -0.5, 1.0)
+
+
+def test_conditioning_tables_match_oracle(pslib, oracle_lib):
+    import numpy as np
+    from partapp_b200 import ExpParam, capi
+    from partapp_b200.objectdetect import PartConf, make_config
+    ep = ExpParam(num_rotation_steps=24)
+    cfg = make_config(ep, PartConf([True], [False], [True]), 30, 20)
+    fp = ctypes.POINTER(ctypes.c_float)
+    a, b = np.zeros(24, np.float32), np.zeros(24, np.float32)
+    pslib.ps_rot_score_table(ctypes.byref(cfg), 0.3, 0.2, a.ctypes.data_as(fp))
+    oracle_lib.lib().orc_rot_score_table(ctypes.byref(oracle_lib.exp_param(ep)), 0.3, 0.2, b.ctypes.data_as(fp))
+    assert np.array_equal(a, b)
+    a, b = np.zeros((30, 20), np.float32), np.zeros((30, 20), np.float32)
+    pslib.ps_pos_score_table(30, 20, 2.0, -3.0, 40.0, 60.0, 9.0, 14.0, a.ctypes.data_as(fp))
+    oracle_lib.lib().orc_pos_score_table(30, 20, 2.0, -3.0, 40.0, 60.0, 9.0, 14.0, b.ctypes.data_as(fp))
+    assert np.array_equal(a, b)
+    pslib.ps_torso_prior_table(30, 20, 1.0, 2.0, 50.0, 80.0, 0.7, a.ctypes.data_as(fp))
+    oracle_lib.lib().orc_torso_prior_table(30, 20, 1.0, 2.0, 50.0, 80.0, 0.7, b.ctypes.data_as(fp))
+    assert np.array_equal(a, b)
+
+
+def test_no_cpu_fallback_without_gpu(pslib):
+    """Without a CUDA device ps_create must fail with PS_ERR_CUDA -- never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from partapp_b200 import ExpParam, PsContext, PsInferError, capi, synth
+    with pytest.raises(PsInferError) as ei:
+        PsContext(ExpParam(num_rotation_steps=8), synth.part_conf(2), 8, 8)
+    assert ei.value.status == capi.PS_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "partapp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "ps_oracle" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
+def test_gaussian_kernels_keep_both_roundings(pslib):
+    """Parity arithmetic in SASS: in the packed Gaussian kernels every FFMA2 (multiply with a run-time -0.0 addend) is
+    paired with an FADD2; a lone FFMA2 would mean ptxas contracted multiply and add."""
+    from partapp_b200 import capi
+    out = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels = re.split(r"\n\s*Function : ", out)
+    seen = 0
+    for k in kernels[1:]:
+        name = k.split("\n", 1)[0]
+        if not any(t in name for t in ("k_conv_cols2", "k_conv_rows2", "k_rotconv3")):
+            continue
+        seen += 1
+        ffma2, fadd2 = len(re.findall(r"\bFFMA2\b", k)), len(re.findall(r"\bFADD2\b", k))
+        assert ffma2 > 0 and ffma2 == fadd2, "%s: %d FFMA2 vs %d FADD2" % (name, ffma2, fadd2)
+        assert not re.search(r"\bFFMA\b", k), "%s contains a scalar FFMA" % name
+    assert seen >= 3

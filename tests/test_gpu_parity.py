@@ -159,3 +159,225 @@ def test_find_local_max_matches_oracle():
                 assert np.array_equal(got, want)  # scan order
             else:
                 assert np.array_equal(np.sort(got[:, 3])[::-1], np.sort(want[:, 3])[::-1])
+
+
+# ---- golden fixtures (oracle outputs committed under tests/golden) -------------------------------------------------
+
+def test_messages_match_golden_fixtures():
+    import os
+    from tests.golden.make_golden import CASES, case_input
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "messages.npz"))
+    for name, spec in CASES.items():
+        ep, g = case_input(name)
+        R, H, W = g.shape
+        oi, oo, Cm, rm, rs, sc, sparse = spec[5:]
+        with _ctx(ep, 2, H, W) as ctx:
+            got = ctx.message(g, oi, oo, Cm, rm, rs, sc, sparse)
+        _cmp(got, z[name], "golden " + name)
+
+
+def test_infer_matches_golden_fixture():
+    import os
+    from tests.golden.make_golden import infer_case
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "infer.npz"))
+    ep, pc, joints, un = infer_case()
+    P, S, R, H, W = un.shape
+    with PsContext(ep, pc, H, W) as ctx:
+        res = od.computeRootPosteriorRot(ctx, [[un[p, s] for s in range(S)] for p in range(P)], joints, True)
+        assert np.array_equal(res.best_conf[:, :6], z["best_conf"][:, :6])
+        _cmp(res.root_part_posterior, z["root_post"], "golden root posterior")
+        for p in range(P):
+            _cmp(ctx.marginal(p), z["marginals"][0, p], "golden marginal %d" % p)
+
+
+# ---- the rest of the seam -------------------------------------------------------------------------------------------
+
+def test_conditioning_adds_match_oracle():
+    """a5: addExtraUnary with rotation / position tables and the torso prior (icps.cpp:137-191,228-281,366-423,526-548)."""
+    import ctypes
+    ep = ExpParam(num_rotation_steps=8)
+    P, H, W = 3, 28, 24
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 2))
+    L = oracle.lib()
+    fp = ctypes.POINTER(ctypes.c_float)
+    rot_t = np.zeros(8, np.float32)
+    L.orc_rot_score_table(ctypes.byref(oracle.exp_param(ep)), 0.4, 0.3, rot_t.ctypes.data_as(fp))
+    pos_t = np.zeros((H, W), np.float32)
+    L.orc_pos_score_table(H, W, 3.0, -2.0, 30.0, 45.0, 10.0, 12.0, pos_t.ctypes.data_as(fp))
+    tor_t = np.zeros((H, W), np.float32)
+    L.orc_torso_prior_table(H, W, 1.0, 2.0, 60.0, 90.0, 0.8, tor_t.ctypes.data_as(fp))
+    want = un.copy()
+    L.orc_add_rot_table(want[1, 0].ctypes.data_as(fp), 8, H, W, rot_t.ctypes.data_as(fp), 0.35)
+    L.orc_add_pos_table(want[1, 0].ctypes.data_as(fp), 8, H, W, pos_t.ctypes.data_as(fp), 0.6)
+    L.orc_add_pos_table_unweighted(want[0, 0].ctypes.data_as(fp), 8, H, W, tor_t.ctypes.data_as(fp))
+    with _ctx(ep, P, H, W) as ctx:
+        for p in range(P):
+            ctx.set_unary(p, 0, un[p, 0])
+        ctx.add_unary_table(1, rot_t, 0, 0.35)
+        ctx.add_unary_table(1, pos_t, 1, 0.6)
+        ctx.add_unary_table(0, tor_t, 2)
+        for p in range(P):
+            assert np.array_equal(ctx.get_unary(p, 0), want[p, 0]), "part %d" % p
+
+
+def test_flipped_joints_match_oracle():
+    ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=10)
+    P, H, W = 4, 36, 32
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 4))
+    joints = [j.flipped() for j in synth.make_joints(P, seed=9, max_offset=6, sigma_range=(1.5, 3))]
+    ref = synth.make_joints(P, seed=9, max_offset=6, sigma_range=(1.5, 3))
+    for a, b in zip(joints, ref):   # ps_flip_joint == orc_flip_joint
+        ob = oracle.joint(b)
+        oracle.lib().orc_flip_joint(ob)
+        assert list(a.offset_c) == [ob.offset_c[0], ob.offset_c[1]] and a.rot_mean == ob.rot_mean
+        assert np.array_equal(np.asarray(a.C).reshape(4), [ob.C[i] for i in range(4)])
+    pc = synth.part_conf(P)
+    want = oracle.infer(ep, pc, joints, un.copy(), sparse=True)
+    with PsContext(ep, pc, H, W) as ctx:
+        res = od.computeRootPosteriorRot(ctx, [[un[p, 0]] for p in range(P)], joints, True)
+        assert np.array_equal(res.best_conf[:, :6], want["best_conf"][:, :6])
+
+
+def test_get_max_states_matches_oracle():
+    import ctypes
+    ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=25)
+    P, H, W = 3, 30, 26
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 6))
+    want = np.zeros((P, 7), np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    oracle.lib().orc_get_max_states(ctypes.byref(oracle.exp_param(ep)), P, H, W, un.ctypes.data_as(fp),
+                                    want.ctypes.data_as(fp))
+    with _ctx(ep, P, H, W) as ctx:
+        best, hyps = od.getMaxStates(ctx, [[un[p, 0]] for p in range(P)], local_max=True)
+        assert np.array_equal(best, want)
+        for p in range(P):
+            lm = oracle.find_local_max(un[p, 0], 25)
+            assert len(hyps[p]) == 1 + len(lm)
+            assert np.array_equal(np.sort(hyps[p][1:, 6])[::-1], np.sort(lm[:, 3])[::-1])
+
+
+def test_infer_local_maxima_and_root_hypotheses():
+    ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=30)
+    P, H, W = 4, 40, 36
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 8))
+    joints = synth.make_joints(P, seed=1, max_offset=6, sigma_range=(1.5, 3))
+    pc = synth.part_conf(P)
+    want = oracle.infer(ep, pc, joints, un.copy(), sparse=True, want_hyps=True)
+    with PsContext(ep, pc, H, W) as ctx:
+        ctx.set_joints(joints)
+        for p in range(P):
+            ctx.set_unary(p, 0, un[p, 0])
+        ctx.infer(sparse=True, local_max=True, root_hyps=True)
+        for p in range(P):
+            got, ref = ctx.part_hyps(p), want["part_hyps"][p]
+            assert len(got) == len(ref)
+            assert np.array_equal(got[0, :6], ref[0, :6])                       # entry 0 = the argmax record
+            np.testing.assert_allclose(np.sort(got[1:, 6])[::-1], np.sort(ref[1:, 6])[::-1], rtol=1e-6)
+        rh = ctx.root_hyps()
+        ref = oracle.find_local_max(want["root_post"], 1000)
+        sel = ref[:, 3] > -5e5
+        got_sel = rh[rh[:, 3] > -5e5]
+        assert len(got_sel) == sel.sum()
+        np.testing.assert_allclose(np.sort(got_sel[:, 3]), np.sort(ref[sel, 3]), rtol=1e-6)
+
+
+def test_keep_unaries_restores_inputs():
+    ep = ExpParam(num_rotation_steps=8, strip_border_detections=0.2)
+    P, H, W = 3, 24, 30
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 12))
+    joints = synth.make_joints(P, seed=1, max_offset=4, sigma_range=(1.5, 2.5))
+    with PsContext(ep, synth.part_conf(P, upright_root=True), H, W) as ctx:
+        ctx.set_joints(joints)
+        for p in range(P):
+            ctx.set_unary(p, 0, un[p, 0])
+        ctx.infer(sparse=True, keep_unaries=True)
+        ctx.best_conf()
+        for p in range(P):
+            assert np.array_equal(ctx.get_unary(p, 0), un[p, 0])
+
+
+def test_22_part_tree_matches_oracle():
+    ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=5)
+    P, H, W = 22, 32, 28
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 21))
+    joints = synth.make_joints(P, seed=11, max_offset=5, sigma_range=(1.2, 2.5))
+    pc = synth.part_conf(P)
+    want = oracle.infer(ep, pc, joints, un.copy(), sparse=True)
+    with PsContext(ep, pc, H, W) as ctx:
+        res = od.computeRootPosteriorRot(ctx, [[un[p, 0]] for p in range(P)], joints, True, write_back_masked=False)
+        assert np.array_equal(res.best_conf[:, :6], want["best_conf"][:, :6])
+        for p in (0, 4, 10, 21):
+            _cmp(ctx.marginal(p), want["marginals"][0, p], "22-part marginal %d" % p)
+
+
+def test_error_statuses_replace_asserts():
+    from partapp_b200 import PsInferError, capi
+    ep = ExpParam(num_rotation_steps=8)
+    with _ctx(ep, 3, 16, 16) as ctx:
+        good = synth.make_joints(3, max_offset=3, sigma_range=(1.5, 2))
+        with pytest.raises(PsInferError) as e:
+            ctx.infer()
+        assert e.value.status == capi.PS_ERR_STATE
+        with pytest.raises(PsInferError) as e:
+            ctx.set_joints(good[:1])                       # aux.cpp:129: need P-1 joints
+        assert e.value.status == capi.PS_ERR_INVALID
+        bad = [Joint(1, 0, [1, 1], [1, 1], [[2, 0], [0, 2]], 0, 0.5, type=capi.PS_JOINT_POS_GAUSSIAN), good[1]]
+        with pytest.raises(PsInferError) as e:
+            ctx.set_joints(bad)                            # findrot.cpp:766
+        assert e.value.status == capi.PS_ERR_UNSUPPORTED
+        notpd = [Joint(1, 0, [1, 1], [1, 1], [[2, 0], [0, -1]], 0, 0.5), good[1]]
+        with pytest.raises(PsInferError):
+            ctx.set_joints(notpd)                          # filter.hpp:219
+    # a non-root part with two children (findrot.cpp:210)
+    with _ctx(ep, 4, 16, 16) as ctx:
+        js = [Joint(1, 0, [1, 1], [1, 1], [[2, 0], [0, 2]], 0, 0.5), Joint(2, 1, [1, 1], [1, 1], [[2, 0], [0, 2]], 0, 0.5),
+              Joint(3, 1, [1, 1], [1, 1], [[2, 0], [0, 2]], 0, 0.5)]
+        with pytest.raises(PsInferError) as e:
+            ctx.set_joints(js)
+        assert e.value.status == capi.PS_ERR_INVALID
+
+
+# ---- full size (BASELINE.json configs[1]: R=24, 600x400) -----------------------------------------------------------
+
+def test_full_size_message_matches_oracle():
+    ep = ExpParam(num_rotation_steps=24)
+    H, W = 600, 400
+    child = oracle.prepare_unary(synth.raw_scores(ep, H, W, 1, 5)[0, 0])
+    j = synth.make_joints(10, seed=7)[1]
+    with _ctx(ep, 2, H, W) as ctx:
+        up = ctx.message(child, j.offset_c, j.offset_p, j.C, j.rot_mean, j.rot_sigma, 1.0, True)
+        want_up = oracle.message(ep, child, j.offset_c, j.offset_p, j.C, j.rot_mean, j.rot_sigma, 1.0, True)
+        _cmp(up, want_up, "full-size upward message")
+        down = ctx.message(want_up, j.offset_p, j.offset_c, j.C, -j.rot_mean, j.rot_sigma, 1.0, False)
+        want_down = oracle.message(ep, want_up, j.offset_p, j.offset_c, j.C, -j.rot_mean, j.rot_sigma, 1.0, False)
+        _cmp(down, want_down, "full-size downward message")
+
+
+def test_full_size_properties():
+    """Size-independent properties at the benchmark size: repeatability (bitwise), shift of the unaries by a constant
+    shifts every marginal by P times that constant up to rounding and leaves the argmax in place, and the root
+    posterior is the log-sum-exp of the root marginal."""
+    ep = ExpParam(num_rotation_steps=24)
+    P, H, W = 10, 600, 400
+    raw = synth.raw_scores(ep, H, W, P, 0)
+    joints = synth.make_joints(P, seed=7)
+    with PsContext(ep, synth.part_conf(P), H, W) as ctx:
+        ctx.set_joints(joints)
+
+        def run():
+            for p in range(P):
+                ctx.set_unary(p, 0, raw[p, 0], raw_scores=True)
+            ctx.infer(sparse=True)
+            return ctx.best_conf(), ctx.marginal(4), ctx.root_posterior()
+
+        b1, m1, r1 = run()
+        b2, m2, r2 = run()
+        assert np.array_equal(b1, b2) and np.array_equal(m1, m2) and np.array_equal(r1, r2)
+        # planted bumps make the argmax meaningful: every part's best score is finite and well above LOG_ZERO
+        assert (b1[:, 6] > -1e5).all()
+        # root posterior = log sum_r exp(root marginal) (findrot.cpp:714-726), checked in float64
+        with np.errstate(under="ignore"):
+            lse = np.log(np.exp(m1.astype(np.float64)).sum(0))
+        ok = np.isfinite(lse) & (r1[0] > -1e5)
+        assert ok.sum() > 1000
+        np.testing.assert_allclose(r1[0][ok], lse[ok], rtol=1e-4, atol=1e-3)
