@@ -248,26 +248,45 @@ def run_ours(args):
         tot_ms = sum(v[0] for v in prof.values())
         dom = max(prof.items(), key=lambda kv: kv[1][0])
         G = 4.0 * N
-        # algorithmic bytes per launch of each kernel class (DESIGN.md "Kernels"): one read + one write of the grid
-        # the launch covers; for conv passes of a full-covariance message that grid is the eigen-frame grid, whose
-        # size we do not know here, so the image-grid figure (a lower bound) is used.
-        alg_per_launch = {"conv_rows": 2 * G, "conv_cols": 2 * G, "rotconv": 2 * G, "epilogue": 3 * G,
-                          "warp_direct": 2 * G, "warp_bilinear": 2 * G, "prepare_unary": 2 * G, "grid_max": G,
-                          "root_combine": 12 * G, "argmax": G, "root_marginal": G}
+        # per-message geometry from the library: filter-grid size (eigen-frame for full covariances) and tap counts
+        J = P - 1
+        infos = [c.plan_info(j, d) for j in range(J) for d in (0, 1)]
+        Ge = float(np.mean([4.0 * w["R"] * i["rows"] * i["cols"] for i in infos]))   # bytes of the filter grid
+        taps = {"rotconv": float(np.mean([N * max(i["rot_taps"], 0) for i in infos])),
+                "conv_rows": float(np.mean([w["R"] * i["rows"] * i["cols"] * i["x_taps"] for i in infos])),
+                "conv_cols": float(np.mean([w["R"] * i["rows"] * i["cols"] * i["y_taps"] for i in infos]))}
+        # algorithmic bytes per launch of each kernel class: each grid read once, written once
+        alg_per_launch = {"conv_rows": 2 * Ge, "conv_cols": 2 * Ge, "rotconv": 2 * G, "epilogue": 3 * G,
+                          "warp_direct": G + Ge, "warp_bilinear": G + Ge, "warp_back": G + Ge, "prepare_unary": 2 * G,
+                          "grid_max": G, "root_combine": 12 * G, "argmax": G, "root_marginal": G}
         dom_ms_per_launch = dom[1][0] / dom[1][1]
         dom_bytes = alg_per_launch.get(dom[0], 2 * G)
         achieved = dom_bytes / (dom_ms_per_launch * 1e-3) / 1e9
+        FP32_PEAK = 18.0e12  # separately rounded mul+add pairs per second, profiles/r01_fp32_pipe_microbench.txt
+        fp32 = {}
+        for k, n_taps in taps.items():
+            if k in prof and prof[k][1]:
+                per_launch_s = prof[k][0] / prof[k][1] * 1e-3
+                fp32[k] = {"tap_outputs_per_launch": round(n_taps), "achieved_per_s": round(n_taps / per_launch_s, -9),
+                           "frac_of_measured_peak": round(n_taps / per_launch_s / FP32_PEAK, 3)}
+        msg_ms = sum(prof[k][0] for k in prof if k in ("rotconv", "warp_direct", "warp_bilinear", "conv_rows",
+                                                          "conv_cols", "warp_back", "epilogue")) / n_img_prof / (2 * J)
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": round(dom_ms_per_launch, 4),
+                    "algorithmic_bytes_per_launch": round(dom_bytes), "ms_per_launch": round(dom_ms_per_launch, 4),
                     "share_of_step": round(dom[1][0] / tot_ms, 3),
                     "how": "CUDA events around every launch on the ctx stream (instrumented pass over %d images)" % n_img_prof,
                     "kernel_ms_per_image": {k: round(v[0] / n_img_prof, 4) for k, v in sorted(prof.items())},
+                    "message": {"algorithmic_bytes": round(3 * G), "ms": round(msg_ms, 4),
+                                "achieved_GBps": round(3 * G / (msg_ms * 1e-3) / 1e9, 1),
+                                "frac": round(3 * G / (msg_ms * 1e-3) / 1e9 / peak, 4)},
                     "whole_image": {"algorithmic_bytes": algorithmic_bytes_per_image(),
                                     "achieved_GBps": round(algorithmic_bytes_per_image() * value / world / 1e9, 1),
                                     "frac": round(algorithmic_bytes_per_image() * value / world / 1e9 / peak, 4)},
-                    "note": "parity mode is bound by the fp32 pipe (separately rounded mul+add per tap), not by HBM; "
-                            "see DESIGN.md"}
+                    "fp32_pipe": {"unit": "separately rounded multiply+add pairs (tap-outputs) per second",
+                                  "peak": FP32_PEAK, "peak_source": "measured, tools/mb_f32x2.cu", "kernels": fp32},
+                    "note": "bit-exact (parity) arithmetic keeps both roundings of every tap, which costs two fp32 pipe "
+                            "slots per tap-output: the Gaussian passes are bound by the fp32 pipe, not by HBM (DESIGN.md 5)"}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_baseline = run_cpu_sample(ep, pc, joints, raws[0], threads=1)

@@ -12,8 +12,10 @@
 // The file is compiled with -fmad=false as a second line of defence.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace psk {
 
@@ -519,17 +521,18 @@ __device__ __forceinline__ BilinearTap bilinear_setup(int h, int w, int pitch, d
 
 // dst[r][cell] = bilinear(src[r]) for r in the thread's slice group.  Used both ways: image -> eigen-frame
 // (TM_BILINEAR of gaussFilter2dOffset, filter.hpp:359) and eigen-frame -> image (filter.hpp:367-368).
+// tr != 0: the destination is stored transposed (dst[r][ix][iy], pitch dpitch over iy) and threadIdx.x walks iy.
 template <int RG>
 __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restrict__ src, float *__restrict__ dst, Affine T,
                                                            int R, int sh, int sw, int spitch, size_t splane, int dh,
-                                                           int dw, int dpitch, size_t dplane) {
+                                                           int dw, int dpitch, size_t dplane, int tr) {
   // 2-D tiles: a tile's rotated footprint in the source stays compact, so the four taps of neighbouring cells
   // hit the same L1 lines
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+  const int ix = blockIdx.x * 16 + (tr ? threadIdx.y : threadIdx.x);
+  const int iy = blockIdx.y * 16 + (tr ? threadIdx.x : threadIdx.y);
   const int r0 = blockIdx.z * RG;
-  if (ix >= dpitch || iy >= dh) return;
-  float *o = dst + (size_t)r0 * dplane + (size_t)iy * dpitch + ix;
+  if (tr ? (ix >= dw || iy >= dh) : (ix >= dpitch || iy >= dh)) return;
+  float *o = dst + (size_t)r0 * dplane + (tr ? (size_t)ix * dpitch + iy : (size_t)iy * dpitch + ix);
   BilinearTap t;
   t.mode = 0;
   if (ix < dw) {
@@ -561,16 +564,17 @@ __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restri
 }
 
 // TM_DIRECT as a gather through the winner map, RG slices per thread.
+// tr != 0: out is stored transposed ([r][ix][iy], pitch EP over iy, plane EW*EP) and threadIdx.x walks iy.
 template <int RG>
 __global__ void __launch_bounds__(256) k_warp_direct2(const float *__restrict__ in, float *__restrict__ out,
                                                       const int2 *__restrict__ map, int R, size_t HW, int EH, int EW,
-                                                      int EP) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-  const int iy = blockIdx.y * blockDim.y + threadIdx.y;
+                                                      int EP, int tr) {
+  const int ix = blockIdx.x * 16 + (tr ? threadIdx.y : threadIdx.x);
+  const int iy = blockIdx.y * 16 + (tr ? threadIdx.x : threadIdx.y);
   const int r0 = blockIdx.z * RG;
-  if (ix >= EP || iy >= EH) return;
-  const size_t eplane = (size_t)EH * EP;
-  float *o = out + (size_t)r0 * eplane + (size_t)iy * EP + ix;
+  if (tr ? (ix >= EW || iy >= EH) : (ix >= EP || iy >= EH)) return;
+  const size_t eplane = tr ? (size_t)EW * EP : (size_t)EH * EP;
+  float *o = out + (size_t)r0 * eplane + (tr ? (size_t)ix * EP + iy : (size_t)iy * EP + ix);
   int2 m = make_int2(-1, -1);
   if (ix < EW) m = map[(size_t)iy * EW + ix];
   float v[RG];
@@ -976,6 +980,158 @@ __global__ void __launch_bounds__(256, 4) k_conv_cols2(ConvArgs a, u64 nz) {
   }
 }
 
+
+// ---- stage 2b v3: Gaussian along y with TMA-fed, double-buffered tiles --------------------------------------------
+// Persistent blocks walk (slice, row-tile, column-strip) tiles.  One elected thread asks the TMA unit for the
+// (8T + 2n) x 64 input box of the NEXT tile (cp.async.bulk.tensor.3d, out-of-bounds rows/columns arrive as zeros =
+// the reference's clipped window) while all warps filter the current one; completion is an mbarrier transaction
+// count, so the fill spends no issue slots and no registers.  Arithmetic is identical to k_conv_cols2.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                            unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+struct ColsTmaArgs {
+  float *out;
+  const float *taps;
+  int len, rows, cols, pitch;  // pitch/plane describe the OUTPUT; the input layout lives in the tensor map
+  size_t plane;
+  int slices, ytiles, xtiles;  // tile grid: ytiles of 8T rows, xtiles of 64 columns
+  int transpose_out;           // 1: out[z][col][row] (the input was stored transposed; this pass restores the layout)
+};
+
+template <int T>
+__global__ void __launch_bounds__(256, 2) k_conv_cols_tma(const __grid_constant__ CUtensorMap tmap, ColsTmaArgs a, u64 nz) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ float s_taps[1000];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n = (a.len - 1) / 2;
+  const int nrows = 8 * T + 2 * n;
+  const unsigned stage_bytes = (unsigned)nrows * 64 * sizeof(float);
+  const unsigned stage_stride = (stage_bytes + 127) & ~127u;
+  for (int i = tid; i < a.len; i += 256) s_taps[i] = a.taps[i];
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ntiles = a.slices * a.ytiles * a.xtiles;
+  auto issue = [&](int tile, int s) {
+    const int xt = tile % a.xtiles, yt = (tile / a.xtiles) % a.ytiles, z = tile / (a.xtiles * a.ytiles);
+    mbar_expect_tx(&s_bar[s], stage_bytes);
+    tma_load_3d(s_raw + s * stage_stride, &tmap, xt * 64, yt * 8 * T - n, z, &s_bar[s]);
+  };
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue(tile, 0);
+  unsigned phases = 0;  // bit s = parity to wait for on stage s
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int s = it & 1;
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) {
+      // stage s^1 was last read (generic proxy) before the __syncthreads that ended the previous iteration
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(next, s ^ 1);
+    }
+    mbar_wait(&s_bar[s], (phases >> s) & 1u);
+    phases ^= 1u << s;
+    const int xt = tile % a.xtiles, yt = (tile / a.xtiles) % a.ytiles, z = tile / (a.xtiles * a.ytiles);
+    if (yt * 8 * T + w * T >= a.rows) {  // warp-uniform: nothing to produce in this tile
+      __syncthreads();
+      continue;
+    }
+    const u64 *win = reinterpret_cast<const u64 *>(s_raw + s * stage_stride) + (w * T) * 32 + lane;
+    u64 acc[T], d[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < T - 1; ++j) d[j] = win[j * 32];
+    const u64 *wp = win + (T - 1) * 32;  // next window row to load
+    int kk = 0;
+    for (; kk + T <= a.len; kk += T, wp += T * 32) {
+#pragma unroll
+      for (int u = 0; u < T; ++u) {
+        d[(u + T - 1) % T] = wp[u * 32];
+        const float f = s_taps[kk + u];
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < T; ++u) {
+      if (kk + u < a.len) {
+        d[(u + T - 1) % T] = wp[u * 32];
+        const float f = s_taps[kk + u];
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+      }
+    }
+    const int x = xt * 64 + lane * 2;
+    if (x < a.cols) {
+      const bool in1 = x + 1 < a.cols;
+      if (a.transpose_out) {
+        // the thread's T filter-axis outputs are contiguous in the restored layout: 2 x float4 per column
+        const int r0 = yt * 8 * T + w * T;
+        float lo[T], hi[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
+        float *o0 = a.out + (size_t)z * a.plane + (size_t)x * a.pitch + r0;
+        if (r0 + T <= a.rows) {
+#pragma unroll
+          for (int t = 0; t < T; t += 4) *reinterpret_cast<float4 *>(o0 + t) = make_float4(lo[t], lo[t + 1], lo[t + 2], lo[t + 3]);
+          if (in1) {
+#pragma unroll
+            for (int t = 0; t < T; t += 4)
+              *reinterpret_cast<float4 *>(o0 + a.pitch + t) = make_float4(hi[t], hi[t + 1], hi[t + 2], hi[t + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+            if (r0 + t < a.rows) {
+              o0[t] = lo[t];
+              if (in1) o0[a.pitch + t] = hi[t];
+            }
+        }
+      } else {
+        float *dst = a.out + (size_t)z * a.plane + x;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int y = yt * 8 * T + w * T + t;
+          if (y < a.rows) {
+            float lo, hi;
+            upk2(acc[t], lo, hi);
+            float *o = dst + (size_t)y * a.pitch;
+            if (in1) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+            else o[0] = lo;
+          }
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with stage s before it is refilled two iterations from now
+  }
+}
+
 // ---- stage 2b v2: Gaussian along x, two adjacent rows per thread -------------------------------------------------
 // A block stages PAIRS row pairs (+halo) as float2 (row 2q, row 2q+1) in the "transposed by T" layout
 // (element i at (i % T) * S + i / T); a thread owns T consecutive outputs of both rows of a pair.
@@ -1056,6 +1212,121 @@ __global__ void __launch_bounds__(256, 4) k_conv_rows2(ConvArgs a, u64 nz, int P
           if (ya + 1 < a.rows) oa[a.pitch + t] = hi[t];
         }
     }
+  }
+}
+
+
+// ---- stage 2b v3: Gaussian along x, persistent blocks, cp.async double buffering ------------------------------------
+// Same layout and arithmetic as k_conv_rows2, but a block walks (slice, row-tile) tiles and copies the NEXT tile's
+// row pairs with 4-byte cp.async (LDGSTS, zero-filled outside the grid via src-size 0) straight into the
+// "transposed by T" float2 layout while it filters the current one: no registers, no exposed load latency.
+__device__ __forceinline__ void cp_async_f32(float *dst_smem, const float *src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(valid ? 4 : 0)
+               : "memory");
+}
+
+template <int T>
+__global__ void __launch_bounds__(256, 2) k_conv_rows3(ConvArgs a, u64 nz, int PAIRS, int S, int slices, int ytiles) {
+  extern __shared__ __align__(16) float2 s_pairs[];  // 2 stages x [PAIRS][T*S]
+  __shared__ float s_taps[1000];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.len; i += 256) s_taps[i] = a.taps[i];
+  const int n = (a.len - 1) / 2;
+  const int G = (a.cols + T - 1) / T;
+  const int span = G * T + 2 * n;
+  const int rowsz = T * S;
+  const int stage_elems = PAIRS * rowsz;  // float2 units
+  const int ntiles = slices * ytiles;
+
+  auto fill = [&](int tile, int st) {
+    const int z = tile / ytiles, y0 = (tile - z * ytiles) * (2 * PAIRS);
+    const float *src = a.in + (size_t)z * a.plane;
+    float *base = reinterpret_cast<float *>(s_pairs + (size_t)st * stage_elems);
+    for (int row = 0; row < 2 * PAIRS; ++row) {
+      const int y = y0 + row;
+      const bool oky = y < a.rows;
+      const float *rp = src + (size_t)(oky ? y : 0) * a.pitch;
+      float *dst = base + ((row >> 1) * rowsz) * 2 + (row & 1);
+      for (int i = tid; i < span; i += 256) {
+        const int x = i - n;
+        const bool ok = oky && x >= 0 && x < a.cols;
+        cp_async_f32(dst + ((i % T) * S + i / T) * 2, ok ? rp + x : a.in, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int tile = blockIdx.x;
+  if (tile < ntiles) fill(tile, 0);
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int st = it & 1;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      fill(next, st ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int z = tile / ytiles, y0 = (tile - z * ytiles) * (2 * PAIRS);
+    float *dst = a.out + (size_t)z * a.plane;
+    const u64 *stage = reinterpret_cast<const u64 *>(s_pairs) + (size_t)st * stage_elems;
+    const int items = PAIRS * G;
+    for (int itx = tid; itx < items; itx += 256) {
+      const int pr = itx / G, g = itx - pr * G;
+      const int ya = y0 + 2 * pr;
+      if (ya >= a.rows) continue;
+      const u64 *tile_p = stage + pr * rowsz + g;
+      u64 acc[T], d[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < T - 1; ++j) d[j] = tile_p[j * S];
+      // window element m (m >= T-1) sits at ((m % T) * S + m / T); m = kk + u + T - 1 with kk a multiple of T
+      const u64 *wp = tile_p;
+      int kk = 0;
+      for (; kk + T <= a.len; kk += T, ++wp) {
+#pragma unroll
+        for (int u = 0; u < T; ++u) {
+          d[(u + T - 1) % T] = wp[((u + T - 1) % T) * S + (u + T - 1) / T];
+          const float f = s_taps[kk + u];
+#pragma unroll
+          for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < T; ++u) {
+        if (kk + u < a.len) {
+          d[(u + T - 1) % T] = wp[((u + T - 1) % T) * S + (u + T - 1) / T];
+          const float f = s_taps[kk + u];
+#pragma unroll
+          for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+        }
+      }
+      float lo[T], hi[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
+      float *oa = dst + (size_t)ya * a.pitch + g * T;
+      const bool full = g * T + T <= a.cols;
+      const bool al = (a.pitch & 3) == 0;
+      if (full && al) {
+#pragma unroll
+        for (int t = 0; t < T; t += 4) *reinterpret_cast<float4 *>(oa + t) = make_float4(lo[t], lo[t + 1], lo[t + 2], lo[t + 3]);
+        if (ya + 1 < a.rows) {
+          float *ob = oa + a.pitch;
+#pragma unroll
+          for (int t = 0; t < T; t += 4) *reinterpret_cast<float4 *>(ob + t) = make_float4(hi[t], hi[t + 1], hi[t + 2], hi[t + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+          if (g * T + t < a.cols) {
+            oa[t] = lo[t];
+            if (ya + 1 < a.rows) oa[a.pitch + t] = hi[t];
+          }
+      }
+    }
+    __syncthreads();  // stage st may be refilled in the next iteration
   }
 }
 

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -80,6 +81,8 @@ struct ps_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   std::string err;
   long long launches = 0;
+  int num_sms = 148;
+  bool disable_tma = false;  // PSINFER_NO_TMA=1: keep the shared-memory staged kernels (A/B testing)
 
   // optional per-kernel-class device timing (ps_profile_enable)
   bool profiling = false;
@@ -231,7 +234,8 @@ int upload_plan(ps_ctx *c, DevPlan &dp) {
 
 size_t plan_scratch_elems(const ps_ctx *c, const DevPlan &dp) {
   if (dp.host.diag) return c->N;
-  return std::max(c->N, (size_t)c->R * dp.host.EH * dp.EP);
+  const size_t ehp = (dp.host.EH + 7) & ~7;
+  return std::max(c->N, std::max((size_t)c->R * dp.host.EH * dp.EP, (size_t)c->R * dp.host.EW * ehp));
 }
 
 int ensure_scratch(ps_ctx *c, size_t elems) {
@@ -299,12 +303,26 @@ int launch_conv_rows(ps_ctx *c, const psk::ConvArgs &a, int slices) {
   const int n = (a.len - 1) / 2;
   const int G = (a.cols + T - 1) / T;
   {
-    // v2: row pairs, packed arithmetic
+    // v3: row pairs, packed arithmetic, persistent blocks with cp.async double buffering
     int S = (G * T + 2 * n + T - 1) / T + 1;
     while (S % 16 != 2) ++S;
     const size_t pair_bytes = (size_t)T * S * sizeof(float2);
     int best = 0;
     double best_eff = 0;
+    for (int pairs = 1; pairs <= 32 && 2 * pairs * pair_bytes <= 100 * 1024; ++pairs) {
+      int items = pairs * G;
+      double eff = (double)items / (((items + 255) / 256) * 256);
+      if (eff >= best_eff - 1e-9) { best_eff = eff; best = pairs; }
+    }
+    if (best > 0 && !c->disable_tma) {
+      const int ytiles = (a.rows + 2 * best - 1) / (2 * best);
+      const int ntiles = slices * ytiles;
+      const int grid = std::min(ntiles, c->num_sms * 2);
+      PS_LAUNCH(c, KC_CONV_ROWS,
+                psk::k_conv_rows3<T><<<grid, 256, 2 * best * pair_bytes, c->stream>>>(a, PS_NEGZERO2, best, S, slices, ytiles));
+      return PS_OK;
+    }
+    best = 0; best_eff = 0;
     for (int pairs = 1; pairs <= 32 && pairs * pair_bytes <= 40 * 1024; ++pairs) {
       int items = pairs * G;
       double eff = (double)items / (((items + 255) / 256) * 256);
@@ -329,11 +347,68 @@ int launch_conv_rows(ps_ctx *c, const psk::ConvArgs &a, int slices) {
   return PS_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Can the TMA column kernel take a filter of `len` taps over an input of this layout?
+bool cols_tma_ok(const ps_ctx *c, const float *in, int len, int pitch, size_t plane) {
+  const int nrows = 64 + (len - 1);
+  const size_t stage = ((size_t)nrows * 64 * sizeof(float) + 127) & ~(size_t)127;
+  return tensor_map_encoder() && !c->disable_tma && nrows <= 256 && 2 * stage <= 110 * 1024 && pitch % 4 == 0 &&
+         plane % 4 == 0 && (uintptr_t)in % 16 == 0;
+}
+
+// TMA column filter.  Input: [slices][rows][in_pitch] with `cols` valid columns (filter along rows).
+// Output: same orientation (transpose_out = 0, out pitch/plane as given) or transposed [slices][cols][out_pitch].
+int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_plane, float *out, int out_pitch,
+                         size_t out_plane, const float *taps, int len, int rows, int cols, int slices, int transpose_out) {
+  constexpr int T = 8;
+  const int n = (len - 1) / 2;
+  const int nrows = 8 * T + 2 * n;
+  const size_t stage = ((size_t)nrows * 64 * sizeof(float) + 127) & ~(size_t)127;
+  CUtensorMap tm;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slices};
+  cuuint64_t strides[2] = {(cuuint64_t)in_pitch * sizeof(float), (cuuint64_t)in_plane * sizeof(float)};
+  cuuint32_t box[3] = {64, (cuuint32_t)nrows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = tensor_map_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)in, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return c->fail(PS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  psk::ColsTmaArgs t;
+  t.out = out; t.taps = taps; t.len = len; t.rows = rows; t.cols = cols; t.pitch = out_pitch; t.plane = out_plane;
+  t.slices = slices; t.ytiles = (rows + 8 * T - 1) / (8 * T); t.xtiles = (cols + 63) / 64;
+  t.transpose_out = transpose_out;
+  const int ntiles = t.slices * t.ytiles * t.xtiles;
+  const int grid = std::min(ntiles, c->num_sms * 2);
+  PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
+            psk::k_conv_cols_tma<T><<<grid, 256, 2 * stage, c->stream>>>(tm, t, PS_NEGZERO2));
+  return PS_OK;
+}
+
 int launch_conv_cols(ps_ctx *c, const psk::ConvArgs &a, int slices) {
   constexpr int T = 8;
   const int n = (a.len - 1) / 2;
-  const size_t smem = (size_t)(8 * T + 2 * n) * 32 * sizeof(float2);
+  const int nrows = 8 * T + 2 * n;
   const bool aligned = (a.pitch % 2 == 0) && (a.plane % 2 == 0) && ((uintptr_t)a.in % 8 == 0) && ((uintptr_t)a.out % 8 == 0);
+  if (aligned && cols_tma_ok(c, a.in, a.len, a.pitch, a.plane))
+    return launch_conv_cols_tma(c, a.in, a.pitch, a.plane, a.out, a.pitch, a.plane, a.taps, a.len, a.rows, a.cols, slices, 0);
+  const size_t smem = (size_t)nrows * 32 * sizeof(float2);
   if (aligned && smem <= kSmemBudget) {
     PS_LAUNCH(c, KC_CONV_COLS,
               psk::k_conv_cols2<T><<<dim3(cdiv(a.cols, 64), cdiv(a.rows, 8 * T), slices), 256, smem, c->stream>>>(a, PS_NEGZERO2));
@@ -414,24 +489,35 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     filtered = c->bufB.as<float>();
     e.general = 0;
   } else {
-    // gaussFilter2dOffset: rotate into the eigen-frame, filter there, bilinear read-back in the epilogue
+    // gaussFilter2dOffset: rotate into the eigen-frame, filter there, bilinear read-back
     const int EH = h.EH, EW = h.EW, EP = dp.EP;
     const size_t eplane = (size_t)EH * EP;
     constexpr int RG = 6;
+    // Transposed route: the resampler writes the eigen-frame grid transposed ([r][x][y]) so that the x filter is a
+    // TMA column filter too; its transposing store restores [r][y][x] for the y filter.
+    const int EHP = (EH + 7) & ~7;
+    const size_t tplane = (size_t)EW * EHP;
+    const bool tr = cols_tma_ok(c, c->bufU.as<float>(), (int)h.fx.size(), EHP, tplane);
     if (sparse) {
       rc = ensure_direct_map(c, dp);
       if (rc) return rc;
       PS_LAUNCH(c, KC_WARP_DIRECT,
-                psk::k_warp_direct2<RG><<<dim3(cdiv(EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
-                    c->bufB.as<float>(), c->bufU.as<float>(), dp.map.as<int2>(), R, c->HW, EH, EW, EP));
+                psk::k_warp_direct2<RG><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                    c->bufB.as<float>(), c->bufU.as<float>(), dp.map.as<int2>(), R, c->HW, EH, EW, tr ? EHP : EP, tr));
     } else {
       Affine T13;
       memcpy(T13.m, h.T13, sizeof T13.m);
       PS_LAUNCH(c, KC_WARP_BILINEAR,
-                psk::k_resample_bilinear<RG><<<dim3(cdiv(EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
-                    c->bufB.as<float>(), c->bufU.as<float>(), T13, R, H, W, W, c->HW, EH, EW, EP, eplane));
+                psk::k_resample_bilinear<RG><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                    c->bufB.as<float>(), c->bufU.as<float>(), T13, R, H, W, W, c->HW, EH, EW, tr ? EHP : EP,
+                    tr ? tplane : eplane, tr));
     }
-    rc = conv_rows(c->bufU.as<float>(), c->bufV.as<float>(), EH, EW, EP, eplane, dp.fx(), (int)h.fx.size());
+    if (tr) {
+      rc = launch_conv_cols_tma(c, c->bufU.as<float>(), EHP, tplane, c->bufV.as<float>(), EP, eplane, dp.fx(),
+                                (int)h.fx.size(), /*rows=*/EW, /*cols=*/EH, R, /*transpose_out=*/1);
+    } else {
+      rc = conv_rows(c->bufU.as<float>(), c->bufV.as<float>(), EH, EW, EP, eplane, dp.fx(), (int)h.fx.size());
+    }
     if (rc) return rc;
     rc = conv_cols(c->bufV.as<float>(), c->bufU.as<float>(), EH, EW, EP, eplane, dp.fy(), (int)h.fy.size());
     if (rc) return rc;
@@ -441,7 +527,7 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     memcpy(T34.m, h.T34, sizeof T34.m);
     PS_LAUNCH(c, KC_WARP_BACK,
               psk::k_resample_bilinear<RG><<<dim3(cdiv(W, 16), cdiv(H, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
-                  c->bufU.as<float>(), c->bufB.as<float>(), T34, R, EH, EW, EP, eplane, H, W, W, c->HW));
+                  c->bufU.as<float>(), c->bufB.as<float>(), T34, R, EH, EW, EP, eplane, H, W, W, c->HW, 0));
     filtered = c->bufB.as<float>();
     e.general = 0;
   }
@@ -729,7 +815,11 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   if (!cu(c->argmax_keys.alloc(c->P * sizeof(unsigned long long)), "alloc argmax")) return PS_ERR_CUDA;
   if (!cu(c->counters.alloc(8 * sizeof(unsigned)), "alloc counters")) return PS_ERR_CUDA;
   if (!cu(cudaMallocHost((void **)&c->host_keys, c->P * sizeof(unsigned long long)), "alloc pinned keys")) return PS_ERR_CUDA;
-  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
+  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr"))
     return PS_ERR_CUDA;
@@ -1249,6 +1339,23 @@ int ps_message(ps_ctx *c, const float *child, float *parent, int mem_kind, const
   if (mem_kind == PS_MEM_HOST)
     PS_CUDA(c, cudaMemcpyAsync(parent, dout, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+int ps_get_plan_info(ps_ctx *c, int joint, int downward, int scale, int out[8]) {
+  if (!c || !out) return PS_ERR_INVALID;
+  if (!c->joints_set) return c->fail(PS_ERR_STATE, "ps_get_plan_info before ps_set_joints");
+  if (joint < 0 || joint >= (int)c->joints.size() || scale < 0 || scale >= c->S)
+    return c->fail(PS_ERR_INVALID, "joint/scale out of range");
+  const psg::MessagePlan &h = c->plans[((size_t)joint * 2 + (downward ? 1 : 0)) * c->S + scale]->host;
+  out[0] = h.diag ? 1 : 0;
+  out[1] = h.diag ? c->H : h.EH;
+  out[2] = h.diag ? c->W : h.EW;
+  out[3] = h.rot_mode == 1 ? (int)h.rot_taps.size() : 0;
+  out[4] = (int)h.fx.size();
+  out[5] = (int)h.fy.size();
+  out[6] = h.rot_shift;
+  out[7] = (h.in_pure ? 1 : 0) | (h.out_pure ? 2 : 0);
   return PS_OK;
 }
 

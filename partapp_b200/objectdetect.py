@@ -241,6 +241,12 @@ class PsContext:
         self._check(self.lib.ps_get_root_hyps(self.h, out.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return out[:n.value].copy()
 
+    def plan_info(self, joint, downward, scale=0):
+        out = (C.c_int * 8)()
+        self._check(self.lib.ps_get_plan_info(self.h, joint, int(downward), scale, out))
+        keys = ("diag", "rows", "cols", "rot_taps", "x_taps", "y_taps", "rot_shift", "shift_flags")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def selftest_math(self, first_bits, count):
         """(exp mismatches, exp tested, log mismatches, log tested) over fp32 bit patterns [first, first+count)."""
         out = (C.c_ulonglong * 4)()
