@@ -164,7 +164,8 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void block_max_to(float v, int *dst) {
   __shared__ float s_part[32];
   v = warp_max(v);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tid_ = threadIdx.y * blockDim.x + threadIdx.x;
+  int lane = tid_ & 31, w = tid_ >> 5;
   int nw = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
   if (lane == 0) s_part[w] = v;
   __syncthreads();
@@ -172,6 +173,38 @@ __device__ __forceinline__ void block_max_to(float v, int *dst) {
     float t = lane < nw ? s_part[lane] : -INFINITY;
     t = warp_max(t);
     if (lane == 0) atomicMax(dst, enc_f(t));
+  }
+}
+
+// First maximum in flat order (findrot.cpp:261-277) as a single 64-bit max: key = (ordered(value) << 32) | ~index
+// picks the largest value and, among equals, the smallest index.  -0.0 and +0.0 compare equal in the reference, so
+// -0.0 is canonicalised to +0.0 before encoding; NaN never wins a '>' comparison and is skipped by the callers.
+__device__ __forceinline__ unsigned long long argmax_key(float v, unsigned idx) {
+  if (v == 0.0f) v = 0.0f;
+  unsigned e = (unsigned)enc_f(v) ^ 0x80000000u;  // order-preserving unsigned
+  return ((unsigned long long)e << 32) | (unsigned)(~idx);
+}
+// Block-wide max of keys folded into *dst with one atomic per block. All threads must call.
+__device__ __forceinline__ void block_key_max_to(unsigned long long best, unsigned long long *dst) {
+  __shared__ unsigned long long s_keys[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+    best = t > best ? t : best;
+  }
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int lane = tid & 31, w = tid >> 5;
+  const int nw = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+  if (lane == 0) s_keys[w] = best;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long t = lane < nw ? s_keys[lane] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long u = __shfl_xor_sync(0xffffffffu, t, o);
+      t = u > t ? u : t;
+    }
+    if (lane == 0 && t) atomicMax(dst, t);
   }
 }
 
@@ -1349,6 +1382,7 @@ struct EpiArgs {
   const float *add1;
   int *max0;            // optional: max over out0
   int *max1;            // optional: max over out1
+  unsigned long long *amax0;  // optional: first-maximum key of out0 (the part's final marginal), see argmax_key
 };
 
 __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
@@ -1356,6 +1390,7 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
   const int y = blockIdx.y;
   const int r = blockIdx.z;
   float m0 = -INFINITY, m1 = -INFINITY;
+  unsigned long long key0 = 0;
   if (x < a.W) {
     const size_t HW = (size_t)a.H * a.W;
     const size_t cell = (size_t)r * HW + (size_t)y * a.W + x;
@@ -1378,6 +1413,7 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
       if (a.add0) o = __fadd_rn(o, a.add0[cell]);
       a.out0[cell] = o;
       m0 = o;
+      if (a.amax0 && o == o) key0 = argmax_key(o, (unsigned)cell);
     }
     if (a.out1) {
       float o = __fadd_rn(a.add1[cell], v);
@@ -1390,8 +1426,8 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
     __syncthreads();
     block_max_to(m1, a.max1);
   }
+  if (a.amax0) block_key_max_to(key0, a.amax0);
 }
-
 
 // ---- message stage 3 v2: four consecutive cells per thread -------------------------------------------------------
 // Same arithmetic as k_epilogue.  The per-row quantities (destination row -> source row, T34 row products, slice
@@ -1403,6 +1439,7 @@ __global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   float m0 = -INFINITY, m1 = -INFINITY;
+  unsigned long long key0 = 0;
   if (it < XG * a.H) {
     const int y = it / XG, x0 = (it - y * XG) * 4;
     const size_t HW = (size_t)a.H * a.W;
@@ -1480,6 +1517,14 @@ __global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (j < nx) m0 = fmaxf(m0, o[j]);
+      if (a.amax0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nx && o[j] == o[j]) {
+            unsigned long long k = argmax_key(o[j], (unsigned)(cell0 + j));
+            key0 = k > key0 ? k : key0;
+          }
+      }
     }
     if (a.out1) {
       float o[4];
@@ -1506,6 +1551,7 @@ __global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4
     __syncthreads();
     block_max_to(m1, a.max1);
   }
+  if (a.amax0) block_key_max_to(key0, a.amax0);
 }
 
 // ---- root: combine the stored upward messages (findrot.cpp:637-654 and :169) -----------------------------
@@ -1515,6 +1561,7 @@ constexpr int kMaxRootChildren = 16;
 struct RootArgs {
   float *m[kMaxRootChildren];
   int *fr_max[kMaxRootChildren];
+  unsigned long long *amax;  // optional: first-maximum key of post[root]
   int n;
   const float *unary;   // may be null (root not is_detect: cannot happen, root needs is_detect)
   float *post;
@@ -1543,6 +1590,7 @@ template <int NC, int NV>
 __global__ void __launch_bounds__(256) k_root_combine(RootArgs a) {
   const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * NV;
   float frmax[NC];
+  unsigned long long key = 0;
 #pragma unroll
   for (int j = 0; j < NC; ++j) frmax[j] = -INFINITY;
   if (i < a.N) {
@@ -1562,6 +1610,14 @@ __global__ void __launch_bounds__(256) k_root_combine(RootArgs a) {
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v) root_combine_cell<NC>(mv[v], u[v], post[v], fr[v]);
+    if (a.amax) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (post[v] == post[v]) {
+          unsigned long long k = argmax_key(post[v], (unsigned)(i + v));
+          key = k > key ? k : key;
+        }
+    }
     if (NV == 4) {
       *reinterpret_cast<float4 *>(a.post + i) = make_float4(post[0], post[1 % NV], post[2 % NV], post[3 % NV]);
 #pragma unroll
@@ -1583,6 +1639,7 @@ __global__ void __launch_bounds__(256) k_root_combine(RootArgs a) {
     block_max_to(frmax[j], a.fr_max[j]);
     __syncthreads();
   }
+  if (a.amax) block_key_max_to(key, a.amax);
 }
 
 // ---- root rotation-marginal (findrot.cpp:694-726) -----------------------------------------------------------
@@ -1597,15 +1654,6 @@ __global__ void k_root_marginal(const float *__restrict__ post, size_t HW, const
 }
 
 // ---- readout --------------------------------------------------------------------------------------------------
-// First maximum in flat order (findrot.cpp:261-277): packed key = (enc(value) << 32) | ~index, max over keys
-// picks the largest value and, among equals, the smallest index.  -0.0 and +0.0 compare equal in the reference,
-// so -0.0 is canonicalised to +0.0 before encoding.
-__device__ __forceinline__ unsigned long long argmax_key(float v, unsigned idx) {
-  if (v == 0.0f) v = 0.0f;
-  unsigned e = (unsigned)enc_f(v) ^ 0x80000000u;  // order-preserving unsigned
-  return ((unsigned long long)e << 32) | (unsigned)(~idx);
-}
-
 __global__ void __launch_bounds__(256) k_argmax(const float *__restrict__ g, size_t n, unsigned long long *dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -100,7 +100,7 @@ struct ps_ctx {
   DevBuf bufB;          // [N] rotation-filtered / diag y-pass output
   DevBuf bufU, bufV;    // eigen-frame scratch [R][EHmax][EPmax] (>= N)
   DevBuf root_post;     // [S][HW]
-  DevBuf maxes;         // int [P + kMaxRootChildren + 4] encoded maxima
+  DevBuf maxes;         // int encoded maxima: [0,P) beliefs | [P,P+16) from_root inputs | [P+16,2P+16) tmp of node q | 4 misc
   DevBuf upright_mask;  // uchar [R]
   DevBuf valid_rots;    // int [R]
   int n_valid_rots = 0;
@@ -446,6 +446,7 @@ struct Sink {
   const float *add1 = nullptr;
   int *max0 = nullptr;
   int *max1 = nullptr;
+  unsigned long long *amax0 = nullptr;
 };
 
 // One computeRotJointMarginal (findrot.cpp:292-456) on device buffers.  `in_max` holds enc(max(in)).
@@ -521,8 +522,9 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     if (rc) return rc;
     rc = conv_cols(c->bufV.as<float>(), c->bufU.as<float>(), EH, EW, EP, eplane, dp.fy(), (int)h.fy.size());
     if (rc) return rc;
-    // bilinear read-back into the image frame (filter.hpp:367-368); the sample position does not depend on the
-    // rotation slice, so it is resolved once per pixel here instead of once per cell inside the epilogue
+    // Bilinear read-back into the image frame (filter.hpp:367-368), then the generic epilogue.  (A fused
+    // read-back + epilogue over source cells was tried in round 1: 63 us per message against 22 + 28 us for the
+    // two kernels -- it loses the 128-bit accumulator/operand traffic of k_epilogue2.)
     Affine T34;
     memcpy(T34.m, h.T34, sizeof T34.m);
     PS_LAUNCH(c, KC_WARP_BACK,
@@ -541,6 +543,7 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
   e.out0 = sink.out0; e.acc0 = sink.acc0; e.add0 = sink.add0;
   e.out1 = sink.out1; e.add1 = sink.add1;
   e.max0 = sink.max0; e.max1 = sink.max1;
+  e.amax0 = sink.amax0;
   {
     const int XG = (W + 3) / 4;
     // the 128-bit paths need 16-byte aligned caller buffers (cudaMalloc'd grids always are)
@@ -811,7 +814,7 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   if (!cu(c->bufU.alloc(G), "alloc scratch") || !cu(c->bufV.alloc(G), "alloc scratch")) return PS_ERR_CUDA;
   c->scratch_elems = c->N;
   if (!cu(c->root_post.alloc(c->HW * c->S * sizeof(float)), "alloc root posterior")) return PS_ERR_CUDA;
-  if (!cu(c->maxes.alloc((c->P + psk::kMaxRootChildren + 4) * sizeof(int)), "alloc maxima")) return PS_ERR_CUDA;
+  if (!cu(c->maxes.alloc((2 * c->P + psk::kMaxRootChildren + 4) * sizeof(int)), "alloc maxima")) return PS_ERR_CUDA;
   if (!cu(c->argmax_keys.alloc(c->P * sizeof(unsigned long long)), "alloc argmax")) return PS_ERR_CUDA;
   if (!cu(c->counters.alloc(8 * sizeof(unsigned)), "alloc counters")) return PS_ERR_CUDA;
   if (!cu(cudaMallocHost((void **)&c->host_keys, c->P * sizeof(unsigned long long)), "alloc pinned keys")) return PS_ERR_CUDA;
@@ -1037,13 +1040,15 @@ int local_max_device(ps_ctx *c, const float *g, int D0, int H, int W, int max_n,
 }
 
 // argmax of grids g[p] for all parts (findrot.cpp:261-277 / :93-98): device part, asynchronous
-int enqueue_readout(ps_ctx *c, const std::vector<const float *> &grids, int scaleidx, int flags) {
+int enqueue_readout(ps_ctx *c, const std::vector<const float *> &grids, int scaleidx, int flags, bool keys_ready = false) {
   const int P = c->P;
-  PS_CUDA(c, cudaMemsetAsync(c->argmax_keys.p, 0, P * sizeof(unsigned long long), c->stream));
-  for (int p = 0; p < P; ++p)
-    PS_LAUNCH(c, KC_ARGMAX,
-              psk::k_argmax<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(
-                  grids[p], c->N, c->argmax_keys.as<unsigned long long>() + p));
+  if (!keys_ready) {
+    PS_CUDA(c, cudaMemsetAsync(c->argmax_keys.p, 0, P * sizeof(unsigned long long), c->stream));
+    for (int p = 0; p < P; ++p)
+      PS_LAUNCH(c, KC_ARGMAX,
+                psk::k_argmax<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(
+                    grids[p], c->N, c->argmax_keys.as<unsigned long long>() + p));
+  }
   PS_CUDA(c, cudaMemcpyAsync(c->host_keys, c->argmax_keys.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              c->stream));
   c->pending_grids = grids;
@@ -1138,6 +1143,13 @@ int ps_infer(ps_ctx *c, int flags) {
         }
     }
 
+    // every max slot is written at most once per scale: one reset for all of them
+    PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<cdiv(2 * P + psk::kMaxRootChildren + 4, 128), 128, 0, st>>>(
+                              c->maxes.as<int>(), 2 * P + psk::kMaxRootChildren + 4, PS_ENC_NEG_INF));
+    const bool last_scale = s == S - 1;
+    if (last_scale) PS_CUDA(c, cudaMemsetAsync(c->argmax_keys.p, 0, P * sizeof(unsigned long long), st));
+    unsigned long long *keys = last_scale ? c->argmax_keys.as<unsigned long long>() : nullptr;
+
     // ---------------- upward pass (findrot.cpp:582-658) ----------------
     // Every root child heads a chain; chains are independent, so they are walked one after another.
     // `belief[p]` is the grid MSG_up reads for part p, `bmax[p]` its encoded maximum.
@@ -1167,7 +1179,6 @@ int ps_infer(ps_ctx *c, int flags) {
           sink.out0 = c->POST(parent, s);
           if (c->cfg.is_detect[parent]) sink.add0 = c->U(parent, s);  // :652-654
           sink.max0 = c->MAXP(parent);
-          if ((rc = reset_max(c, sink.max0))) return rc;
           belief[parent] = sink.out0;
         }
         if ((rc = run_message(c, dp, belief[child], c->MAXP(child), sparse, sink))) return rc;
@@ -1180,8 +1191,8 @@ int ps_infer(ps_ctx *c, int flags) {
       for (int j = 0; j < nrc; ++j) {
         a.m[j] = c->rootmsg.as<float>() + (size_t)j * N;
         a.fr_max[j] = c->MAXP(P + j);
-        if ((rc = reset_max(c, a.fr_max[j]))) return rc;
       }
+      a.amax = keys ? keys + root : nullptr;
       if (!c->cfg.is_detect[root])
         return c->fail(PS_ERR_INVALID, "root part must have is_detect set (findrot.cpp:785)");
       a.unary = c->U(root, s);
@@ -1191,6 +1202,8 @@ int ps_infer(ps_ctx *c, int flags) {
         if ((rc = launch_root_combine(c, a))) return rc;
       } else {
         PS_CUDA(c, cudaMemcpyAsync(a.post, a.unary, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (keys)
+          PS_LAUNCH(c, KC_ARGMAX, psk::k_argmax<<<std::min(cdiv(N / 4 + 1, 256), 148u * 16), 256, 0, st>>>(a.post, N, keys + root));
       }
     }
 
@@ -1206,13 +1219,13 @@ int ps_infer(ps_ctx *c, int flags) {
         // post[q] += from_root[q] (:201).  For a leaf, post[q] is still "0 + unary" held in the unary itself.
         sink.out0 = c->POST(q, s);
         sink.acc0 = belief[q];
+        sink.amax0 = keys ? keys + q : nullptr;  // post[q] is final here: fold the readout's argmax into this write
         int next = nq.children.empty() ? -1 : nq.children[0];
         if (next >= 0) {
           // tmp = unary[q] + from_root[q] (:221-222), input of the next message
           sink.out1 = c->tmp[tsel].as<float>();
           sink.add1 = c->U(q, s);
-          sink.max1 = c->MAXP(P + psk::kMaxRootChildren + tsel);
-          if ((rc = reset_max(c, sink.max1))) return rc;
+          sink.max1 = c->MAXP(P + psk::kMaxRootChildren + q);
         }
         if ((rc = run_message(c, dp, in, in_max, false, sink))) return rc;
         if (next >= 0) {
@@ -1232,7 +1245,7 @@ int ps_infer(ps_ctx *c, int flags) {
   // per-part readout: the reference redoes it for every scale and keeps the last (findrot.cpp:257-259)
   std::vector<const float *> grids(P);
   for (int p = 0; p < P; ++p) grids[p] = c->POST(p, S - 1);
-  if ((rc = enqueue_readout(c, grids, S - 1, flags))) return rc;
+  if ((rc = enqueue_readout(c, grids, S - 1, flags, /*keys_ready=*/true))) return rc;
   c->result_scale = S - 1;
   if (flags & PS_INFER_KEEP_UNARIES) {
     if (flags & (PS_INFER_LOCAL_MAX | PS_INFER_ROOT_HYPS)) {
@@ -1330,7 +1343,7 @@ int ps_message(ps_ctx *c, const float *child, float *parent, int mem_kind, const
     din = c->tmp[0].as<float>();
     dout = c->tmp[1].as<float>();
   }
-  int *mx = c->MAXP(c->P + psk::kMaxRootChildren + 2);
+  int *mx = c->MAXP(2 * c->P + psk::kMaxRootChildren + 2);
   int rc = grid_max(c, din, c->N, mx);
   if (rc) return rc;
   Sink sink;
