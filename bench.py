@@ -8,8 +8,10 @@
 
 A "step" is one pass of the hot path (unary prep a4 -> upward pass -> downward pass -> argmax readout, SURVEY.md
 section 8a) over a batch of synthetic LSP-shape images (BASELINE.json configs[1]: 10-part tree, 24 rotations x 1
-scale, 600x400 grid, generic full-covariance spatial model).  `value` times it with the classifier-score grids
-already resident in HBM; `e2e` times the same work through the host-buffer API (pinned host grids in, best_conf out).
+scale, 600x400 grid, generic full-covariance spatial model).  Inputs are the detector's compact score grids
+(150x100 cells per rotation + grid->image transforms, the format PartApp::loadScoreGrid reads).  `value` times the
+path with those grids already resident in HBM; `e2e` times the same work through the host-buffer API (pinned host
+grids in, best_conf out).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -118,8 +120,11 @@ def make_inputs(n_images, first_index):
     ep = ExpParam(num_rotation_steps=w["R"], num_scale_steps=w["S"])
     pc = synth.part_conf(w["P"])
     joints = synth.make_joints(w["P"], seed=7)
-    raws = [synth.raw_scores(ep, w["H"], w["W"], w["P"], first_index + i) for i in range(n_images)]
-    return ep, pc, joints, raws
+    # the detector's own storage: compact grids + grid->image transforms (reference partapp.cpp:830-903)
+    comp = [synth.compact_scores(ep, w["H"], w["W"], w["P"], first_index + i) for i in range(n_images)]
+    raws = [c[0] for c in comp]
+    Tig = comp[0][1] if comp else None
+    return ep, pc, joints, raws, Tig
 
 
 def run_ours(args):
@@ -146,8 +151,10 @@ def run_ours(args):
     w = WORKLOAD
     B = args.images  # images per rank per step
     # contiguous image-index shards per rank, like the reference's --first/--numimgs (main.cpp:155-192)
-    ep, pc, joints, raws = make_inputs(B, first_index=rank * B)
+    ep, pc, joints, raws, Tig = make_inputs(B, first_index=rank * B)
     P, N = w["P"], w["R"] * w["H"] * w["W"]
+    gh, gw = raws[0].shape[-2:]
+    NC = w["R"] * gh * gw  # compact cells per part
 
     n_ctx = args.streams
     streams = [torch.cuda.Stream() for _ in range(n_ctx)]
@@ -158,9 +165,9 @@ def run_ours(args):
         c.set_joints(joints)
         ctxs.append(c)
 
-    # resident inputs: raw classifier-score grids of B images in HBM, and the same in pinned host memory
-    dev_raw = [torch.from_numpy(r.reshape(P, N)).cuda() for r in raws]
-    pin_raw = [torch.from_numpy(r.reshape(P, N)).pin_memory() for r in raws]
+    # resident inputs: the compact classifier-score grids of B images in HBM, and the same in pinned host memory
+    dev_raw = [torch.from_numpy(r.reshape(P, NC)).cuda() for r in raws]
+    pin_raw = [torch.from_numpy(r.reshape(P, NC)).pin_memory() for r in raws]
     results = np.zeros((B, P, 7), np.float32)
 
     def step(device_resident):
@@ -175,9 +182,9 @@ def run_ours(args):
             for p in range(P):
                 ptr = src[p].data_ptr()
                 if device_resident:
-                    c.set_unary_device(p, 0, ptr, raw_scores=True)
+                    c.set_unary_compact(p, 0, (gh, gw), Tig, device_ptr=ptr)
                 else:
-                    c.set_unary_pinned(p, 0, ptr, raw_scores=True)
+                    c.set_unary_compact_pinned(p, 0, ptr, gh, gw, Tig)
             c.infer_async(sparse=True)
             pending.append((i, c))
         for j, cj in pending:
@@ -239,7 +246,7 @@ def run_ours(args):
         c.profile_enable(True)
         for i in range(min(B, 2)):
             for p in range(P):
-                c.set_unary_device(p, 0, dev_raw[i][p].data_ptr(), raw_scores=True)
+                c.set_unary_compact(p, 0, (gh, gw), Tig, device_ptr=dev_raw[i][p].data_ptr())
             c.infer_async(sparse=True)
             c.best_conf()
         prof = c.profile_read()
@@ -289,14 +296,15 @@ def run_ours(args):
                             "slots per tap-output: the Gaussian passes are bound by the fp32 pipe, not by HBM (DESIGN.md 5)"}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_baseline = run_cpu_sample(ep, pc, joints, raws[0], threads=1)
+            from partapp_b200 import synth as _synth
+            cpu_baseline = run_cpu_sample(ep, pc, joints, _synth.raw_scores(ep, w["H"], w["W"], P, 0), threads=1)
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": workload_config("images sharded over %d GPU(s), %d images/GPU/step, %d stream(s)/GPU, no collective"
                                          % (world, B, n_ctx)),
                "clocks": clocks,
-               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(B * P * N * 4),
+               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(B * P * NC * 4),
                        "d2h_bytes_per_step": int(B * P * 7 * 4), "steps": e2e_steps,
                        "ms_per_step": round(ms_e2e / e2e_steps, 3)},
                "gpu_launches": int(launches),
@@ -337,7 +345,7 @@ def run_reference(args):
     w = WORKLOAD
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, args.ref_threads or cores))
-    ep, pc, joints, _ = make_inputs(0, 0)
+    ep, pc, joints, _, _ = make_inputs(0, 0)
     J = len(joints)
     n_msgs_per_image = 2 * J
     # one sparse unary grid per thread (images are independent)

@@ -122,6 +122,14 @@ int ps_index_from_rot(const ps_config *cfg, double rot_deg);
  * classifier scores as loadScoreGrid returns them (partapp.cpp:830-903) and the device applies
  * clip_scores_fill + computeLogGrid (findrot.cpp:834-845; aux.hpp:42-59; op.hpp:154-167). */
 int ps_set_unary(ps_ctx *ctx, int part, int scale, const float *src, int mem_kind, int raw_scores);
+/* PartApp::loadScoreGrid (libPartApp/partapp.cpp:830-903) + the unary prep, on the device: `cells` is the compact
+ * detector grid `cell_scoregrid{scale,rot}` of one (part, scale), [R][grid_h][grid_w] fp32 with 0 = not evaluated
+ * (part_detect::NO_CLASS_VALUE); `Tig` is [R][3][3] row-major doubles, Tig = Ti2 * T2g (partapp.cpp:881-887).
+ * Every evaluated cell is scattered with TM_DIRECT semantics (transform.hpp:167-192: x outer, y inner, last writer
+ * wins), then clip_scores_fill + computeLogGrid are applied.  Uploading compact grids instead of image-size grids cuts
+ * the host-to-device traffic by the detector stride squared (16x for the shipped configuration, README.md:88). */
+int ps_set_unary_compact(ps_ctx *ctx, int part, int scale, const float *cells, int grid_h, int grid_w,
+                         const double *Tig, int mem_kind);
 /* Reads the resident (possibly masked) unary back. */
 int ps_get_unary(ps_ctx *ctx, int part, int scale, float *dst, int mem_kind);
 

@@ -52,6 +52,7 @@ def lib():
         L.orc_gauss_filter_2d.argtypes = [_fp, _fp, C.c_int, C.c_int, _dp, C.c_int]
         L.orc_enlarged_size.argtypes = [C.c_int, C.c_int, _dp, _ip, _ip]
         L.orc_transform_fixed.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _dp, C.c_float, C.c_int]
+        L.orc_load_score_grid.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _fp]
         L.orc_message.argtypes = [C.POINTER(orc_exp_param), _fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp,
                                   C.c_double, C.c_double, C.c_double, C.c_int, _fp, _fp, _fp]
         L.orc_prepare_unary.argtypes = [_fp, C.c_size_t]
@@ -113,6 +114,16 @@ def message(ep, child, off_in, off_out, Cm, rot_mean, rot_sigma, scale, sparse, 
     lib().orc_message(C.byref(e), _f(child), _f(out), R, H, W, pa, pb, pc, float(rot_mean), float(rot_sigma),
                       float(scale), int(bool(sparse)), *[(_f(d) if d is not None else None) for d in dbg])
     return (out, dbg) if debug else out
+
+
+def load_score_grid(cells, Tig, H, W, interpolate=False):
+    """PartApp::loadScoreGrid mapping (reference libPartApp/partapp.cpp:874-896): cells [R][gh][gw], Tig [R][3][3]."""
+    cells = np.ascontiguousarray(cells, np.float32)
+    R, gh, gw = cells.shape
+    t = np.ascontiguousarray(Tig, np.float64).reshape(R * 9)
+    out = np.empty((R, H, W), np.float32)
+    lib().orc_load_score_grid(_f(cells), R, gh, gw, t.ctypes.data_as(_dp), H, W, int(bool(interpolate)), _f(out))
+    return out
 
 
 def prepare_unary(raw):

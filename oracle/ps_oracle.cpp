@@ -904,6 +904,20 @@ void orc_transform_fixed(const float *in, int in_h, int in_w, float *out, int ou
   transform_grid_helper(in, in_h, in_w, out, out_h, out_w, T21, T23, default_value, method, false);
 }
 
+// PartApp::loadScoreGrid's mapping of one (scale, rotation) compact grid to the image grid
+// (libPartApp/partapp.cpp:874-896): Tig = prod(Ti2, T2g) is formed by the caller; transform_grid_fixed_size(...,
+// Tig, NO_CLASS_VALUE = 0, TM_DIRECT or TM_BILINEAR).
+void orc_load_score_grid(const float *cells, int R, int gh, int gw, const double *Tig /*[R][9]*/, int H, int W,
+                         int interpolate, float *out /*[R][H][W]*/) {
+  for (int r = 0; r < R; ++r) {
+    Mat3 T21, T23;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) T21.m[i][j] = Tig[r * 9 + i * 3 + j];
+    transform_grid_helper(cells + (size_t)r * gh * gw, gh, gw, out + (size_t)r * H * W, H, W, T21, T23, 0.0f,
+                          interpolate ? TM_BILINEAR : TM_DIRECT, false);
+  }
+}
+
 // computeRotJointMarginal (findrot.cpp:292-456). dbg_* may be NULL.
 void orc_message(const orc_exp_param *e, const float *child, float *parent, int R, int H, int W,
                  const double *off_in, const double *off_out, const double *C, double rot_mean,

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "ps_scale_from_index": (C.c_double, [C.POINTER(ps_config), C.c_int]),
     "ps_index_from_rot": (C.c_int, [C.POINTER(ps_config), C.c_double]),
     "ps_set_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "ps_set_unary_compact": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]),
     "ps_get_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "ps_add_unary_table": (C.c_int, [_ctx_p, C.c_int, _fp, C.c_int, C.c_float]),
     "ps_rot_score_table": (None, [C.POINTER(ps_config), C.c_double, C.c_double, _fp]),

@@ -263,6 +263,67 @@ __global__ void __launch_bounds__(256) k_grid_max(const float *__restrict__ p, s
   block_max_to(m, dst);
 }
 
+
+// ---- unary ingest from compact detector grids: PartApp::loadScoreGrid (libPartApp/partapp.cpp:830-903) ------------
+// The reference scatters every evaluated cell of the compact grid (value != NO_CLASS_VALUE = 0) into a zeroed
+// image-size grid with TM_DIRECT (transform.hpp:167-192; x1 outer, y1 inner, later writers overwrite), then applies
+// clip_scores_fill + computeLogGrid (findrot.cpp:834-845).  Device version: (1) every evaluated compact cell does
+// atomicMax(order key) on its target image cell, order = x1 * gh + y1 + 1, so the surviving key is the reference's
+// last writer; (2) a sweep turns keys into log-unaries (0 -> LOG_ZERO) and folds their maximum.
+constexpr int kMaxIngestRot = 64;
+struct TigRows {
+  double m[kMaxIngestRot * 6];  // passed by value as a kernel parameter: no staging copy, no host synchronisation
+};
+struct IngestArgs {
+  const float *cells;   // [R][gh][gw]
+  const double *Tig;    // [R][6]: rows 0,1 of the 3x3 image<-grid transform (Ti2 * T2g); null -> use the by-value rows
+  int *keys;            // [R][H][W] scratch
+  float *out;           // [R][H][W] log-domain unary
+  int R, gh, gw, H, W;
+};
+
+__global__ void __launch_bounds__(256) k_ingest_scatter(IngestArgs a, const __grid_constant__ TigRows rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // flat over gh*gw, x fastest (coalesced read)
+  const int r = blockIdx.y;
+  if (i >= a.gh * a.gw) return;
+  const int y1 = i / a.gw, x1 = i - y1 * a.gw;
+  const float v = a.cells[(size_t)r * a.gh * a.gw + i];
+  if (v == 0.0f) return;
+  const double *T = a.Tig ? a.Tig + r * 6 : rows.m + r * 6;
+  const double x3 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], (double)x1), __dmul_rn(T[1], (double)y1)), T[2]);
+  const double y3 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], (double)x1), __dmul_rn(T[4], (double)y1)), T[5]);
+  const int ix = (int)floor(__dadd_rn(x3, 0.5)), iy = (int)floor(__dadd_rn(y3, 0.5));
+  if (ix >= 0 && ix < a.W && iy >= 0 && iy < a.H)
+    atomicMax(&a.keys[(size_t)r * a.H * a.W + (size_t)iy * a.W + ix], x1 * a.gh + y1 + 1);
+}
+
+__global__ void __launch_bounds__(256) k_ingest_sweep(IngestArgs a, int *max_dst) {
+  const size_t n = (size_t)a.R * a.H * a.W;
+  const size_t HW = (size_t)a.H * a.W;
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  float m = -INFINITY;
+  if (i < n) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j] = kLogZero;
+      if (i + j < n) {
+        const int k = a.keys[i + j];
+        if (k > 0) {
+          const int r = (int)((i + j) / HW);
+          const int x1 = (k - 1) / a.gh, y1 = (k - 1) - x1 * a.gh;
+          o[j] = prepare_cell(__ldg(&a.cells[(size_t)r * a.gh * a.gw + (size_t)y1 * a.gw + x1]));
+        }
+        m = fmaxf(m, o[j]);
+      }
+    }
+    if (i + 3 < n && ((uintptr_t)(a.out + i) & 15) == 0) *reinterpret_cast<float4 *>(a.out + i) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      for (int j = 0; j < 4 && i + j < n; ++j) a.out[i + j] = o[j];
+  }
+  if (max_dst) block_max_to(m, max_dst);
+}
+
 // Upright masking (findrot.cpp:509-523): slices flagged in mask[r] are set to LOG_ZERO.
 __global__ void k_mask_slices(float *__restrict__ g, int R, size_t HW, const unsigned char *__restrict__ mask) {
   int r = blockIdx.y;

@@ -107,6 +107,7 @@ struct ps_ctx {
   DevBuf argmax_keys;   // u64 [P]
   DevBuf cand;          // Cand [N] local-max candidates
   DevBuf counters;      // unsigned [8]
+  DevBuf ingest, ingest_keys;       // ps_set_unary_compact staging: Tig rows + compact cells; order keys [R][H][W]
   size_t scratch_elems = 0;
 
   // model
@@ -959,6 +960,48 @@ int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind,
   if (raw) {
     PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(dst, c->N, nullptr));
   }
+  return PS_OK;
+}
+
+int ps_set_unary_compact(ps_ctx *c, int part, int scale, const float *cells, int gh, int gw, const double *Tig,
+                         int mem_kind) {
+  if (!c || !cells || !Tig) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  if (gh < 1 || gw < 1 || (size_t)gh * gw >= ((size_t)1 << 31)) return c->fail(PS_ERR_INVALID, "compact grid size out of range");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  const size_t ncell = (size_t)c->R * gh * gw;
+  // staging: cells | Tig rows (doubles first for alignment)
+  const size_t need = (size_t)c->R * 6 * sizeof(double) + ncell * sizeof(float);
+  if (c->ingest.bytes < need) {
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PS_CUDA(c, c->ingest.alloc(need));
+  }
+  if (c->ingest_keys.bytes < c->N * sizeof(int)) PS_CUDA(c, c->ingest_keys.alloc(c->N * sizeof(int)));
+  // rows 0,1 of each 3x3 (map_point only reads those, homogeneous_coord.h:79-80)
+  psk::TigRows rows;
+  double *dT = nullptr;
+  float *dcells = (float *)(c->ingest.as<double>() + (size_t)c->R * 6);
+  if (c->R <= psk::kMaxIngestRot) {
+    for (int r = 0; r < c->R; ++r)
+      for (int k = 0; k < 6; ++k) rows.m[(size_t)r * 6 + k] = Tig[(size_t)r * 9 + k];
+  } else {
+    std::vector<double> t((size_t)c->R * 6);
+    for (int r = 0; r < c->R; ++r)
+      for (int k = 0; k < 6; ++k) t[(size_t)r * 6 + k] = Tig[(size_t)r * 9 + k];
+    dT = c->ingest.as<double>();
+    PS_CUDA(c, cudaMemcpy(dT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  const float *src_cells = cells;
+  if (mem_kind == PS_MEM_HOST) {
+    PS_CUDA(c, cudaMemcpyAsync(dcells, cells, ncell * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    src_cells = dcells;
+  }
+  PS_CUDA(c, cudaMemsetAsync(c->ingest_keys.p, 0, c->N * sizeof(int), c->stream));
+  psk::IngestArgs a;
+  a.cells = src_cells; a.Tig = dT; a.keys = c->ingest_keys.as<int>(); a.out = c->U(part, scale);
+  a.R = c->R; a.gh = gh; a.gw = gw; a.H = c->H; a.W = c->W;
+  PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows));
+  PS_LAUNCH(c, KC_PREP, psk::k_ingest_sweep<<<cdiv((c->N + 3) / 4, 256), 256, 0, c->stream>>>(a, nullptr));
   return PS_OK;
 }
 

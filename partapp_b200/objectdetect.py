@@ -192,6 +192,28 @@ class PsContext:
         """Asynchronous H2D from pinned host memory (caller keeps the buffer alive until synchronize)."""
         self._check(self.lib.ps_set_unary(self.h, part, scale, C.c_void_p(host_ptr), capi.PS_MEM_HOST, int(raw_scores)))
 
+    def set_unary_compact(self, part, scale, cells, Tig, device_ptr=None):
+        """loadScoreGrid on the device: cells [R][gh][gw] (0 = not evaluated), Tig [R][3][3] doubles."""
+        Tig = np.ascontiguousarray(Tig, np.float64)
+        if Tig.shape != (self.R, 3, 3):
+            raise ValueError("Tig must be [R][3][3]")
+        if device_ptr is not None:
+            gh, gw = cells
+            self._check(self.lib.ps_set_unary_compact(self.h, part, scale, C.c_void_p(device_ptr), gh, gw,
+                                                      Tig.ctypes.data_as(C.POINTER(C.c_double)), capi.PS_MEM_DEVICE))
+            return
+        g = _f32(cells)
+        if g.ndim != 3 or g.shape[0] != self.R:
+            raise ValueError("cells must be [R][gh][gw]")
+        self._check(self.lib.ps_set_unary_compact(self.h, part, scale, _ptr(g), g.shape[1], g.shape[2],
+                                                  Tig.ctypes.data_as(C.POINTER(C.c_double)), capi.PS_MEM_HOST))
+        self.synchronize()
+
+    def set_unary_compact_pinned(self, part, scale, host_ptr, gh, gw, Tig):
+        """Asynchronous variant for pinned host memory (caller keeps the buffer alive until synchronize)."""
+        self._check(self.lib.ps_set_unary_compact(self.h, part, scale, C.c_void_p(host_ptr), gh, gw,
+                                                  Tig.ctypes.data_as(C.POINTER(C.c_double)), capi.PS_MEM_HOST))
+
     def get_unary(self, part, scale):
         out = np.empty((self.R, self.H, self.W), np.float32)
         self._check(self.lib.ps_get_unary(self.h, part, scale, _ptr(out), capi.PS_MEM_HOST))

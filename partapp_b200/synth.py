@@ -96,3 +96,29 @@ def log_unaries(exp_param: ExpParam, height, width, num_parts, imgidx, seed=1234
     with np.errstate(divide="ignore"):
         lg = np.log(v.astype(np.float64)).astype(np.float32)
     return np.where(v == 0, np.float32(-1e6), lg).astype(np.float32)
+
+
+def compact_scores(exp_param: ExpParam, height, width, num_parts, imgidx, seed=1234, stride=4, rotated=False):
+    """The same classifier scores as raw_scores(), in the form the detector stores them (reference
+    libPartApp/partapp.cpp:830-903): per part and scale a compact grid `cells[R][gh][gw]` (0 = not evaluated) and the
+    grid->image transforms `Tig[R][3][3]`.  rotated=False: axis-aligned lattices whose scatter reproduces raw_scores()
+    exactly; rotated=True: each rotation's lattice is rotated about the image centre like the real detector's."""
+    R, S = exp_param.num_rotation_steps, exp_param.num_scale_steps
+    gh, gw = (height + stride - 1) // stride, (width + stride - 1) // stride
+    cells = np.zeros((num_parts, S, R, gh, gw), np.float32)
+    Tig = np.zeros((R, 3, 3), np.float64)
+    raw = raw_scores(exp_param, height, width, num_parts, imgidx, seed, stride)
+    for r in range(R):
+        ox, oy = r % stride, (r // stride) % stride
+        sub = raw[:, :, r, oy::stride, ox::stride]
+        cells[:, :, r, :sub.shape[2], :sub.shape[3]] = sub
+        if rotated:
+            th = 2 * np.pi * (r + 0.5) / R - np.pi
+            c, s_ = np.cos(th), np.sin(th)
+            cx, cy = (width - 1) / 2.0, (height - 1) / 2.0
+            A = np.array([[c * stride, -s_ * stride], [s_ * stride, c * stride]])
+            t = np.array([cx, cy]) - A @ np.array([(gw - 1) / 2.0, (gh - 1) / 2.0])
+            Tig[r] = [[A[0, 0], A[0, 1], t[0]], [A[1, 0], A[1, 1], t[1]], [0, 0, 1]]
+        else:
+            Tig[r] = [[stride, 0, ox], [0, stride, oy], [0, 0, 1]]
+    return cells, Tig

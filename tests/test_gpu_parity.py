@@ -381,3 +381,36 @@ def test_full_size_properties():
         ok = np.isfinite(lse) & (r1[0] > -1e5)
         assert ok.sum() > 1000
         np.testing.assert_allclose(r1[0][ok], lse[ok], rtol=1e-4, atol=1e-3)
+
+
+# ---- unary ingest from compact detector grids (PartApp::loadScoreGrid, partapp.cpp:830-903) -----------
+
+@pytest.mark.parametrize("rotated", [False, True], ids=["lattice", "rotated_lattice"])
+def test_compact_ingest_matches_load_score_grid(rotated):
+    ep = ExpParam(num_rotation_steps=8)
+    P, H, W = 2, 44, 52
+    cells, Tig = synth.compact_scores(ep, H, W, P, 3, rotated=rotated)
+    with _ctx(ep, P, H, W) as ctx:
+        for p in range(P):
+            want = oracle.prepare_unary(oracle.load_score_grid(cells[p, 0], Tig, H, W))
+            ctx.set_unary_compact(p, 0, cells[p, 0], Tig)
+            got = ctx.get_unary(p, 0)
+            _cmp(got, want, "compact ingest part %d" % p, max_ulp_frac=1e-5)
+
+
+def test_compact_ingest_collisions_last_writer_wins():
+    """A down-scaling transform maps several grid cells onto one image cell: the reference's x-outer / y-inner
+    scatter order decides which one survives (transform.hpp:176-190)."""
+    ep = ExpParam(num_rotation_steps=4)
+    H, W = 20, 24
+    rng = np.random.default_rng(1)
+    cells = rng.uniform(0.05, 1.0, (4, 30, 36)).astype(np.float32)
+    cells[rng.random(cells.shape) < 0.3] = 0.0           # unevaluated cells are skipped, not written
+    Tig = np.zeros((4, 3, 3))
+    for r in range(4):
+        th = 0.3 * r
+        Tig[r] = [[0.6 * np.cos(th), -0.6 * np.sin(th), 4.0 + r], [0.6 * np.sin(th), 0.6 * np.cos(th), 1.5], [0, 0, 1]]
+    want = oracle.prepare_unary(oracle.load_score_grid(cells, Tig, H, W))
+    with _ctx(ep, 2, H, W) as ctx:
+        ctx.set_unary_compact(0, 0, cells, Tig)
+        _cmp(ctx.get_unary(0, 0), want, "colliding scatter", max_ulp_frac=1e-5)
