@@ -1,0 +1,683 @@
+// objectdetect_b200.cpp -- see objectdetect_b200.hpp.  Reference line numbers are relative to
+// /root/reference/src/libs/.
+#include "objectdetect_b200.hpp"
+
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+
+#include "mat5.hpp"
+#include "prototext.hpp"
+
+namespace object_detect {
+
+namespace {
+
+void fail(const std::string &msg) { throw std::runtime_error(msg); }
+
+bool file_exists(const std::string &p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+bool dir_exists(const std::string &p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+void make_dirs(const std::string &p) {  // filesys::create_dir, recursive
+  std::string cur;
+  for (size_t i = 0; i <= p.size(); ++i) {
+    if (i == p.size() || p[i] == '/') {
+      if (!cur.empty() && !dir_exists(cur) && mkdir(cur.c_str(), 0777) != 0 && !dir_exists(cur))
+        fail("cannot create directory " + cur);
+    }
+    if (i < p.size()) cur += p[i];
+  }
+}
+std::string dirname_of(const std::string &p) {
+  size_t k = p.find_last_of('/');
+  return k == std::string::npos ? "." : (k == 0 ? "/" : p.substr(0, k));
+}
+std::string basename_noext(const std::string &p) {
+  size_t k = p.find_last_of('/');
+  std::string b = k == std::string::npos ? p : p.substr(k + 1);
+  size_t d = b.find_last_of('.');
+  return d == std::string::npos ? b : b.substr(0, d);
+}
+// complete_relative_path, partapp.cpp:112-139
+std::string complete_relative_path(std::string in, const std::string &reference_file) {
+  while (!in.empty() && isspace((unsigned char)in.front())) in.erase(in.begin());
+  while (!in.empty() && isspace((unsigned char)in.back())) in.pop_back();
+  if (in.empty() || in[0] == '/') return in;
+  if (in.compare(0, 2, "./") == 0) in = in.substr(2);
+  return dirname_of(reference_file) + "/" + in;
+}
+std::string pad_zeros(int v, int n) {
+  char buf[32];
+  snprintf(buf, sizeof buf, "%0*d", n, v);
+  return buf;
+}
+
+// ---- ps_ctx cache: one context per grid shape ----------------------------------------------------------------
+struct CtxKey {
+  int R, S, H, W, P, root, keep;
+  float rmin, rmax, smin, smax, strip;
+  int K;
+  unsigned char flags[3 * PS_MAX_PARTS];
+  bool operator==(const CtxKey &o) const { return memcmp(this, &o, sizeof(CtxKey)) == 0; }
+};
+struct CtxHolder {
+  ps_ctx *ctx = nullptr;
+  CtxKey key;
+  ~CtxHolder() {
+    if (ctx) ps_destroy(ctx);
+  }
+};
+CtxHolder &holder() {
+  static thread_local CtxHolder h;
+  return h;
+}
+
+void check(ps_ctx *ctx, int st, const char *what) {
+  if (st != PS_OK) fail(std::string(what) + ": " + ps_last_error(ctx));
+}
+
+ps_config make_config(const PartApp &app, int H, int W, int root, bool keep_all) {
+  const ExpParam &ep = app.m_exp_param;
+  ps_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  const char *dev = getenv("PSINFER_DEVICE");
+  cfg.device = dev ? atoi(dev) : 0;
+  cfg.num_parts = (int)app.m_part_conf.part.size();
+  cfg.num_rotation_steps = (int)ep.num_rotation_steps;
+  cfg.min_part_rotation = ep.min_part_rotation;
+  cfg.max_part_rotation = ep.max_part_rotation;
+  cfg.num_scale_steps = (int)ep.num_scale_steps;
+  cfg.min_object_scale = ep.min_object_scale;
+  cfg.max_object_scale = ep.max_object_scale;
+  cfg.height = H;
+  cfg.width = W;
+  cfg.root_idx = root;
+  if (cfg.num_parts > PS_MAX_PARTS) fail("too many parts");
+  for (int p = 0; p < cfg.num_parts; ++p) {
+    cfg.is_detect[p] = app.m_part_conf.part[p].is_detect;
+    cfg.is_upright[p] = app.m_part_conf.part[p].is_upright;
+    cfg.is_root[p] = app.m_part_conf.part[p].is_root;
+  }
+  cfg.strip_border_detections = ep.strip_border_detections;
+  cfg.roi_save_num_samples = (int)ep.roi_save_num_samples;
+  cfg.keep_all_scales = keep_all ? 1 : 0;
+  return cfg;
+}
+
+ps_ctx *get_ctx(const PartApp &app, int H, int W, int root, bool keep_all) {
+  ps_config cfg = make_config(app, H, W, root, keep_all);
+  CtxKey k;
+  memset(&k, 0, sizeof k);
+  k.R = cfg.num_rotation_steps; k.S = cfg.num_scale_steps; k.H = H; k.W = W; k.P = cfg.num_parts; k.root = root;
+  k.keep = cfg.keep_all_scales; k.rmin = cfg.min_part_rotation; k.rmax = cfg.max_part_rotation;
+  k.smin = cfg.min_object_scale; k.smax = cfg.max_object_scale; k.strip = cfg.strip_border_detections;
+  k.K = cfg.roi_save_num_samples;
+  memcpy(k.flags, cfg.is_detect, PS_MAX_PARTS);
+  memcpy(k.flags + PS_MAX_PARTS, cfg.is_upright, PS_MAX_PARTS);
+  memcpy(k.flags + 2 * PS_MAX_PARTS, cfg.is_root, PS_MAX_PARTS);
+  CtxHolder &h = holder();
+  if (h.ctx && h.key == k) return h.ctx;
+  if (h.ctx) ps_destroy(h.ctx);
+  h.ctx = nullptr;
+  if (ps_create(&cfg, &h.ctx) != PS_OK) fail(std::string("ps_create: ") + ps_last_error(nullptr));
+  h.key = k;
+  return h.ctx;
+}
+
+std::vector<ps_joint> to_ps_joints(const std::vector<Joint> &joints) {
+  std::vector<ps_joint> pj(joints.size());
+  for (size_t j = 0; j < joints.size(); ++j) {
+    pj[j].type = joints[j].type;
+    pj[j].child_idx = joints[j].child_idx;
+    pj[j].parent_idx = joints[j].parent_idx;
+    for (int k = 0; k < 2; ++k) {
+      pj[j].offset_c[k] = joints[j].offset_c[k];
+      pj[j].offset_p[k] = joints[j].offset_p[k];
+    }
+    pj[j].C[0] = joints[j].C[0][0]; pj[j].C[1] = joints[j].C[0][1];
+    pj[j].C[2] = joints[j].C[1][0]; pj[j].C[3] = joints[j].C[1][1];
+    pj[j].rot_mean = joints[j].rot_mean;
+    pj[j].rot_sigma = joints[j].rot_sigma;
+  }
+  return pj;
+}
+
+PartHyp hyp_from_row(const float *r) {
+  PartHyp h;
+  h.fromVect(r);
+  return h;
+}
+
+void collect_results(const PartApp &app, ps_ctx *ctx, FloatGrid3 &root_part_posterior,
+                     std::vector<std::vector<PartHyp> > &best_part_hyp, int H, int W) {
+  const int P = (int)app.m_part_conf.part.size(), S = (int)app.m_exp_param.num_scale_steps;
+  root_part_posterior = FloatGrid3(S, H, W);
+  check(ctx, ps_get_root_posterior(ctx, root_part_posterior.data(), PS_MEM_HOST), "ps_get_root_posterior");
+  best_part_hyp.assign(P, std::vector<PartHyp>());
+  const int cap = (int)app.m_exp_param.roi_save_num_samples + 1;
+  std::vector<float> rows((size_t)cap * PS_HYP_VEC);
+  for (int p = 0; p < P; ++p) {
+    int n = 0;
+    check(ctx, ps_get_part_hyps(ctx, p, rows.data(), cap, &n), "ps_get_part_hyps");
+    for (int i = 0; i < n; ++i) best_part_hyp[p].push_back(hyp_from_row(&rows[(size_t)i * PS_HYP_VEC]));
+  }
+}
+
+void save_marginals(const PartApp &app, ps_ctx *ctx, int imgidx, bool flip, int H, int W) {
+  // computePartMarginals :239-253: log_part_posterior_final_imgidx<i>_scaleidx<s>_o<f>_pidx<p>.mat, var log_prob_grid
+  const ExpParam &ep = app.m_exp_param;
+  const std::string dir = ep.log_dir + "/" + ep.log_subdir + "/part_marginals";
+  make_dirs(dir);
+  const int P = (int)app.m_part_conf.part.size(), S = (int)ep.num_scale_steps, R = (int)ep.num_rotation_steps;
+  FloatGrid3 g(R, H, W);
+  for (int s = 0; s < S; ++s)
+    for (int p = 0; p < P; ++p) {
+      check(ctx, ps_get_marginal(ctx, p, s, g.data(), PS_MEM_HOST), "ps_get_marginal");
+      char name[256];
+      snprintf(name, sizeof name, "/log_part_posterior_final_imgidx%d_scaleidx%d_o%d_pidx%d.mat", imgidx, s, (int)flip, p);
+      mat5::Writer w(dir + name);
+      w.put("log_prob_grid", g.data(), {(size_t)R, (size_t)H, (size_t)W});
+    }
+}
+
+}  // namespace
+
+// ---- small public helpers -------------------------------------------------------------------------------------------
+
+double rot_from_index(const ExpParam &ep, int idx) {
+  ps_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.num_rotation_steps = (int)ep.num_rotation_steps;
+  cfg.min_part_rotation = ep.min_part_rotation;
+  cfg.max_part_rotation = ep.max_part_rotation;
+  return ps_rot_from_index(&cfg, idx);
+}
+double scale_from_index(const ExpParam &ep, int idx) {
+  ps_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.num_scale_steps = (int)ep.num_scale_steps;
+  cfg.min_object_scale = ep.min_object_scale;
+  cfg.max_object_scale = ep.max_object_scale;
+  return ps_scale_from_index(&cfg, idx);
+}
+
+std::string getObjectHypFilename(int imgidx, bool flip) {
+  return "/object_hyp_imgidx" + std::to_string(imgidx) + "_o" + std::to_string((int)flip) + "_spmnone.pbuf";
+}
+
+void image_size(const std::string &file, int &width, int &height) {
+  std::ifstream f(file.c_str(), std::ios::binary);
+  if (!f) fail("cannot open image " + file);
+  unsigned char h[32];
+  f.read((char *)h, 32);
+  if (f.gcount() >= 24 && h[0] == 0x89 && h[1] == 'P' && h[2] == 'N' && h[3] == 'G') {  // IHDR at offset 16
+    width = (h[16] << 24) | (h[17] << 16) | (h[18] << 8) | h[19];
+    height = (h[20] << 24) | (h[21] << 16) | (h[22] << 8) | h[23];
+    return;
+  }
+  if (h[0] == 0xff && h[1] == 0xd8) {  // JPEG: walk the segments to a start-of-frame marker
+    f.clear();
+    f.seekg(2);
+    for (;;) {
+      unsigned char m[4];
+      f.read((char *)m, 4);
+      if (!f || m[0] != 0xff) break;
+      int len = (m[2] << 8) | m[3];
+      if (m[1] >= 0xc0 && m[1] <= 0xcf && m[1] != 0xc4 && m[1] != 0xc8 && m[1] != 0xcc) {
+        unsigned char s[5];
+        f.read((char *)s, 5);
+        height = (s[1] << 8) | s[2];
+        width = (s[3] << 8) | s[4];
+        return;
+      }
+      f.seekg(len - 2, std::ios::cur);
+    }
+  }
+  if (h[0] == 'P' && (h[1] == '5' || h[1] == '6' || h[1] == '2' || h[1] == '3')) {  // PNM
+    f.clear();
+    f.seekg(2);
+    f >> width >> height;
+    if (f) return;
+  }
+  fail("cannot read the size of image " + file + " (PNG, JPEG and PNM headers are understood)");
+}
+
+std::string HypothesisList::SerializeAsString() const {
+  using namespace prototext::wire;
+  std::string out;
+  for (const ObjectHypothesis &h : hyp) {
+    std::string m;
+    f32(m, 1, h.x);
+    f32(m, 2, h.y);
+    f32(m, 3, h.scale);
+    f32(m, 4, h.score);
+    boolean(m, 5, h.flip);
+    bytes(out, 1, m);
+  }
+  return out;
+}
+
+HypothesisList HypothesisList::Parse(const std::string &b) {
+  HypothesisList l;
+  size_t i = 0;
+  auto varint = [&](size_t &k) {
+    uint64_t v = 0;
+    int shift = 0;
+    while (k < b.size()) {
+      unsigned char c = (unsigned char)b[k++];
+      v |= (uint64_t)(c & 0x7f) << shift;
+      if (!(c & 0x80)) break;
+      shift += 7;
+    }
+    return v;
+  };
+  while (i < b.size()) {
+    uint64_t key = varint(i);
+    if (key != ((1 << 3) | 2)) fail("HypothesisList: unexpected field");
+    size_t len = (size_t)varint(i), end = i + len;
+    ObjectHypothesis h;
+    while (i < end) {
+      uint64_t k = varint(i);
+      int field = (int)(k >> 3), type = (int)(k & 7);
+      if (type == 5) {
+        float v;
+        memcpy(&v, b.data() + i, 4);
+        i += 4;
+        if (field == 1) h.x = v;
+        if (field == 2) h.y = v;
+        if (field == 3) h.scale = v;
+        if (field == 4) h.score = v;
+      } else if (type == 0) {
+        uint64_t v = varint(i);
+        if (field == 5) h.flip = v != 0;
+      } else {
+        fail("HypothesisList: unsupported wire type");
+      }
+    }
+    l.hyp.push_back(h);
+  }
+  return l;
+}
+
+// ---- PartApp ---------------------------------------------------------------------------------------------------------
+
+std::string PartApp::getScoreGridFileName(int imgidx, int pidx, bool flip) const {
+  return m_exp_param.scoregrid_dir + "/imgidx" + std::to_string(imgidx) + "-pidx" + std::to_string(pidx) + "-o" +
+         std::to_string((int)flip) + "-scoregrid.mat";
+}
+
+void PartApp::init(const std::string &expopt) {
+  prototext::Node n = prototext::parse_file(expopt);
+  ExpParam &e = m_exp_param;
+  for (size_t i = 0; i < n.count("test_dataset"); ++i) e.test_dataset.push_back(n.get("test_dataset", i).scalar);
+  e.log_dir = n.str("log_dir");
+  e.part_conf = n.str("part_conf");
+  e.min_object_scale = (float)n.num("min_object_scale", 1);
+  e.max_object_scale = (float)n.num("max_object_scale", 1);
+  e.num_scale_steps = (unsigned)n.num("num_scale_steps", 1);
+  e.min_part_rotation = (float)n.num("min_part_rotation", -180);
+  e.max_part_rotation = (float)n.num("max_part_rotation", 180);
+  e.num_rotation_steps = (unsigned)n.num("num_rotation_steps", 48);
+  e.flip_orientation = n.boolean("flip_orientation", false);
+  e.num_pose_samples = (int)n.num("num_pose_samples", 0);
+  e.strip_border_detections = (float)n.num("strip_border_detections", 0);
+  e.roi_save_num_samples = (float)n.num("roi_save_num_samples", 1000);
+  e.use_pairwise = n.boolean("use_pairwise", true);
+  e.save_part_marginals = n.boolean("save_part_marginals", false);
+  e.save_part_marginals_local_max = n.boolean("save_part_marginals_local_max", false);
+  e.save_part_detections_local_max = n.boolean("save_part_detections_local_max", false);
+  e.interpolate = n.boolean("interpolate", false);
+  e.force_recompute_scores = n.boolean("force_recompute_scores", true);
+  e.use_torso_pos_prior = n.boolean("use_torso_pos_prior", false);
+  e.torso_pos_prior_weight = (float)n.num("torso_pos_prior_weight", 1);
+  e.pred_unary_rot = n.boolean("pred_unary_rot", false);
+  e.pred_unary_pos = n.boolean("pred_unary_pos", false);
+  e.use_dpm_torso = n.boolean("use_dpm_torso", false);
+  e.use_dpm_head = n.boolean("use_dpm_head", false);
+  e.use_dpm_unary = n.boolean("use_dpm_unary", false);
+  if (e.log_dir.empty()) fail("expopt: log_dir is not set");
+  e.log_dir = complete_relative_path(e.log_dir, expopt);
+  // init_setpath, partapp.cpp:313-441
+  e.log_subdir = n.has("log_subdir") ? n.str("log_subdir") : basename_noext(expopt);
+  const std::string base = e.log_dir + "/" + e.log_subdir;
+  e.class_dir = n.has("class_dir") ? complete_relative_path(n.str("class_dir"), expopt) : base + "/class";
+  e.scoregrid_dir = n.has("scoregrid_dir") ? complete_relative_path(n.str("scoregrid_dir"), expopt) : base + "/test_scoregrid";
+  e.spatial_dir = n.has("spatial_dir") ? complete_relative_path(n.str("spatial_dir"), expopt) : base + "/spatial";
+  e.pred_data_test_dir = n.has("pred_data_test_dir") ? complete_relative_path(n.str("pred_data_test_dir"), expopt)
+                                                     : base + "/pred_data_test";
+  if (e.num_pose_samples != 0) fail("num_pose_samples must be 0 (findrot.cpp:680-682 asserts)");
+
+  // part_conf (PartConfig.proto)
+  if (e.part_conf.empty()) fail("expopt: part_conf is not set");
+  prototext::Node pc = prototext::parse_file(complete_relative_path(e.part_conf, expopt));
+  for (size_t i = 0; i < pc.count("part"); ++i) {
+    const prototext::Node &p = pc.msg("part", i);
+    PartDef d;
+    d.part_id = (int)p.num("part_id", 0);
+    d.is_root = p.boolean("is_root", false);
+    d.is_detect = p.boolean("is_detect", true);
+    d.is_upright = p.boolean("is_upright", false);
+    m_part_conf.part.push_back(d);
+  }
+  for (size_t i = 0; i < pc.count("joint"); ++i) {
+    const prototext::Node &j = pc.msg("joint", i);
+    JointDef d;
+    d.child_idx = (int)j.num("child_idx", 0);
+    d.parent_idx = (int)j.num("parent_idx", 0);
+    d.type = j.str("type", "Gaussian");
+    d.num_joint_types = (unsigned)j.num("num_joint_types", 1);
+    m_part_conf.joint.push_back(d);
+  }
+  for (size_t p = 0; p < m_part_conf.part.size(); ++p)  // aux.cpp:67-69
+    if (m_part_conf.part[p].part_id != (int)p + 1) fail("part_conf: part_id must equal part index + 1 (aux.cpp:68)");
+  m_rootpart_idx = -1;
+  for (size_t p = 0; p < m_part_conf.part.size(); ++p)
+    if (m_part_conf.part[p].is_detect && m_part_conf.part[p].is_root) {
+      if (m_rootpart_idx != -1) fail("part_conf: more than one root part (findrot.cpp:786)");
+      m_rootpart_idx = (int)p;
+    }
+
+  // window_param.txt (partapp.cpp:608-615): only the bbox offsets matter here; absent file -> defaults (0, 0)
+  const std::string wp = e.class_dir + "/window_param.txt";
+  if (file_exists(wp)) {
+    prototext::Node w = prototext::parse_file(wp);
+    m_window_param.bbox_offset_x = w.num("bbox_offset_x", 0);
+    m_window_param.bbox_offset_y = w.num("bbox_offset_y", 0);
+  }
+
+  // test image list: .al (XML, <image><name>..</name>) or .idl ("file": ...;) annotation lists (libAnnotation)
+  for (const std::string &ds : e.test_dataset) {
+    const std::string path = complete_relative_path(ds, expopt);
+    std::ifstream f(path.c_str());
+    if (!f) fail("cannot open test_dataset " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string text = ss.str();
+    std::vector<std::string> names;
+    if (text.find("<name>") != std::string::npos) {
+      size_t pos = 0;
+      while ((pos = text.find("<name>", pos)) != std::string::npos) {
+        size_t end = text.find("</name>", pos);
+        if (end == std::string::npos) break;
+        names.push_back(text.substr(pos + 6, end - pos - 6));
+        pos = end + 7;
+      }
+    } else {
+      std::istringstream ls(text);
+      std::string line;
+      while (std::getline(ls, line)) {
+        size_t a = line.find('"'), b = a == std::string::npos ? a : line.find('"', a + 1);
+        if (b != std::string::npos) names.push_back(line.substr(a + 1, b - a - 1));
+      }
+    }
+    for (std::string nm : names) {  // convertFullPath, partapp.cpp:87-107
+      if (!file_exists(nm)) nm = dirname_of(path) + "/" + nm;
+      if (!file_exists(nm)) fail("image file not found: " + nm);
+      m_test_annolist.push_back(nm);
+    }
+  }
+}
+
+// ---- joints ----------------------------------------------------------------------------------------------------------
+
+static double mat_scalar(const std::vector<mat5::Var> &vars, const std::string &name, const std::string &path) {
+  const mat5::Var &v = mat5::find(vars, name, path);
+  if (v.numel() != 1) fail(path + ": '" + name + "' is not a scalar");
+  return v.at(0);
+}
+
+void load_joint(const PartApp &app, int jidx, Joint &joint, int tidx) {
+  const ExpParam &ep = app.m_exp_param;
+  if (jidx < 0 || jidx >= (int)app.m_part_conf.joint.size()) fail("load_joint: joint index out of range");
+  if (ep.spatial_dir.empty() || !dir_exists(ep.spatial_dir)) fail("spatial_dir does not exist: " + ep.spatial_dir);
+  const int child = app.m_part_conf.joint[jidx].child_idx, parent = app.m_part_conf.joint[jidx].parent_idx;
+  const std::string stem = ep.spatial_dir + "/joint_" + std::to_string(child) + "_" + std::to_string(parent);
+  std::string file = stem + (tidx > -1 ? "_tidx_" + std::to_string(tidx) : "") + ".mat";
+  if (!file_exists(file)) file = stem + ".mat";  // "Empty joint mixture component" fallback, learnparam.cpp:113-117
+  std::vector<mat5::Var> vars = mat5::load(file);
+  const double d_type = mat_scalar(vars, "type", file);
+  if ((int)mat_scalar(vars, "child_idx", file) != child || (int)mat_scalar(vars, "parent_idx", file) != parent)
+    fail(file + ": child_idx / parent_idx do not match part_conf (learnparam.cpp:133)");
+  const mat5::Var &oc = mat5::find(vars, "offset_c", file), &op = mat5::find(vars, "offset_p", file);
+  const mat5::Var &C = mat5::find(vars, "C", file);
+  if (oc.numel() != 2 || op.numel() != 2) fail(file + ": offsets must have two elements");
+  if (C.dims.size() != 2 || C.dims[0] != 2 || C.dims[1] != 2) fail(file + ": C must be 2x2");
+  joint.type = (int)d_type;
+  joint.mix_comp_id = tidx > -1 ? tidx : 0;
+  joint.child_idx = child;
+  joint.parent_idx = parent;
+  for (int k = 0; k < 2; ++k) {
+    joint.offset_c[k] = oc.at(k);
+    joint.offset_p[k] = op.at(k);
+  }
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 2; ++k) joint.C[i][k] = C.at(i * 2 + k);
+  if (joint.type == Joint::ROT_GAUSSIAN) {
+    joint.rot_sigma = mat_scalar(vars, "rot_sigma", file);
+    joint.rot_mean = mat_scalar(vars, "rot_mean", file);
+  }
+}
+
+void loadJoints(const PartApp &app, std::vector<Joint> &joints, bool flip, int imgidx) {
+  const int nJoints = (int)app.m_part_conf.joint.size(), nParts = (int)app.m_part_conf.part.size();
+  joints.assign(nJoints, Joint());
+  std::vector<int> tidx(nJoints, -1);
+  // mixtures of pairwise terms (aux.cpp:76-94).  The reference spawns the MATLAB predictor here (predictFactors);
+  // this host reads its output file and fails if it is missing.
+  if (imgidx > -1 && nJoints > 0 && app.m_part_conf.joint[0].num_joint_types > 1) {
+    const std::string file = app.m_exp_param.pred_data_test_dir + "/testlist_pred_pwise_imgidx_" + std::to_string(imgidx) + ".mat";
+    if (!file_exists(file))
+      fail("poselet-conditioned joints need " + file + " (written by the MATLAB predictor, objectdetect_icps.cpp:608-625)");
+    std::vector<mat5::Var> vars = mat5::load(file);
+    const mat5::Var &cl = mat5::find(vars, "clusidx_test", file);
+    if ((int)cl.numel() < nJoints) fail(file + ": clusidx_test is shorter than the joint list");
+    for (int j = 0; j < nJoints; ++j) tidx[j] = (int)cl.at(j);
+  }
+  for (int j = 0; j < nJoints; ++j) {
+    load_joint(app, j, joints[j], tidx[j]);
+    if (flip) {  // aux.cpp:102-119, done by the library's ps_flip_joint
+      ps_joint pj = to_ps_joints(std::vector<Joint>(1, joints[j]))[0];
+      ps_flip_joint(&pj);
+      for (int k = 0; k < 2; ++k) {
+        joints[j].offset_c[k] = pj.offset_c[k];
+        joints[j].offset_p[k] = pj.offset_p[k];
+      }
+      joints[j].C[0][0] = pj.C[0]; joints[j].C[0][1] = pj.C[1]; joints[j].C[1][0] = pj.C[2]; joints[j].C[1][1] = pj.C[3];
+      joints[j].rot_mean = pj.rot_mean;
+    }
+    joints[j].parent_idx--;  // part ids -> indices (aux.cpp:123-124)
+    joints[j].child_idx--;
+    if (joints[j].child_idx < 0 || joints[j].child_idx >= nParts || joints[j].parent_idx < 0 || joints[j].parent_idx >= nParts)
+      fail("joint refers to a part that does not exist (aux.cpp:126-127)");
+    if (nJoints != nParts - 1) fail("need exactly num_parts-1 joints (aux.cpp:129)");
+    const double (*C)[2] = joints[j].C;
+    joints[j].detC = C[0][0] * C[1][1] - C[1][0] * C[0][1];
+    if (!(joints[j].detC > 0)) fail("joint covariance must have a positive determinant (aux.cpp:133)");
+    joints[j].invC[0][0] = C[1][1] / joints[j].detC; joints[j].invC[0][1] = -C[0][1] / joints[j].detC;
+    joints[j].invC[1][0] = -C[1][0] / joints[j].detC; joints[j].invC[1][1] = C[0][0] / joints[j].detC;
+  }
+}
+
+// ---- inference ---------------------------------------------------------------------------------------------------------
+
+void computeRotJointMarginal(const ExpParam &ep, FloatGrid3 &child, FloatGrid3 &parent, const double offset_c_10[2],
+                             const double offset_p_01[2], const double C[2][2], double rot_mean, double rot_sigma,
+                             double scale, bool bIsSparse) {
+  PartApp app;
+  app.m_exp_param = ep;
+  app.m_part_conf.part.resize(2);
+  app.m_part_conf.part[0].is_root = true;
+  if (child.R != (int)ep.num_rotation_steps) fail("computeRotJointMarginal: rotation count mismatch (findrot.cpp:311)");
+  ps_ctx *ctx = get_ctx(app, child.H, child.W, 0, false);
+  parent = FloatGrid3(child.R, child.H, child.W);
+  const double Cf[4] = {C[0][0], C[0][1], C[1][0], C[1][1]};
+  check(ctx, ps_message(ctx, child.data(), parent.data(), PS_MEM_HOST, offset_c_10, offset_p_01, Cf, rot_mean, rot_sigma,
+                        scale, bIsSparse ? 1 : 0), "ps_message");
+}
+
+void computeRootPosteriorRot(const PartApp &app, std::vector<std::vector<FloatGrid3> > &log_part_detections,
+                             FloatGrid3 &root_part_posterior, int rootpart_idx, std::vector<Joint> joints, bool flip,
+                             bool bIsSparse, int imgidx, std::vector<std::vector<PartHyp> > &best_part_hyp,
+                             bool bSaveMarginals) {
+  const int P = (int)app.m_part_conf.part.size(), S = (int)app.m_exp_param.num_scale_steps;
+  if ((int)log_part_detections.size() != P || (int)log_part_detections[0].size() != S)
+    fail("computeRootPosteriorRot: log_part_detections must be [parts][scales] (findrot.cpp:490-492)");
+  const int H = log_part_detections[0][0].H, W = log_part_detections[0][0].W;
+  ps_ctx *ctx = get_ctx(app, H, W, rootpart_idx, bSaveMarginals);
+  std::vector<ps_joint> pj = to_ps_joints(joints);
+  check(ctx, ps_set_joints(ctx, pj.data(), (int)pj.size()), "ps_set_joints");
+  for (int p = 0; p < P; ++p)
+    for (int s = 0; s < S; ++s)
+      check(ctx, ps_set_unary(ctx, p, s, log_part_detections[p][s].data(), PS_MEM_HOST, 0), "ps_set_unary");
+  check(ctx, ps_infer(ctx, (bIsSparse ? PS_INFER_SPARSE : 0) | PS_INFER_LOCAL_MAX), "ps_infer");
+  collect_results(app, ctx, root_part_posterior, best_part_hyp, H, W);
+  for (int p = 0; p < P; ++p)  // the reference masks its argument in place (findrot.cpp:509-551)
+    for (int s = 0; s < S; ++s)
+      check(ctx, ps_get_unary(ctx, p, s, log_part_detections[p][s].data(), PS_MEM_HOST), "ps_get_unary");
+  if (bSaveMarginals) save_marginals(app, ctx, imgidx, flip, H, W);
+}
+
+void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, HypothesisList &hypothesis_list,
+                              const std::string &qsPartMarginalsDir, const std::string &qsScoreGridDir,
+                              const std::string &qsImgName) {
+  const ExpParam &ep = app.m_exp_param;
+  const int P = (int)app.m_part_conf.part.size(), S = (int)ep.num_scale_steps, R = (int)ep.num_rotation_steps;
+  (void)qsScoreGridDir;
+  if (ep.pred_unary_rot || ep.pred_unary_pos || ep.use_dpm_torso || ep.use_dpm_head || ep.use_dpm_unary)
+    fail("pred_unary_* / use_dpm_* need the MATLAB predictors of the reference (objectdetect_icps.cpp:608-625); "
+         "this host does not emulate them");
+  if (ep.interpolate) fail("interpolate: true (TM_BILINEAR score-grid mapping) is not implemented in this host");
+  int W = 0, H = 0;
+  image_size(qsImgName, W, H);  // findrot.cpp:752-760
+  std::vector<Joint> joints;
+  loadJoints(app, joints, flip, imgidx);
+  for (const Joint &j : joints)
+    if (j.type != Joint::ROT_GAUSSIAN) fail("only ROT_GAUSSIAN joints are supported (findrot.cpp:766)");
+  const int rootpart_idx = app.m_rootpart_idx;
+  if (rootpart_idx < 0) fail("root part not found (findrot.cpp:831)");
+  const bool bSaveMarginals = ep.save_part_marginals;
+  ps_ctx *ctx = get_ctx(app, H, W, rootpart_idx, bSaveMarginals);
+  std::vector<ps_joint> pj = to_ps_joints(joints);
+  check(ctx, ps_set_joints(ctx, pj.data(), (int)pj.size()), "ps_set_joints");
+
+  // loadScoreGrid (partapp.cpp:830-903) + unary prep (findrot.cpp:834-845), on the device
+  std::vector<float> cells;
+  std::vector<double> Tig((size_t)R * 9);
+  for (int p = 0; p < P; ++p) {
+    if (!app.m_part_conf.part[p].is_detect) continue;
+    const std::string file = app.getScoreGridFileName(imgidx, p, flip);
+    std::vector<mat5::Var> vars = mat5::load(file);
+    const mat5::Var &cg = mat5::find(vars, "cell_scoregrid", file);
+    const mat5::Var &Ti2 = mat5::find(vars, "transform_Ti2", file), &T2g = mat5::find(vars, "transform_T2g", file);
+    if (cg.cls != mat5::mxCELL || cg.dims.size() != 2 || (int)cg.dims[0] != S || (int)cg.dims[1] != R)
+      fail(file + ": cell_scoregrid must be a [scales][rotations] cell array (findrot.cpp:811-812)");
+    if (Ti2.numel() != (size_t)S * R * 9 || T2g.numel() != (size_t)S * R * 9) fail(file + ": transforms must be [S][R][3][3]");
+    for (int s = 0; s < S; ++s) {
+      const mat5::Var &c0 = cg.cells[(size_t)s * R];
+      const size_t gh = c0.dims.at(0), gw = c0.dims.at(1);
+      cells.assign((size_t)R * gh * gw, 0.0f);
+      for (int r = 0; r < R; ++r) {
+        const mat5::Var &c = cg.cells[(size_t)s * R + r];
+        if (c.dims.size() != 2 || c.dims[0] != gh || c.dims[1] != gw) fail(file + ": score grids of one scale differ in size");
+        for (size_t i = 0; i < gh * gw; ++i) cells[(size_t)r * gh * gw + i] = (float)c.at(i);
+        // Tig = prod(Ti2, T2g) in double (partapp.cpp:881-887; array_to_matrix widens the floats)
+        const size_t o = ((size_t)s * R + r) * 9;
+        for (int i = 0; i < 3; ++i)
+          for (int k = 0; k < 3; ++k) {
+            double t = 0;
+            for (int l = 0; l < 3; ++l) t += Ti2.at(o + i * 3 + l) * T2g.at(o + l * 3 + k);
+            Tig[(size_t)r * 9 + i * 3 + k] = t;
+          }
+      }
+      check(ctx, ps_set_unary_compact(ctx, p, s, cells.data(), (int)gh, (int)gw, Tig.data(), PS_MEM_HOST), "ps_set_unary_compact");
+      check(ctx, ps_synchronize(ctx), "ps_synchronize");  // `cells` is reused
+    }
+  }
+
+  // torso position prior (findrot.cpp:945-948, icps.cpp:137-191; params from <class_dir>/torso_pos_prior.mat :41-42)
+  if (ep.use_torso_pos_prior) {
+    const std::string file = ep.class_dir + "/torso_pos_prior.mat";
+    std::vector<mat5::Var> vars = mat5::load(file);
+    const mat5::Var &pr = mat5::find(vars, "params", file);
+    if (pr.numel() < 4) fail(file + ": params must hold mu_x, mu_y, var_x, var_y");
+    std::vector<float> table((size_t)H * W);
+    ps_torso_prior_table(H, W, pr.at(0), pr.at(1), pr.at(2), pr.at(3), ep.torso_pos_prior_weight, table.data());
+    check(ctx, ps_add_unary_table(ctx, rootpart_idx, table.data(), 2, 1.0f), "ps_add_unary_table");
+  }
+
+  int flags = PS_INFER_SPARSE | PS_INFER_ROOT_HYPS | PS_INFER_KEEP_UNARIES;
+  if (ep.save_part_marginals_local_max) flags |= PS_INFER_LOCAL_MAX;
+  if (ep.use_pairwise) check(ctx, ps_infer(ctx, flags), "ps_infer");
+  else check(ctx, ps_max_states(ctx, flags & PS_INFER_LOCAL_MAX), "ps_max_states");
+
+  make_dirs(qsPartMarginalsDir);
+  std::vector<float> best_conf((size_t)P * PS_HYP_VEC);
+  check(ctx, ps_get_best_conf(ctx, best_conf.data()), "ps_get_best_conf");
+  {  // findrot.cpp:1005-1011
+    mat5::Writer w(qsPartMarginalsDir + "/pose_est_imgidx" + pad_zeros(imgidx, 4) + ".mat");
+    w.put("best_conf", best_conf.data(), {(size_t)P, (size_t)PS_HYP_VEC});
+  }
+  if (ep.save_part_marginals_local_max) {  // findrot.cpp:1015-1034
+    mat5::Writer w(qsPartMarginalsDir + "/part_post_imgidx" + pad_zeros(imgidx, 4) + ".mat");
+    const int cap = (int)ep.roi_save_num_samples + 1;
+    std::vector<float> rows((size_t)cap * PS_HYP_VEC);
+    for (int p = 0; p < P; ++p) {
+      int n = 0;
+      check(ctx, ps_get_part_hyps(ctx, p, rows.data(), cap, &n), "ps_get_part_hyps");
+      w.put("part" + std::to_string(p), rows.data(), {(size_t)n, (size_t)PS_HYP_VEC});
+    }
+  }
+  if (bSaveMarginals && ep.use_pairwise) save_marginals(app, ctx, imgidx, flip, H, W);
+
+  // root hypotheses (findrot.cpp:1037-1048)
+  hypothesis_list.hyp.clear();
+  if (ep.use_pairwise) {
+    std::vector<float> rows(1000 * 4);
+    int n = 0;
+    check(ctx, ps_get_root_hyps(ctx, rows.data(), 1000, &n), "ps_get_root_hyps");
+    for (int i = 0; i < n; ++i) {
+      ObjectHypothesis h;
+      h.scale = (float)scale_from_index(ep, (int)rows[4 * i]);
+      h.x = (float)(int)(rows[4 * i + 1] + app.m_window_param.bbox_offset_x);
+      h.y = (float)(int)(rows[4 * i + 2] + app.m_window_param.bbox_offset_y);
+      h.score = rows[4 * i + 3];
+      h.flip = flip;
+      hypothesis_list.hyp.push_back(h);
+    }
+  }
+}
+
+void findObjectDataset(const PartApp &app, int firstidx, int lastidx) {
+  const ExpParam &ep = app.m_exp_param;
+  if (firstidx < 0 || firstidx > (int)app.m_test_annolist.size() || lastidx >= (int)app.m_test_annolist.size())
+    fail("image index range outside the test list (aux.cpp:328-329)");
+  const std::string qsHypDir = ep.log_dir + "/" + ep.log_subdir + "/object_hyp";
+  const std::string qsPartMarginalsDir = ep.log_dir + "/" + ep.log_subdir + "/part_marginals";
+  make_dirs(qsHypDir);
+  make_dirs(qsPartMarginalsDir);
+  for (int imgidx = firstidx; imgidx <= lastidx; ++imgidx) {
+    const int flip_count = ep.flip_orientation ? 2 : 1;
+    for (int flip = 0; flip < flip_count; ++flip) {
+      HypothesisList hypothesis_list;
+      findObjectImageRotJoints(app, imgidx, flip != 0, hypothesis_list, qsPartMarginalsDir, ep.scoregrid_dir,
+                               app.m_test_annolist[imgidx]);
+      const std::string file = qsHypDir + getObjectHypFilename(imgidx, flip != 0);
+      std::ofstream f(file.c_str(), std::ios::binary);
+      if (!f) fail("cannot write " + file);
+      const std::string bytes = hypothesis_list.SerializeAsString();
+      f.write(bytes.data(), (std::streamsize)bytes.size());
+    }
+  }
+}
+
+}  // namespace object_detect

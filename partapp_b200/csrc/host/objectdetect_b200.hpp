@@ -1,0 +1,151 @@
+// objectdetect_b200.hpp -- C++ host side of the `--find_obj` path, mirroring the reference's interface
+// (src/libs/libPictStruct/objectdetect.h, src/libs/libPartApp/partapp.h) on top of the C ABI of include/psinfer.h.
+//
+// Same names, argument meaning and file layout as the reference; differences are listed where they occur:
+//   * grids are `FloatGrid3` = contiguous C-order fp32 [rotation][y][x] (boost::multi_array<float,3> there);
+//   * `assert`s become std::runtime_error;
+//   * nothing is computed on the CPU: every grid operation goes through libpsinfer.so.
+#pragma once
+
+#include <cmath>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/psinfer.h"
+
+namespace object_detect {
+
+struct FloatGrid3 {
+  int R = 0, H = 0, W = 0;
+  std::vector<float> v;
+  FloatGrid3() {}
+  FloatGrid3(int r, int h, int w) : R(r), H(h), W(w), v((size_t)r * h * w, 0.0f) {}
+  float *data() { return v.data(); }
+  const float *data() const { return v.data(); }
+  size_t num_elements() const { return v.size(); }
+};
+
+// The ExpParam fields this path reads (libPartApp/ExpParam.proto); defaults are the proto's.
+struct ExpParam {
+  std::vector<std::string> test_dataset;
+  std::string log_dir, log_subdir, class_dir, scoregrid_dir, spatial_dir, part_conf, pred_data_test_dir;
+  float min_object_scale = 1, max_object_scale = 1;
+  unsigned num_scale_steps = 1;
+  float min_part_rotation = -180, max_part_rotation = 180;
+  unsigned num_rotation_steps = 48;
+  bool flip_orientation = false;
+  int num_pose_samples = 0;
+  float strip_border_detections = 0;
+  float roi_save_num_samples = 1000;
+  bool use_pairwise = true, save_part_marginals = false, save_part_marginals_local_max = false;
+  bool save_part_detections_local_max = false, interpolate = false, force_recompute_scores = true;
+  bool use_torso_pos_prior = false;
+  float torso_pos_prior_weight = 1;
+  // conditioning options that need MATLAB-side predictors (objectdetect_icps.cpp:608-625): rejected, not ignored
+  bool pred_unary_rot = false, pred_unary_pos = false, use_dpm_torso = false, use_dpm_head = false, use_dpm_unary = false;
+};
+
+struct PartDef {   // libPartDetect/PartConfig.proto PartDef
+  int part_id = 0;
+  bool is_root = false, is_detect = true, is_upright = false;
+};
+struct JointDef {  // PartConfig.proto Joint
+  int child_idx = 0, parent_idx = 0;
+  std::string type = "Gaussian";
+  unsigned num_joint_types = 1;
+};
+struct PartConfig {
+  std::vector<PartDef> part;
+  std::vector<JointDef> joint;
+};
+struct PartWindowParam {  // only the fields findObjectImageRotJoints reads (findrot.cpp:1044-1045)
+  double bbox_offset_x = 0, bbox_offset_y = 0;
+};
+
+// libPartApp/partapp.h PartApp, reduced to what --find_obj touches
+struct PartApp {
+  ExpParam m_exp_param;
+  PartConfig m_part_conf;
+  PartWindowParam m_window_param;
+  std::vector<std::string> m_test_annolist;  // image file names (AnnotationList::imageName())
+  int m_rootpart_idx = -1;
+  // PartApp::init (partapp.cpp:141) + init_setpath (:294): parse the expopt, resolve relative paths against it,
+  // fill default directories, load part_conf, window_param.txt (if present) and the test image list.
+  void init(const std::string &expopt_file);
+  // partapp.cpp:792-799
+  std::string getScoreGridFileName(int imgidx, int pidx, bool flip) const;
+};
+
+// objectdetect.h:54-86
+struct Joint {
+  enum { POS_GAUSSIAN = 1, ROT_GAUSSIAN = 2 };
+  int type = 0, mix_comp_id = 0, child_idx = 0, parent_idx = 0;
+  double offset_c[2] = {0, 0}, offset_p[2] = {0, 0};
+  double C[2][2] = {{0, 0}, {0, 0}};
+  double rot_mean = 0, rot_sigma = 0, detC = 0;
+  double invC[2][2] = {{0, 0}, {0, 0}};
+};
+
+// objectdetect.h:88-195
+struct PartHyp {
+  int m_imgidx = -1, m_scaleidx = -1, m_rotidx = -1, m_x = -1, m_y = -1;
+  float m_score = -1e6f, m_scale = 0, m_rot = 0;
+  static unsigned vectSize() { return 7; }
+  void toVect(float *r) const {
+    r[0] = (float)m_scaleidx; r[1] = m_scale; r[2] = (float)m_rotidx; r[3] = m_rot;
+    r[4] = (float)m_x; r[5] = (float)m_y; r[6] = m_score;
+  }
+  void fromVect(const float *r) {
+    m_scaleidx = (int)r[0]; m_scale = r[1]; m_rotidx = (int)r[2]; m_rot = r[3];
+    m_x = (int)r[4]; m_y = (int)r[5]; m_score = r[6];
+  }
+};
+
+// HypothesisList.proto
+struct ObjectHypothesis {
+  float x = 0, y = 0, scale = 0, score = 0;
+  bool flip = false;
+};
+struct HypothesisList {
+  std::vector<ObjectHypothesis> hyp;
+  std::string SerializeAsString() const;           // proto2 wire format
+  static HypothesisList Parse(const std::string &);  // for tests
+};
+
+// partapp_aux.hpp
+double rot_from_index(const ExpParam &, int rotidx);
+double scale_from_index(const ExpParam &, int scaleidx);
+
+// objectdetect_learnparam.cpp:92-179 / objectdetect_aux.cpp:54-141
+void load_joint(const PartApp &, int jidx, Joint &, int tidx = -1);
+void loadJoints(const PartApp &, std::vector<Joint> &, bool flip, int imgidx = -1);
+
+// objectdetect_findrot.cpp:292-456
+void computeRotJointMarginal(const ExpParam &, FloatGrid3 &log_prob_child, FloatGrid3 &log_prob_parent,
+                             const double offset_c_10[2], const double offset_p_01[2], const double C[2][2],
+                             double rot_mean, double rot_sigma, double scale, bool bIsSparse);
+
+// objectdetect_findrot.cpp:470-727
+void computeRootPosteriorRot(const PartApp &, std::vector<std::vector<FloatGrid3> > &log_part_detections,
+                             FloatGrid3 &root_part_posterior, int rootpart_idx, std::vector<Joint> joints, bool flip,
+                             bool bIsSparse, int imgidx, std::vector<std::vector<PartHyp> > &best_part_hyp,
+                             bool bSaveMarginals);
+
+// objectdetect_findrot.cpp:729-1058.  Reads the compact score grids of the image straight into the device
+// (PartApp::loadScoreGrid, partapp.cpp:830-903, runs as ps_set_unary_compact) and writes the reference's outputs.
+void findObjectImageRotJoints(const PartApp &, int imgidx, bool flip, HypothesisList &hypothesis_list,
+                              const std::string &qsPartMarginalsDir, const std::string &qsScoreGridDir,
+                              const std::string &qsImgName);
+
+// objectdetect_aux.cpp:322-406
+void findObjectDataset(const PartApp &, int firstidx, int lastidx);
+
+// aux.cpp:311-320
+std::string getObjectHypFilename(int imgidx, bool flip);
+
+// image width/height from a PNG or JPEG header (the reference loads the whole image for this, findrot.cpp:752-760)
+void image_size(const std::string &file, int &width, int &height);
+
+}  // namespace object_detect
