@@ -29,13 +29,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(R=24, S=1, H=600, W=400, P=10)
+# Other BASELINE.json configs, for manual runs only (--workload); the contract line is always configs[1].
+WORKLOADS = {"cfg2": dict(R=24, S=1, H=600, W=400, P=10),
+             "cfg4": dict(R=24, S=1, H=600, W=400, P=22),       # 22-part full model, joint types swapped per image
+             "cfg5": dict(R=48, S=5, H=1000, W=1000, P=10)}     # stress state space
 METRIC = "ps_inference_images_per_sec"
 UNIT = "images/s"
 
 
 def workload_config(parallelism, extra=None):
     cfg = {"workload": "configs[1]: synthetic LSP-shape image, 10-part tree (root 4), R=24 x S=1, 600x400 grid, "
-                       "generic full-covariance joints (sigma 4-16 px), stride-4 sparse unaries",
+                       "generic full-covariance joints (sigma 4-16 px), stride-4 sparse unaries"
+                       if (WORKLOAD["P"], WORKLOAD["R"], WORKLOAD["S"]) == (10, 24, 1) else
+                       "manual run of another BASELINE.json config (not the contract workload)",
            "R": WORKLOAD["R"], "S": WORKLOAD["S"], "H": WORKLOAD["H"], "W": WORKLOAD["W"], "P": WORKLOAD["P"],
            "parallelism": parallelism,
            "l2_policy": "inputs larger than L2: ~0.75 GB of grids touched per image vs 126 MB L2; distinct images per step"}
@@ -117,7 +123,8 @@ class ClockSampler:
 def make_inputs(n_images, first_index):
     from partapp_b200 import ExpParam, synth
     w = WORKLOAD
-    ep = ExpParam(num_rotation_steps=w["R"], num_scale_steps=w["S"])
+    ep = ExpParam(num_rotation_steps=w["R"], num_scale_steps=w["S"], min_object_scale=1.0 if w["S"] == 1 else 0.8,
+                  max_object_scale=1.0 if w["S"] == 1 else 1.2)
     pc = synth.part_conf(w["P"])
     joints = synth.make_joints(w["P"], seed=7)
     # the detector's own storage: compact grids + grid->image transforms (reference partapp.cpp:830-903)
@@ -154,7 +161,8 @@ def run_ours(args):
     ep, pc, joints, raws, Tig = make_inputs(B, first_index=rank * B)
     P, N = w["P"], w["R"] * w["H"] * w["W"]
     gh, gw = raws[0].shape[-2:]
-    NC = w["R"] * gh * gw  # compact cells per part
+    S = w["S"]
+    NC = w["R"] * gh * gw  # compact cells per (part, scale)
 
     n_ctx = args.streams
     streams = [torch.cuda.Stream() for _ in range(n_ctx)]
@@ -166,8 +174,13 @@ def run_ours(args):
         ctxs.append(c)
 
     # resident inputs: the compact classifier-score grids of B images in HBM, and the same in pinned host memory
-    dev_raw = [torch.from_numpy(r.reshape(P, NC)).cuda() for r in raws]
-    pin_raw = [torch.from_numpy(r.reshape(P, NC)).pin_memory() for r in raws]
+    dev_raw = [torch.from_numpy(r.reshape(P * S, NC)).cuda() for r in raws]
+    pin_raw = [torch.from_numpy(r.reshape(P * S, NC)).pin_memory() for r in raws]
+    # configs[3]: every image draws one of 8 types per joint (the whole joint is swapped, aux.cpp:76-99)
+    type_tables = None
+    if args.workload == "cfg4":
+        from partapp_b200 import synth as _s
+        type_tables = [_s.make_joints(P, seed=7, type_id=t) for t in range(8)]
     results = np.zeros((B, P, 7), np.float32)
 
     def step(device_resident):
@@ -179,12 +192,16 @@ def run_ours(args):
                 j, cj = pending.pop(0)
                 results[j] = cj.best_conf()
             src = dev_raw[i] if device_resident else pin_raw[i]
+            if type_tables is not None:
+                rng = np.random.default_rng(rank * B + i)
+                c.set_joints([type_tables[int(rng.integers(0, 8))][j] for j in range(P - 1)])
             for p in range(P):
-                ptr = src[p].data_ptr()
-                if device_resident:
-                    c.set_unary_compact(p, 0, (gh, gw), Tig, device_ptr=ptr)
-                else:
-                    c.set_unary_compact_pinned(p, 0, ptr, gh, gw, Tig)
+                for sc in range(S):
+                    ptr = src[p * S + sc].data_ptr()
+                    if device_resident:
+                        c.set_unary_compact(p, sc, (gh, gw), Tig, device_ptr=ptr)
+                    else:
+                        c.set_unary_compact_pinned(p, sc, ptr, gh, gw, Tig)
             c.infer_async(sparse=True)
             pending.append((i, c))
         for j, cj in pending:
@@ -246,7 +263,8 @@ def run_ours(args):
         c.profile_enable(True)
         for i in range(min(B, 2)):
             for p in range(P):
-                c.set_unary_compact(p, 0, (gh, gw), Tig, device_ptr=dev_raw[i][p].data_ptr())
+                for sc in range(S):
+                    c.set_unary_compact(p, sc, (gh, gw), Tig, device_ptr=dev_raw[i][p * S + sc].data_ptr())
             c.infer_async(sparse=True)
             c.best_conf()
         prof = c.profile_read()
@@ -304,7 +322,7 @@ def run_ours(args):
                "config": workload_config("images sharded over %d GPU(s), %d images/GPU/step, %d stream(s)/GPU, no collective"
                                          % (world, B, n_ctx)),
                "clocks": clocks,
-               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(B * P * NC * 4),
+               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(B * P * S * NC * 4),
                        "d2h_bytes_per_step": int(B * P * 7 * 4), "steps": e2e_steps,
                        "ms_per_step": round(ms_e2e / e2e_steps, 3)},
                "gpu_launches": int(launches),
@@ -392,6 +410,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--images", type=int, default=4, help="images per GPU per step")
     ap.add_argument("--streams", type=int, default=2, help="contexts/streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -402,6 +421,7 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     args = ap.parse_args()
+    WORKLOAD.update(WORKLOADS[args.workload])
     if args.impl == "reference":
         run_reference(args)
     else:

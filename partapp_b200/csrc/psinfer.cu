@@ -115,8 +115,12 @@ struct ps_ctx {
   std::vector<ps_joint> joints;
   std::vector<Node> nodes;
   // plans[(joint*2 + dir) * S + scale], dir 0 = upward, 1 = downward
-  std::vector<std::unique_ptr<DevPlan>> plans;
-  std::map<std::string, std::unique_ptr<DevPlan>> adhoc_plans;  // ps_message cache
+  std::vector<std::shared_ptr<DevPlan>> plans;
+  // Plans are cached by the bytes of (offset_in, offset_out, C, rot_mean, rot_sigma, scale): the poselet-conditioned
+  // model swaps whole joints per image from a finite per-joint table (aux.cpp:76-99), so ps_set_joints is a cache hit
+  // after the first image that used a given type.  ps_message shares the cache.
+  std::map<std::string, std::shared_ptr<DevPlan>> plan_cache;
+  long long plan_cache_hits = 0, plan_cache_misses = 0;
 
   // results.  ps_infer / ps_max_states only enqueue device work; the host part of the readout (decode of the
   // argmax keys, local-maximum selection) runs in finish_result() when a getter needs it.
@@ -230,6 +234,32 @@ int upload_plan(ps_ctx *c, DevPlan &dp) {
     PS_CUDA(c, dp.mats.alloc(sizeof m));
     PS_CUDA(c, cudaMemcpy(dp.mats.p, m, sizeof m, cudaMemcpyHostToDevice));
   }
+  return PS_OK;
+}
+
+int get_plan(ps_ctx *c, const double off_in[2], const double off_out[2], const double C[4], double rot_mean,
+             double rot_sigma, double scale, std::shared_ptr<DevPlan> &out) {
+  double keyv[11] = {off_in[0], off_in[1], off_out[0], off_out[1], C[0], C[1], C[2], C[3], rot_mean, rot_sigma, scale};
+  std::string key((const char *)keyv, sizeof keyv);
+  auto it = c->plan_cache.find(key);
+  if (it != c->plan_cache.end()) {
+    ++c->plan_cache_hits;
+    out = it->second;
+    return PS_OK;
+  }
+  ++c->plan_cache_misses;
+  std::shared_ptr<DevPlan> dp(new DevPlan);
+  dp->host = psg::plan_message(grid_of(c), off_in, off_out, C, rot_mean, rot_sigma, scale);
+  if (!dp->host.error.empty()) return c->fail(PS_ERR_INVALID, "%s", dp->host.error.c_str());
+  int rc = upload_plan(c, *dp);
+  if (rc) return rc;
+  if (c->plan_cache.size() >= 2048) {  // drop what no joint set references any more
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto i = c->plan_cache.begin(); i != c->plan_cache.end();)
+      i = i->second.use_count() == 1 ? c->plan_cache.erase(i) : std::next(i);
+  }
+  c->plan_cache.emplace(key, dp);
+  out = dp;
   return PS_OK;
 }
 
@@ -918,22 +948,22 @@ int ps_set_joints(ps_ctx *c, const ps_joint *joints, int nj) {
   if ((int)nodes[c->root].children.size() > psk::kMaxRootChildren)
     return c->fail(PS_ERR_UNSUPPORTED, "root has more than %d children", psk::kMaxRootChildren);
 
-  psg::Grid g = grid_of(c);
-  std::vector<std::unique_ptr<DevPlan>> plans((size_t)nj * 2 * c->S);
+  std::vector<std::shared_ptr<DevPlan>> plans((size_t)nj * 2 * c->S);
   size_t need = c->N;
   for (int j = 0; j < nj; ++j)
     for (int dir = 0; dir < 2; ++dir)
       for (int s = 0; s < c->S; ++s) {
         const ps_joint &q = joints[j];
-        std::unique_ptr<DevPlan> dp(new DevPlan);
+        std::shared_ptr<DevPlan> dp;
         // upward: (offset_c, offset_p, +rot_mean) findrot.cpp:630-635; downward: (offset_p, offset_c, -rot_mean) :174-179
-        dp->host = dir == 0 ? psg::plan_message(g, q.offset_c, q.offset_p, q.C, q.rot_mean, q.rot_sigma, scale_of(c->cfg, s))
-                            : psg::plan_message(g, q.offset_p, q.offset_c, q.C, -q.rot_mean, q.rot_sigma, scale_of(c->cfg, s));
-        if (!dp->host.error.empty()) return c->fail(PS_ERR_INVALID, "joint %d: %s", j, dp->host.error.c_str());
-        int rc = upload_plan(c, *dp);
-        if (rc) return rc;
+        int rc = dir == 0 ? get_plan(c, q.offset_c, q.offset_p, q.C, q.rot_mean, q.rot_sigma, scale_of(c->cfg, s), dp)
+                          : get_plan(c, q.offset_p, q.offset_c, q.C, -q.rot_mean, q.rot_sigma, scale_of(c->cfg, s), dp);
+        if (rc) {
+          std::string why = c->err;
+          return c->fail(rc, "joint %d: %s", j, why.c_str());
+        }
         need = std::max(need, plan_scratch_elems(c, *dp));
-        plans[((size_t)j * 2 + dir) * c->S + s] = std::move(dp);
+        plans[((size_t)j * 2 + dir) * c->S + s] = dp;
       }
   int rc = ensure_scratch(c, need);
   if (rc) return rc;
@@ -1366,19 +1396,10 @@ int ps_message(ps_ctx *c, const float *child, float *parent, int mem_kind, const
                const double off_out[2], const double C[4], double rot_mean, double rot_sigma, double scale, int sparse) {
   if (!c || !child || !parent || !off_in || !off_out || !C) return PS_ERR_INVALID;
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
-  double keyv[11] = {off_in[0], off_in[1], off_out[0], off_out[1], C[0], C[1], C[2], C[3], rot_mean, rot_sigma, scale};
-  std::string key((const char *)keyv, sizeof keyv);
-  auto it = c->adhoc_plans.find(key);
-  if (it == c->adhoc_plans.end()) {
-    std::unique_ptr<DevPlan> dp(new DevPlan);
-    dp->host = psg::plan_message(grid_of(c), off_in, off_out, C, rot_mean, rot_sigma, scale);
-    if (!dp->host.error.empty()) return c->fail(PS_ERR_INVALID, "%s", dp->host.error.c_str());
-    int rc = upload_plan(c, *dp);
-    if (rc) return rc;
-    if (c->adhoc_plans.size() > 64) c->adhoc_plans.clear();
-    it = c->adhoc_plans.emplace(key, std::move(dp)).first;
-  }
-  DevPlan &dp = *it->second;
+  std::shared_ptr<DevPlan> plan;
+  int prc = get_plan(c, off_in, off_out, C, rot_mean, rot_sigma, scale, plan);
+  if (prc) return prc;
+  DevPlan &dp = *plan;
   const float *din = child;
   float *dout = parent;
   if (mem_kind == PS_MEM_HOST) {

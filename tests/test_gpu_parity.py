@@ -414,3 +414,40 @@ def test_compact_ingest_collisions_last_writer_wins():
     with _ctx(ep, 2, H, W) as ctx:
         ctx.set_unary_compact(0, 0, cells, Tig)
         _cmp(ctx.get_unary(0, 0), want, "colliding scatter", max_ulp_frac=1e-5)
+
+
+# ---- BASELINE.json configs[3] / configs[4] shapes at test size ------------------------------------------------------
+
+def test_conditioned_model_swaps_joints_per_image():
+    """configs[3]: per image, every joint is one entry of a finite per-joint type table (aux.cpp:76-99)."""
+    ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=5)
+    P, H, W = 6, 36, 32
+    pc = synth.part_conf(P)
+    table = [synth.make_joints(P, seed=13, max_offset=6, sigma_range=(1.5, 3), type_id=t) for t in range(3)]
+    with PsContext(ep, pc, H, W) as ctx:
+        for img in range(4):
+            rng = np.random.default_rng(img)
+            joints = [table[int(rng.integers(0, 3))][j] for j in range(P - 1)]
+            un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, img))
+            want = oracle.infer(ep, pc, joints, un.copy(), sparse=True)
+            res = od.computeRootPosteriorRot(ctx, [[un[p, 0]] for p in range(P)], joints, True, write_back_masked=False)
+            assert np.array_equal(res.best_conf[:, :6], want["best_conf"][:, :6]), "image %d" % img
+            _cmp(ctx.marginal(2), want["marginals"][0, 2], "conditioned image %d" % img)
+
+
+def test_stress_shape_48_rotations_multiscale():
+    """configs[4] shape (R = 48, several scales) at a grid the oracle finishes in seconds."""
+    ep = ExpParam(num_rotation_steps=48, num_scale_steps=2, min_object_scale=0.8, max_object_scale=1.2,
+                  roi_save_num_samples=5)
+    P, H, W = 4, 56, 48
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 17))
+    joints = synth.make_joints(P, seed=3, max_offset=8, sigma_range=(1.5, 4))
+    pc = synth.part_conf(P)
+    want = oracle.infer(ep, pc, joints, un.copy(), sparse=True)
+    with PsContext(ep, pc, H, W, keep_all_scales=True) as ctx:
+        res = od.computeRootPosteriorRot(ctx, [[un[p, s] for s in range(2)] for p in range(P)], joints, True,
+                                         write_back_masked=False)
+        assert np.array_equal(res.best_conf[:, :6], want["best_conf"][:, :6])
+        for s in range(2):
+            _cmp(ctx.marginal(1, s), want["marginals"][s, 1], "R48 marginal scale %d" % s)
+        _cmp(res.root_part_posterior, want["root_post"], "R48 root posterior")

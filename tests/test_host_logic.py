@@ -78,3 +78,16 @@ def test_two_rank_shard_and_gather_gloo():
 def test_single_rank_loop_without_gather():
     res = dataset.find_object_dataset(_fake_infer, 2, 4)
     assert sorted(res) == [(2, False), (3, False), (4, False)]
+
+
+def test_pcp_rule():
+    from partapp_b200 import parteval
+    pp = parteval.PartParam(window_size_x=20, window_size_y=60, pos_offset_x=10, pos_offset_y=30)
+    gt = [0, 1.0, 11, -7.5, 100, 200, 0.0]
+    assert parteval.is_gt_match(gt, gt, pp)
+    near = [0, 1.0, 11, -7.5, 110, 210, 0.0]          # 14 px off both endpoints, threshold 0.5 * 60 = 30
+    far = [0, 1.0, 11, -7.5, 140, 200, 0.0]           # 40 px off
+    rot = [0, 1.0, 17, 82.5, 100, 200, 0.0]           # a quarter turn moves the endpoints by ~42 px
+    assert parteval.is_gt_match(gt, near, pp) and not parteval.is_gt_match(gt, far, pp)
+    assert not parteval.is_gt_match(gt, rot, pp)
+    assert parteval.pcp_identical([gt, gt], [near, far], [pp]) == 0.5
