@@ -77,7 +77,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -239,12 +239,12 @@ def run_ours(args):
         for c in ctxs:
             c.close()
         return
+    # clocks are sampled every 50 ms from the first warm-up step to the end of the e2e region (GPU under load throughout)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step(True)
     launches0 = sum(c.launch_count() for c in ctxs)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ms = timed(args.steps, True)
-    clocks = sampler.stop() if sampler else None
     launches = sum(c.launch_count() for c in ctxs) - launches0
     value = world * B * args.steps / (ms / 1e3)
 
@@ -254,6 +254,7 @@ def run_ours(args):
         step(False)
     ms_e2e = timed(e2e_steps, False)
     e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+    clocks = sampler.stop() if sampler else None
 
     out = None
     if rank == 0:
@@ -407,13 +408,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--images", type=int, default=4, help="images per GPU per step")
     ap.add_argument("--streams", type=int, default=2, help="contexts/streams per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling run under ncu: honour a short warmup, skip e2e / instrumented pass / CPU baseline "
