@@ -1615,6 +1615,71 @@ __global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4
   if (a.amax0) block_key_max_to(key0, a.amax0);
 }
 
+
+// ---- message stage 3 v3: lean variant of k_epilogue2<false> for the common case ------------------------------------
+// Preconditions checked by the launcher: the translation is a pure shift (shift_xy), W % 4 == 0 and every grid is
+// 16-byte aligned.  32-bit index arithmetic (R*H*W < 2^31 is enforced by ps_create), no per-cell branches: the four
+// cells are evaluated unconditionally on clamped addresses and invalid ones are replaced by LOG_ZERO at the end.
+// ncu r01c: k_epilogue2 spent 98 warp-instructions per cell, a third of them IMAD/ISETP/BRA bookkeeping.
+__global__ void __launch_bounds__(256) k_epilogue3(EpiArgs a, int XG) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  unsigned long long key0 = 0;
+  if (it < XG * a.H) {
+    const int y = it / XG, x0 = (it - y * XG) * 4;
+    const int HW = a.H * a.W;
+    const int cell0 = r * HW + y * a.W + x0;
+    const float M = dec_f(*a.max_enc);
+    const int dx = a.shift_xy[2 * r], ys = y + a.shift_xy[2 * r + 1];
+    const bool rowok = (unsigned)ys < (unsigned)a.H;
+    const float *srow = a.src + (r * HW + (rowok ? ys : 0) * a.W);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xs = x0 + j + dx;
+      const bool ok = rowok && (unsigned)xs < (unsigned)a.W;
+      const float d = __ldg(srow + (ok ? xs : 0));
+      const float l = __fadd_rn(log_f64(d), M);
+      v[j] = ok ? l : kLogZero;
+    }
+    if (a.out0) {
+      float o[4] = {v[0], v[1], v[2], v[3]};
+      if (a.acc0) {
+        const float4 t = *reinterpret_cast<const float4 *>(a.acc0 + cell0);
+        o[0] = __fadd_rn(t.x, o[0]); o[1] = __fadd_rn(t.y, o[1]); o[2] = __fadd_rn(t.z, o[2]); o[3] = __fadd_rn(t.w, o[3]);
+      }
+      if (a.add0) {
+        const float4 t = *reinterpret_cast<const float4 *>(a.add0 + cell0);
+        o[0] = __fadd_rn(o[0], t.x); o[1] = __fadd_rn(o[1], t.y); o[2] = __fadd_rn(o[2], t.z); o[3] = __fadd_rn(o[3], t.w);
+      }
+      *reinterpret_cast<float4 *>(a.out0 + cell0) = make_float4(o[0], o[1], o[2], o[3]);
+      m0 = fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3]));
+      if (a.amax0) {
+        // first maximum of the four (ascending index, strict '>'), then one key
+        float bv = o[0];
+        int bj = 0;
+        if (o[1] > bv) { bv = o[1]; bj = 1; }
+        if (o[2] > bv) { bv = o[2]; bj = 2; }
+        if (o[3] > bv) { bv = o[3]; bj = 3; }
+        if (bv == bv) key0 = argmax_key(bv, (unsigned)(cell0 + bj));
+      }
+    }
+    if (a.out1) {
+      const float4 t = *reinterpret_cast<const float4 *>(a.add1 + cell0);
+      const float4 o = make_float4(__fadd_rn(t.x, v[0]), __fadd_rn(t.y, v[1]), __fadd_rn(t.z, v[2]), __fadd_rn(t.w, v[3]));
+      *reinterpret_cast<float4 *>(a.out1 + cell0) = o;
+      m1 = fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w));
+    }
+  }
+  if (a.max0) block_max_to(m0, a.max0);
+  if (a.max1) {
+    __syncthreads();
+    block_max_to(m1, a.max1);
+  }
+  if (a.amax0) block_key_max_to(key0, a.amax0);
+}
+
 // ---- root: combine the stored upward messages (findrot.cpp:637-654 and :169) -----------------------------
 //   post[root]  = (((m_0 + m_1) + ...) + m_{n-1}) + unary[root]
 //   fr_j        = (sum over i != j, ascending, starting from 0) + unary[root]     (written over m_j)
@@ -1788,6 +1853,93 @@ __global__ void __launch_bounds__(256) k_local_max(const float *__restrict__ g, 
       cd.score = c;
       cd.key = (unsigned)(((size_t)s * W + x) * H + y);
       out[slot] = cd;
+    }
+  }
+}
+
+
+// ---- top-K of the local-maximum candidates on the device (objectdetect_aux.cpp:233-258) -----------------------------
+// The reference keeps the K highest-scoring candidates (std::sort on the fp32 score, ties unspecified).  Here the
+// order is made total with the scan-order key: composite = (ordered(score) << 32) | ~scan_key, larger is better, all
+// composites are distinct.  A 4-pass radix select (16-bit digits, most significant first) finds the K-th largest
+// composite without sorting; a final pass compacts everything >= it.  Everything stays on the stream: no host
+// round trip until the K winners are copied back.
+struct TopKState {
+  unsigned long long prefix;   // digits decided so far (high bits), rest 0
+  unsigned long long mask;     // which bits of `prefix` are decided
+  unsigned remaining;          // how many more items are needed from inside the current prefix bucket
+  unsigned count;              // clamp(candidates, cap)
+  unsigned k;                  // min(K, count)
+  unsigned out_count;          // compaction cursor
+};
+
+__device__ __forceinline__ unsigned long long cand_composite(const Cand &c) {
+  float v = c.score;
+  if (v == 0.0f) v = 0.0f;
+  unsigned e = (unsigned)enc_f(v) ^ 0x80000000u;
+  return ((unsigned long long)e << 32) | (unsigned)(~c.key);
+}
+
+__global__ void k_topk_init(TopKState *st, const unsigned *count, unsigned cap, unsigned K, unsigned *hist) {
+  for (int i = threadIdx.x; i < 65536; i += blockDim.x) hist[i] = 0;
+  if (threadIdx.x == 0) {
+    unsigned n = min(*count, cap);
+    st->prefix = 0; st->mask = 0;
+    st->count = n;
+    st->k = min(K, n);
+    st->remaining = st->k;
+    st->out_count = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_topk_hist(const Cand *cand, const TopKState *st, int shift, unsigned *hist) {
+  const unsigned n = st->count;
+  const unsigned long long prefix = st->prefix, mask = st->mask;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long ck = cand_composite(cand[i]);
+    if ((ck & mask) == prefix) atomicAdd(&hist[(unsigned)(ck >> shift) & 0xffffu], 1u);
+  }
+}
+
+// One block: walk the 65536 bins from the top until `remaining` items are covered; fix that digit; clear the bins.
+__global__ void __launch_bounds__(1024) k_topk_scan(TopKState *st, int shift, unsigned *hist) {
+  __shared__ unsigned s_sum[1024];
+  __shared__ unsigned s_above;
+  const int t = threadIdx.x;
+  // thread t owns bins [65535 - 64t - 63, 65535 - 64t], i.e. chunk t counted from the top
+  unsigned local = 0;
+  for (int j = 0; j < 64; ++j) local += hist[65535 - (t * 64 + j)];
+  s_sum[t] = local;
+  __syncthreads();
+  if (t == 0) {
+    unsigned need = st->remaining, above = 0;
+    int chunk = 0;
+    while (chunk < 1023 && above + s_sum[chunk] < need) above += s_sum[chunk++];
+    int bin = 65535 - chunk * 64;
+    for (int j = 0; j < 64; ++j, --bin) {
+      unsigned h = hist[bin];
+      if (above + h >= need || j == 63) break;
+      above += h;
+    }
+    if (st->k == 0) bin = 0;
+    st->prefix |= (unsigned long long)(unsigned)bin << shift;
+    st->mask |= 0xffffull << shift;
+    st->remaining = need - above;
+    s_above = above;
+  }
+  __syncthreads();
+  for (int j = 0; j < 64; ++j) hist[t * 64 + j] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_topk_compact(const Cand *cand, TopKState *st, Cand *out, unsigned out_cap) {
+  const unsigned n = st->count;
+  if (st->k == 0) return;
+  const unsigned long long thr = st->prefix;  // all four digits decided: the K-th largest composite
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Cand c = cand[i];
+    if (cand_composite(c) >= thr) {
+      unsigned slot = atomicAdd(&st->out_count, 1u);
+      if (slot < out_cap) out[slot] = c;
     }
   }
 }

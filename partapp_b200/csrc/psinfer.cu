@@ -106,6 +106,12 @@ struct ps_ctx {
   int n_valid_rots = 0;
   DevBuf argmax_keys;   // u64 [P]
   DevBuf cand;          // Cand [N] local-max candidates
+  DevBuf topk_hist;     // unsigned [65536]
+  DevBuf topk_state;    // TopKState [P + 1]
+  DevBuf topk_out;      // Cand [(P + 1)][kmax] winners of every grid of one readout
+  psk::Cand *host_topk = nullptr;       // pinned mirror of topk_out
+  psk::TopKState *host_topk_state = nullptr;
+  size_t topk_slots = 0, topk_kmax = 0;
   DevBuf counters;      // unsigned [8]
   DevBuf ingest, ingest_keys;       // ps_set_unary_compact staging: Tig rows + compact cells; order keys [R][H][W]
   size_t scratch_elems = 0;
@@ -582,6 +588,8 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
                     ((uintptr_t)e.out1 % 16 == 0) && ((uintptr_t)e.add1 % 16 == 0) && ((uintptr_t)e.xout % 16 == 0);
     if (!al) {
       PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e));
+    } else if (!e.general && e.shift_xy && W % 4 == 0 && (uintptr_t)e.src % 16 == 0) {
+      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue3<<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
     } else if (e.general) {
       PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue2<true><<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
     } else {
@@ -897,6 +905,8 @@ void ps_destroy(ps_ctx *ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->host_keys) cudaFreeHost(ctx->host_keys);
+  if (ctx->host_topk) cudaFreeHost(ctx->host_topk);
+  if (ctx->host_topk_state) cudaFreeHost(ctx->host_topk_state);
   delete ctx;
 }
 
@@ -1076,39 +1086,85 @@ void fill_hyp(const ps_config &cfg, float *row, int scaleidx, int rotidx, int x,
   row[6] = score;
 }
 
-// findLocalMax (aux.cpp:193-261) of a device grid [D0][H][W]: returns (d0,x,y,score) rows.
-int local_max_device(ps_ctx *c, const float *g, int D0, int H, int W, int max_n, std::vector<float> &rows) {
-  size_t n = (size_t)D0 * H * W;
-  if (c->cand.bytes < n * sizeof(psk::Cand)) {
+int ensure_topk(ps_ctx *c, size_t slots, size_t kmax, size_t ncand) {
+  if (c->cand.bytes < ncand * sizeof(psk::Cand)) {
     PS_CUDA(c, cudaStreamSynchronize(c->stream));
-    PS_CUDA(c, c->cand.alloc(n * sizeof(psk::Cand)));
+    PS_CUDA(c, c->cand.alloc(ncand * sizeof(psk::Cand)));
   }
+  if (!c->topk_hist.p) PS_CUDA(c, c->topk_hist.alloc(65536 * sizeof(unsigned)));
+  if (slots > c->topk_slots || kmax > c->topk_kmax) {
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    slots = std::max(slots, c->topk_slots);
+    kmax = std::max(kmax, c->topk_kmax);
+    PS_CUDA(c, c->topk_state.alloc(slots * sizeof(psk::TopKState)));
+    PS_CUDA(c, c->topk_out.alloc(slots * std::max<size_t>(kmax, 1) * sizeof(psk::Cand)));
+    if (c->host_topk) cudaFreeHost(c->host_topk);
+    if (c->host_topk_state) cudaFreeHost(c->host_topk_state);
+    PS_CUDA(c, cudaMallocHost((void **)&c->host_topk, slots * std::max<size_t>(kmax, 1) * sizeof(psk::Cand)));
+    PS_CUDA(c, cudaMallocHost((void **)&c->host_topk_state, slots * sizeof(psk::TopKState)));
+    c->topk_slots = slots;
+    c->topk_kmax = kmax;
+  }
+  return PS_OK;
+}
+
+// findLocalMax (aux.cpp:193-261) of a device grid [D0][H][W], asynchronously: candidates -> radix select of the
+// max_n best -> winners in topk_out[slot].  Call decode_local_max(slot) after the stream has been synchronised.
+int enqueue_local_max(ps_ctx *c, const float *g, int D0, int H, int W, int max_n, int slot) {
+  const size_t n = (size_t)D0 * H * W;
   unsigned *cnt = c->counters.as<unsigned>();
+  psk::TopKState *st = c->topk_state.as<psk::TopKState>() + slot;
+  unsigned *hist = c->topk_hist.as<unsigned>();
+  psk::Cand *cand = c->cand.as<psk::Cand>();
+  psk::Cand *out = c->topk_out.as<psk::Cand>() + (size_t)slot * std::max<size_t>(c->topk_kmax, 1);
   PS_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned), c->stream));
-  PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_local_max<<<dim3(cdiv(W, 256), H, D0), 256, 0, c->stream>>>(g, D0, H, W, c->cand.as<psk::Cand>(), (unsigned)n, cnt));
-  unsigned hcnt = 0;
-  PS_CUDA(c, cudaMemcpyAsync(&hcnt, cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  PS_CUDA(c, cudaStreamSynchronize(c->stream));
-  std::vector<psk::Cand> cand(hcnt);
-  if (hcnt)
-    PS_CUDA(c, cudaMemcpy(cand.data(), c->cand.p, hcnt * sizeof(psk::Cand), cudaMemcpyDeviceToHost));
-  // reference order: scan order when everything is kept, descending score otherwise (ties: scan order)
-  std::sort(cand.begin(), cand.end(), [](const psk::Cand &a, const psk::Cand &b) { return a.key < b.key; });
-  if ((int)hcnt > max_n) {
-    std::stable_sort(cand.begin(), cand.end(), [](const psk::Cand &a, const psk::Cand &b) { return a.score > b.score; });
-    cand.resize(max_n);
+  PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_local_max<<<dim3(cdiv(W, 256), H, D0), 256, 0, c->stream>>>(g, D0, H, W, cand, (unsigned)n, cnt));
+  PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_topk_init<<<1, 1024, 0, c->stream>>>(st, cnt, (unsigned)n, (unsigned)max_n, hist));
+  const unsigned blocks = std::min(cdiv(n, 256 * 8), 148u * 8);
+  for (int shift = 48; shift >= 0; shift -= 16) {
+    PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_topk_hist<<<blocks, 256, 0, c->stream>>>(cand, st, shift, hist));
+    PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_topk_scan<<<1, 1024, 0, c->stream>>>(st, shift, hist));
   }
+  PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_topk_compact<<<blocks, 256, 0, c->stream>>>(cand, st, out, (unsigned)std::max(max_n, 0)));
+  return PS_OK;
+}
+
+// Copies the winners of slots [0, nslots) to pinned memory (asynchronous).
+int fetch_local_max(ps_ctx *c, int nslots) {
+  const size_t km = std::max<size_t>(c->topk_kmax, 1);
+  PS_CUDA(c, cudaMemcpyAsync(c->host_topk, c->topk_out.p, (size_t)nslots * km * sizeof(psk::Cand), cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaMemcpyAsync(c->host_topk_state, c->topk_state.p, (size_t)nslots * sizeof(psk::TopKState), cudaMemcpyDeviceToHost, c->stream));
+  return PS_OK;
+}
+
+// Host ordering of one slot's winners: the reference's scan order (dim0, x, y) when nothing was cut, descending
+// score otherwise (ties by scan order; std::sort leaves them unspecified).  Rows of (d0, x, y, score).
+void decode_local_max(ps_ctx *c, int slot, int H, int W, std::vector<float> &rows) {
+  const size_t km = std::max<size_t>(c->topk_kmax, 1);
+  const psk::TopKState &st = c->host_topk_state[slot];
+  const unsigned n = std::min(st.out_count, st.k);
+  std::vector<psk::Cand> cand(c->host_topk + (size_t)slot * km, c->host_topk + (size_t)slot * km + n);
+  std::sort(cand.begin(), cand.end(), [](const psk::Cand &a, const psk::Cand &b) { return a.key < b.key; });
+  if (st.count > st.k)
+    std::stable_sort(cand.begin(), cand.end(), [](const psk::Cand &a, const psk::Cand &b) { return a.score > b.score; });
   rows.resize(cand.size() * 4);
   for (size_t i = 0; i < cand.size(); ++i) {
     unsigned key = cand[i].key;
-    int y = key % H;
-    int x = (key / H) % W;
-    int d0 = key / ((unsigned)H * W);
-    rows[4 * i + 0] = (float)d0;
-    rows[4 * i + 1] = (float)x;
-    rows[4 * i + 2] = (float)y;
+    rows[4 * i + 0] = (float)(key / ((unsigned)H * W));
+    rows[4 * i + 1] = (float)((key / H) % W);
+    rows[4 * i + 2] = (float)(key % H);
     rows[4 * i + 3] = cand[i].score;
   }
+}
+
+// Synchronous convenience used by ps_find_local_max and ps_max_states' slow path.
+int local_max_device(ps_ctx *c, const float *g, int D0, int H, int W, int max_n, std::vector<float> &rows) {
+  int rc = ensure_topk(c, 1, (size_t)std::max(max_n, 1), (size_t)D0 * H * W);
+  if (rc) return rc;
+  if ((rc = enqueue_local_max(c, g, D0, H, W, max_n, 0))) return rc;
+  if ((rc = fetch_local_max(c, 1))) return rc;
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  decode_local_max(c, 0, H, W, rows);
   return PS_OK;
 }
 
@@ -1124,6 +1180,18 @@ int enqueue_readout(ps_ctx *c, const std::vector<const float *> &grids, int scal
   }
   PS_CUDA(c, cudaMemcpyAsync(c->host_keys, c->argmax_keys.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              c->stream));
+  if (flags & (PS_INFER_LOCAL_MAX | PS_INFER_ROOT_HYPS)) {
+    // local maxima of every part (slot p) and of the root posterior (slot P): selected on the device, one copy back
+    const size_t biggest = std::max(c->N, (size_t)c->S * c->HW);
+    int rc = ensure_topk(c, (size_t)P + 1, (size_t)std::max(c->cfg.roi_save_num_samples, 1000), biggest);
+    if (rc) return rc;
+    if (flags & PS_INFER_LOCAL_MAX)
+      for (int p = 0; p < P; ++p)
+        if ((rc = enqueue_local_max(c, grids[p], c->R, c->H, c->W, c->cfg.roi_save_num_samples, p))) return rc;
+    if (flags & PS_INFER_ROOT_HYPS)
+      if ((rc = enqueue_local_max(c, c->root_post.as<float>(), c->S, c->H, c->W, 1000, P))) return rc;
+    if ((rc = fetch_local_max(c, P + 1))) return rc;
+  }
   c->pending_grids = grids;
   c->pending_scaleidx = scaleidx;
   c->pending_flags = flags;
@@ -1157,8 +1225,7 @@ int finish_result(ps_ctx *c) {
   if (local_max)
     for (int p = 0; p < P; ++p) {
       std::vector<float> rows;
-      int rc = local_max_device(c, c->pending_grids[p], c->R, c->H, c->W, c->cfg.roi_save_num_samples, rows);
-      if (rc) return rc;
+      decode_local_max(c, p, c->H, c->W, rows);
       for (size_t i = 0; i < rows.size() / 4; ++i) {
         float h[PS_HYP_VEC];
         // findLocalMax wrapper tags scaleidx 0 (aux.cpp:305)
@@ -1169,8 +1236,7 @@ int finish_result(ps_ctx *c) {
   c->have_local_max = local_max;
   c->have_root_hyps = false;
   if (c->pending_flags & PS_INFER_ROOT_HYPS) {
-    int rc = local_max_device(c, c->root_post.as<float>(), c->S, c->H, c->W, 1000, c->root_hyps);
-    if (rc) return rc;
+    decode_local_max(c, P, c->H, c->W, c->root_hyps);
     c->have_root_hyps = true;
   }
   c->have_result = true;
@@ -1320,12 +1386,8 @@ int ps_infer(ps_ctx *c, int flags) {
   for (int p = 0; p < P; ++p) grids[p] = c->POST(p, S - 1);
   if ((rc = enqueue_readout(c, grids, S - 1, flags, /*keys_ready=*/true))) return rc;
   c->result_scale = S - 1;
-  if (flags & PS_INFER_KEEP_UNARIES) {
-    if (flags & (PS_INFER_LOCAL_MAX | PS_INFER_ROOT_HYPS)) {
-      if ((rc = finish_result(c))) return rc;  // local maxima read the beliefs, not the unaries, but keep order simple
-    }
+  if (flags & PS_INFER_KEEP_UNARIES)
     PS_CUDA(c, cudaMemcpyAsync(c->unary.p, c->unary_backup.p, c->unary.bytes, cudaMemcpyDeviceToDevice, st));
-  }
   return PS_OK;
 }
 
