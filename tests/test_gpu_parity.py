@@ -451,3 +451,51 @@ def test_stress_shape_48_rotations_multiscale():
         for s in range(2):
             _cmp(ctx.marginal(1, s), want["marginals"][s, 1], "R48 marginal scale %d" % s)
         _cmp(res.root_part_posterior, want["root_post"], "R48 root posterior")
+
+
+# ---- randomized sweep ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_messages_match_oracle(seed):
+    """Random shapes (odd and even widths, 4..25 rotations), offsets, covariances (diagonal with probability 1/4),
+    rotation Gaussians (including sigma = 0 and kernels that wrap the whole circle), scales and sparsity flags."""
+    rng = np.random.default_rng(1000 + seed)
+    R = int(rng.integers(4, 26))
+    H, W = int(rng.integers(17, 70)), int(rng.integers(17, 70))
+    ep = ExpParam(num_rotation_steps=R, min_part_rotation=float(rng.choice([-180, -90, -120])),
+                  max_part_rotation=float(rng.choice([180, 90, 150])))
+    dense = bool(rng.integers(0, 2))
+    child = _child_grid(ep, H, W, seed, dense)
+    s1, s2 = rng.uniform(0.6, 6.0, 2)
+    if rng.random() < 0.25:
+        Cm = [[s1 * s1, 0.0], [0.0, s2 * s2]]
+    else:
+        th = rng.uniform(0, np.pi)
+        Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        Cm = Rm @ np.diag([s1 * s1, s2 * s2]) @ Rm.T
+        Cm[1, 0] = Cm[0, 1]
+        Cm = Cm.tolist()
+    oi, oo = rng.uniform(-12, 12, 2), rng.uniform(-12, 12, 2)
+    rm = float(rng.uniform(-1.5, 1.5))
+    rs = float(rng.choice([0.0, rng.uniform(0.05, 3.0)]))
+    sc = float(rng.choice([1.0, rng.uniform(0.7, 1.4)]))
+    sparse = bool(rng.integers(0, 2))
+    want = oracle.message(ep, child, oi, oo, Cm, rm, rs, sc, sparse)
+    with _ctx(ep, 2, H, W) as ctx:
+        got = ctx.message(child, oi, oo, Cm, rm, rs, sc, sparse)
+    _cmp(got, want, "random message %d (R=%d %dx%d dense=%s sparse=%s)" % (seed, R, H, W, dense, sparse))
+
+
+@pytest.mark.parametrize("case", [c for c in MSG_CASES if c[0] in ("general_sparse", "general_dense", "wide_sigma", "diag_dense")],
+                         ids=lambda c: c[0])
+def test_fallback_kernels_without_tma(case, monkeypatch):
+    """PSINFER_NO_TMA=1 routes the Gaussian passes through the shared-memory staged kernels (the path taken when a
+    filter is too long for a TMA box or a pitch is not a multiple of 4); results must not change."""
+    monkeypatch.setenv("PSINFER_NO_TMA", "1")
+    name, R, H, W, oi, oo, Cm, rm, rs, sc, sparse, dense = case
+    ep = ExpParam(num_rotation_steps=R)
+    child = _child_grid(ep, H, W, 11, dense)
+    want = oracle.message(ep, child, oi, oo, Cm, rm, rs, sc, sparse)
+    with _ctx(ep, 2, H, W) as ctx:
+        got = ctx.message(child, oi, oo, Cm, rm, rs, sc, sparse)
+    _cmp(got, want, name + " (no TMA)")
