@@ -206,6 +206,11 @@ int ps_get_plan_info(ps_ctx *ctx, int joint, int downward, int scale, int out[8]
  * out = {exp mismatches, exp inputs tested, log mismatches, log inputs tested}. */
 int ps_selftest_math(ps_ctx *ctx, unsigned first_bits, unsigned long long count, unsigned long long out[4]);
 
+/* Evaluates the device exp/log on the fp32 bit patterns [first_bits, first_bits + count) into a host buffer:
+ * op 0 = exp as used on the path, 1 = log as used on the path, 2 / 3 = CUDA's fp64 exp / log narrowed to fp32.
+ * Lets a test compare them with the host libm the oracle uses. */
+int ps_eval_math(ps_ctx *ctx, int op, unsigned first_bits, unsigned count, float *out_host);
+
 /* Number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches). */
 long long ps_launch_count(const ps_ctx *ctx);
 

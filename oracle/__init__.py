@@ -52,6 +52,8 @@ def lib():
         L.orc_gauss_filter_2d.argtypes = [_fp, _fp, C.c_int, C.c_int, _dp, C.c_int]
         L.orc_enlarged_size.argtypes = [C.c_int, C.c_int, _dp, _ip, _ip]
         L.orc_transform_fixed.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _dp, C.c_float, C.c_int]
+        L.orc_compare_math.restype = C.c_ulonglong
+        L.orc_compare_math.argtypes = [C.c_int, C.c_uint, C.c_uint, _fp]
         L.orc_load_score_grid.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _fp]
         L.orc_message.argtypes = [C.POINTER(orc_exp_param), _fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp,
                                   C.c_double, C.c_double, C.c_double, C.c_int, _fp, _fp, _fp]

@@ -928,6 +928,22 @@ void orc_message(const orc_exp_param *e, const float *child, float *parent, int 
                              scale, sparse != 0, dbg_exp, dbg_rot, dbg_spatial);
 }
 
+// (float)exp((double)x) / (float)log((double)x) over fp32 bit patterns [first, first+count): the oracle's libm
+// convention (multi_array_op.hpp:165,177), for comparison with the device functions.  Returns the number of
+// positions where `dev` differs bitwise (NaNs compare equal to NaNs).
+unsigned long long orc_compare_math(int op, unsigned first, unsigned count, const float *dev) {
+  unsigned long long bad = 0;
+  for (unsigned i = 0; i < count; ++i) {
+    unsigned bits = first + i;
+    float x;
+    memcpy(&x, &bits, 4);
+    float r = op == 0 ? (x < -104.0f ? 0.0f : (float)exp((double)x)) : (x == 0.0f ? (float)LOG_ZERO : (float)log((double)x));
+    if (r != r && dev[i] != dev[i]) continue;
+    if (memcmp(&r, &dev[i], 4) != 0) ++bad;
+  }
+  return bad;
+}
+
 // Unary prep, findrot.cpp:834-845: clip_scores_fill (aux.hpp:42-59) then computeLogGrid.
 void orc_prepare_unary(float *g, size_t n) {
   for (size_t i = 0; i < n; ++i)

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "ps_find_local_max": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _ip]),
     "ps_get_plan_info": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, _ip]),
     "ps_selftest_math": (C.c_int, [_ctx_p, C.c_uint, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
+    "ps_eval_math": (C.c_int, [_ctx_p, C.c_int, C.c_uint, C.c_uint, _fp]),
     "ps_launch_count": (C.c_longlong, [_ctx_p]),
     "ps_profile_enable": (C.c_int, [_ctx_p, C.c_int]),
     "ps_profile_read": (C.c_int, [_ctx_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong), _ip]),

@@ -119,6 +119,21 @@ __device__ __forceinline__ float exp_f64(float x) { return exp_slow(x); }
 __device__ __forceinline__ float log_f64(float d) { return log_slow(d); }
 #endif
 
+// out[i] = f(bits first + i): op 0 exp_f64 (the path's exp), 1 log_f64, 2 exp_slow, 3 log_slow.
+__global__ void k_eval_math(int op, unsigned first, unsigned count, float *out) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned stride = gridDim.x * blockDim.x;
+  for (; i < count; i += stride) {
+    const float x = __uint_as_float(first + i);
+    float r;
+    if (op == 0) r = exp_f64(x);
+    else if (op == 1) r = log_f64(x);
+    else if (op == 2) r = exp_slow(x);
+    else r = log_slow(x);
+    out[i] = r;
+  }
+}
+
 // Exhaustive self-test: every fp32 bit pattern in [first, first + count).
 // out[0]: exp mismatches, out[1]: exp inputs taking the fast path, out[2]: log mismatches, out[3]: log fast path.
 __global__ void k_selftest_math(unsigned first, unsigned long long count, unsigned long long *out) {

@@ -1510,6 +1510,17 @@ int ps_selftest_math(ps_ctx *c, unsigned first_bits, unsigned long long count, u
   return PS_OK;
 }
 
+int ps_eval_math(ps_ctx *c, int op, unsigned first_bits, unsigned count, float *out_host) {
+  if (!c || !out_host || op < 0 || op > 3) return PS_ERR_INVALID;
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  DevBuf d;
+  PS_CUDA(c, d.alloc((size_t)count * sizeof(float)));
+  PS_LAUNCH(c, KC_MISC, psk::k_eval_math<<<148 * 16, 256, 0, c->stream>>>(op, first_bits, count, d.as<float>()));
+  PS_CUDA(c, cudaMemcpyAsync(out_host, d.p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
 int ps_find_local_max(ps_ctx *c, const float *grid, int mem_kind, int d0, int h, int w, int max_n, float *out,
                       int *count) {
   if (!c || !grid || !out || !count || d0 < 1 || h < 1 || w < 1 || max_n < 0) return PS_ERR_INVALID;

@@ -275,6 +275,12 @@ class PsContext:
         self._check(self.lib.ps_selftest_math(self.h, first_bits, count, out))
         return tuple(int(v) for v in out)
 
+    def eval_math(self, op, first_bits, count):
+        """Device exp (op 0) / log (op 1) of the path on fp32 bit patterns [first, first + count)."""
+        out = np.empty(count, np.float32)
+        self._check(self.lib.ps_eval_math(self.h, op, first_bits, count, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     def launch_count(self):
         return int(self.lib.ps_launch_count(self.h))
 
