@@ -312,6 +312,33 @@ __global__ void __launch_bounds__(256) k_ingest_scatter(IngestArgs a, const __gr
     atomicMax(&a.keys[(size_t)r * a.H * a.W + (size_t)iy * a.W + ix], x1 * a.gh + y1 + 1);
 }
 
+// Collision-free variant: when the host has proved that distinct grid cells cannot land on the same image cell
+// (smallest singular value of the 2x2 part of every Tig > sqrt(2): two lattice points are then further apart than
+// the diagonal of a cell), the order of the writers is irrelevant, so evaluated cells are written straight into a
+// LOG_ZERO-filled unary -- one 23 MB fill instead of a key pass, a key sweep and their traffic.
+__global__ void __launch_bounds__(256) k_ingest_scatter_direct(IngestArgs a, const __grid_constant__ TigRows rows,
+                                                               int *max_dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  float m = kLogZero;  // unevaluated cells are LOG_ZERO (the fill)
+  if (i < a.gh * a.gw) {
+    const int y1 = i / a.gw, x1 = i - y1 * a.gw;
+    const float v = a.cells[(size_t)r * a.gh * a.gw + i];
+    if (v != 0.0f) {
+      const double *T = a.Tig ? a.Tig + r * 6 : rows.m + r * 6;
+      const double x3 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], (double)x1), __dmul_rn(T[1], (double)y1)), T[2]);
+      const double y3 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], (double)x1), __dmul_rn(T[4], (double)y1)), T[5]);
+      const int ix = (int)floor(__dadd_rn(x3, 0.5)), iy = (int)floor(__dadd_rn(y3, 0.5));
+      if (ix >= 0 && ix < a.W && iy >= 0 && iy < a.H) {
+        const float o = prepare_cell(v);
+        a.out[(size_t)r * a.H * a.W + (size_t)iy * a.W + ix] = o;
+        m = fmaxf(m, o);
+      }
+    }
+  }
+  if (max_dst) block_max_to(m, max_dst);
+}
+
 __global__ void __launch_bounds__(256) k_ingest_sweep(IngestArgs a, int *max_dst) {
   const size_t n = (size_t)a.R * a.H * a.W;
   const size_t HW = (size_t)a.H * a.W;

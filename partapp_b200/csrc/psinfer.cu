@@ -114,6 +114,8 @@ struct ps_ctx {
   size_t topk_slots = 0, topk_kmax = 0;
   DevBuf counters;      // unsigned [8]
   DevBuf ingest, ingest_keys;       // ps_set_unary_compact staging: Tig rows + compact cells; order keys [R][H][W]
+  DevBuf unary_max;                 // int [P][S]: encoded max of each unary as left by the ingest
+  std::vector<unsigned char> unary_max_valid;  // [P][S]
   size_t scratch_elems = 0;
 
   // model
@@ -856,6 +858,8 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   if (!cu(c->maxes.alloc((2 * c->P + psk::kMaxRootChildren + 4) * sizeof(int)), "alloc maxima")) return PS_ERR_CUDA;
   if (!cu(c->argmax_keys.alloc(c->P * sizeof(unsigned long long)), "alloc argmax")) return PS_ERR_CUDA;
   if (!cu(c->counters.alloc(8 * sizeof(unsigned)), "alloc counters")) return PS_ERR_CUDA;
+  if (!cu(c->unary_max.alloc((size_t)c->P * c->S * sizeof(int)), "alloc unary maxima")) return PS_ERR_CUDA;
+  c->unary_max_valid.assign((size_t)c->P * c->S, 0);
   if (!cu(cudaMallocHost((void **)&c->host_keys, c->P * sizeof(unsigned long long)), "alloc pinned keys")) return PS_ERR_CUDA;
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
@@ -995,6 +999,7 @@ int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind,
   if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   float *dst = c->U(part, scale);
+  c->unary_max_valid[(size_t)part * c->S + scale] = 0;
   PS_CUDA(c, cudaMemcpyAsync(dst, src, c->N * sizeof(float),
                              mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   if (raw) {
@@ -1036,12 +1041,29 @@ int ps_set_unary_compact(ps_ctx *c, int part, int scale, const float *cells, int
     PS_CUDA(c, cudaMemcpyAsync(dcells, cells, ncell * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     src_cells = dcells;
   }
-  PS_CUDA(c, cudaMemsetAsync(c->ingest_keys.p, 0, c->N * sizeof(int), c->stream));
   psk::IngestArgs a;
   a.cells = src_cells; a.Tig = dT; a.keys = c->ingest_keys.as<int>(); a.out = c->U(part, scale);
   a.R = c->R; a.gh = gh; a.gw = gw; a.H = c->H; a.W = c->W;
-  PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows));
-  PS_LAUNCH(c, KC_PREP, psk::k_ingest_sweep<<<cdiv((c->N + 3) / 4, 256), 256, 0, c->stream>>>(a, nullptr));
+  int *mslot = c->unary_max.as<int>() + (size_t)part * c->S + scale;
+  // collision-free? smallest singular value of every 2x2 linear part must exceed sqrt(2) (plus a safety margin)
+  bool collision_free = true;
+  for (int r = 0; r < c->R && collision_free; ++r) {
+    const double a00 = Tig[r * 9 + 0], a01 = Tig[r * 9 + 1], a10 = Tig[r * 9 + 3], a11 = Tig[r * 9 + 4];
+    const double s1 = a00 * a00 + a01 * a01 + a10 * a10 + a11 * a11, det = a00 * a11 - a01 * a10;
+    const double disc = std::sqrt(std::max(0.0, s1 * s1 - 4 * det * det));
+    const double smin2 = 0.5 * (s1 - disc);  // squared smallest singular value
+    collision_free = smin2 > 2.0 * 1.01;
+  }
+  PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mslot, 1, PS_ENC_NEG_INF));
+  if (collision_free) {
+    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 1024), 148u * 16), 256, 0, c->stream>>>(a.out, c->N, psk::kLogZero));
+    PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows, mslot));
+  } else {
+    PS_CUDA(c, cudaMemsetAsync(c->ingest_keys.p, 0, c->N * sizeof(int), c->stream));
+    PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows));
+    PS_LAUNCH(c, KC_PREP, psk::k_ingest_sweep<<<cdiv((c->N + 3) / 4, 256), 256, 0, c->stream>>>(a, mslot));
+  }
+  c->unary_max_valid[(size_t)part * c->S + scale] = 1;
   return PS_OK;
 }
 
@@ -1057,6 +1079,7 @@ int ps_get_unary(ps_ctx *c, int part, int scale, float *dst, int mem_kind) {
 int ps_add_unary_table(ps_ctx *c, int part, const float *table, int kind, float weight) {
   if (!c || !table) return PS_ERR_INVALID;
   if (part < 0 || part >= c->P) return c->fail(PS_ERR_INVALID, "part out of range");
+  for (int s2 = 0; s2 < c->S; ++s2) c->unary_max_valid[(size_t)part * c->S + s2] = 0;
   if (kind < 0 || kind > 2) return c->fail(PS_ERR_INVALID, "table_kind must be 0, 1 or 2");
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   size_t n = kind == 0 ? (size_t)c->R : c->HW;
@@ -1306,7 +1329,14 @@ int ps_infer(ps_ctx *c, int flags) {
         PS_LAUNCH(c, KC_MISC, psk::k_fill<<<std::min(cdiv(N, 1024), 2048u), 256, 0, st>>>(c->POST(leaf, s), N, 0.0f));
         belief[leaf] = c->POST(leaf, s);
       }
-      if ((rc = grid_max(c, belief[leaf], N, c->MAXP(leaf)))) return rc;
+      const bool masked = c->cfg.is_upright[leaf] || (leaf == root && c->cfg.strip_border_detections > 0);
+      if (c->cfg.is_detect[leaf] && !masked && c->unary_max_valid[(size_t)leaf * S + s]) {
+        // the ingest already folded max(unary): copy the scalar instead of sweeping 23 MB
+        PS_CUDA(c, cudaMemcpyAsync(c->MAXP(leaf), c->unary_max.as<int>() + (size_t)leaf * S + s, sizeof(int),
+                                   cudaMemcpyDeviceToDevice, st));
+      } else if ((rc = grid_max(c, belief[leaf], N, c->MAXP(leaf)))) {
+        return rc;
+      }
       for (int k = (int)chain.size() - 1; k >= 0; --k) {
         const int child = chain[k];
         const int parent = c->nodes[child].parent;
