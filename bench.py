@@ -297,8 +297,18 @@ def run_ours(args):
                            "frac_of_measured_peak": round(n_taps / per_launch_s / FP32_PEAK, 3)}
         msg_ms = sum(prof[k][0] for k in prof if k in ("rotconv", "warp_direct", "warp_bilinear", "conv_rows",
                                                           "conv_cols", "warp_back", "epilogue")) / n_img_prof / (2 * J)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            key = "conv_cols" if dom[0] == "conv_rows" else dom[0]  # both Gaussian passes are k_conv_cols_tma
+            if key in tj:
+                traffic = tj[key]["dram_bytes_per_launch"]
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(achieved / peak, 4), "traffic": traffic,
+                    "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram read+write per launch)",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": round(dom_bytes), "ms_per_launch": round(dom_ms_per_launch, 4),
                     "share_of_step": round(dom[1][0] / tot_ms, 3),
                     "how": "CUDA events around every launch on the ctx stream (instrumented pass over %d images)" % n_img_prof,
