@@ -699,6 +699,9 @@ __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restri
   }
 }
 
+
+// (Round 1 also tried staging each tile's 28x28 source bounding box in shared memory -- the direct gathers are bound
+// by the L1 data pipe at ~11 sectors per request -- but the staging loop plus 3x over-fetch made it 2x slower.)
 // TM_DIRECT as a gather through the winner map, RG slices per thread.
 // tr != 0: out is stored transposed ([r][ix][iy], pitch EP over iy, plane EW*EP) and threadIdx.x walks iy.
 template <int RG>

@@ -16,6 +16,9 @@
 #include <string>
 #include <vector>
 
+#ifndef PS_RG
+#define PS_RG 6
+#endif
 #include "ps_geometry.hpp"
 #include "ps_kernels.cuh"
 
@@ -532,7 +535,7 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     // gaussFilter2dOffset: rotate into the eigen-frame, filter there, bilinear read-back
     const int EH = h.EH, EW = h.EW, EP = dp.EP;
     const size_t eplane = (size_t)EH * EP;
-    constexpr int RG = 6;
+    constexpr int RG = PS_RG;
     // Transposed route: the resampler writes the eigen-frame grid transposed ([r][x][y]) so that the x filter is a
     // TMA column filter too; its transposing store restores [r][y][x] for the y filter.
     const int EHP = (EH + 7) & ~7;
