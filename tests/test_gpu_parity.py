@@ -24,7 +24,7 @@ def _cmp(got, want, what, max_ulp_frac=0.0, rtol=1e-4):
     want = np.asarray(want)
     assert got.shape == want.shape, what
     assert np.array_equal(got == LZ, want == LZ), what + ": LOG_ZERO support differs"
-    neq = got != want
+    neq = (got != want) & ~(np.isnan(got) & np.isnan(want))   # the same NaN in the same cell is agreement
     frac = neq.mean()
     if neq.any():
         rel = np.abs(got[neq].astype(np.float64) - want[neq]) / np.maximum(np.abs(want[neq].astype(np.float64)), 1e-30)
@@ -499,3 +499,51 @@ def test_fallback_kernels_without_tma(case, monkeypatch):
     with _ctx(ep, 2, H, W) as ctx:
         got = ctx.message(child, oi, oo, Cm, rm, rs, sc, sparse)
     _cmp(got, want, name + " (no TMA)")
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------------------
+
+def test_tiny_grids_and_single_rotation_bins():
+    """Smallest shapes: a 3x3 grid, a filter far wider than the grid, 2 rotation bins (kernel clipped to 1 tap)."""
+    for (R, H, W, Cm, rs) in ((2, 3, 3, [[30.0, 4.0], [4.0, 20.0]], 2.0), (3, 5, 4, [[2.0, 0], [0, 50.0]], 0.7),
+                              (4, 1, 9, [[3.0, 1.0], [1.0, 2.0]], 0.3)):
+        ep = ExpParam(num_rotation_steps=R)
+        rng = np.random.default_rng(R * 100 + H)
+        child = (rng.standard_normal((R, H, W)) - 2).astype(np.float32)
+        args = ((1.2, -0.7), (-0.4, 1.1), Cm, 0.4, rs, 1.0, False)
+        want = oracle.message(ep, child, *args)
+        with _ctx(ep, 2, H, W) as ctx:
+            _cmp(ctx.message(child, *args), want, "tiny %dx%dx%d" % (R, H, W))
+
+
+def test_all_log_zero_unaries_infer():
+    """Every unary cell unevaluated.  In the reference this degenerates: the LOG_ZERO fill of the shifted grid is
+    *above* the max of a -2e6 belief, exp overflows to inf and inf * 0 taps give NaN.  The device reproduces the same
+    inf / NaN cells."""
+    ep = ExpParam(num_rotation_steps=4, roi_save_num_samples=3)
+    P, H, W = 3, 12, 10
+    un = np.full((P, 1, 4, H, W), LZ, np.float32)
+    joints = synth.make_joints(P, seed=2, max_offset=2, sigma_range=(1.0, 1.5))
+    pc = synth.part_conf(P)
+    want = oracle.infer(ep, pc, joints, un.copy(), sparse=True)
+    with PsContext(ep, pc, H, W) as ctx:
+        res = od.computeRootPosteriorRot(ctx, [[un[p, 0]] for p in range(P)], joints, True, write_back_masked=False)
+        assert np.array_equal(res.best_conf, want["best_conf"], equal_nan=True)
+        for p in range(P):
+            _cmp(ctx.marginal(p), want["marginals"][0, p], "all-LOG_ZERO marginal %d" % p)
+        assert np.isinf(want["best_conf"][:, 6]).any() and np.isnan(want["marginals"]).any()
+
+
+def test_degenerate_configs_are_rejected():
+    from partapp_b200 import PsInferError, capi
+    with pytest.raises(PsInferError) as e:     # min == max rotation needs exactly one bin (partapp_aux.hpp:29-31)
+        PsContext(ExpParam(num_rotation_steps=4, min_part_rotation=0, max_part_rotation=0), synth.part_conf(2), 8, 8)
+    assert e.value.status == capi.PS_ERR_INVALID
+    with pytest.raises(PsInferError):          # strip_border_detections must be < 0.5 (findrot.cpp:529)
+        PsContext(ExpParam(num_rotation_steps=4, strip_border_detections=0.5), synth.part_conf(2), 8, 8)
+    # a single rotation bin with min == max: rot_step_size == 0 trips findrot.cpp:321
+    ep = ExpParam(num_rotation_steps=1, min_part_rotation=0, max_part_rotation=0)
+    with PsContext(ep, synth.part_conf(2), 8, 8) as ctx:
+        with pytest.raises(PsInferError) as e:
+            ctx.message(np.zeros((1, 8, 8), np.float32), (1, 1), (1, 1), [[2, 0], [0, 2]], 0.0, 0.5, 1.0, True)
+        assert "rot_step_size" in str(e.value)
