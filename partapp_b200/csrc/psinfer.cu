@@ -437,6 +437,8 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
   t.slices = slices; t.ytiles = (rows + 8 * T - 1) / (8 * T); t.xtiles = (cols + 63) / 64;
   t.transpose_out = transpose_out;
   const int ntiles = t.slices * t.ytiles * t.xtiles;
+  // 2 resident blocks per SM: 3 were 3 % faster in isolation but slower with two images in flight (less room for the
+  // other stream's kernels), round-1 A/B
   const int grid = std::min(ntiles, c->num_sms * 2);
   PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
             psk::k_conv_cols_tma<T><<<grid, 256, 2 * stage, c->stream>>>(tm, t, PS_NEGZERO2));
