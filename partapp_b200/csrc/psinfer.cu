@@ -1126,6 +1126,8 @@ int ensure_topk(ps_ctx *c, size_t slots, size_t kmax, size_t ncand) {
     kmax = std::max(kmax, c->topk_kmax);
     PS_CUDA(c, c->topk_state.alloc(slots * sizeof(psk::TopKState)));
     PS_CUDA(c, c->topk_out.alloc(slots * std::max<size_t>(kmax, 1) * sizeof(psk::Cand)));
+    PS_CUDA(c, cudaMemset(c->topk_out.p, 0, c->topk_out.bytes));  // unused winner slots are copied back too
+    PS_CUDA(c, cudaMemset(c->topk_state.p, 0, c->topk_state.bytes));
     if (c->host_topk) cudaFreeHost(c->host_topk);
     if (c->host_topk_state) cudaFreeHost(c->host_topk_state);
     PS_CUDA(c, cudaMallocHost((void **)&c->host_topk, slots * std::max<size_t>(kmax, 1) * sizeof(psk::Cand)));

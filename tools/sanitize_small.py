@@ -1,0 +1,20 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): one inference with full
+covariances, local maxima and root hypotheses, plus a compact ingest and a standalone message."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from partapp_b200 import ExpParam, PsContext, synth
+
+ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=10)
+P, H, W = 4, 40, 36
+cells, Tig = synth.compact_scores(ep, H, W, P, 1)
+joints = synth.make_joints(P, seed=5, max_offset=6, sigma_range=(1.5, 3))
+with PsContext(ep, synth.part_conf(P), H, W) as ctx:
+    ctx.set_joints(joints)
+    for p in range(P):
+        ctx.set_unary_compact(p, 0, cells[p, 0], Tig)
+    ctx.infer(sparse=True, local_max=True, root_hyps=True)
+    print(ctx.best_conf()[:, 2:6])
+    j = joints[0]
+    out = ctx.message(ctx.get_unary(0, 0), j.offset_c, j.offset_p, [[4.0, 0], [0, 3.0]], 0.2, 0.5, 1.0, True)
+    print(float(out.max()))
