@@ -205,6 +205,12 @@ struct MessagePlan {
   double T31[6];                // image -> eigen-frame (TM_DIRECT forward scatter), rows 0,1 of the 3x3
   double T13[6];                // eigen-frame -> image (TM_BILINEAR gather into the eigen-frame)
   double T34[6];                // image -> eigen-frame coordinates for the bilinear read-back
+  // Work lists for the tiled Gaussian passes (64 x 64 output tiles).  The eigen-frame grid is the bounding box of
+  // the ROTATED image, so on average ~40 % of its cells are never read by the bilinear read-back (it samples only
+  // inside the rotated image rectangle).  ytiles: (row-tile, col-tile) pairs of the y pass that intersect that
+  // rectangle (dilated by 2 cells for the 2x2 taps); xtiles: (x-tile, y-tile) pairs of the x pass whose outputs some
+  // listed y tile reads (its 64 columns x (64 + 2*ny) rows).  Skipping the rest changes no value that is ever used.
+  std::vector<int> ytiles, xtiles;
   std::string error;            // non-empty: the reference would have hit an assert
 };
 
@@ -348,6 +354,53 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
   }
   p.fx = to_float(fx);
   p.fy = to_float(fy);
+  if (!p.diag) {
+    // rotated image rectangle in eigen-frame coordinates: centre and half-axes from the images of the pixel-centre corners
+    auto map34 = [&](double x, double y, double &ox, double &oy) {
+      ox = p.T34[0] * x + p.T34[1] * y + p.T34[2];
+      oy = p.T34[3] * x + p.T34[4] * y + p.T34[5];
+    };
+    double ax, ay, bx, by, cx, cy;
+    map34(0, 0, ax, ay);
+    map34(W - 1, 0, bx, by);
+    map34(0, H - 1, cx, cy);
+    const double ux = (bx - ax) * 0.5, uy = (by - ay) * 0.5, vx = (cx - ax) * 0.5, vy = (cy - ay) * 0.5;  // half-edges
+    const double mx = ax + ux + vx, my = ay + uy + vy;                                                  // centre
+    const double lu = std::sqrt(ux * ux + uy * uy), lv = std::sqrt(vx * vx + vy * vy);
+    const double eux = lu > 0 ? ux / lu : 1, euy = lu > 0 ? uy / lu : 0, evx = lv > 0 ? vx / lv : 0, evy = lv > 0 ? vy / lv : 1;
+    const double margin = 2.5;
+    auto rect_hits = [&](double x0, double y0, double x1, double y1) {  // separating-axis test, rectangle vs oriented box
+      const double rcx = 0.5 * (x0 + x1), rcy = 0.5 * (y0 + y1), rhx = 0.5 * (x1 - x0), rhy = 0.5 * (y1 - y0);
+      const double dx = rcx - mx, dy = rcy - my;
+      const double hu = lu + margin, hv = lv + margin;
+      // axes of the rectangle
+      if (std::fabs(dx) > rhx + hu * std::fabs(eux) + hv * std::fabs(evx)) return false;
+      if (std::fabs(dy) > rhy + hu * std::fabs(euy) + hv * std::fabs(evy)) return false;
+      // axes of the oriented box
+      if (std::fabs(dx * eux + dy * euy) > hu + rhx * std::fabs(eux) + rhy * std::fabs(euy)) return false;
+      if (std::fabs(dx * evx + dy * evy) > hv + rhx * std::fabs(evx) + rhy * std::fabs(evy)) return false;
+      return true;
+    };
+    const int TS = 64;
+    const int nty = (p.EH + TS - 1) / TS, ntx = (p.EW + TS - 1) / TS;
+    const int ny = ((int)p.fy.size() - 1) / 2;
+    std::vector<char> needx((size_t)ntx * nty, 0);  // x pass runs on the transposed grid: tile (x-tile, y-tile)
+    for (int ty = 0; ty < nty; ++ty)
+      for (int tx = 0; tx < ntx; ++tx)
+        if (rect_hits(tx * TS - 0.5, ty * TS - 0.5, tx * TS + TS - 0.5, ty * TS + TS - 0.5)) {
+          p.ytiles.push_back(ty);
+          p.ytiles.push_back(tx);
+          // this y tile reads x-pass outputs in columns [tx*TS, tx*TS+TS) and rows [ty*TS - ny, ty*TS + TS + ny)
+          const int r0 = std::max(0, ty * TS - ny), r1 = std::min(p.EH - 1, ty * TS + TS - 1 + ny);
+          for (int yt2 = r0 / TS; yt2 <= r1 / TS; ++yt2) needx[(size_t)tx * nty + yt2] = 1;
+        }
+    for (int tx = 0; tx < ntx; ++tx)      // x-pass tile grid: "row tiles" walk x (the filter axis), "col tiles" walk y
+      for (int ty = 0; ty < nty; ++ty)
+        if (needx[(size_t)tx * nty + ty]) {
+          p.xtiles.push_back(tx);
+          p.xtiles.push_back(ty);
+        }
+  }
   return p;
 }
 

@@ -1157,6 +1157,8 @@ struct ColsTmaArgs {
   size_t plane;
   int slices, ytiles, xtiles;  // tile grid: ytiles of 8T rows, xtiles of 64 columns
   int transpose_out;           // 1: out[z][col][row] (the input was stored transposed; this pass restores the layout)
+  const int *tile_list;        // optional (row-tile, col-tile) pairs to compute, same for every slice; null = all tiles
+  int ntile_list;
 };
 
 template <int T>
@@ -1176,9 +1178,22 @@ __global__ void __launch_bounds__(256, 2) k_conv_cols_tma(const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int ntiles = a.slices * a.ytiles * a.xtiles;
+  const int per_slice = a.tile_list ? a.ntile_list : a.ytiles * a.xtiles;
+  const int ntiles = a.slices * per_slice;
+  auto decode = [&](int tile, int &xt, int &yt, int &z) {
+    z = tile / per_slice;
+    const int i = tile - z * per_slice;
+    if (a.tile_list) {
+      yt = a.tile_list[2 * i];
+      xt = a.tile_list[2 * i + 1];
+    } else {
+      yt = i / a.xtiles;
+      xt = i - yt * a.xtiles;
+    }
+  };
   auto issue = [&](int tile, int s) {
-    const int xt = tile % a.xtiles, yt = (tile / a.xtiles) % a.ytiles, z = tile / (a.xtiles * a.ytiles);
+    int xt, yt, z;
+    decode(tile, xt, yt, z);
     mbar_expect_tx(&s_bar[s], stage_bytes);
     tma_load_3d(s_raw + s * stage_stride, &tmap, xt * 64, yt * 8 * T - n, z, &s_bar[s]);
   };
@@ -1195,7 +1210,8 @@ __global__ void __launch_bounds__(256, 2) k_conv_cols_tma(const __grid_constant_
     }
     mbar_wait(&s_bar[s], (phases >> s) & 1u);
     phases ^= 1u << s;
-    const int xt = tile % a.xtiles, yt = (tile / a.xtiles) % a.ytiles, z = tile / (a.xtiles * a.ytiles);
+    int xt, yt, z;
+    decode(tile, xt, yt, z);
     if (yt * 8 * T + w * T >= a.rows) {  // warp-uniform: nothing to produce in this tile
       __syncthreads();
       continue;

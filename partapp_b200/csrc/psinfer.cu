@@ -51,7 +51,7 @@ struct DevBuf {
 // Device-side image of one psg::MessagePlan.
 struct DevPlan {
   psg::MessagePlan host;
-  DevBuf ints;    // xin | xout | yin | yout | in_shift | out_shift (xout stays 16-byte aligned whenever W % 4 == 0)
+  DevBuf ints;    // xin | xout | yin | yout | in_shift | out_shift | ytiles | xtiles (xout stays 16-byte aligned whenever W % 4 == 0)
   DevBuf floats;  // rot taps | fx | fy
   DevBuf map;     // int2 [EH][EW], built on first sparse use
   DevBuf mats;    // T31 | T13 (doubles) for the map builder
@@ -63,6 +63,8 @@ struct DevPlan {
   const int *yout(int R, int H, int W) const { return ints.as<int>() + (size_t)R * (2 * W + H); }
   const int *in_shift(int R, int H, int W) const { return host.in_pure ? ints.as<int>() + (size_t)R * 2 * (W + H) : nullptr; }
   const int *out_shift(int R, int H, int W) const { return host.out_pure ? ints.as<int>() + (size_t)R * 2 * (W + H) + 2 * R : nullptr; }
+  const int *ytiles(int R, int H, int W) const { return ints.as<int>() + (size_t)R * 2 * (W + H) + 4 * R; }
+  const int *xtiles(int R, int H, int W) const { return ytiles(R, H, W) + host.ytiles.size(); }
   const float *rot_taps() const { return floats.as<float>(); }
   const float *fx() const { return floats.as<float>() + host.rot_taps.size(); }
   const float *fy() const { return floats.as<float>() + host.rot_taps.size() + host.fx.size(); }
@@ -86,6 +88,7 @@ struct ps_ctx {
   long long launches = 0;
   int num_sms = 148;
   bool disable_tma = false;  // PSINFER_NO_TMA=1: keep the shared-memory staged kernels (A/B testing)
+  bool disable_tile_lists = false;  // PSINFER_ALL_TILES=1: filter every eigen-frame tile, used or not (A/B testing)
 
   // optional per-kernel-class device timing (ps_profile_enable)
   bool profiling = false;
@@ -228,6 +231,8 @@ int upload_plan(ps_ctx *c, DevPlan &dp) {
   ints.insert(ints.end(), h.yout.begin(), h.yout.end());
   ints.insert(ints.end(), h.in_shift.begin(), h.in_shift.end());
   ints.insert(ints.end(), h.out_shift.begin(), h.out_shift.end());
+  ints.insert(ints.end(), h.ytiles.begin(), h.ytiles.end());
+  ints.insert(ints.end(), h.xtiles.begin(), h.xtiles.end());
   std::vector<float> fl;
   fl.insert(fl.end(), h.rot_taps.begin(), h.rot_taps.end());
   fl.insert(fl.end(), h.fx.begin(), h.fx.end());
@@ -418,7 +423,8 @@ bool cols_tma_ok(const ps_ctx *c, const float *in, int len, int pitch, size_t pl
 // TMA column filter.  Input: [slices][rows][in_pitch] with `cols` valid columns (filter along rows).
 // Output: same orientation (transpose_out = 0, out pitch/plane as given) or transposed [slices][cols][out_pitch].
 int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_plane, float *out, int out_pitch,
-                         size_t out_plane, const float *taps, int len, int rows, int cols, int slices, int transpose_out) {
+                         size_t out_plane, const float *taps, int len, int rows, int cols, int slices, int transpose_out,
+                         const int *tile_list = nullptr, int ntile_list = 0) {
   constexpr int T = 8;
   const int n = (len - 1) / 2;
   const int nrows = 8 * T + 2 * n;
@@ -436,7 +442,9 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
   t.out = out; t.taps = taps; t.len = len; t.rows = rows; t.cols = cols; t.pitch = out_pitch; t.plane = out_plane;
   t.slices = slices; t.ytiles = (rows + 8 * T - 1) / (8 * T); t.xtiles = (cols + 63) / 64;
   t.transpose_out = transpose_out;
-  const int ntiles = t.slices * t.ytiles * t.xtiles;
+  t.tile_list = (tile_list && !c->disable_tile_lists) ? tile_list : nullptr;
+  t.ntile_list = ntile_list;
+  const int ntiles = t.slices * (t.tile_list ? ntile_list : t.ytiles * t.xtiles);
   // 2 resident blocks per SM: 3 were 3 % faster in isolation but slower with two images in flight (less room for the
   // other stream's kernels), round-1 A/B
   const int grid = std::min(ntiles, c->num_sms * 2);
@@ -559,12 +567,17 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     }
     if (tr) {
       rc = launch_conv_cols_tma(c, c->bufU.as<float>(), EHP, tplane, c->bufV.as<float>(), EP, eplane, dp.fx(),
-                                (int)h.fx.size(), /*rows=*/EW, /*cols=*/EH, R, /*transpose_out=*/1);
+                                (int)h.fx.size(), /*rows=*/EW, /*cols=*/EH, R, /*transpose_out=*/1, dp.xtiles(R, H, W),
+                                (int)h.xtiles.size() / 2);
     } else {
       rc = conv_rows(c->bufU.as<float>(), c->bufV.as<float>(), EH, EW, EP, eplane, dp.fx(), (int)h.fx.size());
     }
     if (rc) return rc;
-    rc = conv_cols(c->bufV.as<float>(), c->bufU.as<float>(), EH, EW, EP, eplane, dp.fy(), (int)h.fy.size());
+    if (tr && cols_tma_ok(c, c->bufV.as<float>(), (int)h.fy.size(), EP, eplane))
+      rc = launch_conv_cols_tma(c, c->bufV.as<float>(), EP, eplane, c->bufU.as<float>(), EP, eplane, dp.fy(),
+                                (int)h.fy.size(), EH, EW, R, 0, dp.ytiles(R, H, W), (int)h.ytiles.size() / 2);
+    else
+      rc = conv_cols(c->bufV.as<float>(), c->bufU.as<float>(), EH, EW, EP, eplane, dp.fy(), (int)h.fy.size());
     if (rc) return rc;
     // Bilinear read-back into the image frame (filter.hpp:367-368), then the generic epilogue.  (A fused
     // read-back + epilogue over source cells was tried in round 1: 63 us per message against 22 + 28 us for the
@@ -868,6 +881,7 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   if (!cu(cudaMallocHost((void **)&c->host_keys, c->P * sizeof(unsigned long long)), "alloc pinned keys")) return PS_ERR_CUDA;
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
+  c->disable_tile_lists = getenv("PSINFER_ALL_TILES") != nullptr;
   if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
