@@ -140,6 +140,12 @@ int ps_get_unary(ps_ctx *ctx, int part, int scale, float *dst, int mem_kind);
  * applied to every scale of `part`. */
 int ps_add_unary_table(ps_ctx *ctx, int part, const float *table, int table_kind, float weight);
 
+/* DPM score fusion for full grids `grid[num_rot][H][W]` (num_rot = num_rotation_steps, or 1 = the same grid for every
+ * rotation), applied to every scale of `part`:
+ *   mode 0: addDPMScore     (icps.cpp:488-524)  unary += weight * grid              (grid already log-domain)
+ *   mode 1: addLoadDPMScore (icps.cpp:445-486)  unary += grid > 1e-4 ? weight * log(grid) : log(1e-4) */
+int ps_add_unary_grid(ps_ctx *ctx, int part, const float *grid, int num_rot, int mode, float weight, int mem_kind);
+
 /* Host builders of those tables (same arithmetic as the reference, which builds them on the CPU). */
 void ps_rot_score_table(const ps_config *cfg, double mu, double var, float *table /*[R]*/);
 void ps_pos_score_table(int height, int width, double mu_x, double mu_y, double var_x, double var_y,

@@ -65,6 +65,8 @@ def lib():
         L.orc_add_rot_table.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp, C.c_float]
         L.orc_add_pos_table.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp, C.c_float]
         L.orc_add_pos_table_unweighted.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp]
+        L.orc_add_dpm_score.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_float]
+        L.orc_add_load_dpm_score.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_float]
         L.orc_find_local_max.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
         L.orc_argmax.argtypes = [_fp, C.c_int, _fp]
         L.orc_infer.argtypes = [C.POINTER(orc_exp_param), C.c_int, _ip, _ip, C.c_int, C.POINTER(orc_joint), C.c_int,

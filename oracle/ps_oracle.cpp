@@ -1068,6 +1068,25 @@ void orc_add_pos_table_unweighted(float *g, int R, int H, int W, const float *ta
     for (size_t i = 0; i < HW; ++i) g[r * HW + i] += table[i];
 }
 
+// addDPMScore (icps.cpp:488-524): g += dpm_weight * log_dpmPriorGrid[bRot ? r : 0]
+void orc_add_dpm_score(float *g, int R, int H, int W, const float *grid, int nrot, float dpm_weight) {
+  size_t HW = (size_t)H * W;
+  for (int r = 0; r < R; ++r)
+    for (size_t i = 0; i < HW; ++i) g[r * HW + i] += dpm_weight * grid[(nrot > 1 ? r : 0) * HW + i];
+}
+
+// addLoadDPMScore (icps.cpp:445-486): g += (val > 1e-4 ? dpm_weight*log(val) : log(1e-4)); log(float) is logf there
+void orc_add_load_dpm_score(float *g, int R, int H, int W, const float *grid, int nrot, float dpm_weight) {
+  size_t HW = (size_t)H * W;
+  for (int r = 0; r < R; ++r) {
+    int rd = (nrot == R ? r : 0);
+    for (size_t i = 0; i < HW; ++i) {
+      float val = grid[rd * HW + i];
+      g[r * HW + i] += (val > 1e-4 ? dpm_weight * logf(val) : log(1e-4));
+    }
+  }
+}
+
 // ---- readout ---------------------------------------------------------------------------------
 
 // findLocalMax core (aux.cpp:193-261). out: rows of (d0, x, y, score); returns the count (<= max_n).

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "ps_set_unary_compact": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]),
     "ps_get_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "ps_add_unary_table": (C.c_int, [_ctx_p, C.c_int, _fp, C.c_int, C.c_float]),
+    "ps_add_unary_grid": (C.c_int, [_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]),
     "ps_rot_score_table": (None, [C.POINTER(ps_config), C.c_double, C.c_double, _fp]),
     "ps_pos_score_table": (None, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, _fp]),

@@ -405,6 +405,31 @@ __global__ void k_add_table(float *__restrict__ g, int R, size_t HW, const float
   }
 }
 
+// DPM score fusion (objectdetect_icps.cpp:445-486 addLoadDPMScore, :488-524 addDPMScore): per-cell adds of a score
+// grid g[nrot][H][W] (nrot = R, or 1 broadcast over rotations).
+//   mode 0 (addDPMScore, grid already in the log domain):   u += w * g
+//   mode 1 (addLoadDPMScore, raw DPM scores):                u += (g > 1e-4 ? w * logf(g) : log(1e-4))
+// icps.cpp has "using namespace std", so log(float) is the fp32 logf there; the device evaluates the correctly
+// rounded fp32 logarithm (fp64 log narrowed), which equals glibc's logf except on its rare non-correctly-rounded
+// inputs (glibc documents < 1 ulp).  The else branch is the double constant log(1e-4) added in double and narrowed.
+__global__ void k_add_grid(float *__restrict__ u, int R, size_t HW, const float *__restrict__ g, int nrot, int mode, float w) {
+  const int r = blockIdx.y;
+  float *s = u + (size_t)r * HW;
+  const float *gs = g + (size_t)(nrot == R ? r : 0) * HW;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < HW; i += stride) {
+    const float val = gs[i];
+    if (mode == 0) {
+      s[i] = __fadd_rn(s[i], __fmul_rn(w, val));
+    } else if ((double)val > 1e-4) {
+      s[i] = __fadd_rn(s[i], __fmul_rn(w, log_f64(val)));
+    } else {
+      s[i] = (float)__dadd_rn((double)s[i], -9.2103403719761836);  // log(1e-4)
+    }
+  }
+}
+
 // ---- message stage 1: shift + exp + circular rotation filter ------------------------------------------
 // findrot.cpp:339-420.  One thread per pixel; the R shifted/exponentiated values of the pixel live in a
 // private shared-memory column, then every output rotation is a sequential dot product over the taps.

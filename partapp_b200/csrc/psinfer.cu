@@ -1113,6 +1113,27 @@ int ps_add_unary_table(ps_ctx *c, int part, const float *table, int kind, float 
   return PS_OK;
 }
 
+int ps_add_unary_grid(ps_ctx *c, int part, const float *grid, int num_rot, int mode, float weight, int mem_kind) {
+  if (!c || !grid) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P) return c->fail(PS_ERR_INVALID, "part out of range");
+  if (num_rot != 1 && num_rot != c->R) return c->fail(PS_ERR_INVALID, "num_rot must be 1 or num_rotation_steps");
+  if (mode < 0 || mode > 1) return c->fail(PS_ERR_INVALID, "mode must be 0 (log-domain add) or 1 (raw DPM scores)");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  for (int s2 = 0; s2 < c->S; ++s2) c->unary_max_valid[(size_t)part * c->S + s2] = 0;
+  DevBuf d;
+  const float *dg = grid;
+  if (mem_kind == PS_MEM_HOST) {
+    PS_CUDA(c, d.alloc((size_t)num_rot * c->HW * sizeof(float)));
+    PS_CUDA(c, cudaMemcpyAsync(d.p, grid, (size_t)num_rot * c->HW * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    dg = d.as<float>();
+  }
+  for (int s = 0; s < c->S; ++s)
+    PS_LAUNCH(c, KC_MISC, psk::k_add_grid<<<dim3(std::min(cdiv(c->HW, 256), 1024u), c->R), 256, 0, c->stream>>>(
+                              c->U(part, s), c->R, c->HW, dg, num_rot, mode, weight));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
 // ---- readout helpers ------------------------------------------------------------------------------
 
 namespace {

@@ -223,6 +223,13 @@ class PsContext:
         t = _f32(table)
         self._check(self.lib.ps_add_unary_table(self.h, part, t.ctypes.data_as(C.POINTER(C.c_float)), kind, weight))
 
+    def add_unary_grid(self, part, grid, mode, weight=1.0):
+        """addDPMScore (mode 0) / addLoadDPMScore (mode 1), objectdetect_icps.cpp:445-524; grid [1 or R][H][W]."""
+        g = _f32(grid)
+        if g.ndim == 2:
+            g = g[None]
+        self._check(self.lib.ps_add_unary_grid(self.h, part, _ptr(g), g.shape[0], mode, weight, capi.PS_MEM_HOST))
+
     # -- inference ---------------------------------------------------------------------------------
     def infer(self, sparse=True, local_max=False, root_hyps=False, keep_unaries=False):
         flags = (capi.PS_INFER_SPARSE if sparse else 0) | (capi.PS_INFER_LOCAL_MAX if local_max else 0) | \

@@ -547,3 +547,28 @@ def test_degenerate_configs_are_rejected():
         with pytest.raises(PsInferError) as e:
             ctx.message(np.zeros((1, 8, 8), np.float32), (1, 1), (1, 1), [[2, 0], [0, 2]], 0.0, 0.5, 1.0, True)
         assert "rot_step_size" in str(e.value)
+
+
+def test_dpm_score_fusion_matches_oracle():
+    """a5: addDPMScore / addLoadDPMScore (objectdetect_icps.cpp:445-524), per-rotation and broadcast grids."""
+    import ctypes
+    ep = ExpParam(num_rotation_steps=8)
+    P, H, W = 2, 22, 26
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 5))
+    rng = np.random.default_rng(4)
+    logg = (rng.standard_normal((8, H, W)) - 3).astype(np.float32)         # log-domain DPM prior, per rotation
+    raw1 = rng.uniform(-0.2, 1.0, (1, H, W)).astype(np.float32)            # raw DPM scores, one grid for all rotations
+    raw1[0, :3] = 5e-5                                                      # below the 1e-4 floor
+    fp = ctypes.POINTER(ctypes.c_float)
+    want = un.copy()
+    L = oracle.lib()
+    L.orc_add_dpm_score(want[0, 0].ctypes.data_as(fp), 8, H, W, logg.ctypes.data_as(fp), 8, 0.7)
+    L.orc_add_load_dpm_score(want[1, 0].ctypes.data_as(fp), 8, H, W, raw1.ctypes.data_as(fp), 1, 1.3)
+    with _ctx(ep, P, H, W) as ctx:
+        for p in range(P):
+            ctx.set_unary(p, 0, un[p, 0])
+        ctx.add_unary_grid(0, logg, 0, 0.7)
+        ctx.add_unary_grid(1, raw1, 1, 1.3)
+        assert np.array_equal(ctx.get_unary(0, 0), want[0, 0])               # mode 0 is exact
+        # mode 1 goes through logf: glibc's is < 1 ulp, the device's is correctly rounded -> allow rare last-bit cells
+        _cmp(ctx.get_unary(1, 0), want[1, 0], "addLoadDPMScore", max_ulp_frac=1e-3, rtol=1e-6)
