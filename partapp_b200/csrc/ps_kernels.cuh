@@ -49,8 +49,8 @@ __host__ __device__ inline float dec_f(int i) {
 // back to *_slow whenever the fp64 result lies within kGuard units (of 2^-29 fp32 ulp) of an fp32 rounding boundary,
 // so fast == slow for every input (checked exhaustively by ps_selftest_math / tests/test_gpu_math.py).
 // Tables are filled by the host at ps_create (ps_math_tables_init).
-__device__ double2 d_log_tab[129];   // .x = 1/F_j, .y = log(F_j) - (j >= 54 ? ln2 : 0),  F_j = 1 + j/128
-__device__ double d_eln2_tab[289];   // RN(e*ln2) for e = -160 .. 128
+__device__ double2 d_log_tab[129];   // .x = 2^-23/F_j, .y = log(F_j) - (j >= 54 ? ln2 : 0),  F_j = 1 + j/128
+__device__ double d_eln2_tab[512];   // [b] = RN((b - 127)*ln2), b = biased exponent (+1 when j >= 54); every 9-bit index is in range
 __device__ double d_exp_tab[64];     // 2^(j/64)
 constexpr int kGuard = 64;
 
@@ -90,25 +90,68 @@ __device__ __forceinline__ float exp_fast(float x) {
   return (float)res;
 }
 
-__device__ __forceinline__ float log_fast(float d) {
-  if (d == 0.0f) return kLogZero;
-  const unsigned ib = __float_as_uint(d);
-  if (ib - 0x00800000u >= 0x7f000000u) return (float)log((double)d);  // subnormal, inf, NaN, negative
+// Branch-free form of exp_fast (same arithmetic, same fallback conditions) for kernels that batch several cells per
+// thread; `redo` asks the caller to replace the result by exp_slow_call(x).  Memory-safe for any bit pattern.
+__device__ __noinline__ float exp_slow_call(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float exp_fast_nb(float x, bool &redo) {
+  const double MAGIC = 6755399441055744.0;
+  const double xd = (double)x;
+  const double t = __fma_rn(xd, 92.332482616893656877, MAGIC);
+  const int k = __double2loint(t);
+  const double kd = t - MAGIC;
+  double r = __fma_rn(kd, -0x1.62e42fe800000p-7, xd);
+  r = __fma_rn(kd, -0x1.e8e7bcd5e4f1ep-37, r);
+  double p = __fma_rn(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+  p = __fma_rn(r, p, 1.6666666666666665741e-01);
+  p = __fma_rn(r, p, 0.5);
+  p = __fma_rn(r, p, 1.0);
+  p = __fma_rn(r, p, 1.0);
+  double res = d_exp_tab[k & 63] * p;
+  res = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+  const bool tiny = x < -104.0f;
+  const bool inr = (x > -87.0f) & (x < 88.0f);
+  redo = (!tiny) & ((!inr) | near_f32_boundary(res));
+  return tiny ? 0.0f : (float)res;
+}
+
+// Table-driven fp64 log of a positive normal fp32 given by its bits.  Safe (if meaningless) for any bit pattern.
+//   d = 2^e * m, m in [1,2);  F_j = nearest multiple of 1/128 to m;  log d = (e + c)*ln2 + (log F_j - c*ln2) + log1p(r),
+//   r = (m - F_j)/F_j, |r| < 2^-8, c = (j >= 54) keeps the two big terms from cancelling near d = 1.
+// m - F_j is an exact multiple of 2^-23, so r = RN(int(mant - j*2^16) * (2^-23/F_j)) equals RN((m - F_j) * (1/F_j)).
+__device__ __forceinline__ double log_core(unsigned ib) {
   const unsigned mant = ib & 0x7fffffu;
-  const int j = (int)((mant + 0x8000u) >> 16);                 // nearest multiple of 1/128: 0..128
-  const double m = __hiloint2double((int)(0x3ff00000u | (mant >> 3)), (int)(mant << 29));
-  const double F = __hiloint2double((int)(0x3ff00000u + ((unsigned)j << 13)), 0);
+  const unsigned j = (mant + 0x8000u) >> 16;  // 0..128
+  const int diff = (int)mant - (int)(j << 16);
   const double2 t = d_log_tab[j];
-  const double r = (m - F) * t.x;
-  const int e2 = (int)(ib >> 23) - 127 + (j >= 54 ? 1 : 0);
+  const double r = (double)diff * t.x;
   double p = __fma_rn(r, -1.6666666666666665741e-01, 0.2);
   p = __fma_rn(r, p, -0.25);
   p = __fma_rn(r, p, 3.3333333333333331483e-01);
   p = __fma_rn(r, p, -0.5);
   p = __fma_rn(r * r, p, r);
-  const double res = d_eln2_tab[e2 + 160] + (t.y + p);
+  // j >= 54  <=>  mant >= 0x358000: adding 0x800000 - 0x358000 carries exactly then into the exponent field
+  return d_eln2_tab[(ib + 0x4a8000u) >> 23] + (t.y + p);
+}
+
+__device__ __forceinline__ float log_fast(float d) {
+  if (d == 0.0f) return kLogZero;
+  const unsigned ib = __float_as_uint(d);
+  if (ib - 0x00800000u >= 0x7f000000u) return (float)log((double)d);  // subnormal, inf, NaN, negative
+  const double res = log_core(ib);
   if (near_f32_boundary(res)) return (float)log((double)d);
   return (float)res;
+}
+
+// Branch-free form of log_fast for kernels that evaluate several cells per thread: always runs log_core and reports
+// in `redo` whether the caller must replace the result by log_slow_call(d) -- exactly the conditions under which
+// log_fast leaves its fast path.  d == 0 gives LOG_ZERO directly.
+__device__ __noinline__ float log_slow_call(float d) { return (float)log((double)d); }
+__device__ __forceinline__ float log_fast_nb(float d, bool &redo) {
+  const unsigned ib = __float_as_uint(d);
+  const double res = log_core(ib);
+  const bool zero = d == 0.0f;
+  redo = (!zero) & ((ib - 0x00800000u >= 0x7f000000u) | near_f32_boundary(res));
+  return zero ? kLogZero : (float)res;
 }
 
 #ifndef PS_SLOW_MATH
@@ -169,6 +212,9 @@ __global__ void k_selftest_math(unsigned first, unsigned long long count, unsign
   }
 }
 
+// Operand of an integer max that reproduces the fmaxf folds: NaN never beats a number.
+__device__ __forceinline__ int enc_max_operand(float v) { return v == v ? enc_f(v) : PS_ENC_NEG_INF; }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -222,6 +268,26 @@ __device__ __forceinline__ void block_key_max_to(unsigned long long best, unsign
     if (lane == 0 && t) atomicMax(dst, t);
   }
 }
+
+// Exact unsigned 32-bit division by a run-time constant (Granlund-Montgomery): 4 instructions instead of the
+// ~25 of the software divide.  Valid for every n < 2^32, d >= 1.
+struct FastDiv {
+  unsigned d, m, s1, s2;
+  FastDiv() : d(1), m(1), s1(0), s2(0) {}
+  explicit FastDiv(unsigned div) : d(div) {
+    unsigned l = 0;
+    while ((1ull << l) < div) ++l;
+    m = (unsigned)(((1ull << 32) * ((1ull << l) - div)) / div + 1);
+    s1 = l < 1 ? l : 1;
+    s2 = l > 0 ? l - 1 : 0;
+  }
+#ifdef __CUDACC__
+  __device__ __forceinline__ unsigned div(unsigned n) const {
+    const unsigned t = __umulhi(m, n);
+    return (t + ((n - t) >> s1)) >> s2;
+  }
+#endif
+};
 
 // ---- pointwise sweeps ------------------------------------------------------------------------------
 
@@ -1078,6 +1144,115 @@ __global__ void __launch_bounds__(256) k_rotconv3(RotArgs a, u64 nz) {
   }
 }
 
+// ---- stage 1 v4: k_rotconv3 on an instruction diet (pure-shift tables only) ---------------------------------------
+// ncu r01d: only 16 % of k_rotconv3's instructions were the FFMA2/FADD2 pairs; the rest was index arithmetic --
+// a modulo per window element in phase 2, two table loads, a 64-bit address and three branches per cell in phase 1.
+// Here the exp tile is stored circularly EXTENDED (row i = A[(i - npad) mod R], i < R + L - 1), so a thread's window
+// is OUT + L - 1 loads at compile-time offsets from one address; the per-rotation shift records live in shared
+// memory; a pixel's (x, y) comes from one FastDiv; exp runs branch-free behind one warp vote per cell.
+template <int R, int L, int PX, int OUT>
+__global__ void __launch_bounds__(256) k_rotconv4(RotArgs a, FastDiv Wdiv, u64 nz) {
+  static_assert(R % OUT == 0 && PX % 2 == 0 && 256 % PX == 0 && PX >= 32, "tiling");
+  constexpr int NPAD = (L - 1) / 2, RX = R + L - 1;
+  __shared__ __align__(8) float s_e[RX][PX];
+  __shared__ float s_taps[L];
+  __shared__ int4 s_sh[R];  // per OUTPUT rotation: (dx, dy, r*HW + dy*W + dx, source rotation or -1)
+  const int tid = threadIdx.x;
+  const int HW = a.H * a.W;
+  const int n = (a.len - 1) / 2;
+  if (tid < L) {
+    const int k = tid - (NPAD - n);
+    s_taps[tid] = (a.mode == 1 && k >= 0 && k < a.len) ? a.taps[k] : 0.0f;
+  }
+  if (tid < R) {
+    const int r = tid - a.shift;
+    int4 q = make_int4(0, 0, 0, -1);
+    if (r >= 0 && r < R) {
+      const int dx = a.shift_xy[2 * r], dy = a.shift_xy[2 * r + 1];
+      q = make_int4(dx, dy, r * HW + dy * a.W + dx, r);
+    }
+    s_sh[tid] = q;
+  }
+  const float negM = -dec_f(*a.max_enc);
+  const int base = blockIdx.x * PX;
+  __syncthreads();
+  {
+    const int px = tid % PX, ro0 = tid / PX;
+    const int p = base + px;
+    const bool okp = p < HW;
+    const int y = (int)Wdiv.div((unsigned)p), x = p - y * a.W;
+    constexpr int STEP = 256 / PX, NIT = (R + STEP - 1) / STEP;
+    float v[NIT];
+#pragma unroll
+    for (int c = 0; c < NIT; ++c) {
+      const int ro = ro0 + c * STEP;
+      v[c] = kLogZero;
+      if (ro < R) {
+        const int4 q = s_sh[ro];
+        const bool ok = okp & (q.w >= 0) & ((unsigned)(x + q.x) < (unsigned)a.W) & ((unsigned)(y + q.y) < (unsigned)a.H);
+        if (ok) v[c] = __ldg(a.in + (p + q.z));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NIT; ++c) {
+      const int ro = ro0 + c * STEP;
+      if (ro < R) {
+        const float xv = __fadd_rn(v[c], negM);
+        float e = 0.0f;
+        if (__any_sync(0xffffffffu, !(xv < -104.0f))) {  // sparse unaries: most warps see only LOG_ZERO cells
+#ifndef PS_SLOW_MATH
+          bool redo;
+          e = exp_fast_nb(xv, redo);
+          if (redo) e = exp_slow_call(xv);
+#else
+          e = exp_slow(xv);
+#endif
+        }
+        s_e[ro + NPAD][px] = e;
+        if (ro >= R - NPAD) s_e[ro + NPAD - R][px] = e;
+        if (ro < NPAD) s_e[ro + NPAD + R][px] = e;
+      }
+    }
+  }
+  __syncthreads();
+  constexpr int NPAIR = PX / 2, NRUN = R / OUT;
+  const bool vec = (HW & 1) == 0;
+  for (int it = tid; it < NPAIR * NRUN; it += 256) {
+    const int pp = it % NPAIR, run = it / NPAIR;
+    const int p0 = base + 2 * pp;
+    if (p0 >= HW) continue;
+    const bool has1 = p0 + 1 < HW;
+    const int i0 = run * OUT;
+    const u64 *col = reinterpret_cast<const u64 *>(&s_e[0][0]) + (i0 * NPAIR + pp);
+    float lo[OUT], hi[OUT];
+    if (a.mode == 1) {
+      u64 acc[OUT];
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) acc[o] = pk2(0.0f, 0.0f);
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        const float f = s_taps[k];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) acc[o] = add2_rn(acc[o], mul2_rn(col[(o + k) * NPAIR], f, nz));
+      }
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) upk2(acc[o], lo[o], hi[o]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) {
+        lo[o] = hi[o] = 0.0f;
+        if (a.mode == 0) upk2(col[(o + NPAD) * NPAIR], lo[o], hi[o]);
+      }
+    }
+    float *dst = a.out + (i0 * HW + p0);
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+      if (vec) *reinterpret_cast<float2 *>(dst + o * HW) = make_float2(lo[o], hi[o]);
+      else { dst[o * HW] = lo[o]; if (has1) dst[o * HW + 1] = hi[o]; }
+    }
+  }
+}
+
 // ---- stage 2b v2: Gaussian along y, two adjacent columns per thread, row tile staged in shared memory -----------
 // Block = 8 warps; warp w produces rows [y0 + w*T, y0 + w*T + T) of a 64-column strip.  The strip's
 // (8T + 2n) input rows are staged once (coalesced float2 rows), so each input element is read from L2
@@ -1707,28 +1882,52 @@ __global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4
 // 16-byte aligned.  32-bit index arithmetic (R*H*W < 2^31 is enforced by ps_create), no per-cell branches: the four
 // cells are evaluated unconditionally on clamped addresses and invalid ones are replaced by LOG_ZERO at the end.
 // ncu r01c: k_epilogue2 spent 98 warp-instructions per cell, a third of them IMAD/ISETP/BRA bookkeeping.
-__global__ void __launch_bounds__(256) k_epilogue3(EpiArgs a, int XG) {
+__global__ void __launch_bounds__(256) k_epilogue3(EpiArgs a, FastDiv XG) {
+  // block-level folds: warp redux on the monotone integer encoding, one shared atomic per warp, one global per block
+  __shared__ int s_m0, s_m1;
+  __shared__ unsigned long long s_key;
+  if (threadIdx.x == 0) {
+    s_m0 = PS_ENC_NEG_INF;
+    s_m1 = PS_ENC_NEG_INF;
+    s_key = 0ull;
+  }
+  __syncthreads();
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   float m0 = -INFINITY, m1 = -INFINITY;
   unsigned long long key0 = 0;
-  if (it < XG * a.H) {
-    const int y = it / XG, x0 = (it - y * XG) * 4;
+  if (it < XG.d * a.H) {
+    const int y = (int)XG.div((unsigned)it), x0 = (it - y * (int)XG.d) * 4;
     const int HW = a.H * a.W;
     const int cell0 = r * HW + y * a.W + x0;
     const float M = dec_f(*a.max_enc);
     const int dx = a.shift_xy[2 * r], ys = y + a.shift_xy[2 * r + 1];
     const bool rowok = (unsigned)ys < (unsigned)a.H;
-    const float *srow = a.src + (r * HW + (rowok ? ys : 0) * a.W);
-    float v[4];
+    const int srow = r * HW + (rowok ? ys : 0) * a.W;  // one 32-bit index per load: R*H*W < 2^31
+    float d[4], v[4];
+    bool ok[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int xs = x0 + j + dx;
-      const bool ok = rowok && (unsigned)xs < (unsigned)a.W;
-      const float d = __ldg(srow + (ok ? xs : 0));
-      const float l = __fadd_rn(log_f64(d), M);
-      v[j] = ok ? l : kLogZero;
+      ok[j] = rowok & ((unsigned)xs < (unsigned)a.W);
+      d[j] = __ldg(a.src + (srow + (ok[j] ? xs : 0)));
     }
+#ifndef PS_SLOW_MATH
+    // four independent table-driven logs, no per-cell branches; the rare Ziv fallbacks are patched afterwards
+    bool redo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = log_fast_nb(d[j], redo[j]);
+    if (redo[0] | redo[1] | redo[2] | redo[3]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (redo[j]) v[j] = log_slow_call(d[j]);
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = log_slow(d[j]);
+#endif
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ok[j] ? __fadd_rn(v[j], M) : kLogZero;
     if (a.out0) {
       float o[4] = {v[0], v[1], v[2], v[3]};
       if (a.acc0) {
@@ -1758,12 +1957,27 @@ __global__ void __launch_bounds__(256) k_epilogue3(EpiArgs a, int XG) {
       m1 = fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w));
     }
   }
-  if (a.max0) block_max_to(m0, a.max0);
-  if (a.max1) {
-    __syncthreads();
-    block_max_to(m1, a.max1);
+  const int lane = threadIdx.x & 31;
+  if (a.max0) {
+    const int e = __reduce_max_sync(0xffffffffu, enc_max_operand(m0));
+    if (lane == 0) atomicMax(&s_m0, e);
   }
-  if (a.amax0) block_key_max_to(key0, a.amax0);
+  if (a.max1) {
+    const int e = __reduce_max_sync(0xffffffffu, enc_max_operand(m1));
+    if (lane == 0) atomicMax(&s_m1, e);
+  }
+  if (a.amax0) {
+    const unsigned hi = (unsigned)(key0 >> 32);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)key0 : 0u);
+    if (lane == 0 && (mh | ml)) atomicMax(&s_key, ((unsigned long long)mh << 32) | ml);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (a.max0) atomicMax(a.max0, s_m0);
+    if (a.max1) atomicMax(a.max1, s_m1);
+    if (a.amax0 && s_key) atomicMax(a.amax0, s_key);
+  }
 }
 
 // ---- root: combine the stored upward messages (findrot.cpp:637-654 and :169) -----------------------------

@@ -319,7 +319,12 @@ constexpr size_t kSmemBudget = 96 * 1024;  // per block, leaves room for 2 block
 template <int Rr, int L, int OUT>
 int launch_rotconv_t(ps_ctx *c, const psk::RotArgs &a) {
   constexpr int PX = 128;
-  PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv3<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(a, PS_NEGZERO2));
+  static const bool old_kernel = getenv("PSINFER_ROTCONV3") != nullptr;  // A/B switch
+  if (a.shift_xy && !old_kernel)
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(
+                                 a, psk::FastDiv((unsigned)c->W), PS_NEGZERO2));
+  else
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv3<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(a, PS_NEGZERO2));
   return PS_OK;
 }
 
@@ -609,7 +614,7 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     if (!al) {
       PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e));
     } else if (!e.general && e.shift_xy && W % 4 == 0 && (uintptr_t)e.src % 16 == 0) {
-      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue3<<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
+      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue3<<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, psk::FastDiv((unsigned)XG)));
     } else if (e.general) {
       PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue2<true><<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
     } else {
@@ -636,11 +641,11 @@ int math_tables_init(ps_ctx *c) {
   double2 lt[129];
   for (int j = 0; j <= 128; ++j) {
     double F = 1.0 + j / 128.0;
-    lt[j].x = 1.0 / F;
+    lt[j].x = std::ldexp(1.0 / F, -23);
     lt[j].y = j == 128 ? 0.0 : (j >= 54 ? std::log(F * 0.5) : std::log(F));
   }
-  double et[289];
-  for (int e = -160; e <= 128; ++e) et[e + 160] = e * 0.693147180559945309417232121458;
+  static double et[512];
+  for (int b = 0; b < 512; ++b) et[b] = (b - 127) * 0.693147180559945309417232121458;
   double xt[64];
   for (int j = 0; j < 64; ++j) xt[j] = std::exp2(j / 64.0);
   PS_CUDA(c, cudaMemcpyToSymbol(psk::d_log_tab, lt, sizeof lt));
