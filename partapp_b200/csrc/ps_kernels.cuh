@@ -1487,6 +1487,174 @@ __global__ void __launch_bounds__(256, 2) k_conv_cols_tma(const __grid_constant_
   }
 }
 
+// ---- stage 2b v4: the TMA column filter with a producer warp ------------------------------------------------------
+// ncu r01d on k_conv_cols_tma: 13 % of the warp samples sat in the per-tile __syncthreads and 10 % behind the
+// global loads of the tile list.  Here warp 8 only feeds the pipeline (waits for a stage to be released, issues the
+// next box), the eight filter warps hand a stage back through an `empty` mbarrier instead of a block barrier -- a
+// warp that is done moves on to the next tile, whose box landed a tile ago -- and the tile list sits in shared memory.
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+constexpr int kMaxSmemTiles = 1024;
+constexpr int kMaxTmaStages = 4;
+
+template <int T>
+__global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant__ CUtensorMap tmap, ColsTmaArgs a, u64 nz, int NS) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_full[kMaxTmaStages], s_empty[kMaxTmaStages];
+  __shared__ float s_taps[1000];
+  __shared__ ushort2 s_tiles[kMaxSmemTiles];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n = (a.len - 1) / 2;
+  const int nrows = 8 * T + 2 * n;
+  const unsigned stage_bytes = (unsigned)nrows * 64 * sizeof(float);
+  const unsigned stage_stride = (stage_bytes + 127) & ~127u;
+  for (int i = tid; i < a.len; i += 288) s_taps[i] = a.taps[i];
+  const bool list_smem = a.tile_list && a.ntile_list <= kMaxSmemTiles;
+  if (list_smem)
+    for (int i = tid; i < a.ntile_list; i += 288)
+      s_tiles[i] = make_ushort2((unsigned short)a.tile_list[2 * i], (unsigned short)a.tile_list[2 * i + 1]);
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int per_slice = a.tile_list ? a.ntile_list : a.ytiles * a.xtiles;
+  const int ntiles = a.slices * per_slice;
+  auto decode = [&](int tile, int &xt, int &yt, int &z) {
+    z = tile / per_slice;
+    const int i = tile - z * per_slice;
+    if (list_smem) {
+      const ushort2 t = s_tiles[i];
+      yt = t.x;
+      xt = t.y;
+    } else if (a.tile_list) {
+      yt = a.tile_list[2 * i];
+      xt = a.tile_list[2 * i + 1];
+    } else {
+      yt = i / a.xtiles;
+      xt = i - yt * a.xtiles;
+    }
+  };
+  if (w == 8) {  // producer
+    if (lane == 0) {
+      int s = 0, u = 0;  // stage, use count of that stage
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (u >= 1) {
+          while (!mbar_try_wait(&s_empty[s], (unsigned)(u - 1) & 1u)) {}
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
+        }
+        int xt, yt, z;
+        decode(tile, xt, yt, z);
+        mbar_expect_tx(&s_full[s], stage_bytes);
+        tma_load_3d(s_raw + s * stage_stride, &tmap, xt * 64, yt * 8 * T - n, z, &s_full[s]);
+        if (++s == NS) {
+          s = 0;
+          ++u;
+        }
+      }
+    }
+    return;
+  }
+  int s = -1, u = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (++s == NS) {
+      s = 0;
+      ++u;
+    }
+    int xt, yt, z;
+    decode(tile, xt, yt, z);
+    while (!mbar_try_wait(&s_full[s], (unsigned)u & 1u)) {}
+    if (yt * 8 * T + w * T < a.rows) {  // warp-uniform
+      const u64 *win = reinterpret_cast<const u64 *>(s_raw + s * stage_stride) + (w * T) * 32 + lane;
+      u64 acc[T], d[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
+#pragma unroll
+      for (int q = 0; q < T - 1; ++q) d[q] = win[q * 32];
+      const u64 *wp = win + (T - 1) * 32;
+      int kk = 0;
+      for (; kk + T <= a.len; kk += T, wp += T * 32) {
+#pragma unroll
+        for (int u = 0; u < T; ++u) {
+          d[(u + T - 1) % T] = wp[u * 32];
+          const float f = s_taps[kk + u];
+#pragma unroll
+          for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < T; ++u) {
+        if (kk + u < a.len) {
+          d[(u + T - 1) % T] = wp[u * 32];
+          const float f = s_taps[kk + u];
+#pragma unroll
+          for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+        }
+      }
+      // the stage is no longer needed: release it before the stores
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      const int x = xt * 64 + lane * 2;
+      if (x < a.cols) {
+        const bool in1 = x + 1 < a.cols;
+        if (a.transpose_out) {
+          const int r0 = yt * 8 * T + w * T;
+          float lo[T], hi[T];
+#pragma unroll
+          for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
+          float *o0 = a.out + (size_t)z * a.plane + (size_t)x * a.pitch + r0;
+          if (r0 + T <= a.rows) {
+#pragma unroll
+            for (int t = 0; t < T; t += 4) *reinterpret_cast<float4 *>(o0 + t) = make_float4(lo[t], lo[t + 1], lo[t + 2], lo[t + 3]);
+            if (in1) {
+#pragma unroll
+              for (int t = 0; t < T; t += 4)
+                *reinterpret_cast<float4 *>(o0 + a.pitch + t) = make_float4(hi[t], hi[t + 1], hi[t + 2], hi[t + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+              if (r0 + t < a.rows) {
+                o0[t] = lo[t];
+                if (in1) o0[a.pitch + t] = hi[t];
+              }
+          }
+        } else {
+          float *dst = a.out + (size_t)z * a.plane + x;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int y = yt * 8 * T + w * T + t;
+            if (y < a.rows) {
+              float lo, hi;
+              upk2(acc[t], lo, hi);
+              float *o = dst + (size_t)y * a.pitch;
+              if (in1) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+              else o[0] = lo;
+            }
+          }
+        }
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+    }
+  }
+}
+
 // ---- stage 2b v2: Gaussian along x, two adjacent rows per thread -------------------------------------------------
 // A block stages PAIRS row pairs (+halo) as float2 (row 2q, row 2q+1) in the "transposed by T" layout
 // (element i at (i % T) * S + i / T); a thread owns T consecutive outputs of both rows of a pair.

@@ -421,7 +421,7 @@ EncodeTiledFn tensor_map_encoder() {
 bool cols_tma_ok(const ps_ctx *c, const float *in, int len, int pitch, size_t plane) {
   const int nrows = 64 + (len - 1);
   const size_t stage = ((size_t)nrows * 64 * sizeof(float) + 127) & ~(size_t)127;
-  return tensor_map_encoder() && !c->disable_tma && nrows <= 256 && 2 * stage <= 110 * 1024 && pitch % 4 == 0 &&
+  return tensor_map_encoder() && !c->disable_tma && nrows <= 256 && 2 * stage <= 104 * 1024 && pitch % 4 == 0 &&
          plane % 4 == 0 && (uintptr_t)in % 16 == 0;
 }
 
@@ -450,11 +450,20 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
   t.tile_list = (tile_list && !c->disable_tile_lists) ? tile_list : nullptr;
   t.ntile_list = ntile_list;
   const int ntiles = t.slices * (t.tile_list ? ntile_list : t.ytiles * t.xtiles);
-  // 2 resident blocks per SM: 3 were 3 % faster in isolation but slower with two images in flight (less room for the
-  // other stream's kernels), round-1 A/B
+  // 2 resident blocks per SM.  A third (67 registers, short filters only) shaved 2 us off the 27-tap launch in isolation
+  // and nothing off the two-images-in-flight bench (round-1 A/B), so the 88-register build stays.
   const int grid = std::min(ntiles, c->num_sms * 2);
-  PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
-            psk::k_conv_cols_tma<T><<<grid, 256, 2 * stage, c->stream>>>(tm, t, PS_NEGZERO2));
+  static const bool v1 = getenv("PSINFER_TMA_V1") != nullptr;  // A/B switch
+  if (v1)
+    PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
+              psk::k_conv_cols_tma<T><<<grid, 256, 2 * stage, c->stream>>>(tm, t, PS_NEGZERO2));
+  else {
+    static const int ns_env = getenv("PSINFER_TMA_STAGES") ? atoi(getenv("PSINFER_TMA_STAGES")) : 0;
+    int ns = 2;  // deeper queues (3, 4) measured no faster: the boxes already land a tile ahead
+    if (ns_env >= 2) ns = (int)std::min<size_t>(std::min(ns_env, psk::kMaxTmaStages), (104 * 1024) / stage);
+    PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
+              psk::k_conv_cols_tma2<T><<<grid, 288, ns * stage, c->stream>>>(tm, t, PS_NEGZERO2, ns));
+  }
   return PS_OK;
 }
 
@@ -887,7 +896,8 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
   c->disable_tile_lists = getenv("PSINFER_ALL_TILES") != nullptr;
-  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024), "smem attr") ||
+  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||

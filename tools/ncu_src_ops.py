@@ -8,12 +8,12 @@ fn, hdr, c, done = None, None, collections.Counter(), False
 for row in csv.reader(open(path)):
     if not row:
         continue
-    if row[0] == 'Function Name':
+    if row[0] in ('Function Name', 'Kernel Name'):
         if fn and sub in fn and c:
             break
         fn = row[1]
         continue
-    if row[0] == 'Line No':
+    if row[0] in ('Line No', 'Address'):
         hdr = {}
         for i, h in enumerate(row):
             hdr.setdefault(h, i)
@@ -25,7 +25,7 @@ for row in csv.reader(open(path)):
         n = int(row[hdr['Instructions Executed']].replace(',', '') or 0)
     except (ValueError, IndexError):
         continue
-    sass = row[src_cols[1]] if len(src_cols) > 1 else ''
+    sass = row[src_cols[-1]]
     if not row[hdr['Address']].strip() or sass.strip() in ('', '-'):
         continue  # source-line aggregate rows
     sass = re.sub(r'^\s*@!?U?P\w+\s+', '', sass.strip())

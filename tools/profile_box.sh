@@ -10,4 +10,7 @@ ncu --set full --clock-control none --import-source on -s ${skip} -c ${count} -f
     $B > gpurun_out/prof_${tag}.log 2>&1
 ncu -i gpurun_out/prof_${tag}.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_${tag}.ncu-rep --page source --csv > gpurun_out/src_${tag}.csv 2>/dev/null
+gzip -f gpurun_out/src_${tag}.csv
+# the .ncu-rep itself is too big for the 64 MiB return channel once sources are imported: keep the CSV exports
+rm -f gpurun_out/prof_${tag}.ncu-rep
 ls -la gpurun_out/ | grep ${tag}
