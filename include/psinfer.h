@@ -75,6 +75,8 @@ typedef struct ps_config {
   float strip_border_detections;
   int roi_save_num_samples;   /* K of findLocalMax; ExpParam default 1000 */
   int keep_all_scales;        /* 1: keep the marginals of every scale resident (bSaveMarginals use); 0: last scale only */
+  int interpolate;            /* ExpParam.interpolate: ps_set_unary_compact resamples with TM_BILINEAR instead of TM_DIRECT
+                               * (partapp.cpp:889-894) */
 } ps_config;
 
 /* object_detect::Joint (objectdetect.h:54-86) after loadJoints (aux.cpp:54-141): 0-based ids, flipped. */
@@ -126,7 +128,8 @@ int ps_set_unary(ps_ctx *ctx, int part, int scale, const float *src, int mem_kin
  * detector grid `cell_scoregrid{scale,rot}` of one (part, scale), [R][grid_h][grid_w] fp32 with 0 = not evaluated
  * (part_detect::NO_CLASS_VALUE); `Tig` is [R][3][3] row-major doubles, Tig = Ti2 * T2g (partapp.cpp:881-887).
  * Every evaluated cell is scattered with TM_DIRECT semantics (transform.hpp:167-192: x outer, y inner, last writer
- * wins), then clip_scores_fill + computeLogGrid are applied.  Uploading compact grids instead of image-size grids cuts
+ * wins) -- or, with ps_config.interpolate, every image cell gathers with TM_BILINEAR through inverse(Tig)
+ * (transform.hpp:196-238) -- then clip_scores_fill + computeLogGrid are applied.  Uploading compact grids instead of image-size grids cuts
  * the host-to-device traffic by the detector stride squared (16x for the shipped configuration, README.md:88). */
 int ps_set_unary_compact(ps_ctx *ctx, int part, int scale, const float *cells, int grid_h, int grid_w,
                          const double *Tig, int mem_kind);

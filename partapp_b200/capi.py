@@ -36,6 +36,7 @@ class ps_config(C.Structure):
         ("strip_border_detections", C.c_float),
         ("roi_save_num_samples", C.c_int),
         ("keep_all_scales", C.c_int),
+        ("interpolate", C.c_int),
     ]
 
 

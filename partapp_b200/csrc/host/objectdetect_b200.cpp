@@ -111,6 +111,7 @@ ps_config make_config(const PartApp &app, int H, int W, int root, bool keep_all)
   cfg.strip_border_detections = ep.strip_border_detections;
   cfg.roi_save_num_samples = (int)ep.roi_save_num_samples;
   cfg.keep_all_scales = keep_all ? 1 : 0;
+  cfg.interpolate = ep.interpolate ? 1 : 0;
   return cfg;
 }
 
@@ -121,7 +122,7 @@ ps_ctx *get_ctx(const PartApp &app, int H, int W, int root, bool keep_all) {
   k.R = cfg.num_rotation_steps; k.S = cfg.num_scale_steps; k.H = H; k.W = W; k.P = cfg.num_parts; k.root = root;
   k.keep = cfg.keep_all_scales; k.rmin = cfg.min_part_rotation; k.rmax = cfg.max_part_rotation;
   k.smin = cfg.min_object_scale; k.smax = cfg.max_object_scale; k.strip = cfg.strip_border_detections;
-  k.K = cfg.roi_save_num_samples;
+  k.K = cfg.roi_save_num_samples * 2 + cfg.interpolate;
   memcpy(k.flags, cfg.is_detect, PS_MAX_PARTS);
   memcpy(k.flags + PS_MAX_PARTS, cfg.is_upright, PS_MAX_PARTS);
   memcpy(k.flags + 2 * PS_MAX_PARTS, cfg.is_root, PS_MAX_PARTS);
@@ -556,7 +557,6 @@ void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, Hypothe
   if (ep.pred_unary_rot || ep.pred_unary_pos || ep.use_dpm_torso || ep.use_dpm_head || ep.use_dpm_unary)
     fail("pred_unary_* / use_dpm_* need the MATLAB predictors of the reference (objectdetect_icps.cpp:608-625); "
          "this host does not emulate them");
-  if (ep.interpolate) fail("interpolate: true (TM_BILINEAR score-grid mapping) is not implemented in this host");
   int W = 0, H = 0;
   image_size(qsImgName, W, H);  // findrot.cpp:752-760
   std::vector<Joint> joints;

@@ -405,6 +405,27 @@ __global__ void __launch_bounds__(256) k_ingest_scatter_direct(IngestArgs a, con
   if (max_dst) block_max_to(m, max_dst);
 }
 
+__device__ __forceinline__ float bilinear_at(const float *__restrict__ s, int h, int w, int pitch, double x1, double y1);
+
+// ExpParam.interpolate: TM_BILINEAR gather (transform.hpp:196-238) of every image cell through T13 = inverse(Tig),
+// default NO_CLASS_VALUE = 0, followed by the unary prep.  `rows` / a.Tig hold rows 0,1 of T13 here.
+__global__ void __launch_bounds__(256) k_ingest_bilinear(IngestArgs a, const __grid_constant__ TigRows rows, FastDiv Wdiv,
+                                                         int *max_dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  float m = -INFINITY;
+  if (i < a.H * a.W) {
+    const int y3 = (int)Wdiv.div((unsigned)i), x3 = i - y3 * a.W;
+    const double *T = a.Tig ? a.Tig + r * 6 : rows.m + r * 6;
+    const double x1 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], (double)x3), __dmul_rn(T[1], (double)y3)), T[2]);
+    const double y1 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], (double)x3), __dmul_rn(T[4], (double)y3)), T[5]);
+    const float v = bilinear_at(a.cells + (size_t)r * a.gh * a.gw, a.gh, a.gw, a.gw, x1, y1);
+    m = prepare_cell(v);
+    a.out[(size_t)r * a.H * a.W + i] = m;
+  }
+  if (max_dst) block_max_to(m, max_dst);
+}
+
 __global__ void __launch_bounds__(256) k_ingest_sweep(IngestArgs a, int *max_dst) {
   const size_t n = (size_t)a.R * a.H * a.W;
   const size_t HW = (size_t)a.H * a.W;

@@ -1060,13 +1060,23 @@ int ps_set_unary_compact(ps_ctx *c, int part, int scale, const float *cells, int
   psk::TigRows rows;
   double *dT = nullptr;
   float *dcells = (float *)(c->ingest.as<double>() + (size_t)c->R * 6);
-  if (c->R <= psk::kMaxIngestRot) {
-    for (int r = 0; r < c->R; ++r)
-      for (int k = 0; k < 6; ++k) rows.m[(size_t)r * 6 + k] = Tig[(size_t)r * 9 + k];
-  } else {
-    std::vector<double> t((size_t)c->R * 6);
-    for (int r = 0; r < c->R; ++r)
+  // TM_DIRECT maps forward with Tig; TM_BILINEAR gathers through T13 = prod(inverse(Tig), identity)
+  // (transform.hpp:131,196; the product with the identity changes nothing)
+  std::vector<double> t((size_t)c->R * 6);
+  for (int r = 0; r < c->R; ++r) {
+    if (c->cfg.interpolate) {
+      psg::M3 T;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T.a[i][j] = Tig[(size_t)r * 9 + i * 3 + j];
+      const psg::M3 inv = psg::inverse(T);
+      for (int k = 0; k < 6; ++k) t[(size_t)r * 6 + k] = inv.a[k / 3][k % 3];
+    } else {
       for (int k = 0; k < 6; ++k) t[(size_t)r * 6 + k] = Tig[(size_t)r * 9 + k];
+    }
+  }
+  if (c->R <= psk::kMaxIngestRot) {
+    for (size_t k = 0; k < t.size(); ++k) rows.m[k] = t[k];
+  } else {
     dT = c->ingest.as<double>();
     PS_CUDA(c, cudaMemcpy(dT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
@@ -1089,7 +1099,10 @@ int ps_set_unary_compact(ps_ctx *c, int part, int scale, const float *cells, int
     collision_free = smin2 > 2.0 * 1.01;
   }
   PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mslot, 1, PS_ENC_NEG_INF));
-  if (collision_free) {
+  if (c->cfg.interpolate) {
+    PS_LAUNCH(c, KC_PREP, psk::k_ingest_bilinear<<<dim3(cdiv(c->HW, 256), c->R), 256, 0, c->stream>>>(
+                              a, rows, psk::FastDiv((unsigned)c->W), mslot));
+  } else if (collision_free) {
     PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 1024), 148u * 16), 256, 0, c->stream>>>(a.out, c->N, psk::kLogZero));
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows, mslot));
   } else {

@@ -30,6 +30,7 @@ class ExpParam:
     max_object_scale: float = 1.0
     strip_border_detections: float = 0.0
     roi_save_num_samples: int = 1000
+    interpolate: bool = False  # score grids mapped with TM_BILINEAR instead of TM_DIRECT (partapp.cpp:889-894)
 
 
 @dataclass
@@ -104,6 +105,7 @@ def make_config(exp_param: ExpParam, part_conf: PartConf, height: int, width: in
     cfg.strip_border_detections = exp_param.strip_border_detections
     cfg.roi_save_num_samples = int(exp_param.roi_save_num_samples)
     cfg.keep_all_scales = 1 if keep_all_scales else 0
+    cfg.interpolate = 1 if getattr(exp_param, "interpolate", False) else 0
     return cfg
 
 

@@ -416,6 +416,21 @@ def test_compact_ingest_collisions_last_writer_wins():
         _cmp(ctx.get_unary(0, 0), want, "colliding scatter")
 
 
+@pytest.mark.parametrize("rotated", [False, True], ids=["lattice", "rotated_lattice"])
+def test_compact_ingest_interpolate_matches_load_score_grid(rotated):
+    """ExpParam.interpolate: TM_BILINEAR gather through inverse(Tig) (partapp.cpp:889-891, transform.hpp:196-238)."""
+    ep = ExpParam(num_rotation_steps=8, interpolate=True)
+    P, H, W = 2, 44, 52
+    cells, Tig = synth.compact_scores(ep, H, W, P, 3, rotated=rotated)
+    dense = np.random.default_rng(3).uniform(-0.2, 1.0, cells[0, 0].shape).astype(np.float32)  # fully evaluated grid
+    with _ctx(ep, P, H, W) as ctx:
+        for p, c in ((0, cells[0, 0]), (1, dense)):
+            want = oracle.prepare_unary(oracle.load_score_grid(c, Tig, H, W, interpolate=True))
+            ctx.set_unary_compact(p, 0, c, Tig)
+            _cmp(ctx.get_unary(p, 0), want, "interpolated ingest part %d" % p)
+        assert (ctx.get_unary(1, 0) > -1e5).sum() > 100
+
+
 # ---- BASELINE.json configs[3] / configs[4] shapes at test size ------------------------------------------------------
 
 def test_conditioned_model_swaps_joints_per_image():
