@@ -91,3 +91,100 @@ def test_pcp_rule():
     assert parteval.is_gt_match(gt, near, pp) and not parteval.is_gt_match(gt, far, pp)
     assert not parteval.is_gt_match(gt, rot, pp)
     assert parteval.pcp_identical([gt, gt], [near, far], [pp]) == 0.5
+
+
+# ---- eval_segments: the reference's PCP evaluation (parteval.cpp:1162-1345) ----------------------------
+
+_PART_CONF = """
+# two sticks: a vertical limb between annopoints 1-2, a horizontal one between 3-4
+part { part_id: 1 part_pos: 1 part_pos: 2 part_x_axis_from: 1 part_x_axis_to: 2 part_x_axis_offset: -90
+       ext_y_pos: 6 ext_y_neg: 4 is_root: true }
+part { part_id: 2 part_pos: 3 part_pos: 4 part_x_axis_from: 3 part_x_axis_to: 4 part_x_axis_offset: -90 }
+joint { child_idx: 2 parent_idx: 1 type: "Gaussian" }
+"""
+_WINDOW_PARAM = """
+part { part_id: 1 window_size_x: 40 window_size_y: 100 pos_offset_x: 20 pos_offset_y: 50 }
+part { part_id: 2 window_size_x: 30 window_size_y: 80 pos_offset_x: 15 pos_offset_y: 40 }
+"""
+_ANNOLIST = """<annotationlist>
+<annotation><image><name>im0.png</name></image>
+  <annorect><x1>10</x1><y1>10</y1><x2>200</x2><y2>200</y2>
+    <annopoints>
+      <point><id>1</id><x>100</x><y>50</y><is_visible>1</is_visible></point>
+      <point><id>2</id><x>100</x><y>150</y><is_visible>1</is_visible></point>
+      <point><id>3</id><x>60</x><y>120</y><is_visible>1</is_visible></point>
+      <point><id>4</id><x>140</x><y>120</y><is_visible>1</is_visible></point>
+    </annopoints>
+  </annorect>
+</annotation>
+<annotation><image><name>im1.png</name></image>
+  <annorect><x1>0</x1><y1>0</y1><x2>1</x2><y2>1</y2>
+    <annopoints>
+      <point><id>1</id><x>100</x><y>50</y></point>
+      <point><id>2</id><x>100</x><y>150</y></point>
+    </annopoints>
+  </annorect>
+</annotation>
+</annotationlist>
+"""
+
+
+def test_eval_segments_pcp(tmp_path):
+    from partapp_b200 import parteval as pe
+    (tmp_path / "part_conf.txt").write_text(_PART_CONF)
+    (tmp_path / "window_param.txt").write_text(_WINDOW_PARAM)
+    (tmp_path / "test.al").write_text(_ANNOLIST)
+    conf = pe.load_part_conf(str(tmp_path / "part_conf.txt"))
+    win = pe.load_window_param(str(tmp_path / "window_param.txt"))
+    annos = pe.load_annolist(str(tmp_path / "test.al"))
+    assert [a.image for a in annos] == ["im0.png", "im1.png"] and annos[0].rects[0].points[4] == (140, 120)
+    assert conf[0].part_pos == [1, 2] and conf[0].part_x_axis_offset == -90 and win[1].window_size_y == 80
+
+    gt = pe.get_part_bbox(annos[0].rects[0], conf[0], 1.0)
+    np.testing.assert_allclose(gt.part_pos, [100, 100])
+    np.testing.assert_allclose(gt.part_y_axis, [0, 1], atol=1e-12)          # the limb direction
+    assert abs(gt.min_proj_y - (-50 - 4)) < 1e-9 and abs(gt.max_proj_y - (50 + 6)) < 1e-9
+
+    def conf_rows(x0, rot0, x1, y1, rot1):
+        # best_conf rows: [scaleidx, scale, rotidx, rot_deg, x, y, score]
+        return np.array([[0, 1.0, 0, rot0, x0, 100, 0.5], [0, 1.0, 0, rot1, x1, y1, 0.25]], np.float32)
+
+    runs = {0: conf_rows(100, 0.0, 100, 120, -90.0),   # both sticks exactly on the annotation
+            1: conf_rows(151, 0.0, 0, 0, 0.0)}         # 51 px off with a 100 px stick: miss; part 2 not annotated
+    res = pe.eval_segments(annos, conf, win, lambda i: runs[i], 0, 1, save_dir=str(tmp_path / "seg_endpoints"))
+    assert (res.seg_correct, res.seg_total) == (2, 3) and res.per_part_total == [2, 1] and res.per_part_correct == [1, 1]
+    assert abs(res.ratio - 2 / 3) < 1e-12
+    np.testing.assert_allclose(res.endpoints[0][0], [100, 150, 100, 50, 1, 1], atol=1e-9)   # bottom, top, match, has gt
+    np.testing.assert_allclose(res.endpoints[0][1, :4], [140, 120, 60, 120], atol=1e-4)
+    assert res.endpoints[1][1, 5] == 0 and res.endpoints[1][2, 0] == 0.0
+    import scipy.io
+    np.testing.assert_allclose(scipy.io.loadmat(str(tmp_path / "seg_endpoints" / "endpoints_0001.mat"))["endpoints"],
+                               res.endpoints[1])
+    # the 0.5 * length threshold is strict on both ends
+    runs[1] = conf_rows(149, 0.0, 0, 0, 0.0)
+    assert pe.eval_segments(annos, conf, win, lambda i: runs[i], 1, 1).seg_correct == 1
+    runs[1] = conf_rows(100, 90.0, 0, 0, 0.0)          # right place, wrong orientation
+    assert pe.eval_segments(annos, conf, win, lambda i: runs[i], 1, 1).seg_correct == 0
+
+
+def test_eval_segments_experiment_layout(tmp_path):
+    """The experiment-level entry reads the same files, in the same places, as `partapp --eval_segments`."""
+    import scipy.io
+    from partapp_b200 import parteval as pe
+    (tmp_path / "part_conf.txt").write_text(_PART_CONF)
+    (tmp_path / "test.al").write_text(_ANNOLIST)
+    sub = tmp_path / "logs" / "exp-pcp"
+    (sub / "class").mkdir(parents=True)
+    (sub / "part_marginals").mkdir()
+    (sub / "class" / "window_param.txt").write_text("train_object_height: 200\n" + _WINDOW_PARAM)
+    (tmp_path / "exp-pcp.txt").write_text('test_dataset: "test.al"\nlog_dir: "./logs"\npart_conf: "part_conf.txt"\n'
+                                          "num_rotation_steps: 24\n")
+    rows0 = np.array([[0, 1, 0, 0, 100, 100, 1], [0, 1, 0, -90, 100, 120, 1]], np.float32)
+    rows1 = np.array([[0, 1, 0, 0, 180, 100, 1], [0, 1, 0, 0, 0, 0, 1]], np.float32)
+    for i, rows in enumerate((rows0, rows1)):
+        scipy.io.savemat(str(sub / "part_marginals" / ("pose_est_imgidx%04d.mat" % i)), {"best_conf": rows})
+    r = pe.eval_segments_experiment(str(tmp_path / "exp-pcp.txt"))
+    assert (r.seg_correct, r.seg_total) == (2, 3)
+    assert (sub / "part_marginals" / "seg_endpoints" / "endpoints_0001.mat").exists()
+    r = pe.eval_segments_experiment(str(tmp_path / "exp-pcp.txt"), first=1, numimgs=1, save_endpoints=False)
+    assert (r.seg_correct, r.seg_total) == (0, 1)
