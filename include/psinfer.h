@@ -133,6 +133,18 @@ int ps_set_unary(ps_ctx *ctx, int part, int scale, const float *src, int mem_kin
  * the host-to-device traffic by the detector stride squared (16x for the shipped configuration, README.md:88). */
 int ps_set_unary_compact(ps_ctx *ctx, int part, int scale, const float *cells, int grid_h, int grid_w,
                          const double *Tig, int mem_kind);
+/* The same mapping stopped after clip_scores_fill: the resident grid holds detector scores (negatives clipped to 1e-4,
+ * unevaluated cells 0), which is what findObjectRoiHelper extracts its detection maxima from before it takes the
+ * logarithm (objectdetect_roi.cpp:205-236).  Follow with ps_unary_local_max and ps_log_unary; ps_infer on a raw
+ * grid is the caller's error. */
+int ps_set_unary_compact_raw(ps_ctx *ctx, int part, int scale, const float *cells, int grid_h, int grid_w,
+                             const double *Tig, int mem_kind);
+/* multi_array_op::computeLogGrid (multi_array_op.hpp:154-167) in place on the resident grid of (part, scale)
+ * (objectdetect_roi.cpp:240-242). */
+int ps_log_unary(ps_ctx *ctx, int part, int scale);
+/* findLocalMax (aux.cpp:193-261) on the resident grid of (part, scale): rows of (rotidx, x, y, score), at most max_n
+ * (objectdetect_roi.cpp:226-228). */
+int ps_unary_local_max(ps_ctx *ctx, int part, int scale, int max_n, float *out, int *count);
 /* Reads the resident (possibly masked) unary back. */
 int ps_get_unary(ps_ctx *ctx, int part, int scale, float *dst, int mem_kind);
 

@@ -72,6 +72,9 @@ PROTOTYPES = {
     "ps_index_from_rot": (C.c_int, [C.POINTER(ps_config), C.c_double]),
     "ps_set_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "ps_set_unary_compact": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]),
+    "ps_set_unary_compact_raw": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]),
+    "ps_log_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    "ps_unary_local_max": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, _fp, _ip]),
     "ps_get_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "ps_add_unary_table": (C.c_int, [_ctx_p, C.c_int, _fp, C.c_int, C.c_float]),
     "ps_add_unary_grid": (C.c_int, [_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]),

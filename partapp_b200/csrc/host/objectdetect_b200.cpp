@@ -548,6 +548,54 @@ void computeRootPosteriorRot(const PartApp &app, std::vector<std::vector<FloatGr
   if (bSaveMarginals) save_marginals(app, ctx, imgidx, flip, H, W);
 }
 
+void findObjectRoiHelper(PartApp app, const int roi[4], double scale, const std::vector<ScoreGrid> &score_grid,
+                         std::vector<Joint> joints, std::vector<std::vector<PartHyp> > &best_part_det,
+                         std::vector<std::vector<PartHyp> > &best_part_hyp) {
+  const int P = (int)app.m_part_conf.part.size(), R = (int)app.m_exp_param.num_rotation_steps;
+  if ((int)score_grid.size() != P) fail("findObjectRoiHelper: one ScoreGrid per part");
+  // "hacky way to set scale used during inference" (objectdetect_roi.cpp:82-85)
+  app.m_exp_param.min_object_scale = app.m_exp_param.max_object_scale = (float)scale;
+  app.m_exp_param.num_scale_steps = 1;
+  const ExpParam &ep = app.m_exp_param;
+  const int roi_x1 = roi[0], roi_y1 = roi[1];
+  const int W = std::abs(roi[2] - roi[0]) + 1, H = std::abs(roi[3] - roi[1]) + 1;  // :150-151
+  if (app.m_rootpart_idx < 0) fail("root part not found");
+  ps_ctx *ctx = get_ctx(app, H, W, app.m_rootpart_idx, false);
+  const int K = (int)ep.roi_save_num_samples;
+  best_part_det.assign(P, std::vector<PartHyp>());
+  std::vector<float> rows((size_t)std::max(K, 1) * 4);
+  for (int p = 0; p < P; ++p) {
+    const ScoreGrid &g = score_grid[p];
+    if ((int)g.Tig.size() != R * 9 || g.cells.size() != (size_t)R * g.gh * g.gw) fail("findObjectRoiHelper: ScoreGrid shape");
+    // transform_grid_fixed_size(TM_DIRECT) + clip_scores_fill (:205-215)
+    check(ctx, ps_set_unary_compact_raw(ctx, p, 0, g.cells.data(), g.gh, g.gw, g.Tig.data(), PS_MEM_HOST), "ps_set_unary_compact_raw");
+    int n = 0;  // maxima of the part detections, ROI offset added (:226-236)
+    check(ctx, ps_unary_local_max(ctx, p, 0, K, rows.data(), &n), "ps_unary_local_max");
+    for (int i = 0; i < n; ++i) {
+      PartHyp h;
+      h.m_scaleidx = 0;
+      h.m_scale = (float)scale_from_index(ep, 0);
+      h.m_rotidx = (int)rows[(size_t)i * 4];
+      h.m_rot = (float)rot_from_index(ep, h.m_rotidx);
+      h.m_x = (int)rows[(size_t)i * 4 + 1] + roi_x1;
+      h.m_y = (int)rows[(size_t)i * 4 + 2] + roi_y1;
+      h.m_score = rows[(size_t)i * 4 + 3];
+      best_part_det[p].push_back(h);
+    }
+    check(ctx, ps_log_unary(ctx, p, 0), "ps_log_unary");  // computeLogGrid (:240-242)
+  }
+  std::vector<ps_joint> pj = to_ps_joints(joints);
+  check(ctx, ps_set_joints(ctx, pj.data(), (int)pj.size()), "ps_set_joints");
+  check(ctx, ps_infer(ctx, PS_INFER_SPARSE | PS_INFER_LOCAL_MAX), "ps_infer");  // bIsSparse = true, no marginals (:246-262)
+  FloatGrid3 root_part_posterior;
+  collect_results(app, ctx, root_part_posterior, best_part_hyp, H, W);
+  for (std::vector<PartHyp> &v : best_part_hyp)  // :265-271
+    for (PartHyp &h : v) {
+      h.m_x += roi_x1;
+      h.m_y += roi_y1;
+    }
+}
+
 void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, HypothesisList &hypothesis_list,
                               const std::string &qsPartMarginalsDir, const std::string &qsScoreGridDir,
                               const std::string &qsImgName) {

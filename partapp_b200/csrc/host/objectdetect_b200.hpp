@@ -139,6 +139,20 @@ void findObjectImageRotJoints(const PartApp &, int imgidx, bool flip, Hypothesis
                               const std::string &qsPartMarginalsDir, const std::string &qsScoreGridDir,
                               const std::string &qsImgName);
 
+// The detector responses of one part inside a region of interest: part_detect::ScoreGrid reduced to what
+// findObjectRoiHelper reads (objectdetect_roi.cpp:195-207): the compact grids of every rotation and Tig = getTig().
+struct ScoreGrid {
+  int gh = 0, gw = 0;
+  std::vector<float> cells;  // [R][gh][gw], 0 = not evaluated
+  std::vector<double> Tig;   // [R][3][3]
+};
+
+// objectdetect_roi.cpp:45-278, the inference half: `roi` = (x1, y1, x2, y2) after the border extension and clamping
+// (:141-148).  Computing the responses (computeDescriptorGridRoi / computeScoreGrid, :180-199) is the detector's job.
+void findObjectRoiHelper(PartApp part_app, const int roi[4], double scale, const std::vector<ScoreGrid> &score_grid,
+                         std::vector<Joint> joints, std::vector<std::vector<PartHyp> > &best_part_det,
+                         std::vector<std::vector<PartHyp> > &best_part_hyp);
+
 // objectdetect_aux.cpp:322-406
 void findObjectDataset(const PartApp &, int firstidx, int lastidx);
 

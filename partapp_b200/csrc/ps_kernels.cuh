@@ -361,7 +361,13 @@ struct IngestArgs {
   int *keys;            // [R][H][W] scratch
   float *out;           // [R][H][W] log-domain unary
   int R, gh, gw, H, W;
+  int raw;              // 1: stop after clip_scores_fill (scores stay in the probability domain, unevaluated cells 0):
+                        // what findObjectRoiHelper takes its detection maxima from (objectdetect_roi.cpp:215-236)
 };
+__device__ __forceinline__ float ingest_cell(float v, int raw) {
+  if (raw) return v < 0.0f ? (float)0.0001 : v;
+  return prepare_cell(v);
+}
 
 __global__ void __launch_bounds__(256) k_ingest_scatter(IngestArgs a, const __grid_constant__ TigRows rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // flat over gh*gw, x fastest (coalesced read)
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(256) k_ingest_scatter_direct(IngestArgs a, con
                                                                int *max_dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
-  float m = kLogZero;  // unevaluated cells are LOG_ZERO (the fill)
+  float m = a.raw ? 0.0f : kLogZero;  // unevaluated cells are LOG_ZERO (the fill)
   if (i < a.gh * a.gw) {
     const int y1 = i / a.gw, x1 = i - y1 * a.gw;
     const float v = a.cells[(size_t)r * a.gh * a.gw + i];
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(256) k_ingest_scatter_direct(IngestArgs a, con
       const double y3 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], (double)x1), __dmul_rn(T[4], (double)y1)), T[5]);
       const int ix = (int)floor(__dadd_rn(x3, 0.5)), iy = (int)floor(__dadd_rn(y3, 0.5));
       if (ix >= 0 && ix < a.W && iy >= 0 && iy < a.H) {
-        const float o = prepare_cell(v);
+        const float o = ingest_cell(v, a.raw);
         a.out[(size_t)r * a.H * a.W + (size_t)iy * a.W + ix] = o;
         m = fmaxf(m, o);
       }
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(256) k_ingest_bilinear(IngestArgs a, const __g
     const double x1 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], (double)x3), __dmul_rn(T[1], (double)y3)), T[2]);
     const double y1 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], (double)x3), __dmul_rn(T[4], (double)y3)), T[5]);
     const float v = bilinear_at(a.cells + (size_t)r * a.gh * a.gw, a.gh, a.gw, a.gw, x1, y1);
-    m = prepare_cell(v);
+    m = ingest_cell(v, a.raw);
     a.out[(size_t)r * a.H * a.W + i] = m;
   }
   if (max_dst) block_max_to(m, max_dst);
@@ -435,13 +441,13 @@ __global__ void __launch_bounds__(256) k_ingest_sweep(IngestArgs a, int *max_dst
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      o[j] = kLogZero;
+      o[j] = a.raw ? 0.0f : kLogZero;
       if (i + j < n) {
         const int k = a.keys[i + j];
         if (k > 0) {
           const int r = (int)((i + j) / HW);
           const int x1 = (k - 1) / a.gh, y1 = (k - 1) - x1 * a.gh;
-          o[j] = prepare_cell(__ldg(&a.cells[(size_t)r * a.gh * a.gw + (size_t)y1 * a.gw + x1]));
+          o[j] = ingest_cell(__ldg(&a.cells[(size_t)r * a.gh * a.gw + (size_t)y1 * a.gw + x1]), a.raw);
         }
         m = fmaxf(m, o[j]);
       }

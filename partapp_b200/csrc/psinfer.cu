@@ -1042,8 +1042,29 @@ int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind,
   return PS_OK;
 }
 
+static int set_unary_compact_impl(ps_ctx *c, int part, int scale, const float *cells, int gh, int gw, const double *Tig,
+                                  int mem_kind, int raw);
 int ps_set_unary_compact(ps_ctx *c, int part, int scale, const float *cells, int gh, int gw, const double *Tig,
                          int mem_kind) {
+  return set_unary_compact_impl(c, part, scale, cells, gh, gw, Tig, mem_kind, 0);
+}
+int ps_set_unary_compact_raw(ps_ctx *c, int part, int scale, const float *cells, int gh, int gw, const double *Tig,
+                             int mem_kind) {
+  return set_unary_compact_impl(c, part, scale, cells, gh, gw, Tig, mem_kind, 1);
+}
+int ps_log_unary(ps_ctx *c, int part, int scale) {
+  if (!c) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  int *mslot = c->unary_max.as<int>() + (size_t)part * c->S + scale;
+  PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mslot, 1, PS_ENC_NEG_INF));
+  PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(
+                            c->U(part, scale), c->N, mslot));
+  c->unary_max_valid[(size_t)part * c->S + scale] = 1;
+  return PS_OK;
+}
+static int set_unary_compact_impl(ps_ctx *c, int part, int scale, const float *cells, int gh, int gw, const double *Tig,
+                                  int mem_kind, int raw) {
   if (!c || !cells || !Tig) return PS_ERR_INVALID;
   if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
   if (gh < 1 || gw < 1 || (size_t)gh * gw >= ((size_t)1 << 31)) return c->fail(PS_ERR_INVALID, "compact grid size out of range");
@@ -1088,6 +1109,7 @@ int ps_set_unary_compact(ps_ctx *c, int part, int scale, const float *cells, int
   psk::IngestArgs a;
   a.cells = src_cells; a.Tig = dT; a.keys = c->ingest_keys.as<int>(); a.out = c->U(part, scale);
   a.R = c->R; a.gh = gh; a.gw = gw; a.H = c->H; a.W = c->W;
+  a.raw = raw;
   int *mslot = c->unary_max.as<int>() + (size_t)part * c->S + scale;
   // collision-free? smallest singular value of every 2x2 linear part must exceed sqrt(2) (plus a safety margin)
   bool collision_free = true;
@@ -1103,14 +1125,15 @@ int ps_set_unary_compact(ps_ctx *c, int part, int scale, const float *cells, int
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_bilinear<<<dim3(cdiv(c->HW, 256), c->R), 256, 0, c->stream>>>(
                               a, rows, psk::FastDiv((unsigned)c->W), mslot));
   } else if (collision_free) {
-    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 1024), 148u * 16), 256, 0, c->stream>>>(a.out, c->N, psk::kLogZero));
+    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 1024), 148u * 16), 256, 0, c->stream>>>(
+                              a.out, c->N, raw ? 0.0f : psk::kLogZero));
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows, mslot));
   } else {
     PS_CUDA(c, cudaMemsetAsync(c->ingest_keys.p, 0, c->N * sizeof(int), c->stream));
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows));
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_sweep<<<cdiv((c->N + 3) / 4, 256), 256, 0, c->stream>>>(a, mslot));
   }
-  c->unary_max_valid[(size_t)part * c->S + scale] = 1;
+  c->unary_max_valid[(size_t)part * c->S + scale] = raw ? 0 : 1;  // a raw grid is not what the messages read
   return PS_OK;
 }
 
@@ -1635,6 +1658,18 @@ int ps_find_local_max(ps_ctx *c, const float *grid, int mem_kind, int d0, int h,
   }
   std::vector<float> rows;
   int rc = local_max_device(c, dg, d0, h, w, max_n, rows);
+  if (rc) return rc;
+  memcpy(out, rows.data(), rows.size() * sizeof(float));
+  *count = (int)(rows.size() / 4);
+  return PS_OK;
+}
+
+int ps_unary_local_max(ps_ctx *c, int part, int scale, int max_n, float *out, int *count) {
+  if (!c || !out || !count || max_n < 0) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  std::vector<float> rows;
+  int rc = local_max_device(c, c->U(part, scale), c->R, c->H, c->W, max_n, rows);
   if (rc) return rc;
   memcpy(out, rows.data(), rows.size() * sizeof(float));
   *count = (int)(rows.size() / 4);

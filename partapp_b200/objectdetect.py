@@ -211,6 +211,28 @@ class PsContext:
                                                   Tig.ctypes.data_as(C.POINTER(C.c_double)), capi.PS_MEM_HOST))
         self.synchronize()
 
+    def set_unary_compact_raw(self, part, scale, cells, Tig):
+        """The same mapping stopped after clip_scores_fill (objectdetect_roi.cpp:205-215): scores, not logs."""
+        Tig = np.ascontiguousarray(Tig, np.float64)
+        g = _f32(cells)
+        if g.ndim != 3 or g.shape[0] != self.R or Tig.shape != (self.R, 3, 3):
+            raise ValueError("cells must be [R][gh][gw], Tig [R][3][3]")
+        self._check(self.lib.ps_set_unary_compact_raw(self.h, part, scale, _ptr(g), g.shape[1], g.shape[2],
+                                                      Tig.ctypes.data_as(C.POINTER(C.c_double)), capi.PS_MEM_HOST))
+        self.synchronize()
+
+    def log_unary(self, part, scale):
+        """computeLogGrid in place on the resident grid (objectdetect_roi.cpp:240-242)."""
+        self._check(self.lib.ps_log_unary(self.h, part, scale))
+
+    def unary_local_max(self, part, scale, max_n):
+        """findLocalMax on the resident grid: rows (rotidx, x, y, score)."""
+        out = np.empty((max(max_n, 1), 4), np.float32)
+        n = C.c_int()
+        self._check(self.lib.ps_unary_local_max(self.h, part, scale, max_n, out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                C.byref(n)))
+        return out[:n.value].copy()
+
     def set_unary_compact_pinned(self, part, scale, host_ptr, gh, gw, Tig):
         """Asynchronous variant for pinned host memory (caller keeps the buffer alive until synchronize)."""
         self._check(self.lib.ps_set_unary_compact(self.h, part, scale, C.c_void_p(host_ptr), gh, gw,
@@ -371,3 +393,41 @@ def getMaxStates(ctx: PsContext, log_part_detections, local_max=False):
 def findLocalMax(ctx: PsContext, log_prob_grid, max_hypothesis_number):
     """objectdetect_aux.cpp:193-261: rows of (dim0, x, y, score)."""
     return ctx.find_local_max(log_prob_grid, max_hypothesis_number)
+
+
+def findObjectRoiHelper(exp_param: ExpParam, part_conf: PartConf, roi, scale, score_grids, Tig, joints, device=0,
+                        root_idx=-1):
+    """The inference half of object_detect::findObjectRoiHelper (objectdetect_roi.cpp:45-278) for a region of interest
+    whose detector responses are given: `roi` = (x1, y1, x2, y2) after the reference's border extension and clamping
+    (:141-148), `score_grids[p]` = the compact ScoreGrid of part p, [R][gh][gw], `Tig` [R][3][3] its grid->ROI map
+    (:201-203).  Computing the responses (computeDescriptorGridRoi / computeScoreGrid, :180-199) is the detector and
+    stays outside.  Returns (best_part_det, best_part_hyp): per part, PartHyp rows
+    [scaleidx, scale, rotidx, rot_deg, x, y, score] with the ROI offset added (:230-236, :265-271).
+
+    The reference forces one scale equal to `scale` for the inference (:82-85) and runs computeRootPosteriorRot sparse
+    without saved marginals (:246-262)."""
+    x1, y1, x2, y2 = [int(v) for v in roi]
+    W, H = abs(x2 - x1) + 1, abs(y2 - y1) + 1
+    ep = ExpParam(**{**exp_param.__dict__, "min_object_scale": float(scale), "max_object_scale": float(scale),
+                     "num_scale_steps": 1})
+    K = int(ep.roi_save_num_samples)
+    P = part_conf.num_parts
+    with PsContext(ep, part_conf, H, W, device=device, root_idx=root_idx) as ctx:
+        best_part_det = []
+        for p in range(P):
+            ctx.set_unary_compact_raw(p, 0, score_grids[p], Tig)            # TM_DIRECT + clip_scores_fill
+            rows = ctx.unary_local_max(p, 0, K)                             # findLocalMax on the scores (:226-228)
+            det = np.zeros((len(rows), 7), np.float32)
+            for i, (r, x, y, v) in enumerate(rows):
+                det[i] = [0, np.float32(scale_from_index(ep, 0)), r, np.float32(rot_from_index(ep, int(r))), x + x1, y + y1, v]
+            best_part_det.append(det)
+            ctx.log_unary(p, 0)                                             # computeLogGrid (:240-242)
+        ctx.set_joints(joints)
+        ctx.infer(sparse=True, local_max=True)
+        best_part_hyp = []
+        for p in range(P):
+            h = ctx.part_hyps(p).copy()
+            h[:, 4] += x1
+            h[:, 5] += y1
+            best_part_hyp.append(h)
+    return best_part_det, best_part_hyp

@@ -587,3 +587,39 @@ def test_dpm_score_fusion_matches_oracle():
         assert np.array_equal(ctx.get_unary(0, 0), want[0, 0])               # mode 0 is exact
         # mode 1 goes through logf: glibc's is < 1 ulp, the device's is correctly rounded -> allow rare last-bit cells
         _cmp(ctx.get_unary(1, 0), want[1, 0], "addLoadDPMScore", max_ulp_frac=1e-3, rtol=1e-6)
+
+
+# ---- the other caller of the boundary: findObjectRoiHelper (objectdetect_roi.cpp:45-278) ---------------
+
+def test_find_object_roi_helper_matches_oracle_composition():
+    """Region-of-interest inference: TM_DIRECT ingest + clip, detection maxima on the SCORES, log, sparse inference at
+    one forced scale, ROI offset on every hypothesis."""
+    ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=12)
+    P, scale = 4, 1.3
+    roi = (17, 9, 17 + 43, 9 + 51)                       # x1, y1, x2, y2 -> 44 x 52 cells
+    W, H = roi[2] - roi[0] + 1, roi[3] - roi[1] + 1
+    pc = synth.part_conf(P)
+    joints = synth.make_joints(P, seed=21, max_offset=5, sigma_range=(1.5, 3))
+    cells, Tig = synth.compact_scores(ep, H, W, P, 7)
+    det, hyp = od.findObjectRoiHelper(ep, pc, roi, scale, [cells[p, 0] for p in range(P)], Tig, joints)
+
+    ep1 = ExpParam(num_rotation_steps=8, roi_save_num_samples=12, min_object_scale=scale, max_object_scale=scale)
+    un = np.empty((P, 1, ep.num_rotation_steps, H, W), np.float32)
+    for p in range(P):
+        g = oracle.load_score_grid(cells[p, 0], Tig, H, W)
+        g[g < 0] = np.float32(0.0001)                    # clip_scores_fill (aux.hpp:42-59)
+        want = oracle.find_local_max(g, 12)              # rows (rot, x, y, score), reference order
+        assert len(want) == len(det[p]) and len(want) > 0
+        got = det[p]
+        assert sorted(map(tuple, got[:, [2, 4, 5, 6]].tolist())) == \
+            sorted((r, x + roi[0], y + roi[1], v) for r, x, y, v in want.tolist())
+        assert np.all(got[:, 0] == 0) and np.all(got[:, 1] == np.float32(scale))
+        un[p, 0] = oracle.prepare_unary(g)               # log of the clipped scores
+    ref = oracle.infer(ep1, pc, joints, un.copy(), sparse=True, want_marginals=False, want_hyps=True)
+    for p in range(P):
+        w = ref["part_hyps"][p].copy()
+        w[:, 4] += roi[0]
+        w[:, 5] += roi[1]
+        assert np.array_equal(hyp[p][0], w[0]), "part %d argmax" % p
+        assert hyp[p][0][1] == np.float32(scale)
+        assert sorted(map(tuple, hyp[p][1:].tolist())) == sorted(map(tuple, w[1:].tolist())), "part %d local maxima" % p
