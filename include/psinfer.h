@@ -210,6 +210,14 @@ int ps_message(ps_ctx *ctx, const float *log_prob_child, float *log_prob_parent,
                const double offset_in[2], const double offset_out[2], const double C[4],
                double rot_mean, double rot_sigma, double scale, int sparse);
 
+/* computePosJointMarginal (objectdetect_findpos.cpp:64-89), the message of the legacy POS_GAUSSIAN joints, applied to
+ * each of the ctx's num_rotation_steps slices of [D][H][W] independently (the reference calls it on 2-D grids):
+ * exp without max shift, gaussFilter2dOffset(C * scale^2, offset * scale, unnormalised, sparse) -- always through the
+ * eigen-frame, the offset on the back transform (multi_array_filter.hpp:335-369) -- and log.  Like the reference it
+ * also rewrites `log_prob_child` with log(exp(child)). */
+int ps_pos_message(ps_ctx *ctx, float *log_prob_child, float *log_prob_parent, int mem_kind, const double offset[2],
+                   const double C[4], double scale, int sparse);
+
 /* findLocalMax core (aux.cpp:193-261) on a caller grid [D0][H][W] (H, W may differ from the ctx's):
  * rows of (dim0, x, y, score). */
 int ps_find_local_max(ps_ctx *ctx, const float *grid, int mem_kind, int d0, int height, int width,

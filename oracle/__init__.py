@@ -58,6 +58,7 @@ def lib():
         L.orc_message.argtypes = [C.POINTER(orc_exp_param), _fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp,
                                   C.c_double, C.c_double, C.c_double, C.c_int, _fp, _fp, _fp]
         L.orc_prepare_unary.argtypes = [_fp, C.c_size_t]
+        L.orc_pos_message.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int]
         L.orc_flip_joint.argtypes = [C.POINTER(orc_joint)]
         L.orc_rot_score_table.argtypes = [C.POINTER(orc_exp_param), C.c_double, C.c_double, _fp]
         L.orc_pos_score_table.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6 + [_fp]
@@ -118,6 +119,18 @@ def message(ep, child, off_in, off_out, Cm, rot_mean, rot_sigma, scale, sparse, 
     lib().orc_message(C.byref(e), _f(child), _f(out), R, H, W, pa, pb, pc, float(rot_mean), float(rot_sigma),
                       float(scale), int(bool(sparse)), *[(_f(d) if d is not None else None) for d in dbg])
     return (out, dbg) if debug else out
+
+
+def pos_message(child, offset, Cm, scale, sparse):
+    """computePosJointMarginal (reference objectdetect_findpos.cpp:64-89) on each [H][W] slice of child [D][H][W].
+    Returns (log_prob_parent, log_prob_child as the reference leaves it: log(exp(child)))."""
+    child = np.ascontiguousarray(child, np.float32).copy()
+    D, H, W = child.shape
+    out = np.empty_like(child)
+    _a, pa = _d(offset)
+    _c, pc = _d(Cm)
+    lib().orc_pos_message(_f(child), _f(out), D, H, W, pa, pc, float(scale), int(bool(sparse)))
+    return out, child
 
 
 def load_score_grid(cells, Tig, H, W, interpolate=False):

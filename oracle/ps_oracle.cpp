@@ -402,14 +402,9 @@ void gauss_filter_diag2d(const float *in, float *out, int h, int w, double c00, 
   }
 }
 
-// multi_array_filter.hpp:335-369 (gaussFilter2dOffset with offset = 0) and :375-388 (gaussFilter2d)
-void gauss_filter_2d(const float *in, float *out, int h, int w, const double C[2][2],
-                     bool is_sparse) {
-  bool is_diag = (C[0][1] == 0 && C[1][0] == 0);
-  if (is_diag) {
-    gauss_filter_diag2d(in, out, h, w, C[0][0], C[1][1]);
-    return;
-  }
+// multi_array_filter.hpp:335-369 gaussFilter2dOffset
+void gauss_filter_2d_offset(const float *in, float *out, int h, int w, const double C[2][2], double offset0,
+                            double offset1, bool is_sparse) {
   const float PADDING_VALUE = 0;
   double V[2][2], E[2][2];
   eig2d(C, V, E);
@@ -425,12 +420,37 @@ void gauss_filter_2d(const float *in, float *out, int h, int w, const double C[2
   transform_grid_helper(in, h, w, tr.data(), oh, ow, T21, T23, PADDING_VALUE,
                         is_sparse ? TM_DIRECT : TM_BILINEAR, true);
   gauss_filter_diag2d(tr.data(), trs.data(), oh, ow, E[0][0], E[1][1]);
-  const double offset0 = 0.0, offset1 = 0.0;  // boost_math::double_zero_vector(2), :385
   Mat3 T42 = hc_homogeneous(V, -offset0, -offset1);
   Mat3 T43 = mat3_prod(T42, T23);
   Mat3 dummy;
   transform_grid_helper(trs.data(), oh, ow, out, h, w, T43, dummy, PADDING_VALUE, TM_BILINEAR,
                         false);
+}
+
+// multi_array_filter.hpp:375-388 gaussFilter2d: the diagonal shortcut, else gaussFilter2dOffset with a zero offset
+void gauss_filter_2d(const float *in, float *out, int h, int w, const double C[2][2],
+                     bool is_sparse) {
+  bool is_diag = (C[0][1] == 0 && C[1][0] == 0);
+  if (is_diag) {
+    gauss_filter_diag2d(in, out, h, w, C[0][0], C[1][1]);
+    return;
+  }
+  gauss_filter_2d_offset(in, out, h, w, C, 0.0, 0.0, is_sparse);  // boost_math::double_zero_vector(2), :385
+}
+
+// libPictStruct/objectdetect_findpos.cpp:64-89 computePosJointMarginal (the legacy POS_GAUSSIAN message).
+// Both grids are [H][W]; log_prob_child is rewritten with log(exp(child)) like the reference does (:76, :88).
+void compute_pos_joint_marginal(float *log_prob_child, float *log_prob_parent, int H, int W, const double offset_in[2],
+                                const double C_in[2][2], double scale, bool is_sparse) {
+  assert(scale > 0);
+  const size_t n = (size_t)H * W;
+  const double offset[2] = {offset_in[0] * scale, offset_in[1] * scale};                     // offset *= scale
+  const double s2 = scale * scale;                                                           // C *= square(scale)
+  const double C[2][2] = {{C_in[0][0] * s2, C_in[0][1] * s2}, {C_in[1][0] * s2, C_in[1][1] * s2}};
+  for (size_t i = 0; i < n; ++i) log_prob_child[i] = (float)exp((double)log_prob_child[i]);  // computeExpGrid
+  gauss_filter_2d_offset(log_prob_child, log_prob_parent, H, W, C, offset[0], offset[1], is_sparse);
+  compute_log_grid(log_prob_parent, n);
+  compute_log_grid(log_prob_child, n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -916,6 +936,14 @@ void orc_load_score_grid(const float *cells, int R, int gh, int gw, const double
     transform_grid_helper(cells + (size_t)r * gh * gw, gh, gw, out + (size_t)r * H * W, H, W, T21, T23, 0.0f,
                           interpolate ? TM_BILINEAR : TM_DIRECT, false);
   }
+}
+
+// computePosJointMarginal (findpos.cpp:64-89) on D independent [H][W] slices; child is rewritten like the reference.
+void orc_pos_message(float *child, float *parent, int D, int H, int W, const double *offset, const double *C,
+                     double scale, int sparse) {
+  double c[2][2] = {{C[0], C[1]}, {C[2], C[3]}};
+  for (int d = 0; d < D; ++d)
+    compute_pos_joint_marginal(child + (size_t)d * H * W, parent + (size_t)d * H * W, H, W, offset, c, scale, sparse != 0);
 }
 
 // computeRotJointMarginal (findrot.cpp:292-456). dbg_* may be NULL.

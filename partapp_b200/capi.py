@@ -91,6 +91,7 @@ PROTOTYPES = {
     "ps_get_root_hyps": (C.c_int, [_ctx_p, _fp, C.c_int, _ip]),
     "ps_message": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double,
                              C.c_double, C.c_int]),
+    "ps_pos_message": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_int]),
     "ps_find_local_max": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _ip]),
     "ps_get_plan_info": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, _ip]),
     "ps_selftest_math": (C.c_int, [_ctx_p, C.c_uint, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),

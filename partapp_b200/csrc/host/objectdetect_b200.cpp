@@ -526,6 +526,20 @@ void computeRotJointMarginal(const ExpParam &ep, FloatGrid3 &child, FloatGrid3 &
                         scale, bIsSparse ? 1 : 0), "ps_message");
 }
 
+void computePosJointMarginal(const ExpParam &ep, FloatGrid3 &child, FloatGrid3 &parent, const double offset[2],
+                             const double C[2][2], double scale, bool bIsSparse) {
+  PartApp app;
+  app.m_exp_param = ep;
+  app.m_exp_param.num_rotation_steps = (unsigned)child.R;  // the slice count of the grids handed in
+  app.m_part_conf.part.resize(2);
+  app.m_part_conf.part[0].is_root = true;
+  ps_ctx *ctx = get_ctx(app, child.H, child.W, 0, false);
+  parent = FloatGrid3(child.R, child.H, child.W);
+  const double Cf[4] = {C[0][0], C[0][1], C[1][0], C[1][1]};
+  check(ctx, ps_pos_message(ctx, child.data(), parent.data(), PS_MEM_HOST, offset, Cf, scale, bIsSparse ? 1 : 0),
+        "ps_pos_message");
+}
+
 void computeRootPosteriorRot(const PartApp &app, std::vector<std::vector<FloatGrid3> > &log_part_detections,
                              FloatGrid3 &root_part_posterior, int rootpart_idx, std::vector<Joint> joints, bool flip,
                              bool bIsSparse, int imgidx, std::vector<std::vector<PartHyp> > &best_part_hyp,

@@ -127,6 +127,11 @@ void computeRotJointMarginal(const ExpParam &, FloatGrid3 &log_prob_child, Float
                              const double offset_c_10[2], const double offset_p_01[2], const double C[2][2],
                              double rot_mean, double rot_sigma, double scale, bool bIsSparse);
 
+// objectdetect_findpos.cpp:64-89 (legacy POS_GAUSSIAN joints).  Grids are [D][H][W]; every [H][W] slice is one call of
+// the reference, which works on 2-D grids.  Like there, log_prob_child comes back as log(exp(child)).
+void computePosJointMarginal(const ExpParam &, FloatGrid3 &log_prob_child, FloatGrid3 &log_prob_parent,
+                             const double offset[2], const double C[2][2], double scale, bool bIsSparse);
+
 // objectdetect_findrot.cpp:470-727
 void computeRootPosteriorRot(const PartApp &, std::vector<std::vector<FloatGrid3> > &log_part_detections,
                              FloatGrid3 &root_part_posterior, int rootpart_idx, std::vector<Joint> joints, bool flip,

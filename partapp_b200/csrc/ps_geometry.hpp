@@ -255,8 +255,12 @@ inline bool pure_shift(const int *t, int n, int &d) {
   return true;
 }
 
+// pos_offset != null: the legacy POS_GAUSSIAN message (computePosJointMarginal, objectdetect_findpos.cpp:64-89):
+// gaussFilter2dOffset is entered directly -- the eigen-frame route even for a diagonal covariance -- and the offset
+// (scaled like the covariance, :72-73) rides on the back transform, T42 = [V | -offset] (multi_array_filter.hpp:362).
 inline MessagePlan plan_message(const Grid &g, const double off_in[2], const double off_out[2],
-                                const double C[4], double rot_mean, double rot_sigma, double scale) {
+                                const double C[4], double rot_mean, double rot_sigma, double scale,
+                                const double *pos_offset = nullptr) {
   MessagePlan p;
   const int R = g.R, H = g.H, W = g.W;
 
@@ -317,7 +321,7 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
   // spatial covariance, :423 scaleC = square(scale)*C
   double s2 = scale * scale;
   double Cs[2][2] = {{s2 * C[0], s2 * C[1]}, {s2 * C[2], s2 * C[3]}};
-  p.diag = (Cs[0][1] == 0 && Cs[1][0] == 0);
+  p.diag = (Cs[0][1] == 0 && Cs[1][0] == 0) && !pos_offset;
   double var_x, var_y;
   if (p.diag) {
     var_x = Cs[0][0];
@@ -340,7 +344,8 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
     M3 T23 = translation(minx, miny), T32 = translation(-minx, -miny);
     rows01(mul(T32, T21), p.T31);
     rows01(mul(inverse(T21), T23), p.T13);
-    M3 T43 = mul(homogeneous(V, -0.0, -0.0), T23);
+    const double bo0 = pos_offset ? pos_offset[0] * scale : 0.0, bo1 = pos_offset ? pos_offset[1] * scale : 0.0;
+    M3 T43 = mul(homogeneous(V, -bo0, -bo1), T23);
     rows01(mul(inverse(T43), M3::eye()), p.T34);
   }
   if (!(var_x > 0 && var_y > 0)) {

@@ -329,6 +329,14 @@ __global__ void __launch_bounds__(256) k_prepare_unary(float *__restrict__ p, si
   if (dst) block_max_to(m, dst);
 }
 
+// computeExpGrid followed by computeLogGrid in place (what computePosJointMarginal leaves in its input,
+// objectdetect_findpos.cpp:76,88)
+__global__ void __launch_bounds__(256) k_exp_log(float *__restrict__ p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = log_f64(exp_f64(p[i]));
+}
+
 // getMinMax (multi_array_op.hpp:61-77), max only
 __global__ void __launch_bounds__(256) k_grid_max(const float *__restrict__ p, size_t n, int *dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -254,8 +254,9 @@ int upload_plan(ps_ctx *c, DevPlan &dp) {
 }
 
 int get_plan(ps_ctx *c, const double off_in[2], const double off_out[2], const double C[4], double rot_mean,
-             double rot_sigma, double scale, std::shared_ptr<DevPlan> &out) {
-  double keyv[11] = {off_in[0], off_in[1], off_out[0], off_out[1], C[0], C[1], C[2], C[3], rot_mean, rot_sigma, scale};
+             double rot_sigma, double scale, std::shared_ptr<DevPlan> &out, const double *pos_offset = nullptr) {
+  double keyv[14] = {off_in[0], off_in[1], off_out[0], off_out[1], C[0], C[1], C[2], C[3], rot_mean, rot_sigma, scale,
+                     pos_offset ? 1.0 : 0.0, pos_offset ? pos_offset[0] : 0.0, pos_offset ? pos_offset[1] : 0.0};
   std::string key((const char *)keyv, sizeof keyv);
   auto it = c->plan_cache.find(key);
   if (it != c->plan_cache.end()) {
@@ -265,7 +266,7 @@ int get_plan(ps_ctx *c, const double off_in[2], const double off_out[2], const d
   }
   ++c->plan_cache_misses;
   std::shared_ptr<DevPlan> dp(new DevPlan);
-  dp->host = psg::plan_message(grid_of(c), off_in, off_out, C, rot_mean, rot_sigma, scale);
+  dp->host = psg::plan_message(grid_of(c), off_in, off_out, C, rot_mean, rot_sigma, scale, pos_offset);
   if (!dp->host.error.empty()) return c->fail(PS_ERR_INVALID, "%s", dp->host.error.c_str());
   int rc = upload_plan(c, *dp);
   if (rc) return rc;
@@ -1600,6 +1601,38 @@ int ps_message(ps_ctx *c, const float *child, float *parent, int mem_kind, const
   if ((rc = run_message(c, dp, din, mx, sparse != 0, sink))) return rc;
   if (mem_kind == PS_MEM_HOST)
     PS_CUDA(c, cudaMemcpyAsync(parent, dout, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PS_OK;
+}
+
+int ps_pos_message(ps_ctx *c, float *child, float *parent, int mem_kind, const double offset[2], const double C[4],
+                   double scale, int sparse) {
+  if (!c || !child || !parent || !offset || !C) return PS_ERR_INVALID;
+  if (!(scale > 0)) return c->fail(PS_ERR_INVALID, "scale must be > 0 (objectdetect_findpos.cpp:68)");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  const double zero[2] = {0.0, 0.0};
+  std::shared_ptr<DevPlan> plan;
+  int prc = get_plan(c, zero, zero, C, 0.0, 0.0, scale, plan, offset);
+  if (prc) return prc;
+  float *din = child, *dout = parent;
+  if (mem_kind == PS_MEM_HOST) {
+    PS_CUDA(c, cudaMemcpyAsync(c->tmp[0].p, child, c->N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    din = c->tmp[0].as<float>();
+    dout = c->tmp[1].as<float>();
+  }
+  // computeExpGrid has no max shift on this path (:76): M = +0, so exp(x + -0) = exp(x) and log(d) + 0 = log(d)
+  int *mx = c->MAXP(2 * c->P + psk::kMaxRootChildren + 2);
+  PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mx, 1, psk::enc_f(0.0f)));
+  Sink sink;
+  sink.out0 = dout;
+  int rc = run_message(c, *plan, din, mx, sparse != 0, sink);
+  if (rc) return rc;
+  // the reference leaves log(exp(child)) in its first argument (:88)
+  PS_LAUNCH(c, KC_MISC, psk::k_exp_log<<<std::min(cdiv(c->N, 256), 148u * 16), 256, 0, c->stream>>>(din, c->N));
+  if (mem_kind == PS_MEM_HOST) {
+    PS_CUDA(c, cudaMemcpyAsync(parent, dout, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PS_CUDA(c, cudaMemcpyAsync(child, din, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
   return PS_OK;
 }

@@ -339,6 +339,16 @@ class PsContext:
                                         float(rot_sigma), float(scale), int(bool(sparse))))
         return out
 
+    def pos_message(self, log_prob_child, offset, Cm, scale, sparse):
+        """computePosJointMarginal on each [H][W] slice; returns (log_prob_parent, rewritten log_prob_child)."""
+        g = _f32(log_prob_child, (self.R, self.H, self.W)).copy()
+        out = np.empty_like(g)
+        oo = (C.c_double * 2)(*[float(v) for v in offset])
+        cc = (C.c_double * 4)(*[float(v) for v in np.asarray(Cm, np.float64).reshape(4)])
+        self._check(self.lib.ps_pos_message(self.h, _ptr(g), _ptr(out), capi.PS_MEM_HOST, oo, cc, float(scale),
+                                            int(bool(sparse))))
+        return out, g
+
     def find_local_max(self, grid, max_n):
         g = _f32(grid)
         d0, h, w = g.shape
@@ -393,6 +403,11 @@ def getMaxStates(ctx: PsContext, log_part_detections, local_max=False):
 def findLocalMax(ctx: PsContext, log_prob_grid, max_hypothesis_number):
     """objectdetect_aux.cpp:193-261: rows of (dim0, x, y, score)."""
     return ctx.find_local_max(log_prob_grid, max_hypothesis_number)
+
+
+def computePosJointMarginal(ctx: PsContext, log_prob_child, offset, Cm, scale, bIsSparse):
+    """objectdetect_findpos.cpp:64-89 (legacy POS_GAUSSIAN joints): returns (log_prob_parent, log_prob_child')."""
+    return ctx.pos_message(log_prob_child, offset, Cm, scale, bIsSparse)
 
 
 def findObjectRoiHelper(exp_param: ExpParam, part_conf: PartConf, roi, scale, score_grids, Tig, joints, device=0,

@@ -623,3 +623,27 @@ def test_find_object_roi_helper_matches_oracle_composition():
         assert np.array_equal(hyp[p][0], w[0]), "part %d argmax" % p
         assert hyp[p][0][1] == np.float32(scale)
         assert sorted(map(tuple, hyp[p][1:].tolist())) == sorted(map(tuple, w[1:].tolist())), "part %d local maxima" % p
+
+
+# ---- legacy POS_GAUSSIAN message (objectdetect_findpos.cpp:64-89, multi_array_filter.hpp:335-369) ------
+
+@pytest.mark.parametrize("diag", [False, True], ids=["full_cov", "diag_cov"])
+@pytest.mark.parametrize("sparse", [False, True], ids=["bilinear", "direct"])
+def test_pos_joint_marginal_matches_oracle(diag, sparse):
+    ep = ExpParam(num_rotation_steps=3)
+    H, W = 44, 38
+    rng = np.random.default_rng(11)
+    child = (rng.standard_normal((3, H, W)) * 2 - 3).astype(np.float32)
+    if sparse:
+        child[rng.random(child.shape) < 0.8] = -1e6          # exp -> exactly 0: skipped by the TM_DIRECT scatter
+    th = 0.7
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    Cm = np.diag([9.0, 4.0]) if diag else Rm @ np.diag([10.0, 3.0]) @ Rm.T
+    Cm = (Cm + Cm.T) / 2
+    for offset, scale in (((5.5, -3.25), 1.0), ((-2.0, 7.0), 1.3)):
+        want_parent, want_child = oracle.pos_message(child, offset, Cm, scale, sparse)
+        with _ctx(ep, 2, H, W) as ctx:
+            got_parent, got_child = od.computePosJointMarginal(ctx, child, offset, Cm, scale, sparse)
+        _cmp(got_parent, want_parent, "pos message parent")
+        _cmp(got_child, want_child, "pos message child round trip")
+        assert (want_parent > -1e5).sum() > 100
