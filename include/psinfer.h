@@ -77,6 +77,12 @@ typedef struct ps_config {
   int keep_all_scales;        /* 1: keep the marginals of every scale resident (bSaveMarginals use); 0: last scale only */
   int interpolate;            /* ExpParam.interpolate: ps_set_unary_compact resamples with TM_BILINEAR instead of TM_DIRECT
                                * (partapp.cpp:889-894) */
+  int fast_math;              /* 0 (default): parity arithmetic -- every filter tap rounds its product and its sum
+                               * separately, in the reference's order: results are bit-identical to the CPU path.
+                               * 1: the tap is one fused multiply-add (half the fp32-pipe time of the Gaussian and
+                               * rotation filters); argmax records stay identical on the test sets, marginals agree
+                               * to ~1e-6 relative (north-star bound: 1e-4).  exp/log, resampling, index and order
+                               * rules are the same in both modes. */
 } ps_config;
 
 /* object_detect::Joint (objectdetect.h:54-86) after loadJoints (aux.cpp:54-141): 0-based ids, flipped. */

@@ -37,6 +37,7 @@ class ps_config(C.Structure):
         ("roi_save_num_samples", C.c_int),
         ("keep_all_scales", C.c_int),
         ("interpolate", C.c_int),
+        ("fast_math", C.c_int),
     ]
 
 

@@ -112,6 +112,9 @@ ps_config make_config(const PartApp &app, int H, int W, int root, bool keep_all)
   cfg.roi_save_num_samples = (int)ep.roi_save_num_samples;
   cfg.keep_all_scales = keep_all ? 1 : 0;
   cfg.interpolate = ep.interpolate ? 1 : 0;
+  // arithmetic mode of the library (include/psinfer.h): parity by default; PSINFER_FAST_MATH=1 selects fused taps
+  const char *fm = getenv("PSINFER_FAST_MATH");
+  cfg.fast_math = (fm && fm[0] && fm[0] != '0') ? 1 : 0;
   return cfg;
 }
 
@@ -122,7 +125,7 @@ ps_ctx *get_ctx(const PartApp &app, int H, int W, int root, bool keep_all) {
   k.R = cfg.num_rotation_steps; k.S = cfg.num_scale_steps; k.H = H; k.W = W; k.P = cfg.num_parts; k.root = root;
   k.keep = cfg.keep_all_scales; k.rmin = cfg.min_part_rotation; k.rmax = cfg.max_part_rotation;
   k.smin = cfg.min_object_scale; k.smax = cfg.max_object_scale; k.strip = cfg.strip_border_detections;
-  k.K = cfg.roi_save_num_samples * 2 + cfg.interpolate;
+  k.K = cfg.roi_save_num_samples * 4 + cfg.interpolate * 2 + cfg.fast_math;
   memcpy(k.flags, cfg.is_detect, PS_MAX_PARTS);
   memcpy(k.flags + PS_MAX_PARTS, cfg.is_upright, PS_MAX_PARTS);
   memcpy(k.flags + 2 * PS_MAX_PARTS, cfg.is_root, PS_MAX_PARTS);

@@ -1003,6 +1003,18 @@ __device__ __forceinline__ u64 add2_rn(u64 a, u64 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+// One filter tap on a packed pair.  FMA = false: the parity arithmetic (product and sum rounded separately, like the
+// reference's sdot).  FMA = true (ps_config.fast_math): one fused multiply-add -- one rounding fewer per tap and half
+// the fp32-pipe time; marginals then agree with the reference to ~1e-6 relative instead of bit for bit.
+template <bool FMA>
+__device__ __forceinline__ u64 tap2(u64 acc, u64 x, float f, u64 negzero2) {
+  if (FMA) {
+    u64 r, ff = pk2(f, f);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(ff), "l"(acc));
+    return r;
+  }
+  return add2_rn(acc, mul2_rn(x, f, negzero2));
+}
 
 // ---- stage 1 v2: shift + exp + circular rotation filter, register resident ------------------------------------
 // One thread owns two consecutive flat pixels; its 2 x R exponentiated values live in registers as R packed pairs.
@@ -1185,7 +1197,7 @@ __global__ void __launch_bounds__(256) k_rotconv3(RotArgs a, u64 nz) {
 // Here the exp tile is stored circularly EXTENDED (row i = A[(i - npad) mod R], i < R + L - 1), so a thread's window
 // is OUT + L - 1 loads at compile-time offsets from one address; the per-rotation shift records live in shared
 // memory; a pixel's (x, y) comes from one FastDiv; exp runs branch-free behind one warp vote per cell.
-template <int R, int L, int PX, int OUT>
+template <int R, int L, int PX, int OUT, bool FMA>
 __global__ void __launch_bounds__(256) k_rotconv4(RotArgs a, FastDiv Wdiv, u64 nz) {
   static_assert(R % OUT == 0 && PX % 2 == 0 && 256 % PX == 0 && PX >= 32, "tiling");
   constexpr int NPAD = (L - 1) / 2, RX = R + L - 1;
@@ -1268,7 +1280,7 @@ __global__ void __launch_bounds__(256) k_rotconv4(RotArgs a, FastDiv Wdiv, u64 n
       for (int k = 0; k < L; ++k) {
         const float f = s_taps[k];
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) acc[o] = add2_rn(acc[o], mul2_rn(col[(o + k) * NPAIR], f, nz));
+        for (int o = 0; o < OUT; ++o) acc[o] = tap2<FMA>(acc[o], col[(o + k) * NPAIR], f, nz);
       }
 #pragma unroll
       for (int o = 0; o < OUT; ++o) upk2(acc[o], lo[o], hi[o]);
@@ -1543,7 +1555,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 constexpr int kMaxSmemTiles = 1024;
 constexpr int kMaxTmaStages = 4;
 
-template <int T>
+template <int T, bool FMA>
 __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant__ CUtensorMap tmap, ColsTmaArgs a, u64 nz, int NS) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTmaStages], s_empty[kMaxTmaStages];
@@ -1628,7 +1640,7 @@ __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant
           d[(u + T - 1) % T] = wp[u * 32];
           const float f = s_taps[kk + u];
 #pragma unroll
-          for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+          for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(u + t) % T], f, nz);
         }
       }
 #pragma unroll
@@ -1637,7 +1649,7 @@ __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant
           d[(u + T - 1) % T] = wp[u * 32];
           const float f = s_taps[kk + u];
 #pragma unroll
-          for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
+          for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(u + t) % T], f, nz);
         }
       }
       // the stage is no longer needed: release it before the stores

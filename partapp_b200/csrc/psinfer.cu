@@ -321,8 +321,11 @@ template <int Rr, int L, int OUT>
 int launch_rotconv_t(ps_ctx *c, const psk::RotArgs &a) {
   constexpr int PX = 128;
   static const bool old_kernel = getenv("PSINFER_ROTCONV3") != nullptr;  // A/B switch
-  if (a.shift_xy && !old_kernel)
-    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(
+  if (a.shift_xy && !old_kernel && c->cfg.fast_math)
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT, true><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(
+                                 a, psk::FastDiv((unsigned)c->W), PS_NEGZERO2));
+  else if (a.shift_xy && !old_kernel)
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT, false><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(
                                  a, psk::FastDiv((unsigned)c->W), PS_NEGZERO2));
   else
     PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv3<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(a, PS_NEGZERO2));
@@ -462,8 +465,12 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
     static const int ns_env = getenv("PSINFER_TMA_STAGES") ? atoi(getenv("PSINFER_TMA_STAGES")) : 0;
     int ns = 2;  // deeper queues (3, 4) measured no faster: the boxes already land a tile ahead
     if (ns_env >= 2) ns = (int)std::min<size_t>(std::min(ns_env, psk::kMaxTmaStages), (104 * 1024) / stage);
-    PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
-              psk::k_conv_cols_tma2<T><<<grid, 288, ns * stage, c->stream>>>(tm, t, PS_NEGZERO2, ns));
+    if (c->cfg.fast_math)
+      PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
+                psk::k_conv_cols_tma2<T, true><<<grid, 288, ns * stage, c->stream>>>(tm, t, PS_NEGZERO2, ns));
+    else
+      PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
+                psk::k_conv_cols_tma2<T, false><<<grid, 288, ns * stage, c->stream>>>(tm, t, PS_NEGZERO2, ns));
   }
   return PS_OK;
 }
@@ -898,7 +905,8 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
   c->disable_tile_lists = getenv("PSINFER_ALL_TILES") != nullptr;
   if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||

@@ -85,7 +85,7 @@ class Joint:
 
 
 def make_config(exp_param: ExpParam, part_conf: PartConf, height: int, width: int, device: int = 0,
-                root_idx: int = -1, keep_all_scales: bool = False):
+                root_idx: int = -1, keep_all_scales: bool = False, fast_math: bool = False):
     cfg = capi.ps_config()
     cfg.device = device
     cfg.num_parts = part_conf.num_parts
@@ -106,6 +106,7 @@ def make_config(exp_param: ExpParam, part_conf: PartConf, height: int, width: in
     cfg.roi_save_num_samples = int(exp_param.roi_save_num_samples)
     cfg.keep_all_scales = 1 if keep_all_scales else 0
     cfg.interpolate = 1 if getattr(exp_param, "interpolate", False) else 0
+    cfg.fast_math = 1 if fast_math else 0
     return cfg
 
 
@@ -136,11 +137,11 @@ class PsContext:
     """One ps_ctx: all tree levels of one image resident on one GPU."""
 
     def __init__(self, exp_param: ExpParam, part_conf: PartConf, height: int, width: int, device: int = 0,
-                 root_idx: int = -1, keep_all_scales: bool = False):
+                 root_idx: int = -1, keep_all_scales: bool = False, fast_math: bool = False):
         self.lib = capi.load_library()
         self.exp_param = exp_param
         self.part_conf = part_conf
-        self.cfg = make_config(exp_param, part_conf, height, width, device, root_idx, keep_all_scales)
+        self.cfg = make_config(exp_param, part_conf, height, width, device, root_idx, keep_all_scales, fast_math)
         self.R, self.S = exp_param.num_rotation_steps, exp_param.num_scale_steps
         self.H, self.W, self.P = height, width, part_conf.num_parts
         h = C.c_void_p()

@@ -95,13 +95,17 @@ def test_gaussian_kernels_keep_both_roundings(pslib):
     from partapp_b200 import capi
     out = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     kernels = re.split(r"\n\s*Function : ", out)
-    seen = 0
+    seen = fast = 0
     for k in kernels[1:]:
         name = k.split("\n", 1)[0]
-        if not any(t in name for t in ("k_conv_cols2", "k_conv_rows2", "k_rotconv3")):
+        if not any(t in name for t in ("k_conv_cols2", "k_conv_rows2", "k_rotconv3", "k_conv_cols_tma", "k_rotconv4")):
+            continue
+        ffma2, fadd2 = len(re.findall(r"\bFFMA2\b", k)), len(re.findall(r"\bFADD2\b", k))
+        assert not re.search(r"\bFFMA\b", k), "%s contains a scalar FFMA" % name
+        if re.search(r"k_conv_cols_tma2ILi\d+ELb1E|k_rotconv4I.*ELb1EEE", name):  # the ps_config.fast_math instantiations
+            fast += 1
+            assert ffma2 > 0 and fadd2 == 0, "%s: fast-math variant with %d FADD2" % (name, fadd2)
             continue
         seen += 1
-        ffma2, fadd2 = len(re.findall(r"\bFFMA2\b", k)), len(re.findall(r"\bFADD2\b", k))
         assert ffma2 > 0 and ffma2 == fadd2, "%s: %d FFMA2 vs %d FADD2" % (name, ffma2, fadd2)
-        assert not re.search(r"\bFFMA\b", k), "%s contains a scalar FFMA" % name
-    assert seen >= 3
+    assert seen >= 6 and fast >= 2

@@ -647,3 +647,30 @@ def test_pos_joint_marginal_matches_oracle(diag, sparse):
         _cmp(got_parent, want_parent, "pos message parent")
         _cmp(got_child, want_child, "pos message child round trip")
         assert (want_parent > -1e5).sum() > 100
+
+
+# ---- ps_config.fast_math: fused multiply-add taps, inside the north star's float tolerance ---------------------------
+
+def test_fast_math_mode_within_north_star_tolerance():
+    """BASELINE.json: "argmax part positions and rotations bit-exact, and marginals within 1e-4 relative".
+    The tolerance applies to this mode only; the default mode is compared for exact equality everywhere else.
+    Log-marginals pass through zero, so "relative" is taken against max(|ref|, 1): |got - ref| <= 1e-4 * max(|ref|, 1)."""
+    RTOL = ATOL = 1e-4
+    ep = ExpParam(num_rotation_steps=24, roi_save_num_samples=5)
+    P, H, W = 10, 72, 64
+    pc = synth.part_conf(P)
+    joints = synth.make_joints(P, seed=3, max_offset=8, sigma_range=(1.5, 4))
+    for img in range(2):
+        un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, img))
+        want = oracle.infer(ep, pc, joints, un.copy(), sparse=True)
+        with PsContext(ep, pc, H, W, fast_math=True) as ctx:
+            res = od.computeRootPosteriorRot(ctx, [[un[p, 0]] for p in range(P)], joints, True, write_back_masked=False)
+            assert np.array_equal(res.best_conf[:, :6], want["best_conf"][:, :6]), "argmax records, image %d" % img
+            np.testing.assert_allclose(res.best_conf[:, 6], want["best_conf"][:, 6], rtol=RTOL)
+            exact = 0
+            for p in range(P):
+                got, ref = ctx.marginal(p), want["marginals"][0, p]
+                np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL, err_msg="marginal of part %d" % p)
+                exact += int(np.array_equal(got, ref))
+            np.testing.assert_allclose(res.root_part_posterior, want["root_post"], rtol=RTOL, atol=ATOL)
+        assert exact < P, "fast_math produced the parity bits everywhere: is the mode wired?"
