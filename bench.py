@@ -370,7 +370,7 @@ def run_ours(args):
         out["config"]["arithmetic"] = ARITH[bool(roofline_ctx_mode)]
         if other is not None:
             out["other_mode"] = other
-        print(json.dumps(out))
+        emit(out)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -441,7 +441,25 @@ def run_reference(args):
            "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under
+    NCCL_DEBUG=VERSION, for one), so everything else is sent to stderr and the line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
 
 
 def main():
@@ -465,6 +483,7 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     args = ap.parse_args()
+    claim_stdout()
     WORKLOAD.update(WORKLOADS[args.workload])
     if args.impl == "reference":
         run_reference(args)

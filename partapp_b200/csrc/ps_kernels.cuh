@@ -1374,28 +1374,13 @@ __global__ void __launch_bounds__(256, 4) k_conv_cols2(ConvArgs a, u64 nz) {
 }
 
 
-// ---- stage 2b v3: Gaussian along y with TMA-fed, double-buffered tiles --------------------------------------------
-// Persistent blocks walk (slice, row-tile, column-strip) tiles.  One elected thread asks the TMA unit for the
-// (8T + 2n) x 64 input box of the NEXT tile (cp.async.bulk.tensor.3d, out-of-bounds rows/columns arrive as zeros =
-// the reference's clipped window) while all warps filter the current one; completion is an mbarrier transaction
-// count, so the fill spends no issue slots and no registers.  Arithmetic is identical to k_conv_cols2.
+// ---- stage 2b, TMA plumbing: mbarrier and bulk-tensor wrappers used by k_conv_cols_tma2 below -------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2,
                                             unsigned long long *bar) {
@@ -1415,135 +1400,13 @@ struct ColsTmaArgs {
   int ntile_list;
 };
 
-template <int T>
-__global__ void __launch_bounds__(256, 2) k_conv_cols_tma(const __grid_constant__ CUtensorMap tmap, ColsTmaArgs a, u64 nz) {
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  __shared__ __align__(8) unsigned long long s_bar[2];
-  __shared__ float s_taps[1000];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int n = (a.len - 1) / 2;
-  const int nrows = 8 * T + 2 * n;
-  const unsigned stage_bytes = (unsigned)nrows * 64 * sizeof(float);
-  const unsigned stage_stride = (stage_bytes + 127) & ~127u;
-  for (int i = tid; i < a.len; i += 256) s_taps[i] = a.taps[i];
-  if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const int per_slice = a.tile_list ? a.ntile_list : a.ytiles * a.xtiles;
-  const int ntiles = a.slices * per_slice;
-  auto decode = [&](int tile, int &xt, int &yt, int &z) {
-    z = tile / per_slice;
-    const int i = tile - z * per_slice;
-    if (a.tile_list) {
-      yt = a.tile_list[2 * i];
-      xt = a.tile_list[2 * i + 1];
-    } else {
-      yt = i / a.xtiles;
-      xt = i - yt * a.xtiles;
-    }
-  };
-  auto issue = [&](int tile, int s) {
-    int xt, yt, z;
-    decode(tile, xt, yt, z);
-    mbar_expect_tx(&s_bar[s], stage_bytes);
-    tma_load_3d(s_raw + s * stage_stride, &tmap, xt * 64, yt * 8 * T - n, z, &s_bar[s]);
-  };
-  int tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) issue(tile, 0);
-  unsigned phases = 0;  // bit s = parity to wait for on stage s
-  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
-    const int s = it & 1;
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) {
-      // stage s^1 was last read (generic proxy) before the __syncthreads that ended the previous iteration
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(next, s ^ 1);
-    }
-    mbar_wait(&s_bar[s], (phases >> s) & 1u);
-    phases ^= 1u << s;
-    int xt, yt, z;
-    decode(tile, xt, yt, z);
-    if (yt * 8 * T + w * T >= a.rows) {  // warp-uniform: nothing to produce in this tile
-      __syncthreads();
-      continue;
-    }
-    const u64 *win = reinterpret_cast<const u64 *>(s_raw + s * stage_stride) + (w * T) * 32 + lane;
-    u64 acc[T], d[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
-#pragma unroll
-    for (int j = 0; j < T - 1; ++j) d[j] = win[j * 32];
-    const u64 *wp = win + (T - 1) * 32;  // next window row to load
-    int kk = 0;
-    for (; kk + T <= a.len; kk += T, wp += T * 32) {
-#pragma unroll
-      for (int u = 0; u < T; ++u) {
-        d[(u + T - 1) % T] = wp[u * 32];
-        const float f = s_taps[kk + u];
-#pragma unroll
-        for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < T; ++u) {
-      if (kk + u < a.len) {
-        d[(u + T - 1) % T] = wp[u * 32];
-        const float f = s_taps[kk + u];
-#pragma unroll
-        for (int t = 0; t < T; ++t) acc[t] = add2_rn(acc[t], mul2_rn(d[(u + t) % T], f, nz));
-      }
-    }
-    const int x = xt * 64 + lane * 2;
-    if (x < a.cols) {
-      const bool in1 = x + 1 < a.cols;
-      if (a.transpose_out) {
-        // the thread's T filter-axis outputs are contiguous in the restored layout: 2 x float4 per column
-        const int r0 = yt * 8 * T + w * T;
-        float lo[T], hi[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
-        float *o0 = a.out + (size_t)z * a.plane + (size_t)x * a.pitch + r0;
-        if (r0 + T <= a.rows) {
-#pragma unroll
-          for (int t = 0; t < T; t += 4) *reinterpret_cast<float4 *>(o0 + t) = make_float4(lo[t], lo[t + 1], lo[t + 2], lo[t + 3]);
-          if (in1) {
-#pragma unroll
-            for (int t = 0; t < T; t += 4)
-              *reinterpret_cast<float4 *>(o0 + a.pitch + t) = make_float4(hi[t], hi[t + 1], hi[t + 2], hi[t + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int t = 0; t < T; ++t)
-            if (r0 + t < a.rows) {
-              o0[t] = lo[t];
-              if (in1) o0[a.pitch + t] = hi[t];
-            }
-        }
-      } else {
-        float *dst = a.out + (size_t)z * a.plane + x;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int y = yt * 8 * T + w * T + t;
-          if (y < a.rows) {
-            float lo, hi;
-            upk2(acc[t], lo, hi);
-            float *o = dst + (size_t)y * a.pitch;
-            if (in1) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
-            else o[0] = lo;
-          }
-        }
-      }
-    }
-    __syncthreads();  // every warp is done with stage s before it is refilled two iterations from now
-  }
-}
-
-// ---- stage 2b v4: the TMA column filter with a producer warp ------------------------------------------------------
-// ncu r01d on k_conv_cols_tma: 13 % of the warp samples sat in the per-tile __syncthreads and 10 % behind the
-// global loads of the tile list.  Here warp 8 only feeds the pipeline (waits for a stage to be released, issues the
+// ---- stage 2b v4: Gaussian along y (and, on the transposed grid, along x) with TMA-fed tiles and a producer warp --
+// Persistent blocks walk (slice, row-tile, column-strip) tiles.  The (8T + 2n) x 64 input box of a tile is fetched
+// by cp.async.bulk.tensor.3d -- out-of-bounds rows/columns arrive as zeros = the reference's clipped window -- and
+// completion is an mbarrier transaction count, so the fill spends no issue slots and no registers of the filter
+// warps.  Arithmetic is identical to k_conv_cols2.  The first TMA version (one elected thread of warp 0 issued the
+// box, a __syncthreads per tile) left 13 % of the warp samples in that barrier and 10 % behind the global loads of
+// the tile list (ncu r01d).  Here warp 8 only feeds the pipeline (waits for a stage to be released, issues the
 // next box), the eight filter warps hand a stage back through an `empty` mbarrier instead of a block barrier -- a
 // warp that is done moves on to the next tile, whose box landed a tile ago -- and the tile list sits in shared memory.
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {

@@ -457,11 +457,7 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
   // 2 resident blocks per SM.  A third (67 registers, short filters only) shaved 2 us off the 27-tap launch in isolation
   // and nothing off the two-images-in-flight bench (round-1 A/B), so the 88-register build stays.
   const int grid = std::min(ntiles, c->num_sms * 2);
-  static const bool v1 = getenv("PSINFER_TMA_V1") != nullptr;  // A/B switch
-  if (v1)
-    PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
-              psk::k_conv_cols_tma<T><<<grid, 256, 2 * stage, c->stream>>>(tm, t, PS_NEGZERO2));
-  else {
+  {
     static const int ns_env = getenv("PSINFER_TMA_STAGES") ? atoi(getenv("PSINFER_TMA_STAGES")) : 0;
     int ns = 2;  // deeper queues (3, 4) measured no faster: the boxes already land a tile ahead
     if (ns_env >= 2) ns = (int)std::min<size_t>(std::min(ns_env, psk::kMaxTmaStages), (104 * 1024) / stage);
@@ -904,8 +900,7 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
   c->disable_tile_lists = getenv("PSINFER_ALL_TILES") != nullptr;
-  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
+  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
