@@ -17,7 +17,7 @@
 #include <vector>
 
 #ifndef PS_RG
-#define PS_RG 6
+#define PS_RG 8
 #endif
 #include "ps_geometry.hpp"
 #include "ps_kernels.cuh"
