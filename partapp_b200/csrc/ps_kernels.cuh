@@ -291,10 +291,17 @@ struct FastDiv {
 
 // ---- pointwise sweeps ------------------------------------------------------------------------------
 
-__global__ void k_fill(float *__restrict__ p, size_t n, float v) {
+// setGrid (multi_array_op.hpp:80-90) with 128-bit stores; optionally also resets a maximum slot (saves the separate
+// one-thread launch in front of every ingest).
+__global__ void __launch_bounds__(256) k_fill(float *__restrict__ p, size_t n, float v, int *slot = nullptr, int slot_init = 0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) p[i] = v;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (slot && i == 0) *slot = slot_init;
+  const size_t n4 = ((uintptr_t)p % 16 == 0) ? n / 4 : 0;
+  float4 *p4 = reinterpret_cast<float4 *>(p);
+  const float4 v4 = make_float4(v, v, v, v);
+  for (size_t j = i; j < n4; j += stride) p4[j] = v4;
+  for (size_t j = n4 * 4 + i; j < n; j += stride) p[j] = v;
 }
 
 __global__ void k_set_int(int *p, int n, int v) {

@@ -1124,13 +1124,14 @@ static int set_unary_compact_impl(ps_ctx *c, int part, int scale, const float *c
     const double smin2 = 0.5 * (s1 - disc);  // squared smallest singular value
     collision_free = smin2 > 2.0 * 1.01;
   }
-  PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mslot, 1, PS_ENC_NEG_INF));
+  if (c->cfg.interpolate || !collision_free)  // the direct path resets the slot inside its fill
+    PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mslot, 1, PS_ENC_NEG_INF));
   if (c->cfg.interpolate) {
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_bilinear<<<dim3(cdiv(c->HW, 256), c->R), 256, 0, c->stream>>>(
                               a, rows, psk::FastDiv((unsigned)c->W), mslot));
   } else if (collision_free) {
-    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 1024), 148u * 16), 256, 0, c->stream>>>(
-                              a.out, c->N, raw ? 0.0f : psk::kLogZero));
+    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 4096), 148u * 8), 256, 0, c->stream>>>(
+                              a.out, c->N, raw ? 0.0f : psk::kLogZero, mslot, PS_ENC_NEG_INF));
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows, mslot));
   } else {
     PS_CUDA(c, cudaMemsetAsync(c->ingest_keys.p, 0, c->N * sizeof(int), c->stream));
