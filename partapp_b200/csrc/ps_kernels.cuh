@@ -186,14 +186,22 @@ __global__ void k_selftest_math(unsigned first, unsigned long long count, unsign
   for (; i < count; i += stride) {
     const float x = __uint_as_float(first + (unsigned)i);
     if (x == x) {
+      // both spellings of each fast routine -- the scalar one and the branch-free one of the batch kernels (with its
+      // patch-up call) -- against the libm routine
       if (fabsf(x) <= 104.0f) {
-        float a = exp_fast(x), b = exp_slow(x);
-        if (__float_as_uint(a) != __float_as_uint(b)) ++bad_e;
+        const float a = exp_fast(x), b = exp_slow(x);
+        bool redo;
+        float c = exp_fast_nb(x, redo);
+        if (redo) c = exp_slow_call(x);
+        if (__float_as_uint(a) != __float_as_uint(b) || __float_as_uint(c) != __float_as_uint(b)) ++bad_e;
         ++fast_e;
       }
       if (x >= 0.0f && x < INFINITY) {
-        float a = log_fast(x), b = log_slow(x);
-        if (__float_as_uint(a) != __float_as_uint(b)) ++bad_l;
+        const float a = log_fast(x), b = log_slow(x);
+        bool redo;
+        float c = log_fast_nb(x, redo);
+        if (redo) c = log_slow_call(x);
+        if (__float_as_uint(a) != __float_as_uint(b) || __float_as_uint(c) != __float_as_uint(b)) ++bad_l;
         ++fast_l;
       }
     }

@@ -18,3 +18,20 @@ with PsContext(ep, synth.part_conf(P), H, W) as ctx:
     j = joints[0]
     out = ctx.message(ctx.get_unary(0, 0), j.offset_c, j.offset_p, [[4.0, 0], [0, 3.0]], 0.2, 0.5, 1.0, True)
     print(float(out.max()))
+    # the other entry points: raw ingest + detection maxima + in-place log, the POS_GAUSSIAN message, DPM adds
+    ctx.set_unary_compact_raw(1, 0, cells[1, 0], Tig)
+    print(len(ctx.unary_local_max(1, 0, 10)))
+    ctx.log_unary(1, 0)
+    par, ch = ctx.pos_message(ctx.get_unary(1, 0), (3.5, -2.0), [[5.0, 1.0], [1.0, 3.0]], 1.0, False)
+    print(float(par.max()))
+    ctx.add_unary_grid(0, np.random.default_rng(0).random((H, W), dtype=np.float32), 1, 0.5)
+# rotation counts with a specialised rotation filter (R = 24) in both arithmetic modes, bilinear ingest
+ep24 = ExpParam(num_rotation_steps=24, roi_save_num_samples=10, interpolate=True)
+cells, Tig = synth.compact_scores(ep24, H, W, P, 2)
+for fast in (False, True):
+    with PsContext(ep24, synth.part_conf(P), H, W, fast_math=fast) as ctx:
+        ctx.set_joints(joints)
+        for p in range(P):
+            ctx.set_unary_compact(p, 0, cells[p, 0], Tig)
+        ctx.infer(sparse=True)
+        print(fast, ctx.best_conf()[:, 2:6].tolist())
