@@ -58,6 +58,11 @@ def lib():
         L.orc_message.argtypes = [C.POINTER(orc_exp_param), _fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp,
                                   C.c_double, C.c_double, C.c_double, C.c_int, _fp, _fp, _fp]
         L.orc_prepare_unary.argtypes = [_fp, C.c_size_t]
+        L.orc_gauss_filter_2d_offset.argtypes = [_fp, _fp, C.c_int, C.c_int, _dp, _dp, C.c_int]
+        L.orc_filter_1d_wraparound.argtypes = [_fp, _fp, C.c_int, _fp, C.c_int]
+        L.orc_pointwise.argtypes = [C.c_int, _fp, C.c_size_t]
+        L.orc_hc_inverse.argtypes = [_dp, _dp]
+        L.orc_transformed_bbox.argtypes = [_dp, C.c_int, C.c_int, _dp]
         L.orc_pos_message.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int]
         L.orc_flip_joint.argtypes = [C.POINTER(orc_joint)]
         L.orc_rot_score_table.argtypes = [C.POINTER(orc_exp_param), C.c_double, C.c_double, _fp]

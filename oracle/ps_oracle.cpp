@@ -4,12 +4,21 @@
 // bench.py's cpu_baseline / --impl reference legs may load it.  The product (partapp_b200/,
 // libpsinfer.so) never links, imports or calls anything in oracle/.
 //
-// PARITY STATUS: *parity unpinned*.  The reference ships no golden vectors, known-answer tests or
-// fixtures for this path and cannot be compiled in this container (needs
-// Boost.MultiArray, uBLAS, Qt4, cblas.h, MATLAB libmat).  This file is a line-by-line restatement
-// of the cited reference routines; every function names the reference file:line it follows
-// (paths relative to /root/reference/src/libs).  Conventions for arithmetic that lives outside
-// the reference tree:
+// PARITY STATUS: *pinned for the grid primitives, unpinned for the drivers and for BLAS / libm*.
+// The reference ships no golden vectors, known-answer tests or fixtures for this path,
+// and its translation units do not compile here as they stand (Boost.MultiArray, uBLAS, Qt4, cblas.h,
+// protoc output and MATLAB libmat are absent).  What does compile, UNMODIFIED from /root/reference, is its
+// numeric core -- libMultiArray/multi_array_{op,transform,filter}.hpp, libBoostMath/{boost_math,homogeneous_coord}.cpp,
+// libPartApp/partapp_aux.hpp, libPictStruct/objectdetect_aux.hpp -- against container stand-ins for Boost, Qt and a
+// Netlib-order cblas_sdot (oracle/ref_shim/, oracle/ref_core.cpp -> oracle/_ref/libps_ref_core.so).
+// tests/test_oracle_vs_ref.py holds this file to that code bit for bit: transform_grid_* (nearest / bilinear / direct),
+// gaussFilterDiag2d, gaussFilter2d, gaussFilter2dOffset, grid_filter_1d_blas_wraparound, eig2d, get_gaussian_filter,
+// hc::inverse / get_transformed_bbox, computeLogGrid / computeExpGrid, clip_scores_fill, rot_from_index /
+// index_from_rot -- live where the reference tree exists, and everywhere through tests/golden/ref_core.npz.
+// NOT pinned: the drivers that compose those primitives (computeRotJointMarginal, computeRootPosteriorRot,
+// computePartMarginals, findLocalMax, loadJoints -- their translation units need Qt / protobuf / libmat), which are
+// restated line by line below with the reference file:line next to every function (paths relative to
+// /root/reference/src/libs), and the arithmetic that lives outside the reference tree:
 //   * cblas_sdot  -> Netlib order: sequential ascending-index fp32 multiply-then-add, no FMA.
 //   * exp / log   -> evaluated in double by libm and narrowed to float.
 // Build: g++ -O3 -ffp-contract=off (no -ffast-math, no -mfma) -- see oracle/Makefile.
@@ -901,6 +910,45 @@ void orc_eig2d(const double *M, double *V, double *E) {
 void orc_gauss_filter_2d(const float *in, float *out, int H, int W, const double *C, int sparse) {
   double c[2][2] = {{C[0], C[1]}, {C[2], C[3]}};
   gauss_filter_2d(in, out, H, W, c, sparse != 0);
+}
+
+// gaussFilter2dOffset on one H x W slice (filter.hpp:335-369)
+void orc_gauss_filter_2d_offset(const float *in, float *out, int H, int W, const double *C, const double *offset, int sparse) {
+  double c[2][2] = {{C[0], C[1]}, {C[2], C[3]}};
+  gauss_filter_2d_offset(in, out, H, W, c, offset[0], offset[1], sparse != 0);
+}
+
+// grid_filter_1d_blas_wraparound (filter.hpp:116-155) on one length-n column, the form compute_rot_joint_marginal
+// applies to every pixel: out[i] = sdot over k of in[(i + k - nx) mod n] * f[k]
+void orc_filter_1d_wraparound(const float *in, float *out, int n, const float *f, int f_len) {
+  int nx = (f_len - 1) / 2;
+  for (int i = 0; i < n; ++i) {
+    float acc = 0.0f;
+    for (int k = 0; k < f_len; ++k) acc += in[((i + k - nx) % n + n) % n] * f[k];
+    out[i] = acc;
+  }
+}
+
+// computeLogGrid (op 0) / computeExpGrid (op 1), multi_array_op.hpp:154-180
+void orc_pointwise(int op, float *a, size_t n) {
+  if (op == 0) compute_log_grid(a, n);
+  else compute_exp_grid(a, n);
+}
+
+void orc_hc_inverse(const double *T, double *out) {
+  Mat3 M;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M.m[i][j] = T[i * 3 + j];
+  Mat3 I = hc_inverse(M);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) out[i * 3 + j] = I.m[i][j];
+}
+
+void orc_transformed_bbox(const double *T, int w, int h, double *out4) {
+  Mat3 M;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M.m[i][j] = T[i * 3 + j];
+  hc_transformed_bbox(M, w, h, out4[0], out4[1], out4[2], out4[3]);
 }
 
 // size of the enlarged grid used by gaussFilter2dOffset for covariance C (transform.hpp:290-299)

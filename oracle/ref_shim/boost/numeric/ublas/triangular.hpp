@@ -1,0 +1,3 @@
+// stand-in, see ublas_min.hpp
+#pragma once
+#include "ublas_min.hpp"
