@@ -1,0 +1,28 @@
+// Stand-in for libMatlabIO (MATLAB's libmat is not installed) -- TEST INFRASTRUCTURE.  File output is not part of what
+// oracle/_ref pins: the savers do nothing, the loaders abort.
+#pragma once
+#include <QString>
+#include <cstddef>
+#include <cstdlib>
+#include <libMultiArray/multi_array_def.h>
+#include <libBoostMath/boost_math.h>
+#include <libBoostMath/boost_math.hpp>  // the real header reaches it too; objectdetect_findrot.cpp relies on that
+struct MATFile {};
+namespace matlab_io {
+inline MATFile *mat_open(QString, const char *) { static MATFile f; return &f; }
+inline void mat_close(MATFile *) {}
+// The reference hands its per-part marginals to mat_save_multi_array (objectdetect_findrot.cpp:239-253); the hook lets
+// oracle/ref_drivers.cpp collect them instead of writing files.
+typedef void (*capture_fn)(const char *file, const char *var, const void *data, size_t bytes);
+extern capture_fn g_capture;
+template <class A> bool mat_save_multi_array(QString file, QString var, const A &a) {
+  if (g_capture) g_capture(file.toStdString().c_str(), var.toStdString().c_str(), a.data(), a.num_elements() * sizeof(typename A::element));
+  return true;
+}
+template <class A> bool mat_save_multi_array(MATFile *, QString, const A &) { return true; }
+template <class A> A mat_load_multi_array(QString, QString) { abort(); }
+template <class A> A mat_load_multi_array(MATFile *, QString) { abort(); }
+inline bool mat_load_double_matrix(QString, QString, boost_math::double_matrix &) { abort(); }
+inline bool mat_load_double_vector(QString, QString, boost_math::double_vector &) { abort(); }
+inline bool mat_save_double_matrix(QString, QString, const boost_math::double_matrix &) { return true; }
+}  // namespace matlab_io

@@ -1,17 +1,49 @@
 // Stand-in for the protoc-generated libPartApp/ExpParam.pb.h -- TEST INFRASTRUCTURE (protoc and the protobuf C++
-// runtime are not installed here).  Only the accessors the reference's libPartApp/partapp_aux.hpp reads, with the
-// field types of ExpParam.proto (float ranges, uint32 counts), so that header compiles unmodified into oracle/_ref/.
+// runtime are not installed here).  Plain data with the accessors (and field types: float ranges, uint32 counts) that
+// the reference's partapp_aux.hpp and objectdetect_findrot.cpp read, so those files compile unmodified into oracle/_ref/.
 #pragma once
 #include <cassert>
 #include <cstdint>
+#include <string>
 class ExpParam {
  public:
-  float min_object_scale_ = 1, max_object_scale_ = 1, min_part_rotation_ = -180, max_part_rotation_ = 180;
-  uint32_t num_scale_steps_ = 1, num_rotation_steps_ = 48;
-  float min_object_scale() const { return min_object_scale_; }
-  float max_object_scale() const { return max_object_scale_; }
-  uint32_t num_scale_steps() const { return num_scale_steps_; }
-  float min_part_rotation() const { return min_part_rotation_; }
-  float max_part_rotation() const { return max_part_rotation_; }
-  uint32_t num_rotation_steps() const { return num_rotation_steps_; }
+#define PS_FIELD(type, name, dflt)          \
+  type name##_ = dflt;                      \
+  bool has_##name##_ = false;               \
+  type name() const { return name##_; }     \
+  bool has_##name() const { return has_##name##_; } \
+  void set_##name(type v) { name##_ = v; has_##name##_ = true; }
+  PS_FIELD(float, min_object_scale, 1)
+  PS_FIELD(float, max_object_scale, 1)
+  PS_FIELD(uint32_t, num_scale_steps, 1)
+  PS_FIELD(float, min_part_rotation, -180)
+  PS_FIELD(float, max_part_rotation, 180)
+  PS_FIELD(uint32_t, num_rotation_steps, 48)
+  PS_FIELD(float, strip_border_detections, 0)
+  PS_FIELD(float, roi_save_num_samples, 1000)
+  PS_FIELD(int32_t, num_pose_samples, 0)
+  PS_FIELD(bool, use_pairwise, true)
+  PS_FIELD(bool, use_torso_pos_prior, false)
+  PS_FIELD(bool, pred_unary_rot, false)
+  PS_FIELD(bool, pred_unary_pos, false)
+  PS_FIELD(float, pred_unary_rot_weight, 1)
+  PS_FIELD(float, pred_unary_pos_weight, 1)
+  PS_FIELD(bool, use_dpm_unary, false)
+  PS_FIELD(bool, use_dpm_torso, false)
+  PS_FIELD(bool, use_dpm_head, false)
+  PS_FIELD(float, dpm_unary_weight, 1)
+  PS_FIELD(float, dpm_torso_weight, 1)
+  PS_FIELD(float, dpm_head_weight, 1)
+  PS_FIELD(bool, do_dpm_rot, false)
+  PS_FIELD(bool, save_part_marginals, false)
+  PS_FIELD(bool, save_part_marginals_local_max, false)
+  PS_FIELD(bool, save_part_detections_local_max, false)
+  PS_FIELD(bool, interpolate, false)
+  PS_FIELD(std::string, log_dir, "")
+  PS_FIELD(std::string, log_subdir, "")
+  PS_FIELD(std::string, test_dpm_unary_dir, "")
+  PS_FIELD(std::string, test_dpm_torso_dir, "")
+  PS_FIELD(std::string, test_dpm_head_dir, "")
+  PS_FIELD(std::string, part_conf_type, "")
+#undef PS_FIELD
 };

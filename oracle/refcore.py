@@ -124,3 +124,74 @@ def bins(mn, mx, n):
     centres = np.array([L.ref_bins(0, mn, mx, n, i, 0.0) for i in range(n)])
     back = np.array([L.ref_bins(2, mn, mx, n, 0, float(c)) for c in centres])
     return np.concatenate([centres, back])
+
+
+# ---- the reference's own inference drivers (objectdetect_findrot.cpp compiled unmodified, oracle/ref_drivers.cpp) ------
+DRIVERS_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libps_ref_drivers.so")
+_dlib = None
+
+
+def drivers_available():
+    return os.path.exists(DRIVERS_PATH)
+
+
+def dlib():
+    global _dlib
+    if _dlib is None:
+        L = C.CDLL(DRIVERS_PATH)
+        L.refd_message.argtypes = [_dp, _fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double,
+                                   C.c_double, C.c_int]
+        L.refd_infer.argtypes = [_dp, C.c_int, _ip, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, _fp]
+        _dlib = L
+    return _dlib
+
+
+def _epv(ep):
+    return np.array([ep.min_part_rotation, ep.max_part_rotation, ep.num_rotation_steps, ep.min_object_scale,
+                     ep.max_object_scale, ep.num_scale_steps, ep.strip_border_detections, ep.roi_save_num_samples], np.float64)
+
+
+def _quiet(fn):
+    """The reference prints progress to stdout from C++; keep test logs readable."""
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        return fn()
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+def message(ep, child, off_in, off_out, Cm, rot_mean, rot_sigma, scale, sparse):
+    """object_detect::computeRotJointMarginal as the reference compiled it."""
+    child = np.ascontiguousarray(child, np.float32)
+    R, H, W = child.shape
+    out = np.empty_like(child)
+    e, (_a, pa), (_b, pb), (_c, pc) = _epv(ep), _d(off_in), _d(off_out), _d(Cm)
+    _quiet(lambda: dlib().refd_message(e.ctypes.data_as(_dp), _f(child), _f(out), R, H, W, pa, pb, pc, float(rot_mean),
+                                       float(rot_sigma), float(scale), int(bool(sparse))))
+    return out
+
+
+def infer(ep, part_conf, joints, unaries, sparse=True):
+    """object_detect::computeRootPosteriorRot + computePartMarginals as the reference compiled them.  `unaries`
+    [P][S][R][H][W] is masked in place.  roi_save_num_samples must be 0 unless objectdetect_aux.cpp is part of the build."""
+    assert unaries.dtype == np.float32 and unaries.flags.c_contiguous
+    P, S, R, H, W = unaries.shape
+    det = np.array([int(bool(v)) for v in part_conf.is_detect], np.int32)
+    upr = np.array([int(bool(v)) for v in part_conf.is_upright], np.int32)
+    roots = [p for p in range(P) if part_conf.is_detect[p] and part_conf.is_root[p]]
+    js = np.array([[j.type, j.child_idx, j.parent_idx, j.offset_c[0], j.offset_c[1], j.offset_p[0], j.offset_p[1],
+                    j.C[0][0], j.C[0][1], j.C[1][0], j.C[1][1], j.rot_mean, j.rot_sigma] for j in joints], np.float64)
+    root_post = np.empty((S, H, W), np.float32)
+    best = np.empty((P, 7), np.float32)
+    marg = np.empty((S, P, R, H, W), np.float32)
+    e = _epv(ep)
+    _quiet(lambda: dlib().refd_infer(e.ctypes.data_as(_dp), P, det.ctypes.data_as(_ip), upr.ctypes.data_as(_ip), roots[0],
+                                     js.ctypes.data_as(_dp), len(joints), H, W, _f(unaries), int(bool(sparse)), _f(root_post),
+                                     _f(best), _f(marg)))
+    return {"root_post": root_post, "best_conf": best, "marginals": marg}
