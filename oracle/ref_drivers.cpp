@@ -1,5 +1,6 @@
 // ref_drivers.cpp -- TEST INFRASTRUCTURE: C entry points over the reference's OWN inference drivers.
 // libPictStruct/objectdetect_findrot.cpp (computeRotJointMarginal, computePartMarginals, computeRootPosteriorRot) is
+// and libPictStruct/objectdetect_aux.cpp (findLocalMax, loadJoints) are
 // compiled UNMODIFIED from /root/reference next to this file (`make -C oracle ref`), against the stand-ins of
 // oracle/ref_shim/ for everything the image lacks (Boost, Qt, protoc output, libmat, the detector libraries).  This file
 // defines what that translation unit references but other, uncompilable translation units define.
@@ -28,13 +29,33 @@ void index_from_flat3(int shape0, int shape1, int shape2, int flat_idx, int &idx
 void bbox_from_pos(const ExpParam &, const PartWindowParam::PartParam &, int, int, int, int, PartBBox &) { abort(); }
 void bbox_from_pos(const PartWindowParam::PartParam &, double, double, int, int, PartBBox &) { abort(); }
 
-#ifndef PS_REF_WITH_AUX
+// libPictStruct/objectdetect_aux.cpp (findLocalMax, loadJoints, ...) is compiled next to this file as well; what it
+// references from translation units that read files or run the detector is defined here.
+namespace {
+std::vector<object_detect::Joint> g_joint_table;  // what load_joint "reads": set by refd_load_joints
+}
 namespace object_detect {
-// objectdetect_aux.cpp is not part of this build: the drivers are exercised with roi_save_num_samples = 0, where the
-// local-maximum lists stay empty (the oracle's findLocalMax is checked elsewhere)
-void findLocalMax(const ExpParam &, const FloatGrid3 &, std::vector<PartHyp> &part_hyp, int) { part_hyp.clear(); }
-}  // namespace object_detect
+// objectdetect_learnparam.cpp:92-179 reads joint_<c>_<p>.mat; the table stands in for the files
+void load_joint(const PartApp &, int jidx, Joint &joint, int) { joint = g_joint_table.at((size_t)jidx); }
+int predictFactors(const PartApp &, int, int) { abort(); }
+#ifndef PS_REF_WITH_ICPS
+// objectdetect_icps.cpp (conditioning of the unaries on MATLAB-side predictions) is not part of this build;
+// findObjectImageRotJoints references it but is not called through these entry points
+typedef std::vector<std::vector<FloatGrid3> > Grids;
+void loadDPMScoreGrid(QString, int, std::vector<FloatGrid2> &, bool) { abort(); }
+void getRotParams(const PartApp &, int, boost_math::double_matrix &, bool) { abort(); }
+void getPosParams(const PartApp &, int, boost_math::double_matrix &, int, bool) { abort(); }
+void getTorsoPosPriorParams(const PartApp &, int, int, boost_math::double_matrix &) { abort(); }
+void addDPMScore(const PartApp &, Grids &, std::vector<FloatGrid2>, int, float) { abort(); }
+void addLoadDPMScore(const PartApp &, Grids &, int, float, int, QString, bool, int) { abort(); }
+void getRotScoreGrid(const PartApp &, Grids &, boost_math::double_matrix &) { abort(); }
+void addExtraUnary(const PartApp &, Grids &, const Grids &, float) { abort(); }
+void getRootPosDet(const PartApp &, int, int, boost_math::double_vector &, bool) { abort(); }
+void getPosScoreGrid(const PartApp &, Grids &, int, boost_math::double_matrix &, int, boost_math::double_vector &) { abort(); }
+void setTorsoPosPrior(const PartApp &, Grids &, boost_math::double_matrix &, int) { abort(); }
 #endif
+void findObjectImagePosJoints(const PartApp &, int, bool, HypothesisList &, int) { abort(); }
+}  // namespace object_detect
 
 namespace matlab_io {
 capture_fn g_capture = 0;
@@ -76,7 +97,59 @@ FloatGrid3 grid3(const float *p, int R, int H, int W) {
 }
 }  // namespace
 
+namespace {
+Joint joint_from_row(const double *q) {
+  Joint j;
+  j.type = (int)q[0];
+  j.child_idx = (int)q[1];
+  j.parent_idx = (int)q[2];
+  j.offset_c.resize(2); j.offset_p.resize(2); j.C.resize(2, 2);
+  j.offset_c(0) = q[3]; j.offset_c(1) = q[4];
+  j.offset_p(0) = q[5]; j.offset_p(1) = q[6];
+  j.C(0, 0) = q[7]; j.C(0, 1) = q[8]; j.C(1, 0) = q[9]; j.C(1, 1) = q[10];
+  j.rot_mean = q[11];
+  j.rot_sigma = q[12];
+  return j;
+}
+void joint_to_row(const Joint &j, double *q) {
+  q[0] = j.type; q[1] = j.child_idx; q[2] = j.parent_idx;
+  q[3] = j.offset_c(0); q[4] = j.offset_c(1); q[5] = j.offset_p(0); q[6] = j.offset_p(1);
+  q[7] = j.C(0, 0); q[8] = j.C(0, 1); q[9] = j.C(1, 0); q[10] = j.C(1, 1);
+  q[11] = j.rot_mean; q[12] = j.rot_sigma;
+}
+}  // namespace
+
 extern "C" {
+
+// object_detect::findLocalMax (objectdetect_aux.cpp:193-261): rows of (dim0, x, y, score) as doubles
+int refd_find_local_max(const float *grid, int D0, int H, int W, int max_n, double *out, int cap) {
+  FloatGrid3 g = grid3(grid, D0, H, W);
+  std::vector<double_vector> lm;
+  object_detect::findLocalMax(g, lm, max_n);
+  if ((int)lm.size() > cap) return -(int)lm.size();
+  for (size_t i = 0; i < lm.size(); ++i)
+    for (int k = 0; k < 4; ++k) out[i * 4 + k] = lm[i](k);
+  return (int)lm.size();
+}
+
+// object_detect::loadJoints (objectdetect_aux.cpp:54-141) over a table of joints as load_joint would deliver them
+// (1-based part ids in child/parent); rows of 13 doubles in and out, plus detC and invC (5 more doubles) out.
+void refd_load_joints(int P, const double *table, int J, int flip, double *out13, double *out_det_inv5) {
+  PartApp app;
+  app.m_part_conf.parts_.resize(P);
+  for (int p = 0; p < P; ++p) app.m_part_conf.parts_[p].part_id_ = p + 1;
+  app.m_part_conf.joints_.resize(J);
+  g_joint_table.clear();
+  for (int j = 0; j < J; ++j) g_joint_table.push_back(joint_from_row(table + (size_t)j * 13));
+  std::vector<Joint> joints;
+  object_detect::loadJoints(app, joints, flip != 0, -1, true);
+  for (int j = 0; j < J; ++j) {
+    joint_to_row(joints[j], out13 + (size_t)j * 13);
+    double *d = out_det_inv5 + (size_t)j * 5;
+    d[0] = joints[j].detC;
+    d[1] = joints[j].invC(0, 0); d[2] = joints[j].invC(0, 1); d[3] = joints[j].invC(1, 0); d[4] = joints[j].invC(1, 1);
+  }
+}
 
 // object_detect::computeRotJointMarginal (objectdetect_findrot.cpp:292-456), the reference's code
 void refd_message(const double *ep, const float *child, float *parent, int R, int H, int W, const double *off_c,
@@ -97,7 +170,7 @@ void refd_message(const double *ep, const float *child, float *parent, int R, in
 // unaries [P][S][R][H][W] are masked in place like the reference does; best_conf [P][7] = best_part_hyp[p][0].toVect().
 void refd_infer(const double *ep, int P, const int *is_detect, const int *is_upright, int rootpart_idx, const double *joints,
                 int J, int H, int W, float *unaries, int sparse, float *root_post /*[S][H][W]*/, float *best_conf,
-                float *marginals /*[S][P][R][H][W] or null*/) {
+                float *marginals /*[S][P][R][H][W] or null*/, float *hyps /*[P][cap][7] or null*/, int cap, int *nhyps) {
   PartApp app;
   app.m_exp_param = make_ep(ep);
   app.m_rootpart_idx = rootpart_idx;
@@ -113,18 +186,7 @@ void refd_infer(const double *ep, int P, const int *is_detect, const int *is_upr
   for (int p = 0; p < P; ++p)
     for (int s = 0; s < S; ++s) memcpy(det[p][s].data(), unaries + ((size_t)p * S + s) * G, sizeof(float) * G);
   std::vector<Joint> js(J);
-  for (int j = 0; j < J; ++j) {
-    const double *q = joints + (size_t)j * 13;
-    js[j].type = (int)q[0];
-    js[j].child_idx = (int)q[1];
-    js[j].parent_idx = (int)q[2];
-    js[j].offset_c.resize(2); js[j].offset_p.resize(2); js[j].C.resize(2, 2);
-    js[j].offset_c(0) = q[3]; js[j].offset_c(1) = q[4];
-    js[j].offset_p(0) = q[5]; js[j].offset_p(1) = q[6];
-    js[j].C(0, 0) = q[7]; js[j].C(0, 1) = q[8]; js[j].C(1, 0) = q[9]; js[j].C(1, 1) = q[10];
-    js[j].rot_mean = q[11];
-    js[j].rot_sigma = q[12];
-  }
+  for (int j = 0; j < J; ++j) js[j] = joint_from_row(joints + (size_t)j * 13);
   FloatGrid3 root;
   std::vector<std::vector<object_detect::PartHyp> > best;
   g_marg = marginals;
@@ -137,6 +199,13 @@ void refd_infer(const double *ep, int P, const int *is_detect, const int *is_upr
   for (int p = 0; p < P; ++p) {
     FloatGrid1 v = best[p][0].toVect();
     for (int k = 0; k < 7; ++k) best_conf[p * 7 + k] = v[k];
+    if (hyps) {
+      nhyps[p] = (int)std::min<size_t>(best[p].size(), (size_t)cap);
+      for (int i = 0; i < nhyps[p]; ++i) {
+        FloatGrid1 h = best[p][i].toVect();
+        for (int k = 0; k < 7; ++k) hyps[((size_t)p * cap + i) * 7 + k] = h[k];
+      }
+    }
     for (int s = 0; s < S; ++s) memcpy(unaries + ((size_t)p * S + s) * G, det[p][s].data(), sizeof(float) * G);
   }
 }

@@ -7,6 +7,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <vector>
 
 namespace boost {
@@ -246,6 +247,10 @@ class permutation_matrix : public vector<T> {
  public:
   explicit permutation_matrix(std::size_t n) : vector<T>(n) { for (std::size_t i = 0; i < n; ++i) (*this)(i) = (T)i; }
 };
+
+// LU for n > 2 is reached by nothing on the pictorial-structures path (2 x 2 covariances take the closed forms)
+template <class M, class P> int lu_factorize(M &, P &) { std::abort(); }
+template <class M, class P, class X> void lu_substitute(const M &, const P &, X &) { std::abort(); }
 
 }  // namespace ublas
 }  // namespace numeric

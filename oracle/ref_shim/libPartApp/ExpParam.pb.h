@@ -45,5 +45,15 @@ class ExpParam {
   PS_FIELD(std::string, test_dpm_torso_dir, "")
   PS_FIELD(std::string, test_dpm_head_dir, "")
   PS_FIELD(std::string, part_conf_type, "")
+  PS_FIELD(std::string, pred_data_test_dir, "")
+  PS_FIELD(std::string, mix_dir, "")
+  PS_FIELD(std::string, pred_data_train_dir, "")
+  PS_FIELD(std::string, scoregrid_dir, "")
+  PS_FIELD(std::string, spatial_dir, "")
+  PS_FIELD(bool, flip_orientation, false)
+  PS_FIELD(bool, force_recompute_scores, true)
+  PS_FIELD(float, object_height_width_ratio, 2)
 #undef PS_FIELD
+  std::string test_dataset(int) const { return std::string(); }
+  int test_dataset_size() const { return 0; }
 };

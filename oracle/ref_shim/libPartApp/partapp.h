@@ -22,6 +22,7 @@ namespace filesys {
 inline bool check_dir(QString) { return true; }
 inline bool create_dir(QString) { return true; }
 inline bool check_file(QString) { return false; }
+inline bool copy_file(QString, QString) { return false; }
 }  // namespace filesys
 
 class PartApp {

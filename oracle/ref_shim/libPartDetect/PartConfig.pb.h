@@ -11,10 +11,22 @@ class PartDef {
   bool is_root() const { return is_root_; }
   int part_id() const { return part_id_; }
 };
+class JointDef {
+ public:
+  int child_idx_ = 0, parent_idx_ = 0, num_joint_types_ = 1;
+  std::string type_ = "RotGaussian";
+  int child_idx() const { return child_idx_; }
+  int parent_idx() const { return parent_idx_; }
+  const std::string &type() const { return type_; }
+  bool has_num_joint_types() const { return num_joint_types_ > 1; }
+  int num_joint_types() const { return num_joint_types_; }
+};
 class PartConfig {
  public:
   std::vector<PartDef> parts_;
+  std::vector<JointDef> joints_;
+  const JointDef &joint(int i) const { return joints_.at((size_t)i); }
   int part_size() const { return (int)parts_.size(); }
   const PartDef &part(int i) const { return parts_.at((size_t)i); }
-  int joint_size() const { return 0; }
+  int joint_size() const { return (int)joints_.size(); }
 };

@@ -1,6 +1,8 @@
 // Stand-in for libPartDetect/partdetect.h -- TEST INFRASTRUCTURE.
 #pragma once
+#include <cstdlib>
 #include <libPartDetect/partdef.h>
 namespace part_detect {
 const float NO_CLASS_VALUE = 0;
+template <class... A> void partdetect(const A &...) { abort(); }  // the detector is not part of oracle/_ref
 }

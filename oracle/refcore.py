@@ -141,7 +141,10 @@ def dlib():
         L = C.CDLL(DRIVERS_PATH)
         L.refd_message.argtypes = [_dp, _fp, _fp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double,
                                    C.c_double, C.c_int]
-        L.refd_infer.argtypes = [_dp, C.c_int, _ip, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, _fp]
+        L.refd_infer.argtypes = [_dp, C.c_int, _ip, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, _fp,
+                                 _fp, C.c_int, _ip]
+        L.refd_find_local_max.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
+        L.refd_load_joints.argtypes = [C.c_int, _dp, C.c_int, C.c_int, _dp, _dp]
         _dlib = L
     return _dlib
 
@@ -177,21 +180,52 @@ def message(ep, child, off_in, off_out, Cm, rot_mean, rot_sigma, scale, sparse):
     return out
 
 
+def _joint_rows(joints, one_based=False):
+    k = 1 if one_based else 0
+    return np.array([[j.type, j.child_idx + k, j.parent_idx + k, j.offset_c[0], j.offset_c[1], j.offset_p[0], j.offset_p[1],
+                      j.C[0][0], j.C[0][1], j.C[1][0], j.C[1][1], j.rot_mean, j.rot_sigma] for j in joints], np.float64)
+
+
 def infer(ep, part_conf, joints, unaries, sparse=True):
-    """object_detect::computeRootPosteriorRot + computePartMarginals as the reference compiled them.  `unaries`
-    [P][S][R][H][W] is masked in place.  roi_save_num_samples must be 0 unless objectdetect_aux.cpp is part of the build."""
+    """object_detect::computeRootPosteriorRot + computePartMarginals (+ findLocalMax) as the reference compiled them.
+    `unaries` [P][S][R][H][W] is masked in place."""
     assert unaries.dtype == np.float32 and unaries.flags.c_contiguous
     P, S, R, H, W = unaries.shape
     det = np.array([int(bool(v)) for v in part_conf.is_detect], np.int32)
     upr = np.array([int(bool(v)) for v in part_conf.is_upright], np.int32)
     roots = [p for p in range(P) if part_conf.is_detect[p] and part_conf.is_root[p]]
-    js = np.array([[j.type, j.child_idx, j.parent_idx, j.offset_c[0], j.offset_c[1], j.offset_p[0], j.offset_p[1],
-                    j.C[0][0], j.C[0][1], j.C[1][0], j.C[1][1], j.rot_mean, j.rot_sigma] for j in joints], np.float64)
+    js = _joint_rows(joints)
     root_post = np.empty((S, H, W), np.float32)
     best = np.empty((P, 7), np.float32)
     marg = np.empty((S, P, R, H, W), np.float32)
+    cap = int(ep.roi_save_num_samples) + 1
+    hyps = np.empty((P, cap, 7), np.float32)
+    nh = np.zeros(P, np.int32)
     e = _epv(ep)
     _quiet(lambda: dlib().refd_infer(e.ctypes.data_as(_dp), P, det.ctypes.data_as(_ip), upr.ctypes.data_as(_ip), roots[0],
                                      js.ctypes.data_as(_dp), len(joints), H, W, _f(unaries), int(bool(sparse)), _f(root_post),
-                                     _f(best), _f(marg)))
-    return {"root_post": root_post, "best_conf": best, "marginals": marg}
+                                     _f(best), _f(marg), _f(hyps), cap, nh.ctypes.data_as(_ip)))
+    return {"root_post": root_post, "best_conf": best, "marginals": marg,
+            "part_hyps": [hyps[p, :nh[p]].copy() for p in range(P)]}
+
+
+def find_local_max(grid, max_n):
+    """object_detect::findLocalMax (objectdetect_aux.cpp:193-261): rows (dim0, x, y, score)."""
+    g = np.ascontiguousarray(grid, np.float32)
+    cap = max(g.size, 1)
+    out = np.empty((cap, 4), np.float64)
+    n = _quiet(lambda: dlib().refd_find_local_max(_f(g), g.shape[0], g.shape[1], g.shape[2], int(max_n),
+                                                   out.ctypes.data_as(_dp), cap))
+    assert n >= 0
+    return out[:n].astype(np.float32)
+
+
+def load_joints(num_parts, joints, flip):
+    """object_detect::loadJoints (objectdetect_aux.cpp:54-141) over joints as load_joint would deliver them (0-based
+    here, shifted to the files' 1-based ids on the way in).  Returns (rows of 13 doubles with 0-based ids, detC+invC rows)."""
+    rows = _joint_rows(joints, one_based=True)
+    out = np.empty_like(rows)
+    di = np.empty((len(joints), 5), np.float64)
+    _quiet(lambda: dlib().refd_load_joints(int(num_parts), rows.ctypes.data_as(_dp), len(joints), int(bool(flip)),
+                                           out.ctypes.data_as(_dp), di.ctypes.data_as(_dp)))
+    return out, di

@@ -21,3 +21,32 @@ if not refcore.available():
 out = {name: ref_cases.run(refcore, kind, a) for name, (kind, a) in ref_cases.cases().items()}
 np.savez_compressed(os.path.join(HERE, "ref_core.npz"), **out)
 print("wrote %d reference outputs" % len(out))
+
+# ---- the drivers: objectdetect_findrot.cpp / objectdetect_aux.cpp as the reference compiled them --------------------
+import ref_driver_cases as dc  # noqa: E402
+
+if not refcore.drivers_available():
+    sys.exit("oracle/_ref/libps_ref_drivers.so is missing")
+drv = {}
+for name, c in dc.message_cases().items():
+    child, oi, oo, Cm, rm, rs, sc, sp = dc.message_args(c)
+    drv["msg_" + name] = refcore.message(c["ep"], child, oi, oo, Cm, rm, rs, sc, sp)
+for name, c in dc.infer_cases().items():
+    pc, joints, un = dc.infer_args(c)
+    r = refcore.infer(c["ep"], pc, joints, un, sparse=True)
+    drv["inf_%s_best" % name] = r["best_conf"]
+    drv["inf_%s_root" % name] = r["root_post"]
+    drv["inf_%s_marg" % name] = r["marginals"]
+    drv["inf_%s_masked" % name] = un
+    for p, h in enumerate(r["part_hyps"]):
+        drv["inf_%s_hyps%d" % (name, p)] = h
+for name, c in dc.local_max_cases().items():
+    drv["lm_" + name] = refcore.find_local_max(c["grid"], c["K"])
+for name, joints in dc.joint_cases().items():
+    P = len(joints) + 1
+    for flip in (0, 1):
+        rows, di = refcore.load_joints(P, joints, flip)
+        drv["joints_%s_flip%d" % (name, flip)] = rows
+        drv["joints_%s_flip%d_detinv" % (name, flip)] = di
+np.savez_compressed(os.path.join(HERE, "ref_drivers.npz"), **drv)
+print("wrote %d reference driver outputs" % len(drv))

@@ -79,3 +79,102 @@ def test_oracle_matches_reference_core_on_random_inputs(seed):
     taps = refcore.gaussian_filter(sig)[first:first + ln].astype(np.float32)
     col = rng.random(n).astype(np.float32)
     assert _same(ob.filter_1d_wraparound(col, taps), refcore.filter_1d_wraparound(col, taps))
+
+
+# ---- the drivers: computeRotJointMarginal, computeRootPosteriorRot + computePartMarginals, findLocalMax, loadJoints ---
+# oracle/_ref/libps_ref_drivers.so = libPictStruct/objectdetect_findrot.cpp and objectdetect_aux.cpp compiled unmodified
+# (oracle/ref_drivers.cpp); their outputs on tests/golden/ref_driver_cases.py are recorded in ref_drivers.npz.
+import ref_driver_cases as dc  # noqa: E402
+import oracle  # noqa: E402
+
+DRV = np.load(os.path.join(HERE, "golden", "ref_drivers.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(dc.message_cases()))
+def test_oracle_message_reproduces_reference_message(name):
+    c = dc.message_cases()[name]
+    child, oi, oo, Cm, rm, rs, sc, sp = dc.message_args(c)
+    got = oracle.message(c["ep"], child, oi, oo, Cm, rm, rs, sc, sp)
+    assert _same(got, DRV["msg_" + name]), "computeRotJointMarginal: oracle differs from the reference's own code"
+
+
+def _hyps_equal(a, b):
+    """Argmax row first, then the local maxima: same records; order compared as sets only when the top-K cut sorted
+    them (std::sort leaves ties unspecified) -- here the two implementations happen to agree element for element."""
+    return a.shape == b.shape and np.array_equal(a[0], b[0]) and \
+        sorted(map(tuple, a[1:].tolist())) == sorted(map(tuple, b[1:].tolist()))
+
+
+@pytest.mark.parametrize("name", sorted(dc.infer_cases()))
+def test_oracle_inference_reproduces_reference_inference(name):
+    c = dc.infer_cases()[name]
+    pc, joints, un = dc.infer_args(c)
+    got = oracle.infer(c["ep"], pc, joints, un, sparse=True, want_hyps=True)
+    assert _same(got["best_conf"], DRV["inf_%s_best" % name])
+    assert _same(got["root_post"], DRV["inf_%s_root" % name])
+    assert _same(got["marginals"], DRV["inf_%s_marg" % name])
+    assert _same(un, DRV["inf_%s_masked" % name]), "in-place masking of the unaries (upright parts, border strip)"
+    for p, h in enumerate(got["part_hyps"]):
+        assert _hyps_equal(h, DRV["inf_%s_hyps%d" % (name, p)]), "best_part_hyp of part %d" % p
+
+
+@pytest.mark.parametrize("name", sorted(dc.local_max_cases()))
+def test_oracle_local_maxima_reproduce_reference(name):
+    c = dc.local_max_cases()[name]
+    got, want = oracle.find_local_max(c["grid"], c["K"]), DRV["lm_" + name]
+    assert got.shape == want.shape and sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+    if len(got) < c["K"]:
+        assert np.array_equal(got, want), "scan order (dim0, x, y) below the top-K cut"
+
+
+def _oracle_load_joints(joints, flip):
+    """aux.cpp:54-141 as the oracle states it: the flip transform of every joint (ids are already 0-based here)."""
+    import ctypes as C
+    rows = []
+    for j in joints:
+        o = oracle.joint(j)
+        if flip:
+            oracle.lib().orc_flip_joint(C.byref(o))
+        rows.append([o.type, o.child_idx, o.parent_idx, o.offset_c[0], o.offset_c[1], o.offset_p[0], o.offset_p[1],
+                     o.C[0], o.C[1], o.C[2], o.C[3], o.rot_mean, o.rot_sigma])
+    return np.array(rows, np.float64)
+
+
+@pytest.mark.parametrize("name", sorted(dc.joint_cases()))
+@pytest.mark.parametrize("flip", [0, 1])
+def test_oracle_joint_flip_reproduces_reference_load_joints(name, flip):
+    joints = dc.joint_cases()[name]
+    assert _same(_oracle_load_joints(joints, flip), DRV["joints_%s_flip%d" % (name, flip)])
+
+
+@pytest.mark.skipif(not refcore.drivers_available(), reason="oracle/_ref drivers not built (needs the reference tree)")
+def test_reference_drivers_still_match_fixture_and_random_inference():
+    for name, c in dc.message_cases().items():
+        child, oi, oo, Cm, rm, rs, sc, sp = dc.message_args(c)
+        assert _same(refcore.message(c["ep"], child, oi, oo, Cm, rm, rs, sc, sp), DRV["msg_" + name]), name
+    from partapp_b200 import ExpParam, synth
+    for seed in range(3):  # fresh inputs, live: the reference's code against the oracle
+        rng = np.random.default_rng(500 + seed)
+        P, R = int(rng.integers(3, 8)), int(rng.choice([4, 8, 12]))
+        H, W = int(rng.integers(18, 30)), int(rng.integers(18, 30))
+        ep = ExpParam(num_rotation_steps=R, roi_save_num_samples=int(rng.integers(0, 6)))
+        pc = synth.part_conf(P)
+        joints = synth.make_joints(P, seed=100 + seed, max_offset=5, sigma_range=(1.2, 3.5), diagonal=bool(seed % 2))
+        un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, seed))
+        ua, ub = un.copy(), un.copy()
+        a = oracle.infer(ep, pc, joints, ua, sparse=True, want_hyps=True)
+        b = refcore.infer(ep, pc, joints, ub, sparse=True)
+        assert _same(a["best_conf"], b["best_conf"]) and _same(a["root_post"], b["root_post"])
+        assert _same(a["marginals"], b["marginals"]) and _same(ua, ub)
+        for p in range(P):
+            assert _hyps_equal(a["part_hyps"][p], b["part_hyps"][p])
+
+
+@pytest.mark.parametrize("name", sorted(dc.joint_cases()))
+def test_product_flip_joint_reproduces_reference_load_joints(name):
+    """ps_flip_joint (host helper of libpsinfer.so, no GPU needed) against the reference's loadJoints output."""
+    joints = dc.joint_cases()[name]
+    flipped = [j.flipped() for j in joints]
+    rows = np.array([[j.type, j.child_idx, j.parent_idx, j.offset_c[0], j.offset_c[1], j.offset_p[0], j.offset_p[1],
+                      j.C[0][0], j.C[0][1], j.C[1][0], j.C[1][1], j.rot_mean, j.rot_sigma] for j in flipped], np.float64)
+    assert _same(rows, DRV["joints_%s_flip1" % name])
