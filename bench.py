@@ -374,25 +374,38 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+REF_CODE = {True: "the reference's own objectdetect_findrot.cpp::computeRotJointMarginal, compiled unmodified into "
+                  "oracle/_ref/libps_ref_drivers.so over container stand-ins (DESIGN.md 6)",
+            False: "oracle/ps_oracle.cpp, the line-by-line restatement (bit-identical to the reference's code, ~2.5x faster: "
+                   "no per-pixel BLAS calls and allocations)"}
 ARITH = {False: "parity: every filter tap rounds product and sum separately, results bit-identical to the CPU reference",
          True: "fast_math: fused multiply-add taps, argmax identical, marginals within 1e-4 relative (north star bound)"}
 
 
 def run_cpu_sample(ep, pc, joints, raw, threads=1):
-    """Times the CPU oracle (the only runnable statement of the reference path) on one full image, one thread."""
+    """Times the reference path on one full image, one thread: the reference's own computeRootPosteriorRot
+    (oracle/_ref, kind "reference") when that library travelled with the repo, else the CPU oracle (kind "port")."""
     import oracle
+    from oracle import refcore
     un = oracle.prepare_unary(raw)
+    use_ref = refcore.drivers_available()
     t0 = time.perf_counter()
-    oracle.infer(ep, pc, joints, un, sparse=True, want_marginals=False)
+    if use_ref:
+        refcore.infer(ep, pc, joints, un, sparse=True)
+    else:
+        oracle.infer(ep, pc, joints, un, sparse=True, want_marginals=False)
     dt = time.perf_counter() - t0
-    return {"value": round(1.0 / dt, 5), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "1 full image of the same workload (18 messages + readout) on 1 thread: %.1f s" % dt}
+    return {"value": round(1.0 / dt, 5), "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": "1 full image of the same workload (18 messages + readout) on 1 thread: %.1f s" % dt,
+            "code": REF_CODE[use_ref]}
 
 
 def run_reference(args):
-    """Reference arm: the CPU oracle (kind "port": the reference itself cannot be compiled here), using
-    every host thread the way the reference scales -- independent images per process/thread (main.cpp:155-192).
-    Each step is a bounded sample: every thread runs `m` of the 18 messages of its own image at full size."""
+    """Reference arm: the reference's OWN computeRotJointMarginal (oracle/_ref/libps_ref_drivers.so = its
+    objectdetect_findrot.cpp compiled unmodified, kind "reference") when that library travelled with the repo, else the
+    CPU oracle (kind "port"); every host thread is used the way the reference scales -- independent images per
+    process/thread (main.cpp:155-192).  Each step is a bounded sample: every thread runs 2 of the 18 messages of its
+    own image at full size."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -409,11 +422,23 @@ def run_reference(args):
     # one sparse unary grid per thread (images are independent)
     un = [oracle.prepare_unary(synth.raw_scores(ep, w["H"], w["W"], 1, 100 + t)[0, 0]) for t in range(min(threads, 8))]
 
+    from oracle import refcore
+    use_ref = refcore.drivers_available() and not args.ref_port
+    if use_ref:
+        refcore.dlib()
+        # the reference prints its progress to stdout from every call: send descriptor 1 to /dev/null for the run
+        # (the JSON line goes to the descriptor claim_stdout() saved)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        msg = lambda *a: refcore.message(*a, quiet=False)
+    else:
+        msg = oracle.message
+
     def work(t, step_idx):
         j = joints[(step_idx + t) % J]
         g = un[t % len(un)]
-        up = oracle.message(ep, g, j.offset_c, j.offset_p, j.C, j.rot_mean, j.rot_sigma, 1.0, True)
-        oracle.message(ep, up, j.offset_p, j.offset_c, j.C, -j.rot_mean, j.rot_sigma, 1.0, False)
+        up = msg(ep, g, j.offset_c, j.offset_p, j.C, j.rot_mean, j.rot_sigma, 1.0, True)
+        msg(ep, up, j.offset_p, j.offset_c, j.C, -j.rot_mean, j.rot_sigma, 1.0, False)
         return 2
 
     pool = ThreadPoolExecutor(threads)
@@ -438,7 +463,8 @@ def run_reference(args):
            "steps": done_steps, "warmup": warm, "ms_per_step": round(dt / done_steps * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": workload_config("CPU: one image per host thread, %d threads" % threads),
-           "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+                            "sample": sample, "code": REF_CODE[use_ref]},
            "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
@@ -481,6 +507,7 @@ def main():
                     help="profiling run under ncu: honour a short warmup, skip e2e / instrumented pass / CPU baseline "
                          "(numbers printed by such a run are not bench values)")
     ap.add_argument("--ref-threads", type=int, default=0)
+    ap.add_argument("--ref-port", action="store_true", help="reference arm: time the oracle port even if oracle/_ref exists")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     claim_stdout()

@@ -169,14 +169,16 @@ def _quiet(fn):
         os.close(devnull)
 
 
-def message(ep, child, off_in, off_out, Cm, rot_mean, rot_sigma, scale, sparse):
-    """object_detect::computeRotJointMarginal as the reference compiled it."""
+def message(ep, child, off_in, off_out, Cm, rot_mean, rot_sigma, scale, sparse, quiet=True):
+    """object_detect::computeRotJointMarginal as the reference compiled it.  quiet=False leaves file descriptor 1
+    alone (callers that run several threads redirect it once themselves)."""
     child = np.ascontiguousarray(child, np.float32)
     R, H, W = child.shape
     out = np.empty_like(child)
     e, (_a, pa), (_b, pb), (_c, pc) = _epv(ep), _d(off_in), _d(off_out), _d(Cm)
-    _quiet(lambda: dlib().refd_message(e.ctypes.data_as(_dp), _f(child), _f(out), R, H, W, pa, pb, pc, float(rot_mean),
-                                       float(rot_sigma), float(scale), int(bool(sparse))))
+    call = lambda: dlib().refd_message(e.ctypes.data_as(_dp), _f(child), _f(out), R, H, W, pa, pb, pc, float(rot_mean),
+                                       float(rot_sigma), float(scale), int(bool(sparse)))
+    _quiet(call) if quiet else call()
     return out
 
 
