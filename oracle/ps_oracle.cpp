@@ -14,8 +14,8 @@
 //   oracle/_ref/libps_ref_core.so     libMultiArray/multi_array_{op,transform,filter}.hpp, libBoostMath/{boost_math,
 //                                     homogeneous_coord}.cpp, libPartApp/partapp_aux.hpp, libPictStruct/objectdetect_aux.hpp
 //   oracle/_ref/libps_ref_drivers.so  libPictStruct/objectdetect_findrot.cpp (computeRotJointMarginal,
-//                                     computePartMarginals, computeRootPosteriorRot) and objectdetect_aux.cpp
-//                                     (findLocalMax, loadJoints)
+//                                     computePartMarginals, computeRootPosteriorRot), objectdetect_aux.cpp
+//                                     (findLocalMax, loadJoints) and objectdetect_icps.cpp (the conditioning adds)
 // behind the C entry points of oracle/ref_core.cpp and oracle/ref_drivers.cpp.  tests/test_oracle_vs_ref.py holds this
 // file to that code BIT FOR BIT -- grid primitives, single messages, whole inferences (argmax records, every marginal
 // cell, root posterior, local-maximum lists, the in-place masking of the unaries), local maxima with the top-K cut, and
@@ -25,7 +25,7 @@
 //   * cblas_sdot  -> Netlib order: sequential ascending-index fp32 multiply-then-add, no FMA (the stand-in BLAS and this
 //                    file share the convention; the authors' libblas is unknown);
 //   * exp / log   -> evaluated in double by libm and narrowed to float (this machine's glibc);
-// and the conditioning helpers of objectdetect_icps.cpp and PartApp::loadScoreGrid, which read MATLAB / detector files:
+// and the file-reading helpers (getRotParams, getPosParams, addLoadDPMScore's loader, PartApp::loadScoreGrid):
 // those remain line-by-line restatements (every function below names the reference file:line it follows; paths are
 // relative to /root/reference/src/libs).
 // Build: g++ -O3 -ffp-contract=off (no -ffast-math, no -mfma) -- see oracle/Makefile.
@@ -1067,10 +1067,16 @@ void orc_flip_joint(orc_joint *j) {
 }
 
 // ---- conditioning tables (objectdetect_icps.cpp) ---------------------------------------------
-// icps.cpp:29 has "using namespace std", so on floats log() is std::log(float) (= logf) and, on the
-// reference's C++98 toolchain, pow(float, int) is the float overload (__builtin_powif: x*x in fp32);
-// exp() of the double expression is the double routine, narrowed on assignment to float.
-static inline float powf2(float t) { return t * t; }
+// icps.cpp:29 has "using namespace std", so on floats log() is std::log(float) (= logf); exp() of the double
+// expression is the double routine, narrowed on assignment to float.  pow(float, int) is DIALECT-DEPENDENT: the
+// reference's toolchain (gcc 4.7, -std=gnu++98 by default) has the overload float pow(float, int) = __builtin_powif,
+// i.e. x*x rounded to fp32; since C++11 (LWG 550) the call promotes both arguments and squares in double.  The default
+// here is the authors' dialect.  oracle/_ref compiles the reference's sources as C++17 (the stand-in headers need it),
+// so tests/test_oracle_vs_ref.py switches this restatement to the C++11 rule for the one comparison that involves
+// pow() on non-integral values (getPosScoreGrid) -- which pins everything else about these routines.
+static int g_pow_cxx11 = 0;
+static inline double powf2(float t) { return g_pow_cxx11 ? (double)t * (double)t : (double)(t * t); }
+void orc_set_pow_dialect(int cxx11) { g_pow_cxx11 = cxx11; }
 
 // getRotScoreGrid :228-281: table[r] for one part; mu/var arrive as doubles and are narrowed.
 void orc_rot_score_table(const orc_exp_param *e, double mu_d, double var_d, float *table) {

@@ -1,6 +1,6 @@
 // ref_drivers.cpp -- TEST INFRASTRUCTURE: C entry points over the reference's OWN inference drivers.
 // libPictStruct/objectdetect_findrot.cpp (computeRotJointMarginal, computePartMarginals, computeRootPosteriorRot) is
-// and libPictStruct/objectdetect_aux.cpp (findLocalMax, loadJoints) are
+// libPictStruct/objectdetect_aux.cpp (findLocalMax, loadJoints) and objectdetect_icps.cpp (the conditioning adds) are
 // compiled UNMODIFIED from /root/reference next to this file (`make -C oracle ref`), against the stand-ins of
 // oracle/ref_shim/ for everything the image lacks (Boost, Qt, protoc output, libmat, the detector libraries).  This file
 // defines what that translation unit references but other, uncompilable translation units define.
@@ -26,6 +26,10 @@ void index_from_flat3(int shape0, int shape1, int shape2, int flat_idx, int &idx
 }
 }  // namespace disc_ps
 
+// libPartDetect/partdef.cpp (ground-truth part boxes from annotations) is not compiled; objectdetect_icps.cpp only reaches
+// these from its training-time helpers
+bool annorect_has_part(const AnnoRect &, const PartDef &) { abort(); }
+bool get_part_bbox(const AnnoRect &, const PartDef &, PartBBox &, double) { abort(); }
 void bbox_from_pos(const ExpParam &, const PartWindowParam::PartParam &, int, int, int, int, PartBBox &) { abort(); }
 void bbox_from_pos(const PartWindowParam::PartParam &, double, double, int, int, PartBBox &) { abort(); }
 
@@ -37,10 +41,9 @@ std::vector<object_detect::Joint> g_joint_table;  // what load_joint "reads": se
 namespace object_detect {
 // objectdetect_learnparam.cpp:92-179 reads joint_<c>_<p>.mat; the table stands in for the files
 void load_joint(const PartApp &, int jidx, Joint &joint, int) { joint = g_joint_table.at((size_t)jidx); }
+#ifdef PS_REF_WITHOUT_ICPS
 int predictFactors(const PartApp &, int, int) { abort(); }
-#ifndef PS_REF_WITH_ICPS
-// objectdetect_icps.cpp (conditioning of the unaries on MATLAB-side predictions) is not part of this build;
-// findObjectImageRotJoints references it but is not called through these entry points
+// fallback when objectdetect_icps.cpp is left out of the build
 typedef std::vector<std::vector<FloatGrid3> > Grids;
 void loadDPMScoreGrid(QString, int, std::vector<FloatGrid2> &, bool) { abort(); }
 void getRotParams(const PartApp &, int, boost_math::double_matrix &, bool) { abort(); }
@@ -149,6 +152,52 @@ void refd_load_joints(int P, const double *table, int J, int flip, double *out13
     d[0] = joints[j].detC;
     d[1] = joints[j].invC(0, 0); d[2] = joints[j].invC(0, 1); d[3] = joints[j].invC(1, 0); d[4] = joints[j].invC(1, 1);
   }
+}
+
+// The conditioning adds of objectdetect_icps.cpp on unaries [P][S][R][H][W] (in place), the reference's code:
+//   kind 0: getRotScoreGrid (:228-281) with rot_params [P][2], then addExtraUnary (:526-548) with `weight`
+//   kind 1: getPosScoreGrid (:366-423) with pos_params [P][4] and rootpos_det = params[4P .. 4P+1], then addExtraUnary
+//   kind 2: setTorsoPosPrior (:137-191) with pos_prior_params [1][4]; `weight` = ExpParam.torso_pos_prior_weight
+//   kind 3: addDPMScore (:488-524) on part `pidx` with n_dpm grids [n_dpm][H][W] and `weight`
+void refd_condition(const double *ep, int P, const int *is_detect, int rootpart_idx, int H, int W, float *unaries, int kind,
+                    const double *params, float weight, int pidx, const float *dpm, int n_dpm) {
+  PartApp app;
+  app.m_exp_param = make_ep(ep);
+  app.m_exp_param.set_torso_pos_prior_weight(weight);
+  app.m_rootpart_idx = rootpart_idx;
+  app.m_part_conf.parts_.resize(P);
+  for (int p = 0; p < P; ++p) app.m_part_conf.parts_[p].is_detect_ = is_detect[p] != 0;
+  const int S = (int)app.m_exp_param.num_scale_steps(), R = (int)app.m_exp_param.num_rotation_steps();
+  const size_t G = (size_t)R * H * W;
+  typedef std::vector<std::vector<FloatGrid3> > Grids;
+  Grids det(P, std::vector<FloatGrid3>(S, FloatGrid3(boost::extents[R][H][W])));
+  for (int p = 0; p < P; ++p)
+    for (int s = 0; s < S; ++s) memcpy(det[p][s].data(), unaries + ((size_t)p * S + s) * G, sizeof(float) * G);
+  if (kind == 0 || kind == 1) {
+    Grids extra(P, std::vector<FloatGrid3>(S, FloatGrid3(boost::extents[R][H][W])));  // zero-filled, findrot.cpp:917-932
+    double_matrix prm(P, kind == 0 ? 2 : 4);
+    for (int p = 0; p < P; ++p)
+      for (size_t k = 0; k < prm.size2(); ++k) prm(p, k) = params[(size_t)p * prm.size2() + k];
+    if (kind == 0) {
+      object_detect::getRotScoreGrid(app, extra, prm);
+    } else {
+      double_vector root(2);
+      root(0) = params[(size_t)P * 4];
+      root(1) = params[(size_t)P * 4 + 1];
+      object_detect::getPosScoreGrid(app, extra, 0, prm, rootpart_idx, root);
+    }
+    object_detect::addExtraUnary(app, det, extra, weight);
+  } else if (kind == 2) {
+    double_matrix prm(1, 4);
+    for (int k = 0; k < 4; ++k) prm(0, k) = params[k];
+    object_detect::setTorsoPosPrior(app, det, prm, rootpart_idx);
+  } else {
+    std::vector<FloatGrid2> g(n_dpm, FloatGrid2(boost::extents[H][W]));
+    for (int i = 0; i < n_dpm; ++i) memcpy(g[i].data(), dpm + (size_t)i * H * W, sizeof(float) * (size_t)H * W);
+    object_detect::addDPMScore(app, det, g, pidx, weight);
+  }
+  for (int p = 0; p < P; ++p)
+    for (int s = 0; s < S; ++s) memcpy(unaries + ((size_t)p * S + s) * G, det[p][s].data(), sizeof(float) * G);
 }
 
 // object_detect::computeRotJointMarginal (objectdetect_findrot.cpp:292-456), the reference's code

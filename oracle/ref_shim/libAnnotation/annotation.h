@@ -2,8 +2,19 @@
 #pragma once
 #include <string>
 #include <vector>
+struct AnnoPoint {
+  int id = -1, x = 0, y = 0;
+  bool is_visible = true;
+};
 class AnnoRect {
  public:
+  std::vector<AnnoPoint> m_vAnnoPoints;
+  const AnnoPoint *get_annopoint_by_id(int id) const {
+    for (const AnnoPoint &p : m_vAnnoPoints) if (p.id == id) return &p;
+    return 0;
+  }
+  double scale() const { return -1; }
+  int m_x1 = 0, m_y1 = 0, m_x2 = 0, m_y2 = 0;
   AnnoRect() {}
   AnnoRect(double, double, double, double) {}
   AnnoRect(int, int, int, int, float, int, float) {}

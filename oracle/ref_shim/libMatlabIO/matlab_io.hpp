@@ -25,4 +25,12 @@ template <class A> A mat_load_multi_array(MATFile *, QString) { abort(); }
 inline bool mat_load_double_matrix(QString, QString, boost_math::double_matrix &) { abort(); }
 inline bool mat_load_double_vector(QString, QString, boost_math::double_vector &) { abort(); }
 inline bool mat_save_double_matrix(QString, QString, const boost_math::double_matrix &) { return true; }
+inline bool mat_save_double_matrix(MATFile *, QString, const boost_math::double_matrix &) { return true; }
+inline bool mat_save_double_vector(QString, QString, const boost_math::double_vector &) { return true; }
+inline bool mat_save_double_vector(MATFile *, QString, const boost_math::double_vector &) { return true; }
+inline bool mat_load_double_matrix(MATFile *, QString, boost_math::double_matrix &) { abort(); }
+inline bool mat_load_double_vector(MATFile *, QString, boost_math::double_vector &) { abort(); }
+template <class V> bool mat_load_multi_array_vec2(MATFile *, QString, V &) { abort(); }
+template <class V> bool mat_load_multi_array_vec2(QString, QString, V &) { abort(); }
+template <class V> bool mat_load_stdcpp_vector(QString, QString, V &) { abort(); }
 }  // namespace matlab_io

@@ -53,7 +53,24 @@ class ExpParam {
   PS_FIELD(bool, flip_orientation, false)
   PS_FIELD(bool, force_recompute_scores, true)
   PS_FIELD(float, object_height_width_ratio, 2)
+  PS_FIELD(std::string, class_dir, "")
+  PS_FIELD(float, torso_pos_prior_weight, 1)
+  PS_FIELD(std::string, pred_data_dir, "")
+  PS_FIELD(int32_t, rootidx_det, -1)
+  PS_FIELD(bool, use_gt_torso, false)
+  PS_FIELD(std::string, torso_det_test_dir, "")
+  PS_FIELD(std::string, torso_det_train_dir, "")
+  PS_FIELD(std::string, poselet_resp_val_dir, "")
+  PS_FIELD(std::string, poselet_resp_test_dir, "")
+  PS_FIELD(std::string, poselet_resp_train_dir, "")
+  PS_FIELD(std::string, poselet_strip, "")
+  PS_FIELD(std::string, part_marginals_dir, "")
+  PS_FIELD(int32_t, num_pred_part_types, 1)
 #undef PS_FIELD
+  std::string validation_dataset(int) const { return std::string(); }
+  int validation_dataset_size() const { return 0; }
+  std::string train_dataset(int) const { return std::string(); }
+  int train_dataset_size() const { return 0; }
   std::string test_dataset(int) const { return std::string(); }
   int test_dataset_size() const { return 0; }
 };

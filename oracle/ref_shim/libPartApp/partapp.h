@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <vector>
 #include <libAdaBoost/AdaBoost.h>
+#include <libMisc/misc.hpp>
 #include <libAnnotation/annotationlist.h>
 #include <libMultiArray/multi_array_def.h>
 #include <libPartDetect/AbcDetectorParam.pb.h>
@@ -33,5 +34,7 @@ class PartApp {
   AbcDetectorParam m_abc_param;
   AnnotationList m_test_annolist, m_train_annolist;
   int m_rootpart_idx = -1;
+  bool m_bExternalClassDir = false, m_bExternalSamplesDir = false;
+  QString m_qsExpParam;
   void loadScoreGrid(std::vector<std::vector<FloatGrid2> > &, int, int, bool, bool, QString, QString) const { abort(); }
 };

@@ -10,6 +10,12 @@ class PartDef {
   bool is_upright() const { return is_upright_; }
   bool is_root() const { return is_root_; }
   int part_id() const { return part_id_; }
+  std::vector<int> part_pos_;
+  int part_pos(int i) const { return part_pos_.at((size_t)i); }
+  int part_pos_size() const { return (int)part_pos_.size(); }
+  int num_pred_part_types() const { return 1; }
+  int max_num_part_types() const { return 1; }
+  bool has_mult_types() const { return false; }
 };
 class JointDef {
  public:

@@ -8,3 +8,8 @@ struct PartBBox {
   float x1, x2, y1, y2;
   bool use_endpoints;
 };
+
+#include <libAnnotation/annotation.h>
+#include <libPartDetect/PartConfig.pb.h>
+bool annorect_has_part(const AnnoRect &annorect, const PartDef &partdef);
+bool get_part_bbox(const AnnoRect &annorect, const PartDef &partdef, PartBBox &part_bbox, double scale = 1.0);

@@ -4,5 +4,6 @@
 #include <libPartDetect/partdef.h>
 namespace part_detect {
 const float NO_CLASS_VALUE = 0;
-template <class... A> void partdetect(const A &...) { abort(); }  // the detector is not part of oracle/_ref
+template <class... A> void partdetect(const A &...) { abort(); }
+template <class... A> void runMatlabCode(const A &...) { abort(); }  // the detector is not part of oracle/_ref
 }

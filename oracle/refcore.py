@@ -145,6 +145,8 @@ def dlib():
                                  _fp, C.c_int, _ip]
         L.refd_find_local_max.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
         L.refd_load_joints.argtypes = [C.c_int, _dp, C.c_int, C.c_int, _dp, _dp]
+        L.refd_condition.argtypes = [_dp, C.c_int, _ip, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _dp, C.c_float, C.c_int, _fp,
+                                     C.c_int]
         _dlib = L
     return _dlib
 
@@ -231,3 +233,19 @@ def load_joints(num_parts, joints, flip):
     _quiet(lambda: dlib().refd_load_joints(int(num_parts), rows.ctypes.data_as(_dp), len(joints), int(bool(flip)),
                                            out.ctypes.data_as(_dp), di.ctypes.data_as(_dp)))
     return out, di
+
+
+def condition(ep, part_conf, unaries, kind, params=None, weight=1.0, pidx=0, dpm=None):
+    """The conditioning adds of objectdetect_icps.cpp as the reference compiled them, on a copy of `unaries`
+    [P][S][R][H][W]: kind 0 getRotScoreGrid + addExtraUnary (params [P][2]), 1 getPosScoreGrid + addExtraUnary
+    (params [P][4] followed by the detected root position), 2 setTorsoPosPrior (params [4]), 3 addDPMScore (dpm [n][H][W])."""
+    u = np.ascontiguousarray(unaries, np.float32).copy()
+    P, S, R, H, W = u.shape
+    det = np.array([int(bool(v)) for v in part_conf.is_detect], np.int32)
+    roots = [p for p in range(P) if part_conf.is_detect[p] and part_conf.is_root[p]]
+    prm = np.ascontiguousarray(params if params is not None else [0.0], np.float64).ravel()
+    g = np.ascontiguousarray(dpm, np.float32) if dpm is not None else np.zeros((1, H, W), np.float32)
+    e = _epv(ep)
+    _quiet(lambda: dlib().refd_condition(e.ctypes.data_as(_dp), P, det.ctypes.data_as(_ip), roots[0], H, W, _f(u), int(kind),
+                                         prm.ctypes.data_as(_dp), float(weight), int(pidx), _f(g), g.shape[0]))
+    return u

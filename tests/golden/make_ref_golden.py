@@ -48,5 +48,8 @@ for name, joints in dc.joint_cases().items():
         rows, di = refcore.load_joints(P, joints, flip)
         drv["joints_%s_flip%d" % (name, flip)] = rows
         drv["joints_%s_flip%d_detinv" % (name, flip)] = di
+for name, c in dc.condition_cases().items():
+    pc, un = dc.condition_inputs(c)
+    drv["cond_" + name] = refcore.condition(c["ep"], pc, un, c["kind"], c.get("params"), c["weight"], c.get("pidx", 0), c.get("dpm"))
 np.savez_compressed(os.path.join(HERE, "ref_drivers.npz"), **drv)
 print("wrote %d reference driver outputs" % len(drv))

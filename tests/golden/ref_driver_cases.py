@@ -62,3 +62,78 @@ def local_max_cases():
 
 def joint_cases():
     return {"tree10": synth.make_joints(10, seed=9), "tree6_diag": synth.make_joints(6, seed=2, diagonal=True)}
+
+
+def condition_cases():
+    """The conditioning adds.  Parameters are in the ranges the MATLAB predictors produce: rotation
+    mean / variance in radians, position mean / variance in pixels relative to the detected root."""
+    ep = ExpParam(num_rotation_steps=8, num_scale_steps=2, min_object_scale=0.9, max_object_scale=1.1)
+    P, H, W = 4, 22, 26
+    rng = np.random.default_rng(31)
+    rot = np.stack([rng.uniform(-1.5, 1.5, P), rng.uniform(0.05, 0.8, P)], 1)
+    pos = np.stack([rng.uniform(-6, 6, P), rng.uniform(-6, 6, P), rng.uniform(4, 60, P), rng.uniform(4, 60, P)], 1)
+    root = np.array([12.0, 9.0])
+    dpm1 = np.log(rng.uniform(1e-3, 1.0, (1, H, W))).astype(np.float32)
+    dpmR = np.log(rng.uniform(1e-3, 1.0, (8, H, W))).astype(np.float32)
+    base = dict(ep=ep, P=P, H=H, W=W, seed=6)
+    return {"rot": dict(base, kind=0, params=rot, weight=0.35),
+            "pos": dict(base, kind=1, params=np.concatenate([pos.ravel(), root]), weight=0.6),
+            "torso_prior": dict(base, kind=2, params=np.array([1.0, -2.0, 40.0, 65.0]), weight=0.8),
+            "dpm_one_grid": dict(base, kind=3, pidx=2, dpm=dpm1, weight=0.5),
+            "dpm_per_rotation": dict(base, kind=3, pidx=1, dpm=dpmR, weight=1.5)}
+
+
+def condition_inputs(c):
+    import oracle
+    pc = synth.part_conf(c["P"])
+    un = oracle.prepare_unary(synth.raw_scores(c["ep"], c["H"], c["W"], c["P"], c["seed"]))
+    return pc, un
+
+
+def oracle_condition(c):
+    """The same adds composed from the oracle's restatement (tables built like the reference, then broadcast adds).
+    oracle/_ref is compiled as C++17, where pow(float, int) squares in double; the oracle's default is the authors'
+    gnu++98 rule (fp32 square) -- see ps_oracle.cpp.  The comparison runs the oracle under the C++11 rule."""
+    import ctypes as C
+    import oracle
+    L = oracle.lib()
+    L.orc_set_pow_dialect(1)
+    try:
+        return _oracle_condition(c, L, C, oracle)
+    finally:
+        L.orc_set_pow_dialect(0)
+
+
+def _oracle_condition(c, L, C, oracle):
+    fp = C.POINTER(C.c_float)
+    pc, un = condition_inputs(c)
+    u = un.copy()
+    P, S, R, H, W = u.shape
+    root = [p for p in range(P) if pc.is_detect[p] and pc.is_root[p]][0]
+    f = lambda a: a.ctypes.data_as(fp)
+    if c["kind"] == 0:
+        for p in range(P):
+            t = np.zeros(R, np.float32)
+            if pc.is_detect[p]:
+                L.orc_rot_score_table(C.byref(oracle.exp_param(c["ep"])), float(c["params"][p, 0]), float(c["params"][p, 1]), f(t))
+            for s in range(S):
+                L.orc_add_rot_table(f(u[p, s]), R, H, W, f(t), C.c_float(c["weight"]))
+    elif c["kind"] == 1:
+        prm = c["params"][:4 * P].reshape(P, 4)
+        rx, ry = c["params"][4 * P:]
+        for p in range(P):
+            t = np.zeros((H, W), np.float32)
+            if pc.is_detect[p] and p != root:
+                L.orc_pos_score_table(H, W, *[float(v) for v in prm[p]], float(rx), float(ry), f(t))
+            for s in range(S):
+                L.orc_add_pos_table(f(u[p, s]), R, H, W, f(t), C.c_float(c["weight"]))
+    elif c["kind"] == 2:
+        t = np.zeros((H, W), np.float32)
+        L.orc_torso_prior_table(H, W, *[float(v) for v in c["params"]], C.c_float(c["weight"]), f(t))
+        for s in range(S):
+            L.orc_add_pos_table_unweighted(f(u[root, s]), R, H, W, f(t))
+    else:
+        g = np.ascontiguousarray(c["dpm"], np.float32)
+        for s in range(S):
+            L.orc_add_dpm_score(f(u[c["pidx"], s]), R, H, W, f(g), g.shape[0], C.c_float(c["weight"]))
+    return u

@@ -147,6 +147,25 @@ def test_oracle_joint_flip_reproduces_reference_load_joints(name, flip):
     assert _same(_oracle_load_joints(joints, flip), DRV["joints_%s_flip%d" % (name, flip)])
 
 
+@pytest.mark.parametrize("name", sorted(dc.condition_cases()))
+def test_oracle_conditioning_adds_reproduce_reference(name):
+    """objectdetect_icps.cpp: getRotScoreGrid / getPosScoreGrid + addExtraUnary, setTorsoPosPrior, addDPMScore.
+    One expression in there is dialect-dependent -- pow(float, int) squares in fp32 under the authors' gnu++98 and in
+    double since C++11 (oracle/_ref is built as C++17) -- so the oracle is switched to the C++11 rule for this
+    comparison (ref_driver_cases.oracle_condition); with its default rule only the position prior differs, by one ulp
+    in a few cells, which the second half of this test states."""
+    c = dc.condition_cases()[name]
+    got = dc.oracle_condition(c)
+    assert _same(got, DRV["cond_" + name])
+    if name == "pos":
+        import ctypes as C
+        L = oracle.lib()
+        pc, un = dc.condition_inputs(c)
+        dflt = dc._oracle_condition(c, L, C, oracle)            # the authors' dialect: fp32 square
+        d = np.abs(dflt.astype(np.float64) - DRV["cond_pos"].astype(np.float64))
+        assert 0 < (d > 0).sum() < 0.01 * d.size and d.max() <= 2e-6
+
+
 @pytest.mark.skipif(not refcore.drivers_available(), reason="oracle/_ref drivers not built (needs the reference tree)")
 def test_reference_drivers_still_match_fixture_and_random_inference():
     for name, c in dc.message_cases().items():
