@@ -1,6 +1,7 @@
 // ref_drivers.cpp -- TEST INFRASTRUCTURE: C entry points over the reference's OWN inference drivers.
 // libPictStruct/objectdetect_findrot.cpp (computeRotJointMarginal, computePartMarginals, computeRootPosteriorRot) is
-// libPictStruct/objectdetect_aux.cpp (findLocalMax, loadJoints) and objectdetect_icps.cpp (the conditioning adds) are
+// libPictStruct/objectdetect_aux.cpp (findLocalMax, loadJoints), objectdetect_icps.cpp (the conditioning adds) and
+// objectdetect_findpos.cpp (computePosJointMarginal, the legacy POS_GAUSSIAN message) are
 // compiled UNMODIFIED from /root/reference next to this file (`make -C oracle ref`), against the stand-ins of
 // oracle/ref_shim/ for everything the image lacks (Boost, Qt, protoc output, libmat, the detector libraries).  This file
 // defines what that translation unit references but other, uncompilable translation units define.
@@ -57,7 +58,9 @@ void getRootPosDet(const PartApp &, int, int, boost_math::double_vector &, bool)
 void getPosScoreGrid(const PartApp &, Grids &, int, boost_math::double_matrix &, int, boost_math::double_vector &) { abort(); }
 void setTorsoPosPrior(const PartApp &, Grids &, boost_math::double_matrix &, int) { abort(); }
 #endif
-void findObjectImagePosJoints(const PartApp &, int, bool, HypothesisList &, int) { abort(); }
+// objectdetect_findpos.cpp defines it but declares it in no header
+void computePosJointMarginal(FloatGrid2 &log_prob_child, FloatGrid2 &log_prob_parent, boost_math::double_vector offset,
+                             boost_math::double_matrix C, double scale, bool bIsSparse);
 }  // namespace object_detect
 
 namespace matlab_io {
@@ -198,6 +201,20 @@ void refd_condition(const double *ep, int P, const int *is_detect, int rootpart_
   }
   for (int p = 0; p < P; ++p)
     for (int s = 0; s < S; ++s) memcpy(unaries + ((size_t)p * S + s) * G, det[p][s].data(), sizeof(float) * G);
+}
+
+// object_detect::computePosJointMarginal (objectdetect_findpos.cpp:64-89), the reference's code, on one [H][W] grid;
+// `child` comes back as the reference leaves it
+void refd_pos_message(float *child, float *parent, int H, int W, const double *offset, const double *C, double scale, int sparse) {
+  FloatGrid2 gc(boost::extents[H][W]), gp(boost::extents[H][W]);
+  memcpy(gc.data(), child, sizeof(float) * (size_t)H * W);
+  double_vector off(2);
+  off(0) = offset[0]; off(1) = offset[1];
+  double_matrix Cm(2, 2);
+  Cm(0, 0) = C[0]; Cm(0, 1) = C[1]; Cm(1, 0) = C[2]; Cm(1, 1) = C[3];
+  object_detect::computePosJointMarginal(gc, gp, off, Cm, scale, sparse != 0);
+  memcpy(child, gc.data(), sizeof(float) * (size_t)H * W);
+  memcpy(parent, gp.data(), sizeof(float) * (size_t)H * W);
 }
 
 // object_detect::computeRotJointMarginal (objectdetect_findrot.cpp:292-456), the reference's code

@@ -31,6 +31,8 @@ inline bool mat_save_double_vector(MATFile *, QString, const boost_math::double_
 inline bool mat_load_double_matrix(MATFile *, QString, boost_math::double_matrix &) { abort(); }
 inline bool mat_load_double_vector(MATFile *, QString, boost_math::double_vector &) { abort(); }
 template <class V> bool mat_load_multi_array_vec2(MATFile *, QString, V &) { abort(); }
+template <class V> bool mat_save_multi_array_vec2(MATFile *, QString, const V &) { return true; }
+template <class V> bool mat_save_multi_array_vec2(QString, QString, const V &) { return true; }
 template <class V> bool mat_load_multi_array_vec2(QString, QString, V &) { abort(); }
 template <class V> bool mat_load_stdcpp_vector(QString, QString, V &) { abort(); }
 }  // namespace matlab_io

@@ -36,6 +36,7 @@ class ExpParam {
   PS_FIELD(float, dpm_head_weight, 1)
   PS_FIELD(bool, do_dpm_rot, false)
   PS_FIELD(bool, save_part_marginals, false)
+  PS_FIELD(bool, save_root_marginal, false)
   PS_FIELD(bool, save_part_marginals_local_max, false)
   PS_FIELD(bool, save_part_detections_local_max, false)
   PS_FIELD(bool, interpolate, false)

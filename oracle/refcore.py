@@ -145,6 +145,7 @@ def dlib():
                                  _fp, C.c_int, _ip]
         L.refd_find_local_max.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
         L.refd_load_joints.argtypes = [C.c_int, _dp, C.c_int, C.c_int, _dp, _dp]
+        L.refd_pos_message.argtypes = [_fp, _fp, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int]
         L.refd_condition.argtypes = [_dp, C.c_int, _ip, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _dp, C.c_float, C.c_int, _fp,
                                      C.c_int]
         _dlib = L
@@ -249,3 +250,15 @@ def condition(ep, part_conf, unaries, kind, params=None, weight=1.0, pidx=0, dpm
     _quiet(lambda: dlib().refd_condition(e.ctypes.data_as(_dp), P, det.ctypes.data_as(_ip), roots[0], H, W, _f(u), int(kind),
                                          prm.ctypes.data_as(_dp), float(weight), int(pidx), _f(g), g.shape[0]))
     return u
+
+
+def pos_message(child, offset, Cm, scale, sparse):
+    """object_detect::computePosJointMarginal as the reference compiled it, on each [H][W] slice of child [D][H][W].
+    Returns (log_prob_parent, log_prob_child as the reference leaves it)."""
+    ch = np.ascontiguousarray(child, np.float32).copy()
+    out = np.empty_like(ch)
+    (_o, po), (_c, pc) = _d(offset), _d(Cm)
+    for d in range(ch.shape[0]):
+        _quiet(lambda: dlib().refd_pos_message(_f(ch[d]), _f(out[d]), ch.shape[1], ch.shape[2], po, pc, float(scale),
+                                               int(bool(sparse))))
+    return out, ch

@@ -51,5 +51,9 @@ for name, joints in dc.joint_cases().items():
 for name, c in dc.condition_cases().items():
     pc, un = dc.condition_inputs(c)
     drv["cond_" + name] = refcore.condition(c["ep"], pc, un, c["kind"], c.get("params"), c["weight"], c.get("pidx", 0), c.get("dpm"))
+for name, c in dc.pos_message_cases().items():
+    par, ch = refcore.pos_message(c["child"], c["offset"], c["C"], c["scale"], c["sparse"])
+    drv["posmsg_%s_parent" % name] = par
+    drv["posmsg_%s_child" % name] = ch
 np.savez_compressed(os.path.join(HERE, "ref_drivers.npz"), **drv)
 print("wrote %d reference driver outputs" % len(drv))

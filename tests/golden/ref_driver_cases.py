@@ -137,3 +137,22 @@ def _oracle_condition(c, L, C, oracle):
         for s in range(S):
             L.orc_add_dpm_score(f(u[c["pidx"], s]), R, H, W, f(g), g.shape[0], C.c_float(c["weight"]))
     return u
+
+
+def pos_message_cases():
+    """The legacy POS_GAUSSIAN message (objectdetect_findpos.cpp:64-89) on [D][H][W] stacks of 2-D grids."""
+    rng = np.random.default_rng(11)
+    H, W = 34, 30
+    dense = (rng.standard_normal((2, H, W)) * 2 - 3).astype(np.float32)
+    sparse = dense.copy()
+    sparse[rng.random(sparse.shape) < 0.8] = np.float32(-1e6)
+    th = 0.7
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    full = Rm @ np.diag([10.0, 3.0]) @ Rm.T
+    full = (full + full.T) / 2
+    out = {}
+    for cname, Cm in (("diag", np.diag([9.0, 4.0])), ("full", full)):
+        for gname, g, sp in (("dense", dense, False), ("sparse", sparse, True)):
+            for i, (off, sc) in enumerate((((5.5, -3.25), 1.0), ((-2.0, 7.0), 1.3))):
+                out["%s_%s_%d" % (cname, gname, i)] = dict(child=g, offset=off, C=Cm, scale=sc, sparse=sp)
+    return out

@@ -147,6 +147,14 @@ def test_oracle_joint_flip_reproduces_reference_load_joints(name, flip):
     assert _same(_oracle_load_joints(joints, flip), DRV["joints_%s_flip%d" % (name, flip)])
 
 
+@pytest.mark.parametrize("name", sorted(dc.pos_message_cases()))
+def test_oracle_pos_message_reproduces_reference(name):
+    """computePosJointMarginal (objectdetect_findpos.cpp:64-89): the parent grid and the rewritten child grid."""
+    c = dc.pos_message_cases()[name]
+    par, ch = oracle.pos_message(c["child"], c["offset"], c["C"], c["scale"], c["sparse"])
+    assert _same(par, DRV["posmsg_%s_parent" % name]) and _same(ch, DRV["posmsg_%s_child" % name])
+
+
 @pytest.mark.parametrize("name", sorted(dc.condition_cases()))
 def test_oracle_conditioning_adds_reproduce_reference(name):
     """objectdetect_icps.cpp: getRotScoreGrid / getPosScoreGrid + addExtraUnary, setTorsoPosPrior, addDPMScore.
