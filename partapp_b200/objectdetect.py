@@ -248,6 +248,27 @@ class PsContext:
         t = _f32(table)
         self._check(self.lib.ps_add_unary_table(self.h, part, t.ctypes.data_as(C.POINTER(C.c_float)), kind, weight))
 
+    # host builders of the conditioning tables (same arithmetic as the reference, which builds them on the CPU)
+    def rot_score_table(self, mu, var):
+        """getRotScoreGrid (objectdetect_icps.cpp:228-281): table[R] for one part."""
+        t = np.empty(self.R, np.float32)
+        self.lib.ps_rot_score_table(C.byref(self.cfg), float(mu), float(var), t.ctypes.data_as(C.POINTER(C.c_float)))
+        return t
+
+    def pos_score_table(self, mu_x, mu_y, var_x, var_y, root_x, root_y):
+        """getPosScoreGrid (objectdetect_icps.cpp:366-423): table[H][W] for one non-root part."""
+        t = np.empty((self.H, self.W), np.float32)
+        self.lib.ps_pos_score_table(self.H, self.W, float(mu_x), float(mu_y), float(var_x), float(var_y), float(root_x),
+                                    float(root_y), t.ctypes.data_as(C.POINTER(C.c_float)))
+        return t
+
+    def torso_prior_table(self, mu_x, mu_y, var_x, var_y, weight):
+        """setTorsoPosPrior (objectdetect_icps.cpp:137-191): the weighted table[H][W] added to the root."""
+        t = np.empty((self.H, self.W), np.float32)
+        self.lib.ps_torso_prior_table(self.H, self.W, float(mu_x), float(mu_y), float(var_x), float(var_y), float(weight),
+                                      t.ctypes.data_as(C.POINTER(C.c_float)))
+        return t
+
     def add_unary_grid(self, part, grid, mode, weight=1.0):
         """addDPMScore (mode 0) / addLoadDPMScore (mode 1), objectdetect_icps.cpp:445-524; grid [1 or R][H][W]."""
         g = _f32(grid)
