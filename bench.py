@@ -287,8 +287,8 @@ def run_ours(args):
         infos = [c.plan_info(j, d) for j in range(J) for d in (0, 1)]
         Ge = float(np.mean([4.0 * w["R"] * i["rows"] * i["cols"] for i in infos]))   # bytes of the filter grid
         taps = {"rotconv": float(np.mean([N * max(i["rot_taps"], 0) for i in infos])),
-                "conv_rows": float(np.mean([w["R"] * i["rows"] * i["cols"] * i["x_taps"] for i in infos])),
-                "conv_cols": float(np.mean([w["R"] * i["rows"] * i["cols"] * i["y_taps"] for i in infos]))}
+                "conv_rows": float(np.mean([w["R"] * i["x_cells"] * i["x_taps"] for i in infos])),
+                "conv_cols": float(np.mean([w["R"] * i["y_cells"] * i["y_taps"] for i in infos]))}
         # algorithmic bytes per launch of each kernel class: each grid read once, written once
         alg_per_launch = {"conv_rows": 2 * Ge, "conv_cols": 2 * Ge, "rotconv": 2 * G, "epilogue": 3 * G,
                           "warp_direct": G + Ge, "warp_bilinear": G + Ge, "warp_back": G + Ge, "prepare_unary": 2 * G,
@@ -495,8 +495,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--images", type=int, default=4, help="images per GPU per step")
-    ap.add_argument("--streams", type=int, default=4, help="contexts/streams per GPU (one image in flight on each)")
+    ap.add_argument("--images", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--streams", type=int, default=8, help="contexts/streams per GPU (one image in flight on each)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-math", action="store_true",

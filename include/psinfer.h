@@ -231,9 +231,11 @@ int ps_find_local_max(ps_ctx *ctx, const float *grid, int mem_kind, int d0, int 
 
 /* What ps_set_joints derived for one message (joint, direction, scale):
  * out = {diagonal covariance?, filter-grid rows, filter-grid cols (the eigen-frame grid of gaussFilter2dOffset,
- * transform.hpp:298-299, or the image grid), rotation taps (0: no blur), x taps, y taps, rot_mean_idx, shift flags}.
+ * transform.hpp:298-299, or the image grid), rotation taps (0: no blur), x taps, y taps, rot_mean_idx, shift flags,
+ * cells per rotation slice the x pass computes, cells per slice the y pass computes (the work lists keep only what
+ * the read-back can reach; rows*cols when no list applies)}.
  * Used by bench.py to count tap-outputs for the fp32-pipe roofline. */
-int ps_get_plan_info(ps_ctx *ctx, int joint, int downward, int scale, int out[8]);
+int ps_get_plan_info(ps_ctx *ctx, int joint, int downward, int scale, int out[10]);
 
 /* Exhaustive check of the device exp/log used on the path: for every fp32 bit pattern in
  * [first_bits, first_bits + count) compares the table-driven fast evaluation with CUDA's fp64 libm narrowed to fp32

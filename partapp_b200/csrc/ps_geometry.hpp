@@ -205,12 +205,13 @@ struct MessagePlan {
   double T31[6];                // image -> eigen-frame (TM_DIRECT forward scatter), rows 0,1 of the 3x3
   double T13[6];                // eigen-frame -> image (TM_BILINEAR gather into the eigen-frame)
   double T34[6];                // image -> eigen-frame coordinates for the bilinear read-back
-  // Work lists for the tiled Gaussian passes (64 x 64 output tiles).  The eigen-frame grid is the bounding box of
-  // the ROTATED image, so on average ~40 % of its cells are never read by the bilinear read-back (it samples only
-  // inside the rotated image rectangle).  ytiles: (row-tile, col-tile) pairs of the y pass that intersect that
-  // rectangle (dilated by 2 cells for the 2x2 taps); xtiles: (x-tile, y-tile) pairs of the x pass whose outputs some
-  // listed y tile reads (its 64 columns x (64 + 2*ny) rows).  Skipping the rest changes no value that is ever used.
+  // Work lists for the tiled Gaussian passes.  The eigen-frame grid is the bounding box of the ROTATED image, so on
+  // average ~40 % of its cells are never read by the bilinear read-back (it samples only inside the rotated image
+  // rectangle, dilated by 2 cells for the 2x2 taps).  Entries are (first row, strip | groups << 12): a tile of up
+  // to 64 rows (groups x 8) in a 64-cell strip; see plan_message for how they are cut.  Skipping the rest changes no
+  // value that is ever used.
   std::vector<int> ytiles, xtiles;
+  long long ycells = 0, xcells = 0;  // cells per slice the two lists cover (whole 8 x 64 groups)
   std::string error;            // non-empty: the reference would have hit an assert
 };
 
@@ -386,25 +387,41 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
       if (std::fabs(dx * evx + dy * evy) > hv + rhx * std::fabs(evx) + rhy * std::fabs(evy)) return false;
       return true;
     };
-    const int TS = 64;
-    const int nty = (p.EH + TS - 1) / TS, ntx = (p.EW + TS - 1) / TS;
+    // Work lists of the TMA column kernel: entries (row0, strip | groups << 12).  A strip is 64 cells of the axis the
+    // filter does not run along; within a strip the cells some reader needs form one interval of the filter axis,
+    // found by testing 8-row groups (one warp's share of a tile) against the rectangle.  The interval is cut into
+    // tiles of 64 rows starting at its first group, so only the last tile of a strip is partial (groups < 8: the
+    // remaining warps skip it).  y pass: strips walk x, rows walk y, readers = the read-back.  x pass (transposed
+    // grid): strips walk y, rows walk x, readers = the y pass, which reaches ny rows beyond the rectangle -- a cell
+    // (ex, ey) is needed iff some cell (ex, ey') of the rectangle has |ey' - ey| <= ny.  Cells outside the lists are
+    // never computed and never feed a cell the read-back touches.
+    const int TS = 64, SG = 8;
     const int ny = ((int)p.fy.size() - 1) / 2;
-    std::vector<char> needx((size_t)ntx * nty, 0);  // x pass runs on the transposed grid: tile (x-tile, y-tile)
-    for (int ty = 0; ty < nty; ++ty)
-      for (int tx = 0; tx < ntx; ++tx)
-        if (rect_hits(tx * TS - 0.5, ty * TS - 0.5, tx * TS + TS - 0.5, ty * TS + TS - 0.5)) {
-          p.ytiles.push_back(ty);
-          p.ytiles.push_back(tx);
-          // this y tile reads x-pass outputs in columns [tx*TS, tx*TS+TS) and rows [ty*TS - ny, ty*TS + TS + ny)
-          const int r0 = std::max(0, ty * TS - ny), r1 = std::min(p.EH - 1, ty * TS + TS - 1 + ny);
-          for (int yt2 = r0 / TS; yt2 <= r1 / TS; ++yt2) needx[(size_t)tx * nty + yt2] = 1;
+    auto build = [&](bool xpass, std::vector<int> &list, long long &cells) {
+      const int strips = ((xpass ? p.EH : p.EW) + TS - 1) / TS;
+      const int groups = ((xpass ? p.EW : p.EH) + SG - 1) / SG;
+      cells = 0;
+      for (int st = 0; st < strips; ++st) {
+        int g0 = -1, g1 = -1;
+        for (int g = 0; g < groups; ++g) {
+          const bool hit = xpass ? rect_hits(g * SG - 0.5, st * TS - ny - 0.5, g * SG + SG - 0.5, st * TS + TS - 0.5 + ny)
+                                 : rect_hits(st * TS - 0.5, g * SG - 0.5, st * TS + TS - 0.5, g * SG + SG - 0.5);
+          if (hit) {
+            if (g0 < 0) g0 = g;
+            g1 = g;
+          }
         }
-    for (int tx = 0; tx < ntx; ++tx)      // x-pass tile grid: "row tiles" walk x (the filter axis), "col tiles" walk y
-      for (int ty = 0; ty < nty; ++ty)
-        if (needx[(size_t)tx * nty + ty]) {
-          p.xtiles.push_back(tx);
-          p.xtiles.push_back(ty);
+        if (g0 < 0) continue;
+        for (int g = g0; g <= g1; g += TS / SG) {
+          const int ng = std::min(TS / SG, g1 - g + 1);
+          list.push_back(g * SG);
+          list.push_back(st | (ng << 12));
+          cells += (long long)ng * SG * TS;
         }
+      }
+    };
+    build(false, p.ytiles, p.ycells);
+    build(true, p.xtiles, p.xcells);
   }
   return p;
 }

@@ -1411,12 +1411,12 @@ struct ColsTmaArgs {
   size_t plane;
   int slices, ytiles, xtiles;  // tile grid: ytiles of 8T rows, xtiles of 64 columns
   int transpose_out;           // 1: out[z][col][row] (the input was stored transposed; this pass restores the layout)
-  const int *tile_list;        // optional (row-tile, col-tile) pairs to compute, same for every slice; null = all tiles
+  const int *tile_list;        // optional (first row, strip | groups << 12) pairs, same for every slice; null = all tiles
   int ntile_list;
 };
 
 // ---- stage 2b v4: Gaussian along y (and, on the transposed grid, along x) with TMA-fed tiles and a producer warp --
-// Persistent blocks walk (slice, row-tile, column-strip) tiles.  The (8T + 2n) x 64 input box of a tile is fetched
+// Persistent blocks walk (slice, first row, column-strip) tiles of up to 8T rows.  The (8T + 2n) x 64 input box of a tile is fetched
 // by cp.async.bulk.tensor.3d -- out-of-bounds rows/columns arrive as zeros = the reference's clipped window -- and
 // completion is an mbarrier transaction count, so the fill spends no issue slots and no registers of the filter
 // warps.  Arithmetic is identical to k_conv_cols2.  The first TMA version (one elected thread of warp 0 issued the
@@ -1441,7 +1441,7 @@ constexpr int kMaxSmemTiles = 1024;
 constexpr int kMaxTmaStages = 4;
 
 template <int T, bool FMA>
-__global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant__ CUtensorMap tmap, ColsTmaArgs a, u64 nz, int NS) {
+__global__ void __launch_bounds__(288, PS_TMA_MINB) k_conv_cols_tma2(const __grid_constant__ CUtensorMap tmap, ColsTmaArgs a, u64 nz, int NS) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ __align__(8) unsigned long long s_full[kMaxTmaStages], s_empty[kMaxTmaStages];
   __shared__ float s_taps[1000];
@@ -1466,19 +1466,28 @@ __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant
   __syncthreads();
   const int per_slice = a.tile_list ? a.ntile_list : a.ytiles * a.xtiles;
   const int ntiles = a.slices * per_slice;
-  auto decode = [&](int tile, int &xt, int &yt, int &z) {
+  // tile -> (first row, 64-column strip, 8-row groups to compute, slice); list entries are (row0, strip | groups << 12)
+  auto decode = [&](int tile, int &xt, int &row0, int &ng, int &z) {
     z = tile / per_slice;
     const int i = tile - z * per_slice;
-    if (list_smem) {
-      const ushort2 t = s_tiles[i];
-      yt = t.x;
-      xt = t.y;
-    } else if (a.tile_list) {
-      yt = a.tile_list[2 * i];
-      xt = a.tile_list[2 * i + 1];
+    if (a.tile_list) {
+      int e0, e1;
+      if (list_smem) {
+        const ushort2 t = s_tiles[i];
+        e0 = t.x;
+        e1 = t.y;
+      } else {
+        e0 = a.tile_list[2 * i];
+        e1 = a.tile_list[2 * i + 1];
+      }
+      row0 = e0;
+      xt = e1 & 0xfff;
+      ng = e1 >> 12;
     } else {
-      yt = i / a.xtiles;
+      const int yt = i / a.xtiles;
       xt = i - yt * a.xtiles;
+      row0 = yt * 8 * T;
+      ng = 8;
     }
   };
   if (w == 8) {  // producer
@@ -1489,10 +1498,10 @@ __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant
           while (!mbar_try_wait(&s_empty[s], (unsigned)(u - 1) & 1u)) {}
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
         }
-        int xt, yt, z;
-        decode(tile, xt, yt, z);
+        int xt, row0, ng, z;
+        decode(tile, xt, row0, ng, z);
         mbar_expect_tx(&s_full[s], stage_bytes);
-        tma_load_3d(s_raw + s * stage_stride, &tmap, xt * 64, yt * 8 * T - n, z, &s_full[s]);
+        tma_load_3d(s_raw + s * stage_stride, &tmap, xt * 64, row0 - n, z, &s_full[s]);
         if (++s == NS) {
           s = 0;
           ++u;
@@ -1507,10 +1516,10 @@ __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant
       s = 0;
       ++u;
     }
-    int xt, yt, z;
-    decode(tile, xt, yt, z);
+    int xt, row0, ng, z;
+    decode(tile, xt, row0, ng, z);
     while (!mbar_try_wait(&s_full[s], (unsigned)u & 1u)) {}
-    if (yt * 8 * T + w * T < a.rows) {  // warp-uniform
+    if (w < ng && row0 + w * T < a.rows) {  // warp-uniform
       const u64 *win = reinterpret_cast<const u64 *>(s_raw + s * stage_stride) + (w * T) * 32 + lane;
       u64 acc[T], d[T];
 #pragma unroll
@@ -1544,7 +1553,7 @@ __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant
       if (x < a.cols) {
         const bool in1 = x + 1 < a.cols;
         if (a.transpose_out) {
-          const int r0 = yt * 8 * T + w * T;
+          const int r0 = row0 + w * T;
           float lo[T], hi[T];
 #pragma unroll
           for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
@@ -1569,7 +1578,7 @@ __global__ void __launch_bounds__(288, 2) k_conv_cols_tma2(const __grid_constant
           float *dst = a.out + (size_t)z * a.plane + x;
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            const int y = yt * 8 * T + w * T + t;
+            const int y = row0 + w * T + t;
             if (y < a.rows) {
               float lo, hi;
               upk2(acc[t], lo, hi);

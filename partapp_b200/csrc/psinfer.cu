@@ -19,6 +19,9 @@
 #ifndef PS_RG
 #define PS_RG 8
 #endif
+#ifndef PS_TMA_MINB
+#define PS_TMA_MINB 2  // resident blocks per SM k_conv_cols_tma2 is compiled for (register budget)
+#endif
 #include "ps_geometry.hpp"
 #include "ps_kernels.cuh"
 
@@ -373,7 +376,8 @@ int launch_conv_rows(ps_ctx *c, const psk::ConvArgs &a, int slices) {
     if (best > 0 && !c->disable_tma) {
       const int ytiles = (a.rows + 2 * best - 1) / (2 * best);
       const int ntiles = slices * ytiles;
-      const int grid = std::min(ntiles, c->num_sms * 2);
+      static const int bps_env = getenv("PSINFER_CONV_BLOCKS") ? atoi(getenv("PSINFER_CONV_BLOCKS")) : 0;  // A/B knob
+  const int grid = std::min(ntiles, c->num_sms * (bps_env == 1 ? 1 : 2));
       PS_LAUNCH(c, KC_CONV_ROWS,
                 psk::k_conv_rows3<T><<<grid, 256, 2 * best * pair_bytes, c->stream>>>(a, PS_NEGZERO2, best, S, slices, ytiles));
       return PS_OK;
@@ -456,17 +460,20 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
   const int ntiles = t.slices * (t.tile_list ? ntile_list : t.ytiles * t.xtiles);
   // 2 resident blocks per SM.  A third (67 registers, short filters only) shaved 2 us off the 27-tap launch in isolation
   // and nothing off the two-images-in-flight bench (round-1 A/B), so the 88-register build stays.
-  const int grid = std::min(ntiles, c->num_sms * 2);
+  static const int bps_env = getenv("PSINFER_CONV_BLOCKS") ? atoi(getenv("PSINFER_CONV_BLOCKS")) : 0;  // A/B knob
+  const int grid = std::min(ntiles, c->num_sms * (bps_env == 1 ? 1 : 2));
   {
     static const int ns_env = getenv("PSINFER_TMA_STAGES") ? atoi(getenv("PSINFER_TMA_STAGES")) : 0;
     int ns = 2;  // deeper queues (3, 4) measured no faster: the boxes already land a tile ahead
     if (ns_env >= 2) ns = (int)std::min<size_t>(std::min(ns_env, psk::kMaxTmaStages), (104 * 1024) / stage);
+    static const size_t smem_env = getenv("PSINFER_CONV_SMEM") ? (size_t)atol(getenv("PSINFER_CONV_SMEM")) : 0;  // A/B knob
+    const size_t smem = std::min<size_t>(std::max(ns * stage, smem_env), 104 * 1024);
     if (c->cfg.fast_math)
       PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
-                psk::k_conv_cols_tma2<T, true><<<grid, 288, ns * stage, c->stream>>>(tm, t, PS_NEGZERO2, ns));
+                psk::k_conv_cols_tma2<T, true><<<grid, 288, smem, c->stream>>>(tm, t, PS_NEGZERO2, ns));
     else
       PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
-                psk::k_conv_cols_tma2<T, false><<<grid, 288, ns * stage, c->stream>>>(tm, t, PS_NEGZERO2, ns));
+                psk::k_conv_cols_tma2<T, false><<<grid, 288, smem, c->stream>>>(tm, t, PS_NEGZERO2, ns));
   }
   return PS_OK;
 }
@@ -1641,7 +1648,7 @@ int ps_pos_message(ps_ctx *c, float *child, float *parent, int mem_kind, const d
   return PS_OK;
 }
 
-int ps_get_plan_info(ps_ctx *c, int joint, int downward, int scale, int out[8]) {
+int ps_get_plan_info(ps_ctx *c, int joint, int downward, int scale, int out[10]) {
   if (!c || !out) return PS_ERR_INVALID;
   if (!c->joints_set) return c->fail(PS_ERR_STATE, "ps_get_plan_info before ps_set_joints");
   if (joint < 0 || joint >= (int)c->joints.size() || scale < 0 || scale >= c->S)
@@ -1655,6 +1662,9 @@ int ps_get_plan_info(ps_ctx *c, int joint, int downward, int scale, int out[8]) 
   out[5] = (int)h.fy.size();
   out[6] = h.rot_shift;
   out[7] = (h.in_pure ? 1 : 0) | (h.out_pure ? 2 : 0);
+  const bool lists = !h.diag && !c->disable_tile_lists && !c->disable_tma;
+  out[8] = lists && h.xcells ? (int)h.xcells : out[1] * out[2];
+  out[9] = lists && h.ycells ? (int)h.ycells : out[1] * out[2];
   return PS_OK;
 }
 

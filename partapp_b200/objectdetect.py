@@ -317,9 +317,9 @@ class PsContext:
         return out[:n.value].copy()
 
     def plan_info(self, joint, downward, scale=0):
-        out = (C.c_int * 8)()
+        out = (C.c_int * 10)()
         self._check(self.lib.ps_get_plan_info(self.h, joint, int(downward), scale, out))
-        keys = ("diag", "rows", "cols", "rot_taps", "x_taps", "y_taps", "rot_shift", "shift_flags")
+        keys = ("diag", "rows", "cols", "rot_taps", "x_taps", "y_taps", "rot_shift", "shift_flags", "x_cells", "y_cells")
         return dict(zip(keys, [int(v) for v in out]))
 
     def selftest_math(self, first_bits, count):

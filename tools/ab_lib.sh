@@ -3,7 +3,7 @@
 cp partapp_b200/libpsinfer.so /tmp/libpsinfer_base.so
 for lib in "$@"; do
   cp "$lib" partapp_b200/libpsinfer.so
-  python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-mode-probe 2>/dev/null | tail -1 > /tmp/ab.json
+  python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-mode-probe ${BENCH_ARGS:-} 2>/dev/null | tail -1 > /tmp/ab.json
   python -c "
 import json
 d=json.load(open('/tmp/ab.json')); k=d['roofline']['kernel_ms_per_image']
