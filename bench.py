@@ -290,7 +290,9 @@ def run_ours(args):
                 "conv_rows": float(np.mean([w["R"] * i["x_cells"] * i["x_taps"] for i in infos])),
                 "conv_cols": float(np.mean([w["R"] * i["y_cells"] * i["y_taps"] for i in infos]))}
         # algorithmic bytes per launch of each kernel class: each grid read once, written once
-        alg_per_launch = {"conv_rows": 2 * Ge, "conv_cols": 2 * Ge, "rotconv": 2 * G, "epilogue": 3 * G,
+        Gx = float(np.mean([4.0 * w["R"] * i["x_cells"] for i in infos]))   # the cells the work lists keep: each is
+        Gy = float(np.mean([4.0 * w["R"] * i["y_cells"] for i in infos]))   # read once and written once by its pass
+        alg_per_launch = {"conv_rows": 2 * Gx, "conv_cols": 2 * Gy, "rotconv": 2 * G, "epilogue": 3 * G,
                           "warp_direct": G + Ge, "warp_bilinear": G + Ge, "warp_back": G + Ge, "prepare_unary": 2 * G,
                           "grid_max": G, "root_combine": 12 * G, "argmax": G, "root_marginal": G}
         dom_ms_per_launch = dom[1][0] / dom[1][1]

@@ -211,7 +211,7 @@ struct MessagePlan {
   // to 64 rows (groups x 8) in a 64-cell strip; see plan_message for how they are cut.  Skipping the rest changes no
   // value that is ever used.
   std::vector<int> ytiles, xtiles;
-  long long ycells = 0, xcells = 0;  // cells per slice the two lists cover (whole 8 x 64 groups)
+  long long ycells = 0, xcells = 0;  // grid cells per slice the two lists cover
   std::string error;            // non-empty: the reference would have hit an assert
 };
 
@@ -401,6 +401,7 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
       const int strips = ((xpass ? p.EH : p.EW) + TS - 1) / TS;
       const int groups = ((xpass ? p.EW : p.EH) + SG - 1) / SG;
       cells = 0;
+      if (strips > 0xfff) return;  // the strip index has 12 bits: no list, the kernel walks every tile
       for (int st = 0; st < strips; ++st) {
         int g0 = -1, g1 = -1;
         for (int g = 0; g < groups; ++g) {
@@ -416,7 +417,7 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
           const int ng = std::min(TS / SG, g1 - g + 1);
           list.push_back(g * SG);
           list.push_back(st | (ng << 12));
-          cells += (long long)ng * SG * TS;
+          cells += (long long)std::min(ng * SG, (xpass ? p.EW : p.EH) - g * SG) * std::min(TS, (xpass ? p.EH : p.EW) - st * TS);
         }
       }
     };

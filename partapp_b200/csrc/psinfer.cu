@@ -455,7 +455,7 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
   t.out = out; t.taps = taps; t.len = len; t.rows = rows; t.cols = cols; t.pitch = out_pitch; t.plane = out_plane;
   t.slices = slices; t.ytiles = (rows + 8 * T - 1) / (8 * T); t.xtiles = (cols + 63) / 64;
   t.transpose_out = transpose_out;
-  t.tile_list = (tile_list && !c->disable_tile_lists) ? tile_list : nullptr;
+  t.tile_list = (tile_list && ntile_list > 0 && !c->disable_tile_lists) ? tile_list : nullptr;
   t.ntile_list = ntile_list;
   const int ntiles = t.slices * (t.tile_list ? ntile_list : t.ytiles * t.xtiles);
   // 2 resident blocks per SM.  A third (67 registers, short filters only) shaved 2 us off the 27-tap launch in isolation

@@ -60,7 +60,8 @@ def pcp_identical(best_conf_ref, best_conf_test, part_params: Sequence[PartParam
 #   vis_eval_helper      parteval.cpp:312-383,520-524 (loadPartHyp :186-201 -> PartHyp::getPartBBox)
 #   get_part_bbox & co.  libPartDetect/partdef.cpp:91-340, annorect_has_part :468-482
 #   AnnoRect parsing     libAnnotation/annorect.cpp:30-130 (annopoint coordinates are read as ints)
-# The "human_full_joints" part merging (parteval.cpp:527-570) belongs to another part_conf_type and is not restated.
+#   model -> evaluation parts   parteval.cpp:520-857 (the tail of vis_eval_helper, per ExpParam.part_conf_type),
+#                               bbox_merge :208-285, get_shrink_factor_x :287-297
 
 
 def parse_prototext(text: str) -> dict:
@@ -283,6 +284,135 @@ def is_gt_match_bbox(gt: PartBBox, det: PartBBox, factor: float = 0.5) -> bool: 
     return bool(np.linalg.norm(gt_top - d_top) < factor * gt_len and np.linalg.norm(gt_bot - d_bot) < factor * gt_len)
 
 
+def _copy_bbox(b: PartBBox) -> PartBBox:
+    return PartBBox(b.part_pos.copy(), b.part_x_axis.copy(), b.part_y_axis.copy(), b.min_proj_x, b.max_proj_x,
+                    b.min_proj_y, b.max_proj_y)
+
+
+def bbox_merge2(b1: PartBBox, b2: PartBBox) -> PartBBox:
+    """bbox_merge(bbox1, bbox2) (parteval.cpp:225-235): two joint parts of one limb; axes and x extent of the first."""
+    r = _copy_bbox(b1)
+    r.part_pos = 0.5 * (b1.part_pos + b2.part_pos)
+    r.min_proj_y = float(r.part_y_axis @ (b2.part_pos - r.part_pos))
+    r.max_proj_y = float(r.part_y_axis @ (b1.part_pos - r.part_pos))
+    return r
+
+
+def bbox_merge4(b1: PartBBox, b2: PartBBox, b3: PartBBox, b4: PartBBox) -> PartBBox:
+    """bbox_merge of four corner parts (parteval.cpp:208-223): the torso of "human_full_torso4"."""
+    r = _copy_bbox(b1)
+    r.part_pos = 0.25 * (b1.part_pos + b2.part_pos + b3.part_pos + b4.part_pos)
+    py = lambda b: float(r.part_y_axis @ (b.part_pos - r.part_pos))
+    px = lambda b: float(r.part_x_axis @ (b.part_pos - r.part_pos))
+    r.min_proj_y, r.max_proj_y = min(py(b3), py(b4)), max(py(b1), py(b2))
+    r.min_proj_x, r.max_proj_x = min(px(b1), px(b4)), max(px(b2), px(b3))
+    return r
+
+
+def bbox_merge_rot(b1: PartBBox, b2: PartBBox, rot_range: Tuple[float, float, int]) -> PartBBox:
+    """bbox_merge(bbox1, bbox2, exp_param) (parteval.cpp:237-285): the stick between two joint positions, its axis
+    snapped to the nearest rotation bin centre (first minimum of |atan2 - bin|, bins not wrapped)."""
+    pos = 0.5 * (b1.part_pos + b2.part_pos)
+    min_x = min(b1.part_pos[0], b2.part_pos[0]) - pos[0]
+    max_x = max(b1.part_pos[0], b2.part_pos[0]) - pos[0]
+    min_y = min(b1.part_pos[1], b2.part_pos[1]) - pos[1]
+    max_y = max(b1.part_pos[1], b2.part_pos[1]) - pos[1]
+    lo, hi = (min_x, max_x) if max_x - min_x > max_y - min_y else (min_y, max_y)
+    d = b1.part_pos - b2.part_pos
+    part_rot = math.atan2(d[1], d[0])
+    rmin, rmax, n = rot_range
+    best, best_diff = None, float("inf")
+    for ridx in range(n):
+        deg = rmin if rmin == rmax else rmin + (rmax - rmin) / n * (0.5 + ridx)      # rot_from_index, partapp_aux.hpp:45-58
+        disc = deg / 180.0 * math.pi
+        if best_diff > abs(part_rot - disc):
+            best_diff, best = abs(part_rot - disc), disc
+    ay = np.array([math.cos(best), math.sin(best)])
+    return PartBBox(pos, np.array([-ay[1], ay[0]]), ay, b1.min_proj_x, b1.max_proj_x, lo, hi)
+
+
+def get_shrink_factor_x(ext_x_pos: float, pidx: int, rootidx: int = 4) -> float:
+    """parteval.cpp:287-297; float arithmetic like the reference (the result only scales the x extent)."""
+    off = 30.0 if pidx == rootidx else (20.0 if pidx == rootidx + 1 else 15.0)
+    return float(np.float32(0.7 * off / ext_x_pos)) if ext_x_pos != 0 else float("inf")
+
+
+def convert_eval_bboxes(part_conf_type: str, boxes: Sequence[PartBBox], scales: Sequence[float],
+                        part_conf_eval: Sequence[PartDef], part_conf: Sequence[PartDef],
+                        rot_range: Tuple[float, float, int] = (-180.0, 180.0, 48), merge: bool = True) -> List[PartBBox]:
+    """Tail of vis_eval_helper (parteval.cpp:520-857): from the model's part boxes (PartHyp::getPartBBox of every
+    best_conf row; `scales[i]` = that hypothesis's m_scale) to the boxes of the evaluation parts -- joint parts merged
+    into limbs where the model has them, the y extension of the detection window removed (PCP compares stick ends),
+    the x extent shrunk for display.  `part_conf` is the model's PartConfig (ext_x_pos of the shrink)."""
+    b = [_copy_bbox(x) for x in boxes]
+    ev = part_conf_eval
+
+    def strip_y(box, i, scale=1.0):
+        box.min_proj_y += scale * ev[i].ext_y_neg
+        box.max_proj_y -= scale * ev[i].ext_y_pos
+
+    def shrink(out, ext, rootidx=4, skip=()):
+        for i, box in enumerate(out):
+            if i in skip:
+                continue
+            f = get_shrink_factor_x(ext[i], i, rootidx)
+            box.max_proj_x *= f
+            box.min_proj_x *= f
+        return out
+
+    t = part_conf_type
+    if t == "human_full_joints":                                                      # :527-578
+        assert len(b) == 18
+        out = [bbox_merge2(b[0], b[1]), bbox_merge2(b[2], b[3]), bbox_merge2(b[6], b[7]), bbox_merge2(b[4], b[5]),
+               _copy_bbox(b[8]), _copy_bbox(b[17]),
+               bbox_merge2(b[9], b[10]), bbox_merge2(b[11], b[12]), bbox_merge2(b[15], b[16]), bbox_merge2(b[13], b[14])]
+        strip_y(out[4], 4, scales[8])
+        strip_y(out[5], 5, scales[17])
+        return shrink(out, [part_conf[i].ext_x_pos for i in range(len(out))])
+    if t == "human_full_torso4":                                                      # :579-630
+        assert len(b) == 22
+        out = [bbox_merge2(b[0], b[1]), bbox_merge2(b[2], b[3]), bbox_merge2(b[6], b[7]), bbox_merge2(b[4], b[5]),
+               bbox_merge4(b[16], b[17], b[18], b[19]), _copy_bbox(b[20]),
+               bbox_merge2(b[8], b[9]), bbox_merge2(b[10], b[11]), bbox_merge2(b[14], b[15]), bbox_merge2(b[12], b[13])]
+        strip_y(out[5], 5, scales[20])
+        return shrink(out, [part_conf[i].ext_x_pos for i in range(len(out))], skip=(4,))
+    if t == "human_full_14_parts" and merge:                                          # :631-689
+        assert len(b) == 14
+        m = lambda i, j: bbox_merge_rot(b[i], b[j], rot_range)
+        out = [m(0, 1), m(1, 2), m(4, 3), m(5, 4), _copy_bbox(b[6]), _copy_bbox(b[7]), m(8, 9), m(9, 10), m(12, 11),
+               m(13, 12)]
+        strip_y(out[4], 4, scales[6])
+        strip_y(out[5], 5, scales[7])
+        ext = [part_conf[i].ext_x_pos for i in (0, 1, 2, 3, 6, 7, 9, 10, 11, 12)]
+        return shrink(out, ext)
+    if t == "human_full_22_parts" and merge:                                          # :690-769
+        assert len(b) == 22
+        out = [_copy_bbox(b[i]) for i in (1, 3, 6, 8, 10, 11, 13, 15, 18, 20)]
+        for i in (0, 1, 2, 3, 6, 7, 8, 9):
+            strip_y(out[i], i)
+        strip_y(out[4], 4, scales[10])
+        strip_y(out[5], 5, scales[11])
+        ext = [part_conf[i].ext_x_pos for i in (1, 3, 6, 8, 10, 11, 12, 14, 16, 18)]
+        return shrink(out, ext)
+    if t == "human_full_12_parts" and merge:                                          # :770-824
+        assert len(b) == 12
+        out = [_copy_bbox(b[i]) for i in (0, 1, 3, 5, 8, 10)]
+        strip_y(out[0], 0, scales[0])
+        strip_y(out[1], 1, scales[1])
+        for i in (2, 3, 4, 5):
+            strip_y(out[i], i)
+        ext = [part_conf[i].ext_x_pos for i in (0, 1, 3, 5, 8, 10)]
+        return shrink(out, ext, rootidx=0)
+    # every other type (:825-849): one evaluation part per model part
+    for i, box in enumerate(b):
+        assert scales[i] > 0
+        strip_y(box, i, scales[i])
+        f = get_shrink_factor_x(part_conf[i].ext_x_pos, i) if t == "human_full" else float(np.float32(0.7))
+        box.max_proj_x *= f
+        box.min_proj_x *= f
+    return b
+
+
 @dataclass
 class SegmentEval:
     ratio: float
@@ -295,24 +425,32 @@ class SegmentEval:
 
 def eval_segments(annolist: Sequence[Annotation], part_conf_eval: Sequence[PartDef], window_param: Sequence[PartParam],
                   load_best_conf, firstidx: int, lastidx: int, scale: float = 1.0, eval_didx: int = -1,
-                  save_dir: Optional[str] = None) -> SegmentEval:
+                  save_dir: Optional[str] = None, part_conf: Optional[Sequence[PartDef]] = None,
+                  part_conf_type: str = "human_full", rot_range: Tuple[float, float, int] = (-180.0, 180.0, 48)) -> SegmentEval:
     """EVAL_TYPE_PS branch of eval_segments (parteval.cpp:1162-1345).  `load_best_conf(imgidx)` returns the [P][7]
-    `best_conf` of pose_est_imgidx%04d.mat; `scale` is scale_from_index(exp_param, 0) (:1207-1208).
-    With `save_dir`, the per-image endpoint matrices are written like the reference's seg_endpoints directory."""
+    `best_conf` of pose_est_imgidx%04d.mat; `scale` is scale_from_index(exp_param, 0) (:1207-1208); `part_conf` is the
+    model's part configuration (default: the evaluation one), `part_conf_type` ExpParam.part_conf_type and
+    `rot_range` (min_part_rotation, max_part_rotation, num_rotation_steps) -- what vis_eval_helper needs to turn model
+    parts into evaluation parts.  With `save_dir`, the per-image endpoint matrices are written like the reference's
+    seg_endpoints directory."""
     P = len(part_conf_eval)
+    model_conf = part_conf_eval if part_conf is None else part_conf
     correct, total = [0] * P, [0] * P
     seg_correct = seg_total = 0
     endpoints = {}
     for imgidx in range(firstidx, lastidx + 1):
         best_conf = np.asarray(load_best_conf(imgidx), np.float32).reshape(-1, 7)
-        assert best_conf.shape[0] == P, "eval_bbox.size() == part_conf_eval.part_size() (parteval.cpp:1250)"
+        assert best_conf.shape[0] == len(model_conf), "nParts == best_conf.shape()[0] (parteval.cpp:194)"
+        dets = convert_eval_bboxes(part_conf_type, [bbox_from_hyp(best_conf[i], window_param[i]) for i in range(len(best_conf))],
+                                   [float(r[1]) for r in best_conf], part_conf_eval, model_conf, rot_range)
+        assert len(dets) == P, "eval_bbox.size() == part_conf_eval.part_size() (parteval.cpp:1250)"
         ep = np.zeros((P + 1, 6))
         n_ok = n_seg = 0
         rects = annolist[imgidx].rects
         assert len(rects) > 0
         rect = rects[eval_didx if eval_didx >= 0 else 0]
         for pidx in range(P):
-            det = bbox_from_hyp(best_conf[pidx], window_param[pidx])
+            det = dets[pidx]
             top, bot, _ = get_bbox_endpoints(det)
             ep[pidx, :4] = [bot[0], bot[1], top[0], top[1]]
             if not rect.points or not annorect_has_part(rect, part_conf_eval[pidx]):
@@ -356,7 +494,8 @@ def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: 
     log_dir = rel(one("log_dir", "."))
     log_subdir = one("log_subdir") or os.path.splitext(os.path.basename(expopt))[0]   # partapp.cpp:300-306
     class_dir = rel(one("class_dir")) if one("class_dir") else os.path.join(log_dir, log_subdir, "class")
-    conf = load_part_conf(rel(one("part_conf_eval") or one("part_conf")))
+    model_conf = load_part_conf(rel(one("part_conf")))
+    conf = load_part_conf(rel(one("part_conf_eval"))) if one("part_conf_eval") else model_conf
     win = load_window_param(os.path.join(class_dir, "window_param.txt"))
     annos: List[Annotation] = []
     for ds in ep.get("test_dataset", []):
@@ -368,8 +507,12 @@ def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: 
     scale = smin if smin == smax else smin + (smax - smin) / ns * 0.5                  # scale_from_index(exp_param, 0)
     hyp_dir = os.path.join(log_dir, log_subdir, "part_marginals")
     load = lambda i: scipy.io.loadmat(os.path.join(hyp_dir, "pose_est_imgidx%04d.mat" % i))["best_conf"]
+    rot_range = (float(one("min_part_rotation", -180.0)), float(one("max_part_rotation", 180.0)),
+                 int(one("num_rotation_steps", 48)))                                    # ExpParam.proto defaults
     return eval_segments(annos, conf, win, load, firstidx, lastidx, scale,
-                         save_dir=os.path.join(hyp_dir, "seg_endpoints") if save_endpoints else None)
+                         save_dir=os.path.join(hyp_dir, "seg_endpoints") if save_endpoints else None,
+                         part_conf=model_conf, part_conf_type=str(one("part_conf_type", "human_full")),
+                         rot_range=rot_range)
 
 
 if __name__ == "__main__":

@@ -516,6 +516,61 @@ def test_fallback_kernels_without_tma(case, monkeypatch):
     _cmp(got, want, name + " (no TMA)")
 
 
+@pytest.mark.parametrize("k", range(8))
+def test_multi_tile_work_lists_match_oracle(k):
+    """Grids of several 64-cell strips and covariance axes at eight angles: the Gaussian work lists (one interval of
+    8-row groups per strip, partial last tile) leave out most of the eigen-frame bounding box; every cell the
+    read-back touches must still carry the reference's bits."""
+    rng = np.random.default_rng(4200 + k)
+    R = 4
+    H, W = [(150, 230), (260, 140), (129, 191), (200, 200)][k % 4]
+    ep = ExpParam(num_rotation_steps=R)
+    th = (k + 0.37) * np.pi / 8
+    s1, s2 = rng.uniform(2.0, 9.0, 2)
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    Cm = Rm @ np.diag([s1 * s1, s2 * s2]) @ Rm.T
+    Cm[1, 0] = Cm[0, 1]
+    Cm = Cm.tolist()
+    dense = bool(k & 1)
+    child = _child_grid(ep, H, W, 70 + k, dense)
+    oi, oo = rng.uniform(-20, 20, 2), rng.uniform(-20, 20, 2)
+    want = oracle.message(ep, child, oi, oo, Cm, 0.3, 0.6, 1.0, not dense)
+    with _ctx(ep, 2, H, W) as ctx:
+        got = ctx.message(child, oi, oo, Cm, 0.3, 0.6, 1.0, not dense)
+    _cmp(got, want, "multi-tile message %d (%dx%d, angle %.2f)" % (k, H, W, th))
+
+
+def test_work_lists_change_no_bit_and_skip_cells(monkeypatch):
+    """Same inference with and without the work lists (PSINFER_ALL_TILES=1 filters every eigen-frame tile): identical
+    marginals; and the lists really leave cells out (ps_get_plan_info reports fewer cells than rows x cols)."""
+    ep = ExpParam(num_rotation_steps=6, roi_save_num_samples=5)
+    P, H, W = 4, 170, 140
+    raw = synth.raw_scores(ep, H, W, P, 3)
+    joints = synth.make_joints(P, seed=9, max_offset=15, sigma_range=(2, 7))
+
+    def run():
+        with _ctx(ep, P, H, W) as ctx:
+            ctx.set_joints(joints)
+            for p in range(P):
+                ctx.set_unary(p, 0, raw[p, 0], raw_scores=True)
+            ctx.infer(sparse=True)
+            infos = [ctx.plan_info(j, d) for j in range(P - 1) for d in (0, 1)]
+            return ctx.best_conf(), [ctx.marginal(p) for p in range(P)], infos
+
+    best_a, marg_a, infos_a = run()
+    monkeypatch.setenv("PSINFER_ALL_TILES", "1")
+    best_b, marg_b, infos_b = run()
+    assert np.array_equal(best_a, best_b)
+    for p in range(P):
+        assert np.array_equal(marg_a[p], marg_b[p]), "marginal %d changes with the work lists" % p
+    full = [i for i in infos_a if not i["diag"]]
+    assert full, "the synthetic joints should have full covariances"
+    for ia, ib in zip(infos_a, infos_b):
+        assert ib["x_cells"] == ib["rows"] * ib["cols"] and ib["y_cells"] == ib["rows"] * ib["cols"]
+        if not ia["diag"]:
+            assert ia["y_cells"] < ib["y_cells"] and ia["x_cells"] <= ib["x_cells"]
+
+
 # ---- edge cases -------------------------------------------------------------------------------------------------------
 
 def test_tiny_grids_and_single_rotation_bins():

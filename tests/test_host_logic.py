@@ -102,8 +102,10 @@ part { part_id: 1 part_pos: 1 part_pos: 2 part_x_axis_from: 1 part_x_axis_to: 2 
 part { part_id: 2 part_pos: 3 part_pos: 4 part_x_axis_from: 3 part_x_axis_to: 4 part_x_axis_offset: -90 }
 joint { child_idx: 2 parent_idx: 1 type: "Gaussian" }
 """
+# the detection window of part 1 is the 100 px stick plus the part's y extension (4 above, 6 below), like the windows
+# the reference derives from the part configuration; the evaluation strips the extension again (parteval.cpp:836-837)
 _WINDOW_PARAM = """
-part { part_id: 1 window_size_x: 40 window_size_y: 100 pos_offset_x: 20 pos_offset_y: 50 }
+part { part_id: 1 window_size_x: 40 window_size_y: 110 pos_offset_x: 20 pos_offset_y: 54 }
 part { part_id: 2 window_size_x: 30 window_size_y: 80 pos_offset_x: 15 pos_offset_y: 40 }
 """
 _ANNOLIST = """<annotationlist>
@@ -165,6 +167,60 @@ def test_eval_segments_pcp(tmp_path):
     assert pe.eval_segments(annos, conf, win, lambda i: runs[i], 1, 1).seg_correct == 1
     runs[1] = conf_rows(100, 90.0, 0, 0, 0.0)          # right place, wrong orientation
     assert pe.eval_segments(annos, conf, win, lambda i: runs[i], 1, 1).seg_correct == 0
+
+
+def test_model_parts_to_evaluation_parts():
+    """vis_eval_helper's conversions (parteval.cpp:520-857): joint parts merge into limbs whose stick ends are the
+    joints; directly copied parts lose the window's y extension; the 14-part model snaps the limb axis to a bin."""
+    from partapp_b200 import parteval as pe
+    pp = pe.PartParam(window_size_x=30, window_size_y=40, pos_offset_x=15, pos_offset_y=20)
+
+    def box(x, y, rot=0.0, scale=1.0):
+        return pe.bbox_from_hyp(np.array([0, scale, 0, rot, x, y, 1.0], np.float32), pp)
+
+    ev = [pe.PartDef(part_id=i + 1, ext_x_pos=15.0, ext_y_pos=5.0, ext_y_neg=3.0) for i in range(10)]
+    # human_full_joints: 18 joint parts; limb 0 = parts 0 (lower joint) and 1 (upper joint) of a vertical stick
+    pos = [(50 + 7 * i, 100 + 11 * i) for i in range(18)]
+    pos[0], pos[1] = (60, 200), (60, 140)
+    boxes = [box(x, y) for x, y in pos]
+    model = [pe.PartDef(part_id=i + 1, ext_x_pos=10.0 + i) for i in range(18)]
+    out = pe.convert_eval_bboxes("human_full_joints", boxes, [1.0] * 18, ev, model)
+    assert len(out) == 10
+    top, bot, seg = pe.get_bbox_endpoints(out[0])
+    np.testing.assert_allclose(out[0].part_pos, [60, 170])
+    np.testing.assert_allclose([top, bot], [[60, 140], [60, 200]], atol=1e-9)      # the two joints
+    assert abs(seg - 60) < 1e-9
+    # torso (model part 8) and head (17) are copied, their windows shortened by the evaluation part's extension
+    assert abs(out[4].min_proj_y - (-20 + 3)) < 1e-9 and abs(out[4].max_proj_y - (20 - 5)) < 1e-9
+    np.testing.assert_allclose(out[5].part_pos, pos[17])
+    # x shrink: 0.7 * 15 / ext_x_pos of model part pidx (30 for the root slot 4, 20 for slot 5)
+    assert abs(out[0].max_proj_x - 15 * float(np.float32(0.7 * 15 / 10.0))) < 1e-6
+    assert abs(out[4].max_proj_x - 15 * float(np.float32(0.7 * 30 / 14.0))) < 1e-6
+    # inputs are not modified
+    assert boxes[8].min_proj_y == -20
+
+    # human_full_torso4: the torso is the mean of four corner parts
+    pos22 = [(10 * i, 5 * i) for i in range(22)]
+    pos22[16], pos22[17], pos22[18], pos22[19] = (100, 200), (140, 200), (140, 100), (100, 100)   # lower-left .. upper-left
+    out = pe.convert_eval_bboxes("human_full_torso4", [box(x, y) for x, y in pos22], [1.0] * 22, ev,
+                                 [pe.PartDef(ext_x_pos=12.0)] * 22)
+    np.testing.assert_allclose(out[4].part_pos, [120, 150])
+    assert (out[4].min_proj_y, out[4].max_proj_y, out[4].min_proj_x, out[4].max_proj_x) == (-50.0, 50.0, -20.0, 20.0)
+
+    # human_full_14_parts: the limb axis is the rotation bin centre nearest to atan2 of the joint difference
+    pos14 = [(20 * i, 300 - 9 * i) for i in range(14)]
+    pos14[0], pos14[1] = (100, 100), (100, 160)          # difference (0, -60): atan2 = -90 deg
+    out = pe.convert_eval_bboxes("human_full_14_parts", [box(x, y) for x, y in pos14], [1.0] * 14, ev,
+                                 [pe.PartDef(ext_x_pos=12.0)] * 14, rot_range=(-180.0, 180.0, 24))
+    assert len(out) == 10
+    ang = np.degrees(np.arctan2(out[0].part_y_axis[1], out[0].part_y_axis[0]))
+    assert abs(ang - (-82.5)) < 1e-9 or abs(ang - (-97.5)) < 1e-9     # bins are 15 deg wide, centres at +-7.5 + 15 k
+    assert abs(ang - (-97.5)) < 1e-9                                   # first minimum in ascending bin order
+    assert (out[0].min_proj_y, out[0].max_proj_y) == (-30.0, 30.0)     # the larger of the x / y spans, centred
+
+    # every other type: one evaluation part per model part, extension scaled by the hypothesis scale
+    out = pe.convert_eval_bboxes("human_full", [box(5, 5, scale=2.0)] * 10, [2.0] * 10, ev, ev)
+    assert abs(out[3].min_proj_y - (-40 + 6)) < 1e-9 and abs(out[3].max_proj_y - (40 - 10)) < 1e-9
 
 
 def test_eval_segments_experiment_layout(tmp_path):
