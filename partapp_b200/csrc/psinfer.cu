@@ -294,6 +294,10 @@ int ensure_scratch(ps_ctx *c, size_t elems) {
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
   PS_CUDA(c, c->bufU.alloc(elems * sizeof(float)));
   PS_CUDA(c, c->bufV.alloc(elems * sizeof(float)));
+  // the Gaussian work lists leave cells of the scratch grids unwritten; a later box may carry them into outputs
+  // nobody reads -- give them a defined value once (keeps initcheck quiet and NaN bit patterns out of the pipes)
+  PS_CUDA(c, cudaMemsetAsync(c->bufU.p, 0, elems * sizeof(float), c->stream));
+  PS_CUDA(c, cudaMemsetAsync(c->bufV.p, 0, elems * sizeof(float), c->stream));
   c->scratch_elems = elems;
   return PS_OK;
 }
@@ -606,7 +610,9 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     if (rc) return rc;
     // Bilinear read-back into the image frame (filter.hpp:367-368), then the generic epilogue.  (A fused
     // read-back + epilogue over source cells was tried in round 1: 63 us per message against 22 + 28 us for the
-    // two kernels -- it loses the 128-bit accumulator/operand traffic of k_epilogue2.)
+    // two kernels -- it loses the 128-bit accumulator/operand traffic of k_epilogue2.  Moving only log(D) + M into
+    // the read-back, to hide the fp64 log behind its gathers, was measured too: epilogue 0.46 -> 0.32 ms per image,
+    // read-back 0.39 -> 0.55 ms, 409 -> 403 images/s -- the log costs the same ~8 us per message wherever it runs.)
     Affine T34;
     memcpy(T34.m, h.T34, sizeof T34.m);
     PS_LAUNCH(c, KC_WARP_BACK,

@@ -35,3 +35,13 @@ for fast in (False, True):
             ctx.set_unary_compact(p, 0, cells[p, 0], Tig)
         ctx.infer(sparse=True)
         print(fast, ctx.best_conf()[:, 2:6].tolist())
+# a grid of several 64-cell strips with an oblique covariance: the Gaussian work lists hold partial tiles and leave
+# most of the eigen-frame bounding box out
+ep4 = ExpParam(num_rotation_steps=4)
+H2, W2 = 150, 100
+rng = np.random.default_rng(3)
+child = (rng.standard_normal((4, H2, W2)) * 2 - 3).astype(np.float32)
+with PsContext(ep4, synth.part_conf(2), H2, W2) as ctx:
+    for sparse in (True, False):
+        out = ctx.message(child, (5.0, -3.0), (-4.0, 6.0), [[20.0, 9.0], [9.0, 14.0]], 0.2, 0.5, 1.0, sparse)
+        print(sparse, float(out.max()))
