@@ -799,7 +799,10 @@ __device__ __forceinline__ BilinearTap bilinear_setup(int h, int w, int pitch, d
 // dst[r][cell] = bilinear(src[r]) for r in the thread's slice group.  Used both ways: image -> eigen-frame
 // (TM_BILINEAR of gaussFilter2dOffset, filter.hpp:359) and eigen-frame -> image (filter.hpp:367-368).
 // tr != 0: the destination is stored transposed (dst[r][ix][iy], pitch dpitch over iy) and threadIdx.x walks iy.
-template <int RG>
+// FULL: R is a multiple of RG, so no slice of the group needs a guard (ncu r01h: with the guards a warp issued 458
+// instructions per 32 cells x 8 slices, 91 of them predicate logic and 126 address IMAD/LEA behind the predicates,
+// against 102 loads, multiplies, adds and stores).
+template <int RG, bool FULL>
 __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restrict__ src, float *__restrict__ dst, Affine T,
                                                            int R, int sh, int sw, int spitch, size_t splane, int dh,
                                                            int dw, int dpitch, size_t dplane, int tr) {
@@ -823,25 +826,31 @@ __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restri
     t = bilinear_setup(sh, sw, spitch, x1, y1);
   }
   const float *p = src + (size_t)r0 * splane + t.off;
+  const int nu = FULL ? RG : min(RG, R - r0);
   if (t.mode == 2) {
     float q[RG][4];
+    const float *s = p;
 #pragma unroll
-    for (int u = 0; u < RG; ++u)
-      if (r0 + u < R) {
-        const float *s = p + (size_t)u * splane;
-        q[u][0] = __ldg(s); q[u][1] = __ldg(s + 1); q[u][2] = __ldg(s + spitch); q[u][3] = __ldg(s + spitch + 1);
+    for (int u = 0; u < RG; ++u, s += splane)
+      if (FULL || u < nu) {
+        const float *s1 = s + spitch;
+        q[u][0] = __ldg(s); q[u][1] = __ldg(s + 1); q[u][2] = __ldg(s1); q[u][3] = __ldg(s1 + 1);
       }
 #pragma unroll
     for (int u = 0; u < RG; ++u)
-      if (r0 + u < R) {
+      if (FULL || u < nu) {
         float t0 = __fmul_rn(t.w00, q[u][0]), t1 = __fmul_rn(t.w01, q[u][1]);
         float t2 = __fmul_rn(t.w10, q[u][2]), t3 = __fmul_rn(t.w11, q[u][3]);
         o[(size_t)u * dplane] = __fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3);
       }
+  } else if (t.mode == 1) {
+#pragma unroll
+    for (int u = 0; u < RG; ++u)
+      if (FULL || u < nu) o[(size_t)u * dplane] = __ldg(p + (size_t)u * splane);
   } else {
 #pragma unroll
     for (int u = 0; u < RG; ++u)
-      if (r0 + u < R) o[(size_t)u * dplane] = t.mode == 1 ? __ldg(p + (size_t)u * splane) : 0.0f;
+      if (FULL || u < nu) o[(size_t)u * dplane] = 0.0f;
   }
 }
 
@@ -850,7 +859,7 @@ __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restri
 // by the L1 data pipe at ~11 sectors per request -- but the staging loop plus 3x over-fetch made it 2x slower.)
 // TM_DIRECT as a gather through the winner map, RG slices per thread.
 // tr != 0: out is stored transposed ([r][ix][iy], pitch EP over iy, plane EW*EP) and threadIdx.x walks iy.
-template <int RG>
+template <int RG, bool FULL>
 __global__ void __launch_bounds__(256) k_warp_direct2(const float *__restrict__ in, float *__restrict__ out,
                                                       const int2 *__restrict__ map, int R, size_t HW, int EH, int EW,
                                                       int EP, int tr) {
@@ -864,17 +873,26 @@ __global__ void __launch_bounds__(256) k_warp_direct2(const float *__restrict__ 
   float *o = out + (size_t)r0 * eplane + (tr ? (size_t)ix * EP + iy : (size_t)iy * EP + ix);
   int2 m = make_int2(-1, -1);
   if (ix < EW) m = map[(size_t)iy * EW + ix];
+  const int nu = FULL ? RG : min(RG, R - r0);  // FULL: R % RG == 0, no slice of the group needs a guard
+  const float *base = in + (size_t)r0 * HW;
   float v[RG];
 #pragma unroll
-  for (int u = 0; u < RG; ++u) v[u] = (m.x >= 0 && r0 + u < R) ? __ldg(in + (size_t)(r0 + u) * HW + m.x) : 0.0f;
-  if (m.y >= 0) {
+  for (int u = 0; u < RG; ++u) v[u] = 0.0f;
+  if (m.x >= 0) {
+    const float *s = base + m.x;
 #pragma unroll
-    for (int u = 0; u < RG; ++u)
-      if (r0 + u < R && v[u] == 0.0f) v[u] = __ldg(in + (size_t)(r0 + u) * HW + m.y);
+    for (int u = 0; u < RG; ++u, s += HW)
+      if (FULL || u < nu) v[u] = __ldg(s);
+  }
+  if (m.y >= 0) {
+    const float *s = base + m.y;
+#pragma unroll
+    for (int u = 0; u < RG; ++u, s += HW)
+      if ((FULL || u < nu) && v[u] == 0.0f) v[u] = __ldg(s);
   }
 #pragma unroll
   for (int u = 0; u < RG; ++u)
-    if (r0 + u < R) o[(size_t)u * eplane] = v[u];
+    if (FULL || u < nu) o[(size_t)u * eplane] = v[u];
 }
 
 // ---- message stage 2b: separable Gaussian, zero padded, unnormalised taps -------------------------------

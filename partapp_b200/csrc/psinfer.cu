@@ -583,16 +583,27 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     if (sparse) {
       rc = ensure_direct_map(c, dp);
       if (rc) return rc;
-      PS_LAUNCH(c, KC_WARP_DIRECT,
-                psk::k_warp_direct2<RG><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
-                    c->bufB.as<float>(), c->bufU.as<float>(), dp.map.as<int2>(), R, c->HW, EH, EW, tr ? EHP : EP, tr));
+      if (R % RG == 0)
+        PS_LAUNCH(c, KC_WARP_DIRECT,
+                  psk::k_warp_direct2<RG, true><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), R / RG), dim3(16, 16), 0, st>>>(
+                      c->bufB.as<float>(), c->bufU.as<float>(), dp.map.as<int2>(), R, c->HW, EH, EW, tr ? EHP : EP, tr));
+      else
+        PS_LAUNCH(c, KC_WARP_DIRECT,
+                  psk::k_warp_direct2<RG, false><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                      c->bufB.as<float>(), c->bufU.as<float>(), dp.map.as<int2>(), R, c->HW, EH, EW, tr ? EHP : EP, tr));
     } else {
       Affine T13;
       memcpy(T13.m, h.T13, sizeof T13.m);
-      PS_LAUNCH(c, KC_WARP_BILINEAR,
-                psk::k_resample_bilinear<RG><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
-                    c->bufB.as<float>(), c->bufU.as<float>(), T13, R, H, W, W, c->HW, EH, EW, tr ? EHP : EP,
-                    tr ? tplane : eplane, tr));
+      if (R % RG == 0)
+        PS_LAUNCH(c, KC_WARP_BILINEAR,
+                  psk::k_resample_bilinear<RG, true><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), R / RG), dim3(16, 16), 0, st>>>(
+                      c->bufB.as<float>(), c->bufU.as<float>(), T13, R, H, W, W, c->HW, EH, EW, tr ? EHP : EP,
+                      tr ? tplane : eplane, tr));
+      else
+        PS_LAUNCH(c, KC_WARP_BILINEAR,
+                  psk::k_resample_bilinear<RG, false><<<dim3(cdiv(tr ? EW : EP, 16), cdiv(EH, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                      c->bufB.as<float>(), c->bufU.as<float>(), T13, R, H, W, W, c->HW, EH, EW, tr ? EHP : EP,
+                      tr ? tplane : eplane, tr));
     }
     if (tr) {
       rc = launch_conv_cols_tma(c, c->bufU.as<float>(), EHP, tplane, c->bufV.as<float>(), EP, eplane, dp.fx(),
@@ -615,9 +626,14 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     // read-back 0.39 -> 0.55 ms, 409 -> 403 images/s -- the log costs the same ~8 us per message wherever it runs.)
     Affine T34;
     memcpy(T34.m, h.T34, sizeof T34.m);
-    PS_LAUNCH(c, KC_WARP_BACK,
-              psk::k_resample_bilinear<RG><<<dim3(cdiv(W, 16), cdiv(H, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
-                  c->bufU.as<float>(), c->bufB.as<float>(), T34, R, EH, EW, EP, eplane, H, W, W, c->HW, 0));
+    if (R % RG == 0)
+      PS_LAUNCH(c, KC_WARP_BACK,
+                psk::k_resample_bilinear<RG, true><<<dim3(cdiv(W, 16), cdiv(H, 16), R / RG), dim3(16, 16), 0, st>>>(
+                    c->bufU.as<float>(), c->bufB.as<float>(), T34, R, EH, EW, EP, eplane, H, W, W, c->HW, 0));
+    else
+      PS_LAUNCH(c, KC_WARP_BACK,
+                psk::k_resample_bilinear<RG, false><<<dim3(cdiv(W, 16), cdiv(H, 16), cdiv(R, RG)), dim3(16, 16), 0, st>>>(
+                    c->bufU.as<float>(), c->bufB.as<float>(), T34, R, EH, EW, EP, eplane, H, W, W, c->HW, 0));
     filtered = c->bufB.as<float>();
     e.general = 0;
   }
