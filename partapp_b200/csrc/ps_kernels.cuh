@@ -1442,14 +1442,17 @@ struct ColsTmaArgs {
 // the tile list (ncu r01d).  Here warp 8 only feeds the pipeline (waits for a stage to be released, issues the
 // next box), the eight filter warps hand a stage back through an `empty` mbarrier instead of a block barrier -- a
 // warp that is done moves on to the next tile, whose box landed a tile ago -- and the tile list sits in shared memory.
+// try_wait suspends the warp until the phase completes or a time limit passes; the default limit is short (ncu r01h:
+// the producer warp came back ~900 times per tile while the filter warps worked, 1.8 M branches of a 26.6 M-instruction
+// launch -- issue slots taken from the tap loops).  The hint raises the limit; completion still wakes the warp at once.
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
   unsigned ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
-      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(PS_MBAR_HINT_NS) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {

@@ -19,6 +19,9 @@
 #ifndef PS_RG
 #define PS_RG 8
 #endif
+#ifndef PS_MBAR_HINT_NS
+#define PS_MBAR_HINT_NS 100000u  // suspend-time hint of mbarrier.try_wait (ns)
+#endif
 #ifndef PS_TMA_MINB
 #define PS_TMA_MINB 2  // resident blocks per SM k_conv_cols_tma2 is compiled for (register budget)
 #endif
