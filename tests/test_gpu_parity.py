@@ -540,6 +540,25 @@ def test_multi_tile_work_lists_match_oracle(k):
     _cmp(got, want, "multi-tile message %d (%dx%d, angle %.2f)" % (k, H, W, th))
 
 
+def test_work_list_longer_than_shared_memory_copy():
+    """A 2400 x 2400 grid with an oblique covariance needs more than 1024 tiles per slice: the Gaussian kernel then
+    reads its work list from global memory instead of its shared-memory copy."""
+    ep = ExpParam(num_rotation_steps=2)
+    H = W = 2400
+    rng = np.random.default_rng(77)
+    child = np.full((2, H, W), LZ, np.float32)
+    ys, xs = rng.integers(0, H, 4000), rng.integers(0, W, 4000)
+    child[rng.integers(0, 2, 4000), ys, xs] = rng.uniform(-6, 0, 4000).astype(np.float32)
+    th = 0.7
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    Cm = Rm @ np.diag([9.0, 4.0]) @ Rm.T
+    Cm[1, 0] = Cm[0, 1]
+    want = oracle.message(ep, child, (3.0, -2.0), (-1.0, 4.0), Cm.tolist(), 0.0, 0.0, 1.0, True)
+    with _ctx(ep, 2, H, W) as ctx:
+        got = ctx.message(child, (3.0, -2.0), (-1.0, 4.0), Cm.tolist(), 0.0, 0.0, 1.0, True)
+    _cmp(got, want, "message on a 2400 x 2400 grid")   # 5.76 M cells of footprint > 1024 tiles of 64 x 64
+
+
 def test_work_lists_change_no_bit_and_skip_cells(monkeypatch):
     """Same inference with and without the work lists (PSINFER_ALL_TILES=1 filters every eigen-frame tile): identical
     marginals; and the lists really leave cells out (ps_get_plan_info reports fewer cells than rows x cols)."""
