@@ -23,7 +23,7 @@
 #define PS_MBAR_HINT_NS 100000u  // suspend-time hint of mbarrier.try_wait (ns)
 #endif
 #ifndef PS_TMA_MINB
-#define PS_TMA_MINB 2  // resident blocks per SM k_conv_cols_tma2 is compiled for (register budget)
+#define PS_TMA_MINB 4  // register budget of k_conv_cols_tma2: 65536 / (4 * 288) -> 56 registers (see launch_conv_cols_tma)
 #endif
 #include "ps_geometry.hpp"
 #include "ps_kernels.cuh"
@@ -465,15 +465,21 @@ int launch_conv_cols_tma(ps_ctx *c, const float *in, int in_pitch, size_t in_pla
   t.tile_list = (tile_list && ntile_list > 0 && !c->disable_tile_lists) ? tile_list : nullptr;
   t.ntile_list = ntile_list;
   const int ntiles = t.slices * (t.tile_list ? ntile_list : t.ytiles * t.xtiles);
-  // 2 resident blocks per SM.  A third (67 registers, short filters only) shaved 2 us off the 27-tap launch in isolation
-  // and nothing off the two-images-in-flight bench (round-1 A/B), so the 88-register build stays.
+  // Two blocks per SM, and never a third.  With images in flight on several streams the memory-bound kernels of other
+  // images (resampling, epilogue, rotation filter) run beside the tap loops, and how much room they find decides the
+  // bench (round-1 A/B, cfg-2, 8 streams): 88 registers, nothing else constrained: 424 img/s (one small block fits
+  // beside two Gaussian blocks); Gaussian blocks that fill the SM's shared memory, nothing co-resident: 380; 67
+  // registers and no cap: 383 -- a third Gaussian block moves in, 219 KB of shared memory leave the gathers of the
+  // other kernels almost no L1; 67 / 56 registers with the dynamic shared memory padded so that three Gaussian blocks
+  // cannot fit: 430.6 / 431.8 -- half of the register file and ~100 KB of L1 stay free for three or four small blocks.
   static const int bps_env = getenv("PSINFER_CONV_BLOCKS") ? atoi(getenv("PSINFER_CONV_BLOCKS")) : 0;  // A/B knob
   const int grid = std::min(ntiles, c->num_sms * (bps_env == 1 ? 1 : 2));
   {
     static const int ns_env = getenv("PSINFER_TMA_STAGES") ? atoi(getenv("PSINFER_TMA_STAGES")) : 0;
     int ns = 2;  // deeper queues (3, 4) measured no faster: the boxes already land a tile ahead
     if (ns_env >= 2) ns = (int)std::min<size_t>(std::min(ns_env, psk::kMaxTmaStages), (104 * 1024) / stage);
-    static const size_t smem_env = getenv("PSINFER_CONV_SMEM") ? (size_t)atol(getenv("PSINFER_CONV_SMEM")) : 0;  // A/B knob
+    // 3 * (dynamic + 8 KB static + 1 KB reserved) must exceed the 228 KB of an SM: 70 KB of dynamic shared memory at least
+    static const size_t smem_env = getenv("PSINFER_CONV_SMEM") ? (size_t)atol(getenv("PSINFER_CONV_SMEM")) : 70 * 1024;
     const size_t smem = std::min<size_t>(std::max(ns * stage, smem_env), 104 * 1024);
     if (c->cfg.fast_math)
       PS_LAUNCH(c, transpose_out ? KC_CONV_ROWS : KC_CONV_COLS,
