@@ -237,6 +237,17 @@ int ps_find_local_max(ps_ctx *ctx, const float *grid, int mem_kind, int d0, int 
  * Used by bench.py to count tap-outputs for the fp32-pipe roofline. */
 int ps_get_plan_info(ps_ctx *ctx, int joint, int downward, int scale, int out[10]);
 
+/* Host-only (no GPU, no ctx): the work lists of the two Gaussian passes that ps_set_joints derives for a message with
+ * covariance C (row-major 2x2) at `scale` on the cfg's height x width grid -- which cells of the eigen-frame grid of
+ * gaussFilter2dOffset (multi_array_filter.hpp:335-369) are filtered at all.
+ * dims = {EH, EW, x reach (taps - 1)/2, y reach, x-list entries, y-list entries}; T34 = rows 0,1 of the affine map from
+ * image to eigen-frame coordinates that the bilinear read-back uses (filter.hpp:364-368); each list entry is
+ * (first row along the filtered axis, 64-cell strip of the other axis, 8-row groups).  At most `cap` entries are
+ * written to each list.  Returns PS_ERR_INVALID for a diagonal covariance (no eigen-frame, no lists).
+ * Lets the CPU tests check by brute force that every cell the read-back can touch is covered. */
+int ps_plan_work_lists(const ps_config *cfg, const double C[4], double scale, int dims[6], double T34[6],
+                       int *xlist, int *ylist, int cap);
+
 /* Exhaustive check of the device exp/log used on the path: for every fp32 bit pattern in
  * [first_bits, first_bits + count) compares the table-driven fast evaluation with CUDA's fp64 libm narrowed to fp32
  * (the reference calls the double libm routines on floats: multi_array_op.hpp:165,177).

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "ps_pos_message": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_int]),
     "ps_find_local_max": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _ip]),
     "ps_get_plan_info": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, _ip]),
+    "ps_plan_work_lists": (C.c_int, [C.POINTER(ps_config), _dp, C.c_double, _ip, _dp, _ip, _ip, C.c_int]),
     "ps_selftest_math": (C.c_int, [_ctx_p, C.c_uint, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "ps_eval_math": (C.c_int, [_ctx_p, C.c_int, C.c_uint, C.c_uint, _fp]),
     "ps_launch_count": (C.c_longlong, [_ctx_p]),

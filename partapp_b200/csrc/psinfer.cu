@@ -778,6 +778,31 @@ double ps_rot_from_index(const ps_config *cfg, int idx) {
   return psg::value_from_index(cfg->min_part_rotation, cfg->max_part_rotation, cfg->num_rotation_steps, idx);
 }
 double ps_scale_from_index(const ps_config *cfg, int idx) { return scale_of(*cfg, idx); }
+int ps_plan_work_lists(const ps_config *cfg, const double C[4], double scale, int dims[6], double T34[6], int *xlist,
+                       int *ylist, int cap) {
+  if (!cfg || !C || !dims || !T34 || cap < 0 || (cap > 0 && (!xlist || !ylist))) return PS_ERR_INVALID;
+  psg::Grid g;
+  g.R = cfg->num_rotation_steps; g.H = cfg->height; g.W = cfg->width;
+  g.min_rot = cfg->min_part_rotation; g.max_rot = cfg->max_part_rotation;
+  const double zero[2] = {0.0, 0.0};
+  const psg::MessagePlan p = psg::plan_message(g, zero, zero, C, 0.0, 0.0, scale);
+  if (!p.error.empty() || p.diag) return PS_ERR_INVALID;
+  dims[0] = p.EH; dims[1] = p.EW;
+  dims[2] = ((int)p.fx.size() - 1) / 2; dims[3] = ((int)p.fy.size() - 1) / 2;
+  dims[4] = (int)p.xtiles.size() / 2; dims[5] = (int)p.ytiles.size() / 2;
+  for (int k = 0; k < 6; ++k) T34[k] = p.T34[k];
+  const auto put = [cap](const std::vector<int> &src, int *dst) {
+    for (size_t i = 0; i + 1 < src.size() && (int)(i / 2) < cap; i += 2) {
+      dst[3 * (i / 2) + 0] = src[i];
+      dst[3 * (i / 2) + 1] = src[i + 1] & 0xfff;
+      dst[3 * (i / 2) + 2] = src[i + 1] >> 12;
+    }
+  };
+  put(p.xtiles, xlist);
+  put(p.ytiles, ylist);
+  return PS_OK;
+}
+
 int ps_index_from_rot(const ps_config *cfg, double rot) {
   return psg::index_from_value(cfg->min_part_rotation, cfg->max_part_rotation, cfg->num_rotation_steps, rot);
 }

@@ -244,3 +244,73 @@ def test_eval_segments_experiment_layout(tmp_path):
     assert (sub / "part_marginals" / "seg_endpoints" / "endpoints_0001.mat").exists()
     r = pe.eval_segments_experiment(str(tmp_path / "exp-pcp.txt"), first=1, numimgs=1, save_endpoints=False)
     assert (r.seg_correct, r.seg_total) == (0, 1)
+
+
+# ---- Gaussian work lists: brute-force coverage on the CPU ---------------------------------------
+
+def _work_lists(H, W, Cm, scale=1.0):
+    import ctypes
+    from partapp_b200 import ExpParam, capi
+    from partapp_b200.objectdetect import PartConf, make_config
+    lib = capi.load_library()
+    cfg = make_config(ExpParam(num_rotation_steps=8), PartConf([True], [False], [True]), H, W)
+    dims = (ctypes.c_int * 6)()
+    T34 = (ctypes.c_double * 6)()
+    cap = 1 << 16
+    xl, yl = (ctypes.c_int * (3 * cap))(), (ctypes.c_int * (3 * cap))()
+    Cc = (ctypes.c_double * 4)(*np.asarray(Cm, np.float64).ravel())
+    rc = lib.ps_plan_work_lists(ctypes.byref(cfg), Cc, scale, dims, T34, xl, yl, cap)
+    assert rc == 0
+    EH, EW, nx, ny, nxl, nyl = [int(v) for v in dims]
+    xs = np.array(xl[:3 * nxl], np.int64).reshape(-1, 3)
+    ys = np.array(yl[:3 * nyl], np.int64).reshape(-1, 3)
+    return EH, EW, nx, ny, np.array(T34[:]), xs, ys
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_work_lists_cover_every_cell_the_read_back_touches(k):
+    """plan_message's work lists against a brute-force statement of what is needed: the bilinear read-back of every
+    image pixel touches up to 2 x 2 eigen-frame cells (transform.hpp:196-238) -- all of them must lie in a listed
+    group of the y pass, and every x-pass output such a cell's y window reaches must lie in a listed group of the x
+    pass.  Also: the lists stay well below the full bounding box."""
+    rng = np.random.default_rng(900 + k)
+    H, W = [(150, 230), (260, 140), (64, 64), (600, 400), (33, 500), (129, 191), (400, 37), (300, 300), (90, 70),
+            (512, 256)][k]
+    th = rng.uniform(0, np.pi) if k else 0.6
+    s1, s2 = rng.uniform(1.0, 12.0, 2)
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    Cm = Rm @ np.diag([s1 * s1, s2 * s2]) @ Rm.T
+    Cm[1, 0] = Cm[0, 1]
+    scale = [1.0, 1.2, 0.8][k % 3]
+    EH, EW, nx, ny, T34, xs, ys = _work_lists(H, W, Cm, scale)
+    ycov = np.zeros((EH + 64, EW + 64), bool)          # [ey][ex]; lists may run past the grid edge
+    for row0, strip, ng in ys:                          # y pass: rows walk y, strips walk x
+        assert row0 % 8 == 0 and 1 <= ng <= 8
+        ycov[row0:row0 + 8 * ng, strip * 64:strip * 64 + 64] = True
+    xcov = np.zeros((EH + 64, EW + 64), bool)
+    for row0, strip, ng in xs:                          # x pass: rows walk x, strips walk y
+        assert row0 % 8 == 0 and 1 <= ng <= 8
+        xcov[strip * 64:strip * 64 + 64, row0:row0 + 8 * ng] = True
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    x1 = T34[0] * xx + T34[1] * yy + T34[2]
+    y1 = T34[3] * xx + T34[4] * yy + T34[5]
+    ix, iy = np.floor(x1).astype(np.int64), np.floor(y1).astype(np.int64)
+    touched = np.zeros((EH + 64, EW + 64), bool)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            cx, cy = ix + dx, iy + dy
+            ok = (cx >= 0) & (cx < EW) & (cy >= 0) & (cy < EH)
+            touched[cy[ok], cx[ok]] = True
+    assert touched.sum() >= 0.9 * H * W                 # the read-back really lands inside the eigen-frame grid
+    assert not (touched & ~ycov).any(), "a cell the read-back touches is not in the y list"
+    # x-pass outputs the y pass needs: every cell within ny rows of a touched cell, same column
+    need_x = np.zeros_like(touched)
+    cols_any = np.flatnonzero(touched.any(axis=0))
+    for ex in cols_any:
+        rows = np.flatnonzero(touched[:, ex])
+        lo, hi = max(0, rows.min() - ny), min(EH - 1, rows.max() + ny)
+        # the footprint of a convex rectangle in one column is an interval, so is its dilation
+        need_x[lo:hi + 1, ex] = True
+    assert not (need_x[:EH, :EW] & ~xcov[:EH, :EW]).any(), "an x-pass output the y pass reads is not in the x list"
+    if min(H, W) >= 256:                                # the point of the lists: the work stays close to the image's
+        assert ycov[:EH, :EW].sum() <= 1.5 * H * W and xcov[:EH, :EW].sum() <= 1.8 * H * W
