@@ -497,7 +497,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--images", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--images", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams per GPU (one image in flight on each)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
