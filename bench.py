@@ -497,7 +497,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--images", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--images", type=int, default=0,
+                    help="images per GPU per step (default: 32 for cfg2, 16 for cfg4, 4 for the 5-scale 1000x1000 cfg5)")
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams per GPU (one image in flight on each)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -514,6 +515,9 @@ def main():
     args = ap.parse_args()
     claim_stdout()
     WORKLOAD.update(WORKLOADS[args.workload])
+    if args.images <= 0:
+        args.images = {"cfg2": 32, "cfg4": 16, "cfg5": 4}[args.workload]
+    args.streams = max(1, min(args.streams, args.images))
     if args.impl == "reference":
         run_reference(args)
     else:
