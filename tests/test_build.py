@@ -109,3 +109,26 @@ def test_gaussian_kernels_keep_both_roundings(pslib):
         seen += 1
         assert ffma2 > 0 and ffma2 == fadd2, "%s: %d FFMA2 vs %d FADD2" % (name, ffma2, fadd2)
     assert seen >= 6 and fast >= 2
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
+def test_kernel_footprints_leave_room_for_co_resident_blocks(pslib):
+    """The shapes DESIGN.md section 5 measured its way to: the Gaussian kernel fits two blocks into half of an SM's
+    register file (56 registers x 288 threads), the full-slice-group resampling kernels stay at 32 registers (eight
+    blocks per SM, four beside two Gaussian blocks), the TMA wait sleeps on its barrier instead of polling it, and the
+    Gaussian kernel really is fed by cp.async.bulk.tensor (UTMALDG)."""
+    from partapp_b200 import capi
+    res = subprocess.run(["cuobjdump", "--dump-resource-usage", capi.LIB_PATH], capture_output=True, text=True,
+                         check=True).stdout
+    regs = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+)", res):
+        regs[m.group(1)] = int(m.group(2))
+    conv = [r for n, r in regs.items() if "k_conv_cols_tma2ILi8" in n]
+    assert len(conv) == 2 and max(conv) <= 56, conv
+    full = [r for n, r in regs.items() if "k_resample_bilinearILi8ELb1" in n or "k_warp_direct2ILi8ELb1" in n]
+    assert len(full) == 2 and max(full) <= 32, full
+    assert all(r <= 40 for n, r in regs.items() if "k_epilogue3" in n or "k_rotconv4ILi24E" in n)   # the cfg-2 shapes
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for k in re.split(r"\n\s*Function : ", sass)[1:]:
+        if "k_conv_cols_tma2ILi8" in k.split("\n", 1)[0]:
+            assert "UTMALDG.3D" in k and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in k and "NANOSLEEP.SYNCS" in k
