@@ -781,6 +781,7 @@ double ps_scale_from_index(const ps_config *cfg, int idx) { return scale_of(*cfg
 int ps_plan_work_lists(const ps_config *cfg, const double C[4], double scale, int dims[6], double T34[6], int *xlist,
                        int *ylist, int cap) {
   if (!cfg || !C || !dims || !T34 || cap < 0 || (cap > 0 && (!xlist || !ylist))) return PS_ERR_INVALID;
+  if (cfg->num_rotation_steps < 1 || cfg->height < 1 || cfg->width < 1 || !(scale > 0)) return PS_ERR_INVALID;
   psg::Grid g;
   g.R = cfg->num_rotation_steps; g.H = cfg->height; g.W = cfg->width;
   g.min_rot = cfg->min_part_rotation; g.max_rot = cfg->max_part_rotation;
