@@ -156,6 +156,16 @@ struct ps_ctx {
   std::vector<float> root_hyps;               // rows of 4
   bool have_local_max = false, have_root_hyps = false;
 
+  ~ps_ctx() {  // shared by ps_destroy and by the error returns of ps_create
+    if (own_stream) {
+      cudaStreamSynchronize(own_stream);
+      cudaStreamDestroy(own_stream);
+    }
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    if (host_keys) cudaFreeHost(host_keys);
+    if (host_topk) cudaFreeHost(host_topk);
+    if (host_topk_state) cudaFreeHost(host_topk_state);
+  }
   int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -683,7 +693,7 @@ int reset_max(ps_ctx *c, int *slot) {
 int grid_max(ps_ctx *c, const float *g, size_t n, int *slot) {
   int rc = reset_max(c, slot);
   if (rc) return rc;
-  PS_LAUNCH(c, KC_MAX, psk::k_grid_max<<<std::min(cdiv(n / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(g, n, slot));
+  PS_LAUNCH(c, KC_MAX, psk::k_grid_max<<<std::min(cdiv(n / 4 + 1, 256), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(g, n, slot));
   return PS_OK;
 }
 
@@ -1008,11 +1018,6 @@ void ps_destroy(ps_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-  if (ctx->host_keys) cudaFreeHost(ctx->host_keys);
-  if (ctx->host_topk) cudaFreeHost(ctx->host_topk);
-  if (ctx->host_topk_state) cudaFreeHost(ctx->host_topk_state);
   delete ctx;
 }
 
@@ -1105,7 +1110,7 @@ int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind,
   PS_CUDA(c, cudaMemcpyAsync(dst, src, c->N * sizeof(float),
                              mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   if (raw) {
-    PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(dst, c->N, nullptr));
+    PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(dst, c->N, nullptr));
   }
   return PS_OK;
 }
@@ -1126,7 +1131,7 @@ int ps_log_unary(ps_ctx *c, int part, int scale) {
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   int *mslot = c->unary_max.as<int>() + (size_t)part * c->S + scale;
   PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mslot, 1, PS_ENC_NEG_INF));
-  PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(
+  PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(
                             c->U(part, scale), c->N, mslot));
   c->unary_max_valid[(size_t)part * c->S + scale] = 1;
   return PS_OK;
@@ -1166,8 +1171,12 @@ static int set_unary_compact_impl(ps_ctx *c, int part, int scale, const float *c
   if (c->R <= psk::kMaxIngestRot) {
     for (size_t k = 0; k < t.size(); ++k) rows.m[k] = t[k];
   } else {
+    // the staging rows are shared by every (part, scale) call and c->stream does not synchronise with the legacy
+    // stream: wait for the previous call's scatter kernel before its transforms are overwritten, copy in stream order
     dT = c->ingest.as<double>();
-    PS_CUDA(c, cudaMemcpy(dT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PS_CUDA(c, cudaMemcpyAsync(dT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));  // `t` goes out of scope
   }
   const float *src_cells = cells;
   if (mem_kind == PS_MEM_HOST) {
@@ -1194,7 +1203,7 @@ static int set_unary_compact_impl(ps_ctx *c, int part, int scale, const float *c
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_bilinear<<<dim3(cdiv(c->HW, 256), c->R), 256, 0, c->stream>>>(
                               a, rows, psk::FastDiv((unsigned)c->W), mslot));
   } else if (collision_free) {
-    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 4096), 148u * 8), 256, 0, c->stream>>>(
+    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 4096), (unsigned)c->num_sms * 8), 256, 0, c->stream>>>(
                               a.out, c->N, raw ? 0.0f : psk::kLogZero, mslot, PS_ENC_NEG_INF));
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct<<<dim3(cdiv((size_t)gh * gw, 256), c->R), 256, 0, c->stream>>>(a, rows, mslot));
   } else {
@@ -1305,7 +1314,7 @@ int enqueue_local_max(ps_ctx *c, const float *g, int D0, int H, int W, int max_n
   PS_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned), c->stream));
   PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_local_max<<<dim3(cdiv(W, 256), H, D0), 256, 0, c->stream>>>(g, D0, H, W, cand, (unsigned)n, cnt));
   PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_topk_init<<<1, 1024, 0, c->stream>>>(st, cnt, (unsigned)n, (unsigned)max_n, hist));
-  const unsigned blocks = std::min(cdiv(n, 256 * 8), 148u * 8);
+  const unsigned blocks = std::min(cdiv(n, 256 * 8), (unsigned)c->num_sms * 8);
   for (int shift = 48; shift >= 0; shift -= 16) {
     PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_topk_hist<<<blocks, 256, 0, c->stream>>>(cand, st, shift, hist));
     PS_LAUNCH(c, KC_LOCAL_MAX, psk::k_topk_scan<<<1, 1024, 0, c->stream>>>(st, shift, hist));
@@ -1343,7 +1352,11 @@ void decode_local_max(ps_ctx *c, int slot, int H, int W, std::vector<float> &row
 }
 
 // Synchronous convenience used by ps_find_local_max and ps_max_states' slow path.
+int finish_result(ps_ctx *c);
 int local_max_device(ps_ctx *c, const float *g, int D0, int H, int W, int max_n, std::vector<float> &rows) {
+  // slot 0 and the pinned winner buffers are shared with a pending ps_infer / ps_max_states readout: decode that first
+  if (c->result_pending)
+    if (int frc = finish_result(c)) return frc;
   int rc = ensure_topk(c, 1, (size_t)std::max(max_n, 1), (size_t)D0 * H * W);
   if (rc) return rc;
   if ((rc = enqueue_local_max(c, g, D0, H, W, max_n, 0))) return rc;
@@ -1360,7 +1373,7 @@ int enqueue_readout(ps_ctx *c, const std::vector<const float *> &grids, int scal
     PS_CUDA(c, cudaMemsetAsync(c->argmax_keys.p, 0, P * sizeof(unsigned long long), c->stream));
     for (int p = 0; p < P; ++p)
       PS_LAUNCH(c, KC_ARGMAX,
-                psk::k_argmax<<<std::min(cdiv(c->N / 4 + 1, 256), 148u * 16), 256, 0, c->stream>>>(
+                psk::k_argmax<<<std::min(cdiv(c->N / 4 + 1, 256), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(
                     grids[p], c->N, c->argmax_keys.as<unsigned long long>() + p));
   }
   PS_CUDA(c, cudaMemcpyAsync(c->host_keys, c->argmax_keys.p, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -1534,7 +1547,7 @@ int ps_infer(ps_ctx *c, int flags) {
       } else {
         PS_CUDA(c, cudaMemcpyAsync(a.post, a.unary, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
         if (keys)
-          PS_LAUNCH(c, KC_ARGMAX, psk::k_argmax<<<std::min(cdiv(N / 4 + 1, 256), 148u * 16), 256, 0, st>>>(a.post, N, keys + root));
+          PS_LAUNCH(c, KC_ARGMAX, psk::k_argmax<<<std::min(cdiv(N / 4 + 1, 256), (unsigned)c->num_sms * 16), 256, 0, st>>>(a.post, N, keys + root));
       }
     }
 
@@ -1696,7 +1709,7 @@ int ps_pos_message(ps_ctx *c, float *child, float *parent, int mem_kind, const d
   int rc = run_message(c, *plan, din, mx, sparse != 0, sink);
   if (rc) return rc;
   // the reference leaves log(exp(child)) in its first argument (:88)
-  PS_LAUNCH(c, KC_MISC, psk::k_exp_log<<<std::min(cdiv(c->N, 256), 148u * 16), 256, 0, c->stream>>>(din, c->N));
+  PS_LAUNCH(c, KC_MISC, psk::k_exp_log<<<std::min(cdiv(c->N, 256), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(din, c->N));
   if (mem_kind == PS_MEM_HOST) {
     PS_CUDA(c, cudaMemcpyAsync(parent, dout, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     PS_CUDA(c, cudaMemcpyAsync(child, din, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1731,7 +1744,7 @@ int ps_selftest_math(ps_ctx *c, unsigned first_bits, unsigned long long count, u
   DevBuf d;
   PS_CUDA(c, d.alloc(4 * sizeof(unsigned long long)));
   PS_CUDA(c, cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), c->stream));
-  PS_LAUNCH(c, KC_MISC, psk::k_selftest_math<<<148 * 16, 256, 0, c->stream>>>(first_bits, count, d.as<unsigned long long>()));
+  PS_LAUNCH(c, KC_MISC, psk::k_selftest_math<<<c->num_sms * 16, 256, 0, c->stream>>>(first_bits, count, d.as<unsigned long long>()));
   PS_CUDA(c, cudaMemcpyAsync(out, d.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
   return PS_OK;
@@ -1742,7 +1755,7 @@ int ps_eval_math(ps_ctx *c, int op, unsigned first_bits, unsigned count, float *
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   DevBuf d;
   PS_CUDA(c, d.alloc((size_t)count * sizeof(float)));
-  PS_LAUNCH(c, KC_MISC, psk::k_eval_math<<<148 * 16, 256, 0, c->stream>>>(op, first_bits, count, d.as<float>()));
+  PS_LAUNCH(c, KC_MISC, psk::k_eval_math<<<c->num_sms * 16, 256, 0, c->stream>>>(op, first_bits, count, d.as<float>()));
   PS_CUDA(c, cudaMemcpyAsync(out_host, d.p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
   return PS_OK;

@@ -431,6 +431,54 @@ def test_compact_ingest_interpolate_matches_load_score_grid(rotated):
         assert (ctx.get_unary(1, 0) > -1e5).sum() > 100
 
 
+def test_compact_ingest_many_rotations_back_to_back():
+    """R > 64: the per-rotation transforms go through a device staging buffer shared by every (part, scale) call.
+    Calls issued back to back, each with its OWN transforms, must not overwrite the rows a previous call's scatter
+    kernel is still reading."""
+    ep = ExpParam(num_rotation_steps=72)
+    P, H, W = 4, 36, 44
+    cells, Tig0 = synth.compact_scores(ep, H, W, P, 5, rotated=True)
+    tigs = []
+    for p in range(P):
+        T = Tig0.copy()
+        T[:, 0, 2] += 1.5 * p          # a different lattice per part
+        T[:, 1, 2] -= 0.75 * p
+        tigs.append(T)
+    with _ctx(ep, P, H, W) as ctx:
+        for p in range(P):             # no synchronisation between the calls
+            ctx.set_unary_compact(p, 0, cells[p, 0], tigs[p])
+        for p in range(P):
+            want = oracle.prepare_unary(oracle.load_score_grid(cells[p, 0], tigs[p], H, W))
+            _cmp(ctx.get_unary(p, 0), want, "R=72 ingest part %d" % p)
+
+
+def test_find_local_max_between_infer_and_getters():
+    """ps_infer only enqueues; a synchronous ps_find_local_max issued before the getters shares the top-K slot and
+    the pinned winner buffers with the pending readout and must not clobber it (also when it needs a larger top-K)."""
+    ep = ExpParam(num_rotation_steps=8, roi_save_num_samples=30)
+    P, H, W = 4, 40, 36
+    un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 2))
+    joints = synth.make_joints(P, seed=4, max_offset=6, sigma_range=(1.5, 3))
+    pc = synth.part_conf(P)
+    with PsContext(ep, pc, H, W) as ctx:
+        ctx.set_joints(joints)
+
+        def run(disturb):
+            for p in range(P):
+                ctx.set_unary(p, 0, un[p, 0])
+            ctx.infer(sparse=True, local_max=True, root_hyps=True)
+            if disturb:
+                ctx.find_local_max(un[1, 0], 5000)   # > the readout's top-K capacity: buffers are reallocated
+            return [ctx.part_hyps(p) for p in range(P)], ctx.root_hyps(), ctx.best_conf()
+
+        h0, r0, b0 = run(False)
+        h1, r1, b1 = run(True)
+        assert np.array_equal(b0, b1)
+        assert np.array_equal(r0, r1)
+        for p in range(P):
+            assert np.array_equal(h0[p], h1[p]), "part %d hypotheses clobbered" % p
+
+
 # ---- BASELINE.json configs[3] / configs[4] shapes at test size ------------------------------------------------------
 
 def test_conditioned_model_swaps_joints_per_image():
