@@ -305,8 +305,8 @@ def run_ours(args):
                 per_launch_s = prof[k][0] / prof[k][1] * 1e-3
                 fp32[k] = {"tap_outputs_per_launch": round(n_taps), "achieved_per_s": round(n_taps / per_launch_s, -9),
                            "frac_of_measured_peak": round(n_taps / per_launch_s / FP32_PEAK, 3)}
-        msg_ms = sum(prof[k][0] for k in prof if k in ("rotconv", "warp_direct", "warp_bilinear", "conv_rows",
-                                                          "conv_cols", "warp_back", "epilogue")) / n_img_prof / (2 * J)
+        msg_ms = sum(prof[k][0] for k in prof if k in ("rotconv", "warp_direct", "warp_bilinear", "conv_rows", "conv_cols",
+                                                          "gauss_xy", "warp_back", "epilogue")) / n_img_prof / (2 * J * S)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tpath):

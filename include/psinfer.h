@@ -160,6 +160,12 @@ int ps_get_unary(ps_ctx *ctx, int part, int scale, float *dst, int mem_kind);
  *   table_kind 2: table[H][W]  (setTorsoPosPrior, icps.cpp:183-190)  unary += table[y][x]
  * applied to every scale of `part`. */
 int ps_add_unary_table(ps_ctx *ctx, int part, const float *table, int table_kind, float weight);
+/* Up to 4 such tables applied to `part` in one pass over its grids, in array order -- the reference adds the rotation
+ * score, then the position score, then the torso prior (findrot.cpp:913-949), and every add rounds, so the order is
+ * part of the result.  mem_kind says where the tables live (PS_MEM_HOST tables are staged in stream order; the call
+ * does not synchronise). */
+int ps_add_unary_tables(ps_ctx *ctx, int part, int n, const float *const *tables, const int *table_kinds,
+                        const float *weights, int mem_kind);
 
 /* DPM score fusion for full grids `grid[num_rot][H][W]` (num_rot = num_rotation_steps, or 1 = the same grid for every
  * rotation), applied to every scale of `part`:
@@ -247,6 +253,15 @@ int ps_get_plan_info(ps_ctx *ctx, int joint, int downward, int scale, int out[10
  * Lets the CPU tests check by brute force that every cell the read-back can touch is covered. */
 int ps_plan_work_lists(const ps_config *cfg, const double C[4], double scale, int dims[6], double T34[6],
                        int *xlist, int *ylist, int cap);
+
+/* Host-only (no GPU, no ctx): the work of the fused x+y Gaussian kernel for the same message -- one walk per 64-column
+ * strip of the eigen-frame grid.  dims = {EH, EW, x reach, y reach, halo (y reach rounded up to 8), lag K, walks}.
+ * walks[4*i..] = (strip, first row, 8-row groups, offset of the walk's x-block masks in `masks`): the y filter runs over
+ * rows [first row, first row + 8*groups) of the strip; x block j of the walk covers rows first row - halo + 64 j ..+63
+ * and masks[offset + j] says which of the strip's eight 8-column groups are x-filtered there (groups + 7)/8 + K blocks
+ * per walk).  At most `cap` walks / `mask_cap` mask bytes are written; *nmasks receives the number of mask bytes. */
+int ps_plan_walks(const ps_config *cfg, const double C[4], double scale, int dims[7], int *walks, int cap,
+                  unsigned char *masks, int mask_cap, int *nmasks);
 
 /* Exhaustive check of the device exp/log used on the path: for every fp32 bit pattern in
  * [first_bits, first_bits + count) compares the table-driven fast evaluation with CUDA's fp64 libm narrowed to fp32

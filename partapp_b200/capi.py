@@ -78,6 +78,7 @@ PROTOTYPES = {
     "ps_unary_local_max": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, _fp, _ip]),
     "ps_get_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "ps_add_unary_table": (C.c_int, [_ctx_p, C.c_int, _fp, C.c_int, C.c_float]),
+    "ps_add_unary_tables": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), _ip, _fp, C.c_int]),
     "ps_add_unary_grid": (C.c_int, [_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]),
     "ps_rot_score_table": (None, [C.POINTER(ps_config), C.c_double, C.c_double, _fp]),
     "ps_pos_score_table": (None, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -96,6 +97,7 @@ PROTOTYPES = {
     "ps_find_local_max": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _ip]),
     "ps_get_plan_info": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, _ip]),
     "ps_plan_work_lists": (C.c_int, [C.POINTER(ps_config), _dp, C.c_double, _ip, _dp, _ip, _ip, C.c_int]),
+    "ps_plan_walks": (C.c_int, [C.POINTER(ps_config), _dp, C.c_double, _ip, _ip, C.c_int, C.POINTER(C.c_ubyte), C.c_int, _ip]),
     "ps_selftest_math": (C.c_int, [_ctx_p, C.c_uint, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "ps_eval_math": (C.c_int, [_ctx_p, C.c_int, C.c_uint, C.c_uint, _fp]),
     "ps_launch_count": (C.c_longlong, [_ctx_p]),

@@ -13,6 +13,7 @@
 // so no FMA contraction happens here.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <string>
@@ -212,6 +213,17 @@ struct MessagePlan {
   // value that is ever used.
   std::vector<int> ytiles, xtiles;
   long long ycells = 0, xcells = 0;  // grid cells per slice the two lists cover
+  // Work of the fused x+y Gaussian kernel (k_gauss_xy): one WALK per 64-column strip of the eigen-frame grid = the
+  // interval of rows some reader needs, (strip, first row, 8-row groups, offset into xmasks), longest walk first.
+  // The kernel walks down the strip in 64-row blocks; the x-filtered rows live in a shared-memory ring, so block i of
+  // the x pass (rows first_row - halo + 64 i ...) runs `lag` blocks ahead of the y pass.  xmasks holds, per x block,
+  // which of its eight 8-column groups some y output of the rectangle can reach (bit g = columns 8g .. 8g+7).
+  // walks_all / xmasks_all: the same without skipping (every strip top to bottom) for A/B runs.
+  std::vector<int> walks, walks_all;
+  std::vector<unsigned char> xmasks, xmasks_all;
+  int halo = 0;    // ny rounded up to 8: the x pass starts this many rows above a walk's first row
+  int lag = 0;     // K: y block b needs x blocks b .. b + K;  ring = 64 (K + 1) rows
+  long long fcells_x = 0, fcells_y = 0;  // cells per slice the fused kernel filters along x / along y
   std::string error;            // non-empty: the reference would have hit an assert
 };
 
@@ -423,6 +435,53 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
     };
     build(false, p.ytiles, p.ycells);
     build(true, p.xtiles, p.xcells);
+    // walks of the fused kernel: the y list's intervals, one entry per strip
+    p.halo = (ny + 7) & ~7;
+    p.lag = (ny + p.halo + 63) / 64;
+    if (p.lag < 1) p.lag = 1;
+    {
+      const int strips = (p.EW + TS - 1) / TS, groups = (p.EH + SG - 1) / SG;
+      struct W { int st, g0, ng; };
+      std::vector<W> ws, wa;
+      for (int st = 0; st < strips; ++st) {
+        int g0 = -1, g1 = -1;
+        for (int g = 0; g < groups; ++g)
+          if (rect_hits(st * TS - 0.5, g * SG - 0.5, st * TS + TS - 0.5, g * SG + SG - 0.5)) {
+            if (g0 < 0) g0 = g;
+            g1 = g;
+          }
+        if (g0 >= 0) ws.push_back({st, g0, g1 - g0 + 1});
+        wa.push_back({st, 0, groups});
+      }
+      auto emit = [&](std::vector<W> &v, bool all, std::vector<int> &walks, std::vector<unsigned char> &masks, bool count) {
+        std::stable_sort(v.begin(), v.end(), [](const W &a, const W &b) { return a.ng > b.ng; });
+        for (const W &w : v) {
+          const int nb = (w.ng + 7) / 8, nxb = nb + p.lag;
+          walks.push_back(w.st);
+          walks.push_back(w.g0 * SG);
+          walks.push_back(w.ng);
+          walks.push_back((int)masks.size());
+          const int yor = w.g0 * SG - p.halo;
+          for (int i = 0; i < nxb; ++i) {
+            unsigned m = 0;
+            for (int g = 0; g < 8; ++g) {
+              const int ex0 = w.st * TS + g * SG;
+              if (ex0 >= p.EW) break;
+              if (all || rect_hits(ex0 - 0.5, yor + 64 * i - ny - 0.5, ex0 + SG - 0.5, yor + 64 * i + 64 - 0.5 + ny)) m |= 1u << g;
+            }
+            masks.push_back((unsigned char)m);
+            if (count) {
+              int bits = 0;
+              for (int g = 0; g < 8; ++g) bits += (m >> g) & 1;
+              p.fcells_x += (long long)bits * SG * 64;
+            }
+          }
+          if (count) p.fcells_y += (long long)std::min(w.ng * SG, p.EH - w.g0 * SG) * std::min(TS, p.EW - w.st * TS);
+        }
+      };
+      emit(ws, false, p.walks, p.xmasks, true);
+      emit(wa, true, p.walks_all, p.xmasks_all, false);
+    }
   }
   return p;
 }

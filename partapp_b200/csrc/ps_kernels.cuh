@@ -521,6 +521,34 @@ __global__ void k_add_table(float *__restrict__ g, int R, size_t HW, const float
   }
 }
 
+// Several conditioning tables applied to one unary in ONE pass, in call order (the reference adds the rotation score,
+// then the position score, then the torso prior -- findrot.cpp:913-949; every add is its own fp32 rounding, so the
+// order is part of the result).  kinds as in k_add_table.
+constexpr int kMaxTables = 4;
+struct TableArgs {
+  const float *table[kMaxTables];
+  float weight[kMaxTables];
+  int kind[kMaxTables];
+  int n;
+};
+__global__ void k_add_tables(float *__restrict__ g, int R, size_t HW, const __grid_constant__ TableArgs a) {
+  const int r = blockIdx.y;
+  float *s = g + (size_t)r * HW;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < HW; i += stride) {
+    float v = s[i];
+#pragma unroll
+    for (int k = 0; k < kMaxTables; ++k)
+      if (k < a.n) {
+        if (a.kind[k] == 0) v = __fadd_rn(v, __fmul_rn(a.weight[k], a.table[k][r]));
+        else if (a.kind[k] == 1) v = __fadd_rn(v, __fmul_rn(a.weight[k], a.table[k][i]));
+        else v = __fadd_rn(v, a.table[k][i]);
+      }
+    s[i] = v;
+  }
+}
+
 // DPM score fusion (objectdetect_icps.cpp:445-486 addLoadDPMScore, :488-524 addDPMScore): per-cell adds of a score
 // grid g[nrot][H][W] (nrot = R, or 1 broadcast over rotations).
 //   mode 0 (addDPMScore, grid already in the log domain):   u += w * g
@@ -549,6 +577,7 @@ __global__ void k_add_grid(float *__restrict__ u, int R, size_t HW, const float 
 // ---- message stage 1: shift + exp + circular rotation filter ------------------------------------------
 // findrot.cpp:339-420.  One thread per pixel; the R shifted/exponentiated values of the pixel live in a
 // private shared-memory column, then every output rotation is a sequential dot product over the taps.
+constexpr int kMaxBatch = 8;  // messages of one tree level that share a launch (blockIdx.y / .z selects the message)
 struct RotArgs {
   const float *in;      // [R][H][W] child belief (log domain)
   float *out;           // [R][H][W] rotation-filtered probabilities
@@ -563,6 +592,9 @@ struct RotArgs {
   int len;
 };
 
+struct RotBatch {
+  RotArgs a[kMaxBatch];
+};
 constexpr int kRotThreads = 64;
 
 __global__ void __launch_bounds__(kRotThreads) k_rotconv(RotArgs a) {
@@ -803,9 +835,9 @@ __device__ __forceinline__ BilinearTap bilinear_setup(int h, int w, int pitch, d
 // instructions per 32 cells x 8 slices, 91 of them predicate logic and 126 address IMAD/LEA behind the predicates,
 // against 102 loads, multiplies, adds and stores).
 template <int RG, bool FULL>
-__global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restrict__ src, float *__restrict__ dst, Affine T,
-                                                           int R, int sh, int sw, int spitch, size_t splane, int dh,
-                                                           int dw, int dpitch, size_t dplane, int tr) {
+__device__ __forceinline__ void resample_bilinear_block(const float *__restrict__ src, float *__restrict__ dst, const Affine &T,
+                                                        int R, int sh, int sw, int spitch, size_t splane, int dh,
+                                                        int dw, int dpitch, size_t dplane, int tr, int bx, int by, int bz) {
   // 2-D tiles: a tile's rotated footprint in the source stays compact, so the four taps of neighbouring cells
   // hit the same L1 lines
   // a warp owns an 8 x 4 patch of the 16 x 16 tile (8 along the contiguous destination axis): its rotated footprint in
@@ -813,9 +845,9 @@ __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restri
   // per gather request (ncu r01d: 11 sectors, 3.7 wavefronts per request with the strip)
   const int tid = threadIdx.y * 16 + threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int tu = (wrp & 1) * 8 + (lane & 7), tv = (wrp >> 1) * 4 + (lane >> 3);  // u: contiguous axis of dst
-  const int ix = blockIdx.x * 16 + (tr ? tv : tu);
-  const int iy = blockIdx.y * 16 + (tr ? tu : tv);
-  const int r0 = blockIdx.z * RG;
+  const int ix = bx * 16 + (tr ? tv : tu);
+  const int iy = by * 16 + (tr ? tu : tv);
+  const int r0 = bz * RG;
   if (tr ? (ix >= dw || iy >= dh) : (ix >= dpitch || iy >= dh)) return;
   float *o = dst + (size_t)r0 * dplane + (tr ? (size_t)ix * dpitch + iy : (size_t)iy * dpitch + ix);
   BilinearTap t;
@@ -855,19 +887,48 @@ __global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restri
 }
 
 
+template <int RG, bool FULL>
+__global__ void __launch_bounds__(256) k_resample_bilinear(const float *__restrict__ src, float *__restrict__ dst, Affine T,
+                                                           int R, int sh, int sw, int spitch, size_t splane, int dh,
+                                                           int dw, int dpitch, size_t dplane, int tr) {
+  resample_bilinear_block<RG, FULL>(src, dst, T, R, sh, sw, spitch, splane, dh, dw, dpitch, dplane, tr, blockIdx.x, blockIdx.y,
+                                    blockIdx.z);
+}
+// Several messages of one tree level per launch: blockIdx.z = message * (R / RG) + slice group; the grid spans the
+// largest destination of the batch, blocks outside their own message's grid leave at once.
+struct ResampleMsg {
+  const float *src;
+  float *dst;
+  Affine T;
+  size_t splane, dplane;
+  int sh, sw, spitch, dh, dw, dpitch;
+};
+struct ResampleBatch {
+  ResampleMsg m[kMaxBatch];
+  int R, tr, zgroups;
+};
+template <int RG>
+__global__ void __launch_bounds__(256) k_resample_bilinear_b(const __grid_constant__ ResampleBatch rb) {
+  const int mi = blockIdx.z / rb.zgroups, zg = blockIdx.z - mi * rb.zgroups;
+  const ResampleMsg &m = rb.m[mi];
+  if ((int)blockIdx.x * 16 >= (rb.tr ? m.dw : m.dpitch) || (int)blockIdx.y * 16 >= m.dh) return;
+  resample_bilinear_block<RG, true>(m.src, m.dst, m.T, rb.R, m.sh, m.sw, m.spitch, m.splane, m.dh, m.dw, m.dpitch, m.dplane,
+                                    rb.tr, blockIdx.x, blockIdx.y, zg);
+}
+
 // (Round 1 also tried staging each tile's 28x28 source bounding box in shared memory -- the direct gathers are bound
 // by the L1 data pipe at ~11 sectors per request -- but the staging loop plus 3x over-fetch made it 2x slower.)
 // TM_DIRECT as a gather through the winner map, RG slices per thread.
 // tr != 0: out is stored transposed ([r][ix][iy], pitch EP over iy, plane EW*EP) and threadIdx.x walks iy.
 template <int RG, bool FULL>
-__global__ void __launch_bounds__(256) k_warp_direct2(const float *__restrict__ in, float *__restrict__ out,
-                                                      const int2 *__restrict__ map, int R, size_t HW, int EH, int EW,
-                                                      int EP, int tr) {
+__device__ __forceinline__ void warp_direct_block(const float *__restrict__ in, float *__restrict__ out,
+                                                  const int2 *__restrict__ map, int R, size_t HW, int EH, int EW,
+                                                  int EP, int tr, int bx, int by, int bz) {
   const int tid = threadIdx.y * 16 + threadIdx.x, lane = tid & 31, wrp = tid >> 5;  // 8 x 4 warp patches, see above
   const int tu = (wrp & 1) * 8 + (lane & 7), tv = (wrp >> 1) * 4 + (lane >> 3);
-  const int ix = blockIdx.x * 16 + (tr ? tv : tu);
-  const int iy = blockIdx.y * 16 + (tr ? tu : tv);
-  const int r0 = blockIdx.z * RG;
+  const int ix = bx * 16 + (tr ? tv : tu);
+  const int iy = by * 16 + (tr ? tu : tv);
+  const int r0 = bz * RG;
   if (tr ? (ix >= EW || iy >= EH) : (ix >= EP || iy >= EH)) return;
   const size_t eplane = tr ? (size_t)EW * EP : (size_t)EH * EP;
   float *o = out + (size_t)r0 * eplane + (tr ? (size_t)ix * EP + iy : (size_t)iy * EP + ix);
@@ -893,6 +954,31 @@ __global__ void __launch_bounds__(256) k_warp_direct2(const float *__restrict__ 
 #pragma unroll
   for (int u = 0; u < RG; ++u)
     if (FULL || u < nu) o[(size_t)u * eplane] = v[u];
+}
+
+template <int RG, bool FULL>
+__global__ void __launch_bounds__(256) k_warp_direct2(const float *__restrict__ in, float *__restrict__ out,
+                                                      const int2 *__restrict__ map, int R, size_t HW, int EH, int EW,
+                                                      int EP, int tr) {
+  warp_direct_block<RG, FULL>(in, out, map, R, HW, EH, EW, EP, tr, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+struct DirectMsg {
+  const float *in;
+  float *out;
+  const int2 *map;
+  int EH, EW, EP;
+};
+struct DirectBatch {
+  DirectMsg m[kMaxBatch];
+  size_t HW;
+  int R, tr, zgroups;
+};
+template <int RG>
+__global__ void __launch_bounds__(256) k_warp_direct_b(const __grid_constant__ DirectBatch db) {
+  const int mi = blockIdx.z / db.zgroups, zg = blockIdx.z - mi * db.zgroups;
+  const DirectMsg &m = db.m[mi];
+  if ((int)blockIdx.x * 16 >= (db.tr ? m.EW : m.EP) || (int)blockIdx.y * 16 >= m.EH) return;
+  warp_direct_block<RG, true>(m.in, m.out, m.map, db.R, db.HW, m.EH, m.EW, m.EP, db.tr, blockIdx.x, blockIdx.y, zg);
 }
 
 // ---- message stage 2b: separable Gaussian, zero padded, unnormalised taps -------------------------------
@@ -1238,8 +1324,9 @@ __global__ void __launch_bounds__(256) k_rotconv3(RotArgs a, u64 nz) {
 // is OUT + L - 1 loads at compile-time offsets from one address; the per-rotation shift records live in shared
 // memory; a pixel's (x, y) comes from one FastDiv; exp runs branch-free behind one warp vote per cell.
 template <int R, int L, int PX, int OUT, bool FMA>
-__global__ void __launch_bounds__(256) k_rotconv4(RotArgs a, FastDiv Wdiv, u64 nz) {
+__global__ void __launch_bounds__(256) k_rotconv4(const __grid_constant__ RotBatch rb, FastDiv Wdiv, u64 nz) {
   static_assert(R % OUT == 0 && PX % 2 == 0 && 256 % PX == 0 && PX >= 32, "tiling");
+  const RotArgs &a = rb.a[blockIdx.y];
   constexpr int NPAD = (L - 1) / 2, RX = R + L - 1;
   __shared__ __align__(8) float s_e[RX][PX];
   __shared__ float s_taps[L];
@@ -1613,6 +1700,240 @@ __global__ void __launch_bounds__(288, PS_TMA_MINB) k_conv_cols_tma2(const __gri
     } else {
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[s]);
+    }
+  }
+}
+
+// ---- stage 2b v5: both Gaussian passes in ONE kernel, several messages per launch ---------------------------------
+// gaussFilterDiag2d on the eigen-frame grid (multi_array_filter.hpp:277-317) without the intermediate grid: the
+// x-filtered rows of a 64-column strip live in a shared-memory ring while a block walks down the strip.
+//
+// Input: the eigen-frame grid stored TRANSPOSED, UT[z][ex][ey] (the resampler writes it that way), so the x filter is a
+// column filter over TMA boxes of (64 + 2 nx) ex-rows x 64 ey-columns, exactly like k_conv_cols_tma2.  Work item =
+// (message, walk, slice): a walk is one 64-wide ex-strip and the interval of ey-rows some reader needs (MessagePlan::
+// walks).  Step i of a walk:
+//   X(i): box i (ey origin y0 - halo + 64 i) -> 64 x 64 x-filtered values, stored transposed into the ring as
+//         ring[(64 i + c - dshift) mod cap][ex], c = ey column of the box; dshift = halo - ny makes the y windows start
+//         on multiples of 8 ring rows, so the origin of every box stays 16-byte aligned AND an 8-row chunk of a y
+//         window never straddles the wrap.  Warps whose 8 ex-rows no y output of the rectangle can reach (xmask) skip.
+//   Y(i - K): 64 output rows (8 per warp) filtered along ey from the ring, stored to out[z][ey][ex].
+// Arithmetic per output is the same ascending-tap RN(acc + RN(x f)) chain as the two-kernel route: bit-identical.
+// Warp 8 is the producer: it draws work items from an atomic counter (messages in launch order, longest walk first),
+// publishes (message, walk, block, slice) next to each box and issues the TMA; the eight filter warps follow the
+// published records, hand a stage back through its `empty` mbarrier right after the x phase and meet at a named
+// barrier between the phases.
+constexpr int kRingPitch = 68;  // floats per ring row: 64 + 4 keeps rows 16-byte aligned and the transposed stores 2-way at worst
+struct GaussMsg {
+  float *out;                  // [z][ey][ex], pitch EP, plane oplane
+  const float *taps_x, *taps_y;
+  const int *walks;            // [nwalks][4] = strip, first row, 8-row groups, offset into masks
+  const unsigned char *masks;  // per x block: which 8-column groups to filter
+  size_t oplane;
+  int len_x, len_y, EH, EW, EP, nwalks, lag, halo;
+  int item0;                   // first work item of this message in the launch; items = nwalks * R, slice innermost
+};
+struct GaussBatch {
+  GaussMsg m[kMaxBatch];
+  unsigned *counter;           // zero at launch
+  int nmsg, R, total_items;
+  unsigned stage_stride;       // bytes between the TMA stages (the largest box of the batch, 128-byte multiple)
+  int ring_rows;               // 64 * (largest lag of the batch + 1)
+};
+constexpr int kMaxFusedTaps = 256;
+struct alignas(64) TmapBatch {
+  CUtensorMap t[kMaxBatch];
+};
+__device__ __forceinline__ void bar_sync_filter() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <bool FMA>
+__global__ void __launch_bounds__(288, 2) k_gauss_xy(const __grid_constant__ TmapBatch tm, const __grid_constant__ GaussBatch b, u64 nz) {
+  constexpr int T = 8, NS = 2;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_full[NS], s_empty[NS];
+  __shared__ int4 s_meta[NS][2];  // [0] = (message or -1, strip, first row, groups)  [1] = (block index, slice, mask, 0)
+  __shared__ float s_tx[kMaxFusedTaps], s_ty[kMaxFusedTaps];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float *ring = reinterpret_cast<float *>(s_raw + NS * b.stage_stride);
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (w == 8) {  // producer
+    if (lane == 0) {
+      int s = 0, u = 0;
+      auto next_stage = [&]() {
+        if (++s == NS) {
+          s = 0;
+          ++u;
+        }
+      };
+      auto wait_free = [&]() {
+        if (u >= 1) {
+          while (!mbar_try_wait(&s_empty[s], (unsigned)(u - 1) & 1u)) {}
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
+        }
+      };
+      for (;;) {
+        const int item = (int)atomicAdd(b.counter, 1u);
+        if (item >= b.total_items) break;
+        int mi = 0;
+        while (mi + 1 < b.nmsg && item >= b.m[mi + 1].item0) ++mi;
+        const GaussMsg &g = b.m[mi];
+        const int local = item - g.item0;
+        const int wk = local / b.R, z = local - wk * b.R;
+        const int4 we = *reinterpret_cast<const int4 *>(g.walks + 4 * wk);
+        const int nxb = (we.z + 7) / 8 + g.lag;
+        const int nx = (g.len_x - 1) / 2;
+        const unsigned bytes = (unsigned)(64 + 2 * nx) * 64u * sizeof(float);
+        for (int i = 0; i < nxb; ++i) {
+          wait_free();
+          s_meta[s][0] = make_int4(mi, we.x, we.y, we.z);
+          s_meta[s][1] = make_int4(i, z, (int)g.masks[we.w + i], 0);
+          mbar_expect_tx(&s_full[s], bytes);
+          tma_load_3d(s_raw + s * b.stage_stride, &tm.t[mi], we.y - g.halo + 64 * i, we.x * 64 - nx, z, &s_full[s]);
+          next_stage();
+        }
+      }
+      wait_free();
+      s_meta[s][0] = make_int4(-1, 0, 0, 0);
+      mbar_arrive(&s_full[s]);
+    }
+    return;
+  }
+  // the ring starts defined: skipped x groups leave stale cells that only feed outputs nobody reads
+  {
+    for (int i = tid; i < b.ring_rows * kRingPitch; i += 256) ring[i] = 0.0f;
+  }
+  bar_sync_filter();
+  int s = -1, u = 0, cur = -1;
+  for (;;) {
+    if (++s == NS) {
+      s = 0;
+      ++u;
+    }
+    while (!mbar_try_wait(&s_full[s], (unsigned)u & 1u)) {}
+    const int4 m0 = s_meta[s][0], m1 = s_meta[s][1];
+    if (m0.x < 0) break;
+    const GaussMsg &g = b.m[m0.x];
+    const int nx = (g.len_x - 1) / 2, ny = (g.len_y - 1) / 2;
+    const int cap = 64 * (g.lag + 1), dshift = g.halo - ny;
+    const int i = m1.x, z = m1.y;
+    if (i == 0 && m0.x != cur) {  // every warp is past the previous walk's last barrier: the tap arrays are free
+      cur = m0.x;
+      for (int k = tid; k < g.len_x; k += 256) s_tx[k] = g.taps_x[k];
+      for (int k = tid; k < g.len_y; k += 256) s_ty[k] = g.taps_y[k];
+      bar_sync_filter();
+    }
+    // ---- X(i): filter along ex, store transposed into the ring ----
+    if ((m1.z >> w) & 1) {
+      const u64 *win = reinterpret_cast<const u64 *>(s_raw + s * b.stage_stride) + (w * T) * 32 + lane;
+      u64 acc[T], d[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
+#pragma unroll
+      for (int q = 0; q < T - 1; ++q) d[q] = win[q * 32];
+      const u64 *wp = win + (T - 1) * 32;
+      int kk = 0;
+      for (; kk + T <= g.len_x; kk += T, wp += T * 32) {
+#pragma unroll
+        for (int uu = 0; uu < T; ++uu) {
+          d[(uu + T - 1) % T] = wp[uu * 32];
+          const float f = s_tx[kk + uu];
+#pragma unroll
+          for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f, nz);
+        }
+      }
+#pragma unroll
+      for (int uu = 0; uu < T; ++uu) {
+        if (kk + uu < g.len_x) {
+          d[(uu + T - 1) % T] = wp[uu * 32];
+          const float f = s_tx[kk + uu];
+#pragma unroll
+          for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f, nz);
+        }
+      }
+      float lo[T], hi[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
+      int q0 = 64 * (i % (g.lag + 1)) + 2 * lane - dshift;  // ring row of ey column 2*lane of this box
+      if (q0 < 0) q0 += cap;
+      int q1 = q0 + 1;
+      if (q1 == cap) q1 = 0;
+      float4 *r0 = reinterpret_cast<float4 *>(ring + q0 * kRingPitch + w * T);
+      float4 *r1 = reinterpret_cast<float4 *>(ring + q1 * kRingPitch + w * T);
+      r0[0] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      r0[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+      r1[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      r1[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);  // the box is consumed: the producer may refill the stage
+    bar_sync_filter();
+    // ---- Y(i - K): filter along ey from the ring ----
+    const int ob = i - g.lag;
+    if (ob >= 0) {
+      const int row0 = m0.z + 64 * ob + w * T;
+      if (w < m0.w - 8 * ob && row0 < g.EH) {  // warp-uniform
+        int q = (64 * ob + w * T) % cap;  // multiple of 8; rows q .. q + 7 + 2 ny (mod cap) hold the window
+        const u64 *rbase = reinterpret_cast<const u64 *>(ring) + lane;
+        u64 acc[T], d[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] = pk2(0.0f, 0.0f);
+#pragma unroll
+        for (int t = 0; t < T - 1; ++t) d[t] = rbase[(q + t) * (kRingPitch / 2)];
+        q += T - 1;  // next row to load; q - (T-1) was a multiple of 8, so q + 1 may hit cap only after this row
+        int kk = 0;
+        for (; kk + T <= g.len_y; kk += T) {
+          const u64 *wp = rbase + q * (kRingPitch / 2);  // rows q, then (q + 1 wrapped) .. : q % 8 == 7
+          d[T - 1] = wp[0];
+          q = q + 1 == cap ? 0 : q + 1;
+          const u64 *wq = rbase + q * (kRingPitch / 2);  // q % 8 == 0: seven more rows without a wrap
+          {
+            const float f = s_ty[kk];
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[t % T], f, nz);
+          }
+#pragma unroll
+          for (int uu = 1; uu < T; ++uu) {
+            d[(uu + T - 1) % T] = wq[(uu - 1) * (kRingPitch / 2)];
+            const float f = s_ty[kk + uu];
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f, nz);
+          }
+          q += T - 1;  // q % 8 == 7 again (never reaches cap: cap % 8 == 0)
+        }
+#pragma unroll
+        for (int uu = 0; uu < T; ++uu) {
+          if (kk + uu < g.len_y) {
+            d[(uu + T - 1) % T] = rbase[q * (kRingPitch / 2)];
+            q = q + 1 == cap ? 0 : q + 1;
+            const float f = s_ty[kk + uu];
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f, nz);
+          }
+        }
+        const int x = m0.y * 64 + lane * 2;
+        if (x < g.EW) {
+          const bool in1 = x + 1 < g.EW;
+          float *dst = g.out + (size_t)z * g.oplane + x;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int y = row0 + t;
+            if (y < g.EH) {
+              float lo, hi;
+              upk2(acc[t], lo, hi);
+              float *o = dst + (size_t)y * g.EP;
+              if (in1) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+              else o[0] = lo;
+            }
+          }
+        }
+      }
+      bar_sync_filter();  // the next x block overwrites ring rows this y block read
     }
   }
 }
@@ -2012,7 +2333,11 @@ __global__ void __launch_bounds__(256) k_epilogue2(EpiArgs a, int XG /* ceil(W/4
 // 16-byte aligned.  32-bit index arithmetic (R*H*W < 2^31 is enforced by ps_create), no per-cell branches: the four
 // cells are evaluated unconditionally on clamped addresses and invalid ones are replaced by LOG_ZERO at the end.
 // ncu r01c: k_epilogue2 spent 98 warp-instructions per cell, a third of them IMAD/ISETP/BRA bookkeeping.
-__global__ void __launch_bounds__(256) k_epilogue3(EpiArgs a, FastDiv XG) {
+struct EpiBatch {
+  EpiArgs a[kMaxBatch];
+};
+__global__ void __launch_bounds__(256) k_epilogue3(const __grid_constant__ EpiBatch eb, FastDiv XG) {
+  const EpiArgs &a = eb.a[blockIdx.z];
   // block-level folds: warp redux on the monotone integer encoding, one shared atomic per warp, one global per block
   __shared__ int s_m0, s_m1;
   __shared__ unsigned long long s_key;

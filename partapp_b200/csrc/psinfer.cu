@@ -61,6 +61,8 @@ struct DevPlan {
   DevBuf floats;  // rot taps | fx | fy
   DevBuf map;     // int2 [EH][EW], built on first sparse use
   DevBuf mats;    // T31 | T13 (doubles) for the map builder
+  DevBuf walks;   // fused Gaussian kernel: int4 walks | x-block masks (bytes)
+  int nwalks = 0;
   bool map_ready = false;
   int EP = 0;     // eigen-frame row pitch
   const int *xin() const { return ints.as<int>(); }
@@ -111,6 +113,13 @@ struct ps_ctx {
   DevBuf tmp[2];        // [N] down-pass inputs (unary + from_root)
   DevBuf bufB;          // [N] rotation-filtered / diag y-pass output
   DevBuf bufU, bufV;    // eigen-frame scratch [R][EHmax][EPmax] (>= N)
+  // level-batched schedule: one (B, UT, V) scratch triple per message of a launch
+  std::vector<DevBuf> slotB, slotU, slotV;
+  size_t slot_elems = 0;
+  DevBuf chain_tmp;     // [n_root_children][N]: down-pass inputs of the chains (ping-pong partner of rootmsg)
+  DevBuf work_counters; // unsigned [kWorkCounters]: one zeroed work-item counter per fused Gaussian launch
+  int work_counter_next = 0;
+  bool disable_batch = false;  // PSINFER_NO_BATCH=1: one message per launch through the two-pass Gaussian route (A/B testing)
   DevBuf root_post;     // [S][HW]
   DevBuf maxes;         // int encoded maxima: [0,P) beliefs | [P,P+16) from_root inputs | [P+16,2P+16) tmp of node q | 4 misc
   DevBuf upright_mask;  // uchar [R]
@@ -126,6 +135,7 @@ struct ps_ctx {
   size_t topk_slots = 0, topk_kmax = 0;
   DevBuf counters;      // unsigned [8]
   DevBuf ingest, ingest_keys;       // ps_set_unary_compact staging: Tig rows + compact cells; order keys [R][H][W]
+  DevBuf table_stage, grid_stage;   // ps_add_unary_table(s) / ps_add_unary_grid: stream-ordered staging of host inputs
   DevBuf unary_max;                 // int [P][S]: encoded max of each unary as left by the ingest
   std::vector<unsigned char> unary_max_valid;  // [P][S]
   size_t scratch_elems = 0;
@@ -191,11 +201,12 @@ struct ps_ctx {
 // kernel classes for ps_profile_read / DESIGN.md
 enum KClass {
   KC_PREP = 0, KC_MAX, KC_MASK, KC_ROTCONV, KC_WARP_DIRECT, KC_WARP_BILINEAR, KC_CONV_ROWS, KC_CONV_COLS,
-  KC_WARP_BACK, KC_EPILOGUE, KC_ROOT_COMBINE, KC_ROOT_MARGINAL, KC_ARGMAX, KC_LOCAL_MAX, KC_MISC, KC_COUNT
+  KC_WARP_BACK, KC_EPILOGUE, KC_ROOT_COMBINE, KC_ROOT_MARGINAL, KC_ARGMAX, KC_LOCAL_MAX, KC_MISC, KC_GAUSS_XY, KC_COUNT
 };
 static const char *const kClassNames[KC_COUNT] = {
     "prepare_unary", "grid_max", "mask", "rotconv", "warp_direct", "warp_bilinear", "conv_rows", "conv_cols",
-    "warp_back", "epilogue", "root_combine", "root_marginal", "argmax", "local_max", "misc"};
+    "warp_back", "epilogue", "root_combine", "root_marginal", "argmax", "local_max", "misc", "gauss_xy"};
+constexpr int kWorkCounters = 1024;
 
 static size_t prof_event(ps_ctx *c) {
   if (c->ev_used == c->ev_pool.size()) {
@@ -265,6 +276,14 @@ int upload_plan(ps_ctx *c, DevPlan &dp) {
     memcpy(m + 6, h.T13, sizeof h.T13);
     PS_CUDA(c, dp.mats.alloc(sizeof m));
     PS_CUDA(c, cudaMemcpy(dp.mats.p, m, sizeof m, cudaMemcpyHostToDevice));
+    const std::vector<int> &wl = c->disable_tile_lists ? h.walks_all : h.walks;
+    const std::vector<unsigned char> &ml = c->disable_tile_lists ? h.xmasks_all : h.xmasks;
+    dp.nwalks = (int)wl.size() / 4;
+    PS_CUDA(c, dp.walks.alloc(wl.size() * sizeof(int) + ml.size()));
+    if (!wl.empty()) {
+      PS_CUDA(c, cudaMemcpy(dp.walks.p, wl.data(), wl.size() * sizeof(int), cudaMemcpyHostToDevice));
+      PS_CUDA(c, cudaMemcpy((char *)dp.walks.p + wl.size() * sizeof(int), ml.data(), ml.size(), cudaMemcpyHostToDevice));
+    }
   }
   return PS_OK;
 }
@@ -338,25 +357,32 @@ int ensure_direct_map(ps_ctx *c, DevPlan &dp) {
 constexpr size_t kSmemBudget = 96 * 1024;  // per block, leaves room for 2 blocks per SM
 
 template <int Rr, int L, int OUT>
-int launch_rotconv_t(ps_ctx *c, const psk::RotArgs &a) {
+int launch_rotconv_t(ps_ctx *c, const psk::RotBatch &rb, int nmsg) {
   constexpr int PX = 128;
   static const bool old_kernel = getenv("PSINFER_ROTCONV3") != nullptr;  // A/B switch
-  if (a.shift_xy && !old_kernel && c->cfg.fast_math)
-    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT, true><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(
-                                 a, psk::FastDiv((unsigned)c->W), PS_NEGZERO2));
-  else if (a.shift_xy && !old_kernel)
-    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT, false><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(
-                                 a, psk::FastDiv((unsigned)c->W), PS_NEGZERO2));
+  bool pure = true;
+  for (int i = 0; i < nmsg; ++i) pure = pure && rb.a[i].shift_xy;
+  const dim3 grid(cdiv(c->HW, PX), nmsg);
+  if (pure && !old_kernel && c->cfg.fast_math)
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT, true><<<grid, 256, 0, c->stream>>>(
+                                 rb, psk::FastDiv((unsigned)c->W), PS_NEGZERO2));
+  else if (pure && !old_kernel)
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv4<Rr, L, PX, OUT, false><<<grid, 256, 0, c->stream>>>(
+                                 rb, psk::FastDiv((unsigned)c->W), PS_NEGZERO2));
   else
-    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv3<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(a, PS_NEGZERO2));
+    for (int i = 0; i < nmsg; ++i)
+      PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv3<Rr, L, PX, OUT><<<cdiv(c->HW, PX), 256, 0, c->stream>>>(rb.a[i], PS_NEGZERO2));
   return PS_OK;
 }
 
 // Block-cooperative rotation filter for the common rotation counts, generic shared-memory kernel otherwise.
-int launch_rotconv(ps_ctx *c, const psk::RotArgs &a) {
-  const int len = a.mode == 1 ? a.len : 1;
+// All messages of the batch share one launch when every translation table is a pure shift.
+int launch_rotconv(ps_ctx *c, const psk::RotBatch &rb, int nmsg) {
+  int len = 1;
+  for (int i = 0; i < nmsg; ++i) len = std::max(len, rb.a[i].mode == 1 ? rb.a[i].len : 1);
+  const int R = rb.a[0].R;
 #define ROT_CASE(Rr, L, OUT) \
-  if (a.R == Rr && len <= L) return launch_rotconv_t<Rr, L, OUT>(c, a)
+  if (R == Rr && len <= L) return launch_rotconv_t<Rr, L, OUT>(c, rb, nmsg)
   ROT_CASE(8, 7, 4);
   ROT_CASE(12, 11, 6);
   ROT_CASE(24, 7, 6);
@@ -367,11 +393,19 @@ int launch_rotconv(ps_ctx *c, const psk::RotArgs &a) {
   ROT_CASE(48, 23, 8);
   ROT_CASE(48, 47, 8);
 #undef ROT_CASE
-  size_t smem = (size_t)a.R * psk::kRotThreads * sizeof(float);
-  if (smem > 48 * 1024)
-    PS_CUDA(c, cudaFuncSetAttribute(psk::k_rotconv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv<<<cdiv(c->HW, psk::kRotThreads), psk::kRotThreads, smem, c->stream>>>(a));
+  for (int i = 0; i < nmsg; ++i) {
+    const psk::RotArgs &a = rb.a[i];
+    size_t smem = (size_t)a.R * psk::kRotThreads * sizeof(float);
+    if (smem > 48 * 1024)
+      PS_CUDA(c, cudaFuncSetAttribute(psk::k_rotconv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PS_LAUNCH(c, KC_ROTCONV, psk::k_rotconv<<<cdiv(c->HW, psk::kRotThreads), psk::kRotThreads, smem, c->stream>>>(a));
+  }
   return PS_OK;
+}
+int launch_rotconv(ps_ctx *c, const psk::RotArgs &a) {
+  psk::RotBatch rb{};
+  rb.a[0] = a;
+  return launch_rotconv(c, rb, 1);
 }
 
 int launch_conv_rows(ps_ctx *c, const psk::ConvArgs &a, int slices) {
@@ -675,12 +709,250 @@ int run_message(ps_ctx *c, DevPlan &dp, const float *in, const int *in_max, bool
     if (!al) {
       PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue<<<dim3(cdiv(W, 256), H, R), 256, 0, st>>>(e));
     } else if (!e.general && e.shift_xy && W % 4 == 0 && (uintptr_t)e.src % 16 == 0) {
-      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue3<<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, psk::FastDiv((unsigned)XG)));
+      psk::EpiBatch eb{};
+      eb.a[0] = e;
+      PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue3<<<dim3(cdiv((size_t)XG * H, 256), R, 1), 256, 0, st>>>(eb, psk::FastDiv((unsigned)XG)));
     } else if (e.general) {
       PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue2<true><<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
     } else {
       PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue2<false><<<dim3(cdiv((size_t)XG * H, 256), R), 256, 0, st>>>(e, XG));
     }
+  }
+  return PS_OK;
+}
+
+// ---- level-batched schedule ---------------------------------------------------------------------------------------
+// The messages of one tree level (findrot.cpp:582-658 upward, :158-236 downward) are independent; those that take the
+// eigen-frame route share five launches: rotation filter, resampling into the (transposed) eigen-frame, the fused
+// x+y Gaussian, the read-back and the epilogue, each indexed by message.
+struct MsgJob {
+  DevPlan *dp;
+  const float *in;
+  const int *in_max;
+  bool sparse;
+  Sink sink;
+};
+
+size_t fused_smem_bytes(const psg::MessagePlan &h, unsigned &stage) {
+  const int nx = ((int)h.fx.size() - 1) / 2;
+  stage = (unsigned)(64 + 2 * nx) * 64u * sizeof(float);
+  return 2 * (size_t)stage + (size_t)64 * (h.lag + 1) * psk::kRingPitch * sizeof(float);
+}
+
+constexpr size_t kFusedSmemMax = 200 * 1024;
+
+bool can_batch(const ps_ctx *c, const MsgJob &j) {
+  const psg::MessagePlan &h = j.dp->host;
+  if (c->disable_batch || c->disable_tma || h.diag || !tensor_map_encoder()) return false;
+  if (c->R % PS_RG != 0 || c->W % 4 != 0 || !h.in_pure || !h.out_pure || j.dp->nwalks == 0) return false;
+  if ((int)h.fx.size() > 193 || (int)h.fy.size() > psk::kMaxFusedTaps) return false;
+  unsigned stage;
+  if (fused_smem_bytes(h, stage) > kFusedSmemMax) return false;
+  const Sink &k = j.sink;
+  return ((uintptr_t)k.out0 % 16 == 0) && ((uintptr_t)k.acc0 % 16 == 0) && ((uintptr_t)k.add0 % 16 == 0) &&
+         ((uintptr_t)k.out1 % 16 == 0) && ((uintptr_t)k.add1 % 16 == 0) && ((uintptr_t)j.in % 16 == 0);
+}
+
+int ensure_slots(ps_ctx *c, size_t nslots, size_t elems) {
+  if (nslots <= c->slotB.size() && elems <= c->slot_elems) return PS_OK;
+  PS_CUDA(c, cudaStreamSynchronize(c->stream));
+  nslots = std::max(nslots, c->slotB.size());
+  elems = std::max(elems, c->slot_elems);
+  const bool grow = elems > c->slot_elems;
+  const size_t old = c->slotB.size();
+  if (nslots > old) {
+    c->slotB.resize(nslots);
+    c->slotU.resize(nslots);
+    c->slotV.resize(nslots);
+  }
+  for (size_t i = grow ? 0 : old; i < nslots; ++i) {
+    if (!c->slotB[i].p) PS_CUDA(c, c->slotB[i].alloc(c->N * sizeof(float)));
+    PS_CUDA(c, c->slotU[i].alloc(elems * sizeof(float)));
+    PS_CUDA(c, c->slotV[i].alloc(elems * sizeof(float)));
+    // cells outside the work lists are never written; give them a defined value once (see ensure_scratch)
+    PS_CUDA(c, cudaMemsetAsync(c->slotU[i].p, 0, elems * sizeof(float), c->stream));
+    PS_CUDA(c, cudaMemsetAsync(c->slotV[i].p, 0, elems * sizeof(float), c->stream));
+  }
+  c->slot_elems = elems;
+  return PS_OK;
+}
+
+int take_work_counter(ps_ctx *c, unsigned **out) {
+  if (!c->work_counters.p) {
+    PS_CUDA(c, c->work_counters.alloc(kWorkCounters * sizeof(unsigned)));
+    c->work_counter_next = kWorkCounters;
+  }
+  if (c->work_counter_next >= kWorkCounters) {  // stream-ordered behind every launch that still uses an old counter
+    PS_CUDA(c, cudaMemsetAsync(c->work_counters.p, 0, kWorkCounters * sizeof(unsigned), c->stream));
+    c->work_counter_next = 0;
+  }
+  *out = c->work_counters.as<unsigned>() + c->work_counter_next++;
+  return PS_OK;
+}
+
+int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
+  const int R = c->R, H = c->H, W = c->W;
+  constexpr int RG = PS_RG;
+  cudaStream_t st = c->stream;
+  size_t elems = c->N;
+  for (int i = 0; i < n; ++i) elems = std::max(elems, plan_scratch_elems(c, *jobs[i]->dp));
+  int rc = ensure_slots(c, (size_t)n, elems);
+  if (rc) return rc;
+  const bool sparse = jobs[0]->sparse;
+
+  // stage 1: shift + exp + rotation filter -> B[i]
+  {
+    psk::RotBatch rb{};
+    for (int i = 0; i < n; ++i) {
+      const DevPlan &dp = *jobs[i]->dp;
+      psk::RotArgs &a = rb.a[i];
+      a.in = jobs[i]->in; a.out = c->slotB[i].as<float>();
+      a.xin = dp.xin(); a.yin = dp.yin(R, W);
+      a.shift_xy = dp.in_shift(R, H, W);
+      a.taps = dp.rot_taps(); a.max_enc = jobs[i]->in_max;
+      a.R = R; a.H = H; a.W = W;
+      a.shift = dp.host.rot_shift; a.mode = dp.host.rot_mode; a.len = (int)dp.host.rot_taps.size();
+    }
+    if ((rc = launch_rotconv(c, rb, n))) return rc;
+  }
+  // stage 2: into the eigen-frame, stored transposed [r][ex][ey]
+  int maxEW = 0, maxEH = 0;
+  for (int i = 0; i < n; ++i) {
+    maxEW = std::max(maxEW, jobs[i]->dp->host.EW);
+    maxEH = std::max(maxEH, jobs[i]->dp->host.EH);
+  }
+  if (sparse) {
+    psk::DirectBatch db{};
+    db.HW = c->HW; db.R = R; db.tr = 1; db.zgroups = R / RG;
+    for (int i = 0; i < n; ++i) {
+      DevPlan &dp = *jobs[i]->dp;
+      if ((rc = ensure_direct_map(c, dp))) return rc;
+      psk::DirectMsg &m = db.m[i];
+      m.in = c->slotB[i].as<float>(); m.out = c->slotU[i].as<float>(); m.map = dp.map.as<int2>();
+      m.EH = dp.host.EH; m.EW = dp.host.EW; m.EP = (dp.host.EH + 7) & ~7;
+    }
+    PS_LAUNCH(c, KC_WARP_DIRECT, psk::k_warp_direct_b<RG><<<dim3(cdiv(maxEW, 16), cdiv(maxEH, 16), n * (R / RG)), dim3(16, 16), 0, st>>>(db));
+  } else {
+    psk::ResampleBatch rb{};
+    rb.R = R; rb.tr = 1; rb.zgroups = R / RG;
+    for (int i = 0; i < n; ++i) {
+      const psg::MessagePlan &h = jobs[i]->dp->host;
+      const int EHP = (h.EH + 7) & ~7;
+      psk::ResampleMsg &m = rb.m[i];
+      m.src = c->slotB[i].as<float>(); m.dst = c->slotU[i].as<float>();
+      memcpy(m.T.m, h.T13, sizeof m.T.m);
+      m.sh = H; m.sw = W; m.spitch = W; m.splane = c->HW;
+      m.dh = h.EH; m.dw = h.EW; m.dpitch = EHP; m.dplane = (size_t)h.EW * EHP;
+    }
+    PS_LAUNCH(c, KC_WARP_BILINEAR, psk::k_resample_bilinear_b<RG><<<dim3(cdiv(maxEW, 16), cdiv(maxEH, 16), n * (R / RG)), dim3(16, 16), 0, st>>>(rb));
+  }
+  // stage 3: both Gaussian passes, UT[i] -> V[i] ([r][ey][ex])
+  {
+    psk::TmapBatch tm;
+    memset(&tm, 0, sizeof tm);
+    psk::GaussBatch gb{};
+    gb.nmsg = n; gb.R = R;
+    size_t smem = 0;
+    unsigned stride = 0;
+    int lagmax = 1, items = 0;
+    for (int i = 0; i < n; ++i) {
+      const DevPlan &dp = *jobs[i]->dp;
+      const psg::MessagePlan &h = dp.host;
+      const int EHP = (h.EH + 7) & ~7;
+      const int nx = ((int)h.fx.size() - 1) / 2;
+      cuuint64_t dims[3] = {(cuuint64_t)h.EH, (cuuint64_t)h.EW, (cuuint64_t)R};
+      cuuint64_t strides[2] = {(cuuint64_t)EHP * sizeof(float), (cuuint64_t)h.EW * EHP * sizeof(float)};
+      cuuint32_t box[3] = {64, (cuuint32_t)(64 + 2 * nx), 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = tensor_map_encoder()(&tm.t[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->slotU[i].p, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return c->fail(PS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+      psk::GaussMsg &g = gb.m[i];
+      g.out = c->slotV[i].as<float>();
+      g.taps_x = dp.fx(); g.taps_y = dp.fy();
+      g.walks = dp.walks.as<int>();
+      g.masks = (const unsigned char *)(dp.walks.as<int>() + 4 * (size_t)dp.nwalks);
+      g.oplane = (size_t)h.EH * dp.EP;
+      g.len_x = (int)h.fx.size(); g.len_y = (int)h.fy.size();
+      g.EH = h.EH; g.EW = h.EW; g.EP = dp.EP; g.nwalks = dp.nwalks; g.lag = h.lag; g.halo = h.halo;
+      g.item0 = items;
+      items += dp.nwalks * R;
+      unsigned stage;
+      fused_smem_bytes(h, stage);
+      stride = std::max(stride, (stage + 127u) & ~127u);
+      lagmax = std::max(lagmax, h.lag);
+    }
+    gb.total_items = items;
+    gb.stage_stride = stride;
+    gb.ring_rows = 64 * (lagmax + 1);
+    smem = 2 * (size_t)stride + (size_t)gb.ring_rows * psk::kRingPitch * sizeof(float);
+    if ((rc = take_work_counter(c, &gb.counter))) return rc;
+    // two blocks per SM when two fit beside their static shared memory, else one
+    const int bps = smem <= 108 * 1024 ? 2 : 1;
+    const int grid = std::min(items, c->num_sms * bps);
+    if (c->cfg.fast_math)
+      PS_LAUNCH(c, KC_GAUSS_XY, psk::k_gauss_xy<true><<<grid, 288, smem, st>>>(tm, gb, PS_NEGZERO2));
+    else
+      PS_LAUNCH(c, KC_GAUSS_XY, psk::k_gauss_xy<false><<<grid, 288, smem, st>>>(tm, gb, PS_NEGZERO2));
+  }
+  // stage 4: bilinear read-back into the image frame, V[i] -> B[i]
+  {
+    psk::ResampleBatch rb{};
+    rb.R = R; rb.tr = 0; rb.zgroups = R / RG;
+    for (int i = 0; i < n; ++i) {
+      const DevPlan &dp = *jobs[i]->dp;
+      const psg::MessagePlan &h = dp.host;
+      psk::ResampleMsg &m = rb.m[i];
+      m.src = c->slotV[i].as<float>(); m.dst = c->slotB[i].as<float>();
+      memcpy(m.T.m, h.T34, sizeof m.T.m);
+      m.sh = h.EH; m.sw = h.EW; m.spitch = dp.EP; m.splane = (size_t)h.EH * dp.EP;
+      m.dh = H; m.dw = W; m.dpitch = W; m.dplane = c->HW;
+    }
+    PS_LAUNCH(c, KC_WARP_BACK, psk::k_resample_bilinear_b<RG><<<dim3(cdiv(W, 16), cdiv(H, 16), n * (R / RG)), dim3(16, 16), 0, st>>>(rb));
+  }
+  // stage 5: log, +M, shift, combine
+  {
+    psk::EpiBatch eb{};
+    for (int i = 0; i < n; ++i) {
+      const DevPlan &dp = *jobs[i]->dp;
+      const Sink &sink = jobs[i]->sink;
+      psk::EpiArgs &e = eb.a[i];
+      e.src = c->slotB[i].as<float>();
+      e.general = 0;
+      e.xout = dp.xout(R, H, W); e.yout = dp.yout(R, H, W);
+      e.shift_xy = dp.out_shift(R, H, W);
+      e.max_enc = jobs[i]->in_max;
+      e.R = R; e.H = H; e.W = W;
+      e.out0 = sink.out0; e.acc0 = sink.acc0; e.add0 = sink.add0;
+      e.out1 = sink.out1; e.add1 = sink.add1;
+      e.max0 = sink.max0; e.max1 = sink.max1;
+      e.amax0 = sink.amax0;
+    }
+    const int XG = W / 4;
+    PS_LAUNCH(c, KC_EPILOGUE, psk::k_epilogue3<<<dim3(cdiv((size_t)XG * H, 256), R, n), 256, 0, st>>>(eb, psk::FastDiv((unsigned)XG)));
+  }
+  return PS_OK;
+}
+
+// All messages of one tree level.  Messages the batched route cannot take (diagonal covariance, unaligned or
+// non-shift cases, filters beyond the shared-memory ring) go through run_message one by one.
+int run_level(ps_ctx *c, std::vector<MsgJob> &jobs) {
+  std::vector<MsgJob *> batch;
+  for (MsgJob &j : jobs) {
+    if (can_batch(c, j)) {
+      batch.push_back(&j);
+    } else {
+      int rc = run_message(c, *j.dp, j.in, j.in_max, j.sparse, j.sink);
+      if (rc) return rc;
+    }
+  }
+  for (size_t i = 0; i < batch.size();) {
+    size_t k = i + 1;
+    while (k < batch.size() && k - i < (size_t)psk::kMaxBatch && batch[k]->sparse == batch[i]->sparse) ++k;
+    int rc = run_batch(c, &batch[i], (int)(k - i));
+    if (rc) return rc;
+    i = k;
   }
   return PS_OK;
 }
@@ -811,6 +1083,26 @@ int ps_plan_work_lists(const ps_config *cfg, const double C[4], double scale, in
   };
   put(p.xtiles, xlist);
   put(p.ytiles, ylist);
+  return PS_OK;
+}
+
+int ps_plan_walks(const ps_config *cfg, const double C[4], double scale, int dims[7], int *walks, int cap,
+                  unsigned char *masks, int mask_cap, int *nmasks) {
+  if (!cfg || !C || !dims || !nmasks || cap < 0 || mask_cap < 0 || (cap > 0 && !walks) || (mask_cap > 0 && !masks))
+    return PS_ERR_INVALID;
+  if (cfg->num_rotation_steps < 1 || cfg->height < 1 || cfg->width < 1 || !(scale > 0)) return PS_ERR_INVALID;
+  psg::Grid g;
+  g.R = cfg->num_rotation_steps; g.H = cfg->height; g.W = cfg->width;
+  g.min_rot = cfg->min_part_rotation; g.max_rot = cfg->max_part_rotation;
+  const double zero[2] = {0.0, 0.0};
+  const psg::MessagePlan p = psg::plan_message(g, zero, zero, C, 0.0, 0.0, scale);
+  if (!p.error.empty() || p.diag) return PS_ERR_INVALID;
+  dims[0] = p.EH; dims[1] = p.EW;
+  dims[2] = ((int)p.fx.size() - 1) / 2; dims[3] = ((int)p.fy.size() - 1) / 2;
+  dims[4] = p.halo; dims[5] = p.lag; dims[6] = (int)p.walks.size() / 4;
+  for (size_t i = 0; i < p.walks.size() && (int)(i / 4) < cap; ++i) walks[i] = p.walks[i];
+  for (size_t i = 0; i < p.xmasks.size() && (int)i < mask_cap; ++i) masks[i] = p.xmasks[i];
+  *nmasks = (int)p.xmasks.size();
   return PS_OK;
 }
 
@@ -974,6 +1266,10 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
   c->disable_tile_lists = getenv("PSINFER_ALL_TILES") != nullptr;
+  c->disable_batch = getenv("PSINFER_NO_BATCH") != nullptr;
+  if (!cu(cudaFuncSetAttribute(psk::k_gauss_xy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
+      !cu(cudaFuncSetAttribute(psk::k_gauss_xy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr"))
+    return PS_ERR_CUDA;
   if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
@@ -1089,7 +1385,16 @@ int ps_set_joints(ps_ctx *c, const ps_joint *joints, int nj) {
   int rc = ensure_scratch(c, need);
   if (rc) return rc;
   size_t nroot = nodes[c->root].children.size();
-  if (c->rootmsg.bytes < nroot * c->N * sizeof(float)) PS_CUDA(c, c->rootmsg.alloc(nroot * c->N * sizeof(float)));
+  if (c->rootmsg.bytes < nroot * c->N * sizeof(float)) {
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PS_CUDA(c, c->rootmsg.alloc(nroot * c->N * sizeof(float)));
+  }
+  bool deep = false;
+  for (int q : nodes[c->root].children) deep = deep || !nodes[q].children.empty();
+  if (deep && c->chain_tmp.bytes < nroot * c->N * sizeof(float)) {
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PS_CUDA(c, c->chain_tmp.alloc(nroot * c->N * sizeof(float)));
+  }
   c->plans = std::move(plans);
   c->nodes = std::move(nodes);
   c->joints.assign(joints, joints + nj);
@@ -1224,22 +1529,53 @@ int ps_get_unary(ps_ctx *c, int part, int scale, float *dst, int mem_kind) {
   return PS_OK;
 }
 
+// Stream-ordered staging for host tables / grids: the copy, the kernel that reads it and the next call's copy are all
+// on ctx->stream, and cudaMemcpyAsync from pageable memory returns once the source has been staged -- no host
+// synchronisation is needed (growing the buffer is the exception).
+static int stage_host(ps_ctx *c, DevBuf &buf, size_t &used, const float *src, size_t n, const float **dev) {
+  if (buf.bytes < (used + n) * sizeof(float)) return c->fail(PS_ERR_INVALID, "staging buffer too small");
+  float *d = buf.as<float>() + used;
+  PS_CUDA(c, cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  used += n;
+  *dev = d;
+  return PS_OK;
+}
+
+int ps_add_unary_tables(ps_ctx *c, int part, int n, const float *const *tables, const int *kinds, const float *weights,
+                        int mem_kind) {
+  if (!c || !tables || !kinds || !weights) return PS_ERR_INVALID;
+  if (part < 0 || part >= c->P) return c->fail(PS_ERR_INVALID, "part out of range");
+  if (n < 1 || n > psk::kMaxTables) return c->fail(PS_ERR_INVALID, "1 to %d tables per call", psk::kMaxTables);
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  size_t need = 0;
+  for (int k = 0; k < n; ++k) {
+    if (!tables[k]) return PS_ERR_INVALID;
+    if (kinds[k] < 0 || kinds[k] > 2) return c->fail(PS_ERR_INVALID, "table_kind must be 0, 1 or 2");
+    need += kinds[k] == 0 ? (size_t)c->R : c->HW;
+  }
+  for (int s2 = 0; s2 < c->S; ++s2) c->unary_max_valid[(size_t)part * c->S + s2] = 0;
+  psk::TableArgs a{};
+  a.n = n;
+  if (mem_kind == PS_MEM_HOST && c->table_stage.bytes < need * sizeof(float)) {
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PS_CUDA(c, c->table_stage.alloc(need * sizeof(float)));
+  }
+  size_t used = 0;
+  for (int k = 0; k < n; ++k) {
+    a.kind[k] = kinds[k];
+    a.weight[k] = weights[k];
+    a.table[k] = tables[k];
+    if (mem_kind == PS_MEM_HOST)
+      if (int rc = stage_host(c, c->table_stage, used, tables[k], kinds[k] == 0 ? (size_t)c->R : c->HW, &a.table[k])) return rc;
+  }
+  for (int s = 0; s < c->S; ++s)
+    PS_LAUNCH(c, KC_MISC, psk::k_add_tables<<<dim3(std::min(cdiv(c->HW, 256), 1024u), c->R), 256, 0, c->stream>>>(c->U(part, s), c->R, c->HW, a));
+  return PS_OK;
+}
+
 int ps_add_unary_table(ps_ctx *c, int part, const float *table, int kind, float weight) {
   if (!c || !table) return PS_ERR_INVALID;
-  if (part < 0 || part >= c->P) return c->fail(PS_ERR_INVALID, "part out of range");
-  for (int s2 = 0; s2 < c->S; ++s2) c->unary_max_valid[(size_t)part * c->S + s2] = 0;
-  if (kind < 0 || kind > 2) return c->fail(PS_ERR_INVALID, "table_kind must be 0, 1 or 2");
-  PS_CUDA(c, cudaSetDevice(c->cfg.device));
-  size_t n = kind == 0 ? (size_t)c->R : c->HW;
-  DevBuf d;
-  PS_CUDA(c, d.alloc(n * sizeof(float)));
-  PS_CUDA(c, cudaMemcpyAsync(d.p, table, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  for (int s = 0; s < c->S; ++s) {
-    PS_LAUNCH(c, KC_MISC, psk::k_add_table<<<dim3(std::min(cdiv(c->HW, 256), 1024u), c->R), 256, 0, c->stream>>>(c->U(part, s), c->R, c->HW,
-                                                                                       d.as<float>(), kind, weight));
-  }
-  PS_CUDA(c, cudaStreamSynchronize(c->stream));
-  return PS_OK;
+  return ps_add_unary_tables(c, part, 1, &table, &kind, &weight, PS_MEM_HOST);
 }
 
 int ps_add_unary_grid(ps_ctx *c, int part, const float *grid, int num_rot, int mode, float weight, int mem_kind) {
@@ -1249,17 +1585,19 @@ int ps_add_unary_grid(ps_ctx *c, int part, const float *grid, int num_rot, int m
   if (mode < 0 || mode > 1) return c->fail(PS_ERR_INVALID, "mode must be 0 (log-domain add) or 1 (raw DPM scores)");
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   for (int s2 = 0; s2 < c->S; ++s2) c->unary_max_valid[(size_t)part * c->S + s2] = 0;
-  DevBuf d;
   const float *dg = grid;
   if (mem_kind == PS_MEM_HOST) {
-    PS_CUDA(c, d.alloc((size_t)num_rot * c->HW * sizeof(float)));
-    PS_CUDA(c, cudaMemcpyAsync(d.p, grid, (size_t)num_rot * c->HW * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    dg = d.as<float>();
+    const size_t n = (size_t)num_rot * c->HW;
+    if (c->grid_stage.bytes < n * sizeof(float)) {
+      PS_CUDA(c, cudaStreamSynchronize(c->stream));
+      PS_CUDA(c, c->grid_stage.alloc(n * sizeof(float)));
+    }
+    size_t used = 0;
+    if (int rc = stage_host(c, c->grid_stage, used, grid, n, &dg)) return rc;
   }
   for (int s = 0; s < c->S; ++s)
     PS_LAUNCH(c, KC_MISC, psk::k_add_grid<<<dim3(std::min(cdiv(c->HW, 256), 1024u), c->R), 256, 0, c->stream>>>(
                               c->U(part, s), c->R, c->HW, dg, num_rot, mode, weight));
-  PS_CUDA(c, cudaStreamSynchronize(c->stream));
   return PS_OK;
 }
 
@@ -1488,14 +1826,18 @@ int ps_infer(ps_ctx *c, int flags) {
     unsigned long long *keys = last_scale ? c->argmax_keys.as<unsigned long long>() : nullptr;
 
     // ---------------- upward pass (findrot.cpp:582-658) ----------------
-    // Every root child heads a chain; chains are independent, so they are walked one after another.
+    // Every root child heads a chain; chains are independent, so level t carries the t-th message (counted from the
+    // leaf) of every chain that long, all in the same launches (run_level).
     // `belief[p]` is the grid MSG_up reads for part p, `bmax[p]` its encoded maximum.
     std::vector<const float *> belief(P, nullptr);
+    std::vector<std::vector<int>> chains(nrc);
+    size_t maxlen = 0;
     for (int ci = 0; ci < nrc; ++ci) {
       // collect the chain root-child -> ... -> leaf
-      std::vector<int> chain;
+      std::vector<int> &chain = chains[ci];
       for (int q = rn.children[ci]; q >= 0; q = c->nodes[q].children.empty() ? -1 : c->nodes[q].children[0])
         chain.push_back(q);
+      maxlen = std::max(maxlen, chain.size());
       const int leaf = chain.back();
       // leaf belief: 0 + unary (is_detect) or all zeros
       if (c->cfg.is_detect[leaf]) {
@@ -1512,21 +1854,30 @@ int ps_infer(ps_ctx *c, int flags) {
       } else if ((rc = grid_max(c, belief[leaf], N, c->MAXP(leaf)))) {
         return rc;
       }
-      for (int k = (int)chain.size() - 1; k >= 0; --k) {
-        const int child = chain[k];
+    }
+    for (size_t t = 0; t < maxlen; ++t) {
+      std::vector<MsgJob> jobs;
+      for (int ci = 0; ci < nrc; ++ci) {
+        const std::vector<int> &chain = chains[ci];
+        if (chain.size() <= t) continue;
+        const int child = chain[chain.size() - 1 - t];
         const int parent = c->nodes[child].parent;
-        DevPlan &dp = *c->plans[((size_t)c->nodes[child].joint * 2 + 0) * S + s];
-        Sink sink;
+        MsgJob job;
+        job.dp = c->plans[((size_t)c->nodes[child].joint * 2 + 0) * S + s].get();
+        job.in = belief[child];
+        job.in_max = c->MAXP(child);
+        job.sparse = sparse;
         if (parent == root) {
-          sink.out0 = c->rootmsg.as<float>() + (size_t)ci * N;  // combined later, in joint order
+          job.sink.out0 = c->rootmsg.as<float>() + (size_t)ci * N;  // combined later, in joint order
         } else {
-          sink.out0 = c->POST(parent, s);
-          if (c->cfg.is_detect[parent]) sink.add0 = c->U(parent, s);  // :652-654
-          sink.max0 = c->MAXP(parent);
-          belief[parent] = sink.out0;
+          job.sink.out0 = c->POST(parent, s);
+          if (c->cfg.is_detect[parent]) job.sink.add0 = c->U(parent, s);  // :652-654
+          job.sink.max0 = c->MAXP(parent);
+          belief[parent] = job.sink.out0;
         }
-        if ((rc = run_message(c, dp, belief[child], c->MAXP(child), sparse, sink))) return rc;
+        jobs.push_back(job);
       }
+      if ((rc = run_level(c, jobs))) return rc;
     }
     // root: post = sum of messages (joint order) + unary; fr_j = sum_{i != j} + unary (:637-654, :169)
     {
@@ -1552,33 +1903,34 @@ int ps_infer(ps_ctx *c, int flags) {
     }
 
     // ---------------- downward pass (computePartMarginals, findrot.cpp:158-236) ----------------
-    for (int ci = 0; ci < nrc; ++ci) {
-      const float *in = c->rootmsg.as<float>() + (size_t)ci * N;
-      const int *in_max = c->MAXP(P + ci);
-      int tsel = 0;
-      for (int q = rn.children[ci]; q >= 0;) {
+    // Level t carries the message into the t-th node of every chain.  A chain's inputs alternate between its root
+    // message buffer (fr_j, consumed by level 0) and its chain_tmp grid.
+    for (size_t t = 0; t < maxlen; ++t) {
+      std::vector<MsgJob> jobs;
+      for (int ci = 0; ci < nrc; ++ci) {
+        const std::vector<int> &chain = chains[ci];
+        if (chain.size() <= t) continue;
+        const int q = chain[t];
         const Node &nq = c->nodes[q];
-        DevPlan &dp = *c->plans[((size_t)nq.joint * 2 + 1) * S + s];
-        Sink sink;
+        float *const bufs[2] = {c->rootmsg.as<float>() + (size_t)ci * N, c->chain_tmp.as<float>() + (size_t)ci * N};
+        MsgJob job;
+        job.dp = c->plans[((size_t)nq.joint * 2 + 1) * S + s].get();
+        job.in = bufs[t & 1];
+        job.in_max = t == 0 ? c->MAXP(P + ci) : c->MAXP(P + psk::kMaxRootChildren + chain[t - 1]);
+        job.sparse = false;
         // post[q] += from_root[q] (:201).  For a leaf, post[q] is still "0 + unary" held in the unary itself.
-        sink.out0 = c->POST(q, s);
-        sink.acc0 = belief[q];
-        sink.amax0 = keys ? keys + q : nullptr;  // post[q] is final here: fold the readout's argmax into this write
-        int next = nq.children.empty() ? -1 : nq.children[0];
-        if (next >= 0) {
+        job.sink.out0 = c->POST(q, s);
+        job.sink.acc0 = belief[q];
+        job.sink.amax0 = keys ? keys + q : nullptr;  // post[q] is final here: fold the readout's argmax into this write
+        if (t + 1 < chain.size()) {
           // tmp = unary[q] + from_root[q] (:221-222), input of the next message
-          sink.out1 = c->tmp[tsel].as<float>();
-          sink.add1 = c->U(q, s);
-          sink.max1 = c->MAXP(P + psk::kMaxRootChildren + q);
+          job.sink.out1 = bufs[(t + 1) & 1];
+          job.sink.add1 = c->U(q, s);
+          job.sink.max1 = c->MAXP(P + psk::kMaxRootChildren + q);
         }
-        if ((rc = run_message(c, dp, in, in_max, false, sink))) return rc;
-        if (next >= 0) {
-          in = sink.out1;
-          in_max = sink.max1;
-          tsel ^= 1;
-        }
-        q = next;
+        jobs.push_back(job);
       }
+      if ((rc = run_level(c, jobs))) return rc;
     }
 
     // root rotation-marginal of this scale (findrot.cpp:694-726)
@@ -1679,7 +2031,11 @@ int ps_message(ps_ctx *c, const float *child, float *parent, int mem_kind, const
   if (rc) return rc;
   Sink sink;
   sink.out0 = dout;
-  if ((rc = run_message(c, dp, din, mx, sparse != 0, sink))) return rc;
+  {
+    std::vector<MsgJob> jobs(1);
+    jobs[0].dp = &dp; jobs[0].in = din; jobs[0].in_max = mx; jobs[0].sparse = sparse != 0; jobs[0].sink = sink;
+    if ((rc = run_level(c, jobs))) return rc;
+  }
   if (mem_kind == PS_MEM_HOST)
     PS_CUDA(c, cudaMemcpyAsync(parent, dout, c->N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   PS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1706,7 +2062,9 @@ int ps_pos_message(ps_ctx *c, float *child, float *parent, int mem_kind, const d
   PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mx, 1, psk::enc_f(0.0f)));
   Sink sink;
   sink.out0 = dout;
-  int rc = run_message(c, *plan, din, mx, sparse != 0, sink);
+  std::vector<MsgJob> jobs(1);
+  jobs[0].dp = plan.get(); jobs[0].in = din; jobs[0].in_max = mx; jobs[0].sparse = sparse != 0; jobs[0].sink = sink;
+  int rc = run_level(c, jobs);
   if (rc) return rc;
   // the reference leaves log(exp(child)) in its first argument (:88)
   PS_LAUNCH(c, KC_MISC, psk::k_exp_log<<<std::min(cdiv(c->N, 256), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(din, c->N));

@@ -248,6 +248,23 @@ class PsContext:
         t = _f32(table)
         self._check(self.lib.ps_add_unary_table(self.h, part, t.ctypes.data_as(C.POINTER(C.c_float)), kind, weight))
 
+    def add_unary_tables(self, part, tables, kinds, weights, pointers=None, device=False):
+        """Up to 4 conditioning tables applied in order in one pass (rotation score, position score, torso prior:
+        findrot.cpp:913-949).  `tables`: numpy arrays, or -- with `pointers` -- raw addresses of float32 tables that
+        already live in device memory (device=True) or in pinned host memory (device=False)."""
+        n = len(kinds)
+        keep = None
+        if pointers is None:
+            keep = [_f32(t) for t in tables]
+            pointers = [t.ctypes.data for t in keep]
+        ptrs = (C.c_void_p * n)(*[int(p) for p in pointers])
+        ks = (C.c_int * n)(*[int(k) for k in kinds])
+        ws = (C.c_float * n)(*[float(w) for w in weights])
+        self._check(self.lib.ps_add_unary_tables(self.h, part, n, ptrs, ks, ws,
+                                                 capi.PS_MEM_DEVICE if device else capi.PS_MEM_HOST))
+        if keep is not None:
+            self.synchronize()   # pageable sources are staged at call time; stay conservative for numpy temporaries
+
     # host builders of the conditioning tables (same arithmetic as the reference, which builds them on the CPU)
     def rot_score_table(self, mu, var):
         """getRotScoreGrid (objectdetect_icps.cpp:228-281): table[R] for one part."""

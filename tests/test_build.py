@@ -98,11 +98,11 @@ def test_gaussian_kernels_keep_both_roundings(pslib):
     seen = fast = 0
     for k in kernels[1:]:
         name = k.split("\n", 1)[0]
-        if not any(t in name for t in ("k_conv_cols2", "k_conv_rows2", "k_rotconv3", "k_conv_cols_tma", "k_rotconv4")):
+        if not any(t in name for t in ("k_conv_cols2", "k_conv_rows2", "k_rotconv3", "k_conv_cols_tma", "k_rotconv4", "k_gauss_xy")):
             continue
         ffma2, fadd2 = len(re.findall(r"\bFFMA2\b", k)), len(re.findall(r"\bFADD2\b", k))
         assert not re.search(r"\bFFMA\b", k), "%s contains a scalar FFMA" % name
-        if re.search(r"k_conv_cols_tma2ILi\d+ELb1E|k_rotconv4I.*ELb1EEE", name):  # the ps_config.fast_math instantiations
+        if re.search(r"k_conv_cols_tma2ILi\d+ELb1E|k_rotconv4I.*ELb1EEE|k_gauss_xyILb1E", name):  # the ps_config.fast_math instantiations
             fast += 1
             assert ffma2 > 0 and fadd2 == 0, "%s: fast-math variant with %d FADD2" % (name, fadd2)
             continue
@@ -127,8 +127,15 @@ def test_kernel_footprints_leave_room_for_co_resident_blocks(pslib):
     assert len(conv) == 2 and max(conv) <= 56, conv
     full = [r for n, r in regs.items() if "k_resample_bilinearILi8ELb1" in n or "k_warp_direct2ILi8ELb1" in n]
     assert len(full) == 2 and max(full) <= 32, full
-    assert all(r <= 40 for n, r in regs.items() if "k_epilogue3" in n or "k_rotconv4ILi24E" in n)   # the cfg-2 shapes
+    full = [r for n, r in regs.items() if "k_resample_bilinear_bILi8" in n or "k_warp_direct_bILi8" in n]   # level-batched
+    assert len(full) == 2 and max(full) <= 32, full
+    # the cfg-2 shapes (the fused-multiply-add build of the 7-tap rotation filter may take 48)
+    assert all(r <= 40 for n, r in regs.items() if "k_epilogue3" in n or ("k_rotconv4ILi24E" in n and "ELb0EEE" in n))
+    assert all(r <= 48 for n, r in regs.items() if "k_rotconv4ILi24E" in n)
+    # fused x+y Gaussian: two blocks of 288 threads must fit the register file (65536 / 576 = 113)
+    fused = [r for n, r in regs.items() if "k_gauss_xy" in n]
+    assert len(fused) == 2 and max(fused) <= 112, fused
     sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     for k in re.split(r"\n\s*Function : ", sass)[1:]:
-        if "k_conv_cols_tma2ILi8" in k.split("\n", 1)[0]:
+        if "k_conv_cols_tma2ILi8" in k.split("\n", 1)[0] or "k_gauss_xy" in k.split("\n", 1)[0]:
             assert "UTMALDG.3D" in k and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in k and "NANOSLEEP.SYNCS" in k

@@ -314,3 +314,77 @@ def test_work_lists_cover_every_cell_the_read_back_touches(k):
     assert not (need_x[:EH, :EW] & ~xcov[:EH, :EW]).any(), "an x-pass output the y pass reads is not in the x list"
     if min(H, W) >= 256:                                # the point of the lists: the work stays close to the image's
         assert ycov[:EH, :EW].sum() <= 1.5 * H * W and xcov[:EH, :EW].sum() <= 1.8 * H * W
+
+
+def _walks(H, W, Cm, scale=1.0):
+    import ctypes
+    from partapp_b200 import ExpParam, capi
+    from partapp_b200.objectdetect import PartConf, make_config
+    lib = capi.load_library()
+    cfg = make_config(ExpParam(num_rotation_steps=8), PartConf([True], [False], [True]), H, W)
+    dims = (ctypes.c_int * 7)()
+    cap, mcap = 4096, 1 << 16
+    wl = (ctypes.c_int * (4 * cap))()
+    ml = (ctypes.c_ubyte * mcap)()
+    nm = ctypes.c_int(0)
+    Cc = (ctypes.c_double * 4)(*np.asarray(Cm, np.float64).ravel())
+    rc = lib.ps_plan_walks(ctypes.byref(cfg), Cc, scale, dims, wl, cap, ml, mcap, ctypes.byref(nm))
+    assert rc == 0
+    EH, EW, nx, ny, halo, lag, nw = [int(v) for v in dims]
+    assert nw <= cap and nm.value <= mcap
+    return EH, EW, nx, ny, halo, lag, np.array(wl[:4 * nw], np.int64).reshape(-1, 4), np.array(ml[:nm.value], np.uint8)
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_fused_gaussian_walks_cover_every_cell_the_read_back_touches(k):
+    """The walks of the fused x+y Gaussian kernel (k_gauss_xy) against the same brute-force statement: every
+    eigen-frame cell the bilinear read-back touches lies in its strip's y interval, every x-filtered value within the y
+    reach of such a cell (same column) lies in an x block whose mask keeps its 8-column group, the ring of 64 (K + 1)
+    rows holds a whole y window, and each strip appears once, longest first."""
+    rng = np.random.default_rng(900 + k)
+    H, W = [(150, 230), (260, 140), (64, 64), (600, 400), (33, 500), (129, 191), (400, 37), (300, 300), (90, 70),
+            (512, 256)][k]
+    th = rng.uniform(0, np.pi) if k else 0.6
+    s1, s2 = rng.uniform(1.0, 12.0, 2)
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    Cm = Rm @ np.diag([s1 * s1, s2 * s2]) @ Rm.T
+    Cm[1, 0] = Cm[0, 1]
+    scale = [1.0, 1.2, 0.8][k % 3]
+    EH, EW, nx, ny, halo, lag, walks, masks = _walks(H, W, Cm, scale)
+    _, _, _, _, T34, _, _ = _work_lists(H, W, Cm, scale)
+    assert halo % 8 == 0 and ny <= halo < ny + 8 and 64 * lag >= ny + halo and 64 * (lag - 1) < ny + halo
+    assert 64 * (lag + 1) >= 64 + 2 * ny                 # a y window of 64 + 2 ny rows fits the ring
+    assert len(set(walks[:, 0].tolist())) == len(walks) and (np.diff(walks[:, 2]) <= 0).all()
+    pad = 64 * (lag + 2)
+    ycov = np.zeros((EH + 2 * pad, EW + 64), bool)       # [ey + pad][ex]
+    xcov = np.zeros_like(ycov)
+    for strip, row0, ng, moff in walks:
+        assert row0 % 8 == 0 and ng >= 1
+        ycov[pad + row0:pad + row0 + 8 * ng, strip * 64:strip * 64 + 64] = True
+        nxb = (ng + 7) // 8 + lag
+        for j in range(nxb):
+            r0 = row0 - halo + 64 * j
+            for g in range(8):
+                if masks[moff + j] >> g & 1:
+                    xcov[pad + r0:pad + r0 + 64, strip * 64 + 8 * g:strip * 64 + 8 * g + 8] = True
+        # the last y block's window ends inside the last x block
+        assert row0 + 8 * ng - 1 + ny <= row0 - halo + 64 * nxb - 1
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    x1 = T34[0] * xx + T34[1] * yy + T34[2]
+    y1 = T34[3] * xx + T34[4] * yy + T34[5]
+    ix, iy = np.floor(x1).astype(np.int64), np.floor(y1).astype(np.int64)
+    touched = np.zeros_like(ycov)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            cx, cy = ix + dx, iy + dy
+            ok = (cx >= 0) & (cx < EW) & (cy >= 0) & (cy < EH)
+            touched[cy[ok] + pad, cx[ok]] = True
+    assert not (touched & ~ycov).any(), "a cell the read-back touches is not in a walk"
+    need_x = np.zeros_like(touched)
+    for ex in np.flatnonzero(touched.any(axis=0)):
+        rows = np.flatnonzero(touched[:, ex]) - pad
+        lo, hi = max(0, rows.min() - ny), min(EH - 1, rows.max() + ny)   # rows outside the grid are zeros by construction
+        need_x[pad + lo:pad + hi + 1, ex] = True
+    assert not (need_x & ~xcov).any(), "an x-filtered value the y pass reads is masked out"
+    if min(H, W) >= 256:
+        assert ycov[pad:pad + EH, :EW].sum() <= 1.5 * H * W and xcov[pad:pad + EH, :EW].sum() <= 1.9 * H * W
