@@ -37,11 +37,18 @@ METRIC = "ps_inference_images_per_sec"
 UNIT = "images/s"
 
 
+WORKLOAD_TEXT = {
+    "cfg2": "configs[1]: synthetic LSP-shape image, 10-part tree (root 4), R=24 x S=1, 600x400 grid, generic "
+            "full-covariance joints (sigma 4-16 px), stride-4 sparse unaries",
+    "cfg4": "configs[3]: poselet-conditioned full model, 22-part tree (root 10), R=24 x S=1, 600x400 grid; per image every "
+            "joint is drawn from an 8-entry type table (whole joint swapped, aux.cpp:76-99) and every part's unary is "
+            "conditioned by a rotation score and a position score / the torso prior (findrot.cpp:913-949)",
+    "cfg5": "configs[4]: stress state space, 10-part tree, R=48 x S=5, 1000x1000 grid, marginals + argmax readout"}
+WORKLOAD_NAME = ["cfg2"]
+
+
 def workload_config(parallelism, extra=None):
-    cfg = {"workload": "configs[1]: synthetic LSP-shape image, 10-part tree (root 4), R=24 x S=1, 600x400 grid, "
-                       "generic full-covariance joints (sigma 4-16 px), stride-4 sparse unaries"
-                       if (WORKLOAD["P"], WORKLOAD["R"], WORKLOAD["S"]) == (10, 24, 1) else
-                       "manual run of another BASELINE.json config (not the contract workload)",
+    cfg = {"workload": WORKLOAD_TEXT[WORKLOAD_NAME[0]],
            "R": WORKLOAD["R"], "S": WORKLOAD["S"], "H": WORKLOAD["H"], "W": WORKLOAD["W"], "P": WORKLOAD["P"],
            "parallelism": parallelism,
            "l2_policy": "inputs larger than L2: ~0.75 GB of grids touched per image vs 126 MB L2; distinct images per step"}
@@ -134,6 +141,14 @@ def make_inputs(n_images, first_index):
     return ep, pc, joints, raws, Tig
 
 
+def n_msg_of(klass, prof, n_msg, n_img):
+    """Messages per image that go through kernel class `klass` (upward messages use the direct warp, downward ones the
+    bilinear warp; every message passes the other stages once)."""
+    if klass in ("warp_direct", "warp_bilinear"):
+        return n_msg / 2.0
+    return float(n_msg)
+
+
 def run_ours(args):
     import torch
     from partapp_b200 import PsContext, capi
@@ -189,6 +204,32 @@ def run_ours(args):
         from partapp_b200 import synth as _s
         type_tables = [_s.make_joints(P, seed=7, type_id=t) for t in range(8)]
     results = np.zeros((B, P, 7), np.float32)
+    # configs[3] also conditions the unaries per image (findrot.cpp:913-949): a rotation score for every part, a position
+    # score for every non-root part, the torso prior for the root.  The predictors that produce the parameters are
+    # outside the path (MATLAB); the tables are inputs, drawn per image from a pool of 4 per part.
+    cond = None
+    if args.workload == "cfg4":
+        from partapp_b200 import synth as _s
+        _, root = _s.tree(P)
+        c0 = ctxs[0]
+        cond = {"dev": [], "pin": [], "kinds": [], "weights": []}
+        for p in range(P):
+            dv, pn = [], []
+            for v in range(4):
+                rng = np.random.default_rng([4242, p, v])
+                rot = c0.rot_score_table(rng.uniform(-1, 1), rng.uniform(0.05, 0.5))
+                if p == root:
+                    pos = c0.torso_prior_table(rng.uniform(-20, 20), rng.uniform(-20, 20), 8000.0, 12000.0, 0.7)
+                else:
+                    pos = c0.pos_score_table(rng.uniform(-80, 80), rng.uniform(-80, 80), 2500.0, 4900.0, w["W"] / 2, w["H"] / 2)
+                tabs = [torch.from_numpy(rot), torch.from_numpy(pos.reshape(-1))]
+                dv.append([t.cuda() for t in tabs])
+                pn.append([t.pin_memory() for t in tabs])
+            cond["dev"].append(dv)
+            cond["pin"].append(pn)
+            cond["kinds"].append([0, 2] if p == root else [0, 1])
+            cond["weights"].append([0.8, 1.0] if p == root else [0.8, 0.6])
+    cond_bytes = (P * (w["R"] + w["H"] * w["W"]) * 4) if cond else 0
 
     def step(device_resident):
         # software pipeline over ctxs: enqueue image i on ctx i % n_ctx; results are read (host sync) one image late
@@ -209,6 +250,11 @@ def run_ours(args):
                         c.set_unary_compact(p, sc, (gh, gw), Tig, device_ptr=ptr)
                     else:
                         c.set_unary_compact_pinned(p, sc, ptr, gh, gw, Tig)
+                if cond is not None:
+                    v = int(rng.integers(0, 4))
+                    tabs = (cond["dev"] if device_resident else cond["pin"])[p][v]
+                    c.add_unary_tables(p, None, cond["kinds"][p], cond["weights"][p],
+                                       pointers=[t.data_ptr() for t in tabs], device=device_resident)
             c.infer_async(sparse=True)
             pending.append((i, c))
         for j, cj in pending:
@@ -264,7 +310,13 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
 
     out = None
+    cpu_result = parity_check = None
     roofline_ctx_mode = args.fast_math
+
+    def feed_image0(c):
+        for p in range(P):
+            for sc in range(S):
+                c.set_unary_compact(p, sc, (gh, gw), Tig, device_ptr=dev_raw[0][p * S + sc].data_ptr())
     if rank == 0:
         peak, peak_src = read_peaks()
         # ---- instrumented pass: CUDA events around every launch of one ctx, for the per-kernel roofline ----
@@ -280,73 +332,88 @@ def run_ours(args):
         c.profile_enable(False)
         n_img_prof = min(B, 2)
         tot_ms = sum(v[0] for v in prof.values())
-        dom = max(prof.items(), key=lambda kv: kv[1][0])
         G = 4.0 * N
-        # per-message geometry from the library: filter-grid size (eigen-frame for full covariances) and tap counts
         J = P - 1
-        infos = [c.plan_info(j, d) for j in range(J) for d in (0, 1)]
+        # per-message geometry from the library: filter-grid size (eigen-frame for full covariances) and tap counts
+        infos = [c.plan_info(j, d, sc) for j in range(J) for d in (0, 1) for sc in range(S)]
+        n_msg = 2 * J * S                                  # messages per image
         Ge = float(np.mean([4.0 * w["R"] * i["rows"] * i["cols"] for i in infos]))   # bytes of the filter grid
-        taps = {"rotconv": float(np.mean([N * max(i["rot_taps"], 0) for i in infos])),
-                "conv_rows": float(np.mean([w["R"] * i["x_cells"] * i["x_taps"] for i in infos])),
-                "conv_cols": float(np.mean([w["R"] * i["y_cells"] * i["y_taps"] for i in infos]))}
-        # algorithmic bytes per launch of each kernel class: each grid read once, written once
-        Gx = float(np.mean([4.0 * w["R"] * i["x_cells"] for i in infos]))   # the cells the work lists keep: each is
-        Gy = float(np.mean([4.0 * w["R"] * i["y_cells"] for i in infos]))   # read once and written once by its pass
-        alg_per_launch = {"conv_rows": 2 * Gx, "conv_cols": 2 * Gy, "rotconv": 2 * G, "epilogue": 3 * G,
-                          "warp_direct": G + Ge, "warp_bilinear": G + Ge, "warp_back": G + Ge, "prepare_unary": 2 * G,
-                          "grid_max": G, "root_combine": 12 * G, "argmax": G, "root_marginal": G}
-        dom_ms_per_launch = dom[1][0] / dom[1][1]
-        dom_bytes = alg_per_launch.get(dom[0], 2 * G)
-        achieved = dom_bytes / (dom_ms_per_launch * 1e-3) / 1e9
+        Gx = float(np.mean([4.0 * w["R"] * i["x_cells"] for i in infos]))   # the cells the work lists keep
+        Gy = float(np.mean([4.0 * w["R"] * i["y_cells"] for i in infos]))
+        taps_msg = float(np.mean([w["R"] * (i["x_cells"] * i["x_taps"] + i["y_cells"] * i["y_taps"]) for i in infos]))
+        MSG_CLASSES = ("rotconv", "warp_direct", "warp_bilinear", "conv_rows", "conv_cols", "gauss_xy", "warp_back", "epilogue")
+        msg_ms_img = sum(prof[k][0] for k in prof if k in MSG_CLASSES) / n_img_prof      # ms per image in message kernels
+        msg_ms = msg_ms_img / n_msg
+        # The contract's roofline object: SURVEY 8(d)'s per-unit figure is 3 G per message (read source, read destination,
+        # write destination).  The "kernel" is the message pipeline (five launches per tree level, each carrying every
+        # message of the level); achieved = algorithmic bytes of the messages of one image / their device time.
+        msg_alg = 3.0 * G
+        achieved = msg_alg / (msg_ms * 1e-3) / 1e9
+        traffic = traffic_ratio = None
+        tsrc = None
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                if "message" in tj:
+                    traffic = tj["message"]["dram_bytes"]
+                    traffic_ratio = round(traffic / msg_alg, 2)
+                    tsrc = "profiles/%s (ncu --set full, dram read+write summed over the launches of one level / messages)" % name
+                    break
+        # per-kernel detail: device time per launch, the bytes a launch must move at least, the fp32-pipe view of the taps
         FP32_PEAK = 18.0e12  # separately rounded mul+add pairs per second, profiles/r01_fp32_pipe_microbench.txt
-        fp32 = {}
-        for k, n_taps in taps.items():
-            if k in prof and prof[k][1]:
-                per_launch_s = prof[k][0] / prof[k][1] * 1e-3
-                fp32[k] = {"tap_outputs_per_launch": round(n_taps), "achieved_per_s": round(n_taps / per_launch_s, -9),
-                           "frac_of_measured_peak": round(n_taps / per_launch_s / FP32_PEAK, 3)}
-        msg_ms = sum(prof[k][0] for k in prof if k in ("rotconv", "warp_direct", "warp_bilinear", "conv_rows", "conv_cols",
-                                                          "gauss_xy", "warp_back", "epilogue")) / n_img_prof / (2 * J * S)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            key = "conv_cols" if dom[0] == "conv_rows" else dom[0]  # both Gaussian passes are k_conv_cols_tma
-            if key in tj:
-                traffic = tj[key]["dram_bytes_per_launch"]
-        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": traffic,
-                    "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram read+write per launch)",
+        dom = max(((k, v) for k, v in prof.items() if k in MSG_CLASSES), key=lambda kv: kv[1][0])
+        per_msg_bytes = {"gauss_xy": Gx + Gy, "conv_rows": 2 * Gx, "conv_cols": 2 * Gy, "rotconv": 2 * G, "epilogue": 3 * G,
+                         "warp_direct": G + Ge, "warp_bilinear": G + Ge, "warp_back": G + Ge}
+        kernels = {}
+        for k, (ms_k, n_k) in sorted(prof.items()):
+            d = {"ms_per_image": round(ms_k / n_img_prof, 4), "launches_per_image": round(n_k / n_img_prof, 1)}
+            if k in per_msg_bytes:
+                gbps = per_msg_bytes[k] * n_msg_of(k, prof, n_msg, n_img_prof) / (ms_k / n_img_prof * 1e-3) / 1e9
+                d["algorithmic_GBps"] = round(gbps, 1)
+                d["frac_of_hbm_peak"] = round(gbps / peak, 4)
+            kernels[k] = d
+        gauss_ms = sum(prof[k][0] for k in prof if k in ("gauss_xy", "conv_rows", "conv_cols")) / n_img_prof
+        fp32 = {"unit": "separately rounded multiply+add pairs (tap-outputs) per second", "peak": FP32_PEAK,
+                "peak_source": "measured, tools/mb_f32x2.cu",
+                "tap_outputs_per_message": round(taps_msg),
+                "achieved_per_s": round(taps_msg * n_msg / (gauss_ms * 1e-3), -9) if gauss_ms else None,
+                "frac_of_measured_peak": round(taps_msg * n_msg / (gauss_ms * 1e-3) / FP32_PEAK, 3) if gauss_ms else None}
+        roofline = {"bound": "hbm", "kernel": "message pipeline (rotation filter, resampling, fused x+y Gaussian, read-back, "
+                                              "epilogue; one launch of each per tree level)",
+                    "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": traffic, "traffic_over_algorithmic": traffic_ratio, "traffic_source": tsrc,
                     "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": round(dom_bytes), "ms_per_launch": round(dom_ms_per_launch, 4),
-                    "share_of_step": round(dom[1][0] / tot_ms, 3),
-                    "how": "CUDA events around every launch on the ctx stream (instrumented pass over %d images)" % n_img_prof,
-                    "kernel_ms_per_image": {k: round(v[0] / n_img_prof, 4) for k, v in sorted(prof.items())},
-                    "message": {"algorithmic_bytes": round(3 * G), "ms": round(msg_ms, 4),
-                                "achieved_GBps": round(3 * G / (msg_ms * 1e-3) / 1e9, 1),
-                                "frac": round(3 * G / (msg_ms * 1e-3) / 1e9 / peak, 4)},
+                    "algorithmic_bytes_per_message": round(msg_alg), "ms_per_message": round(msg_ms, 4),
+                    "messages_per_image": n_msg, "share_of_step": round(msg_ms_img * n_img_prof / tot_ms, 3),
+                    "how": "CUDA events around every launch on the ctx stream (instrumented pass over %d images, one image "
+                           "in flight); SURVEY 8(d): 3 G per message" % n_img_prof,
+                    "dominant_kernel": {"class": dom[0], "share_of_step": round(dom[1][0] / tot_ms, 3)},
+                    "kernels": kernels,
                     "whole_image": {"algorithmic_bytes": algorithmic_bytes_per_image(),
                                     "achieved_GBps": round(algorithmic_bytes_per_image() * value / world / 1e9, 1),
-                                    "frac": round(algorithmic_bytes_per_image() * value / world / 1e9 / peak, 4)},
-                    "fp32_pipe": {"unit": "separately rounded multiply+add pairs (tap-outputs) per second",
-                                  "peak": FP32_PEAK, "peak_source": "measured, tools/mb_f32x2.cu", "kernels": fp32},
+                                    "frac": round(algorithmic_bytes_per_image() * value / world / 1e9 / peak, 4),
+                                    "note": "B_img = S G (6J + 3P + 1) over the measured images/s (eight images in flight)"},
+                    "fp32_pipe": fp32,
                     "note": "bit-exact (parity) arithmetic keeps both roundings of every tap, which costs two fp32 pipe "
-                            "slots per tap-output: the Gaussian passes are bound by the fp32 pipe, not by HBM (DESIGN.md 5)"}
+                            "slots per tap-output: the Gaussian taps are bound by the fp32 pipe, not by HBM (DESIGN.md 5)"}
         cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and cond is None:
             from partapp_b200 import synth as _synth
-            cpu_baseline = run_cpu_sample(ep, pc, joints, _synth.raw_scores(ep, w["H"], w["W"], P, 0), threads=1)
+            cpu_baseline, cpu_result = run_cpu_sample(ep, pc, joints, _synth.raw_scores(ep, w["H"], w["W"], P, 0), threads=1)
+            parity_check = {ARITH_KEY[bool(args.fast_math)]: parity_against_cpu(ctxs[0], cpu_result, feed_image0)}
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": workload_config("images sharded over %d GPU(s), %d images/GPU/step, %d stream(s)/GPU, no collective"
                                          % (world, B, n_ctx)),
                "clocks": clocks,
-               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(B * P * S * NC * 4),
+               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(B * (P * S * NC * 4 + cond_bytes)),
                        "d2h_bytes_per_step": int(B * P * 7 * 4), "steps": e2e_steps,
                        "ms_per_step": round(ms_e2e / e2e_steps, 3)},
                "gpu_launches": int(launches),
+               "launches_per_image": round(launches / float(B * args.steps), 1),
                "roofline": roofline,
                "cpu_baseline": cpu_baseline}
     # ---- the other arithmetic mode, reported next to the headline (short run, same workload and protocol) ----
@@ -363,6 +430,8 @@ def run_ours(args):
         ms_oe = timed(n_oe, False)
         other = {"arithmetic": ARITH[not args.fast_math], "value": round(world * B * n_o / (ms_o / 1e3), 2),
                  "e2e": round(world * B * n_oe / (ms_oe / 1e3), 2), "unit": UNIT, "steps": n_o, "e2e_steps": n_oe}
+        if cpu_result is not None:
+            parity_check[ARITH_KEY[not args.fast_math]] = parity_against_cpu(ctxs[0], cpu_result, feed_image0)
     for c in ctxs:
         c.close()
     if dist is not None:
@@ -372,6 +441,8 @@ def run_ours(args):
         out["config"]["arithmetic"] = ARITH[bool(roofline_ctx_mode)]
         if other is not None:
             out["other_mode"] = other
+        if parity_check is not None:
+            out["parity_check"] = parity_check
         emit(out)
 
 
@@ -380,6 +451,7 @@ REF_CODE = {True: "the reference's own objectdetect_findrot.cpp::computeRotJoint
                   "oracle/_ref/libps_ref_drivers.so over container stand-ins (DESIGN.md 6)",
             False: "oracle/ps_oracle.cpp, the line-by-line restatement (bit-identical to the reference's code, ~2.5x faster: "
                    "no per-pixel BLAS calls and allocations)"}
+ARITH_KEY = {False: "parity", True: "fast_math"}
 ARITH = {False: "parity: every filter tap rounds product and sum separately, results bit-identical to the CPU reference",
          True: "fast_math: fused multiply-add taps, argmax identical, marginals within 1e-4 relative (north star bound)"}
 
@@ -393,13 +465,39 @@ def run_cpu_sample(ep, pc, joints, raw, threads=1):
     use_ref = refcore.drivers_available()
     t0 = time.perf_counter()
     if use_ref:
-        refcore.infer(ep, pc, joints, un, sparse=True)
+        res = refcore.infer(ep, pc, joints, un, sparse=True)
     else:
-        oracle.infer(ep, pc, joints, un, sparse=True, want_marginals=False)
+        res = oracle.infer(ep, pc, joints, un, sparse=True, want_marginals=True)
     dt = time.perf_counter() - t0
     return {"value": round(1.0 / dt, 5), "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
-            "sample": "1 full image of the same workload (18 messages + readout) on 1 thread: %.1f s" % dt,
-            "code": REF_CODE[use_ref]}
+            "sample": "1 full image of the same workload (%d messages + readout) on 1 thread: %.1f s"
+                      % (2 * (len(joints)) * un.shape[1], dt),
+            "code": REF_CODE[use_ref]}, res
+
+
+def parity_against_cpu(ctx, cpu, feed_image0):
+    """Image 0 through `ctx` against the CPU result computed for cpu_baseline: argmax records and every marginal cell."""
+    feed_image0(ctx)
+    ctx.infer(sparse=True)
+    best = ctx.best_conf()
+    P = best.shape[0]
+    out = {"argmax_equal": bool(np.array_equal(best[:, :6], cpu["best_conf"][:, :6])),
+           "argmax_rows_equal": int((best[:, :6] == cpu["best_conf"][:, :6]).all(axis=1).sum()), "parts": int(P),
+           "best_score_bits_equal": bool(np.array_equal(best[:, 6], cpu["best_conf"][:, 6]))}
+    worst, differing, cells = 0.0, 0, 0
+    S_last = cpu["marginals"].shape[0] - 1
+    for p in range(P):
+        g = ctx.marginal(p)
+        r = cpu["marginals"][S_last, p]
+        neq = g != r
+        differing += int(neq.sum())
+        cells += g.size
+        if neq.any():
+            worst = max(worst, float((np.abs(g[neq].astype(np.float64) - r[neq]) / np.maximum(np.abs(r[neq].astype(np.float64)), 1.0)).max()))
+    out.update({"marginal_cells": cells, "marginal_cells_differing": differing, "marginal_max_rel": worst,
+                "checked": "image 0 of the bench batch: best_conf and all %d marginals of the last scale vs the CPU run of "
+                           "cpu_baseline" % P})
+    return out
 
 
 def run_reference(args):
@@ -444,7 +542,7 @@ def run_reference(args):
         return 2
 
     pool = ThreadPoolExecutor(threads)
-    warm = min(args.warmup, 1)
+    warm = max(0, args.warmup)
     for s in range(warm):
         list(pool.map(lambda t: work(t, s), range(threads)))
     steps = args.steps
@@ -466,7 +564,7 @@ def run_reference(args):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": workload_config("CPU: one image per host thread, %d threads" % threads),
            "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
-                            "sample": sample, "code": REF_CODE[use_ref]},
+                            "sample": sample, "code": REF_CODE[use_ref], "per_core": round(value / threads, 5)},
            "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
@@ -515,6 +613,7 @@ def main():
     args = ap.parse_args()
     claim_stdout()
     WORKLOAD.update(WORKLOADS[args.workload])
+    WORKLOAD_NAME[0] = args.workload
     if args.images <= 0:
         args.images = {"cfg2": 32, "cfg4": 16, "cfg5": 4}[args.workload]
     args.streams = max(1, min(args.streams, args.images))

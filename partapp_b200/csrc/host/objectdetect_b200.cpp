@@ -5,11 +5,14 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <fstream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
+#include <thread>
 
 #include "mat5.hpp"
 #include "prototext.hpp"
@@ -82,6 +85,10 @@ CtxHolder &holder() {
   return h;
 }
 
+// Device of the calling worker thread (findObjectDataset sets it); -1: PSINFER_DEVICE or device 0.
+thread_local int t_device = -1;
+int g_gpus = 0, g_ctx_per_gpu = 0;  // 0: take PSINFER_GPUS / PSINFER_CTX_PER_GPU, else 1 GPU x 4 contexts
+
 void check(ps_ctx *ctx, int st, const char *what) {
   if (st != PS_OK) fail(std::string(what) + ": " + ps_last_error(ctx));
 }
@@ -91,7 +98,7 @@ ps_config make_config(const PartApp &app, int H, int W, int root, bool keep_all)
   ps_config cfg;
   memset(&cfg, 0, sizeof cfg);
   const char *dev = getenv("PSINFER_DEVICE");
-  cfg.device = dev ? atoi(dev) : 0;
+  cfg.device = t_device >= 0 ? t_device : (dev ? atoi(dev) : 0);
   cfg.num_parts = (int)app.m_part_conf.part.size();
   cfg.num_rotation_steps = (int)ep.num_rotation_steps;
   cfg.min_part_rotation = ep.min_part_rotation;
@@ -125,7 +132,7 @@ ps_ctx *get_ctx(const PartApp &app, int H, int W, int root, bool keep_all) {
   k.R = cfg.num_rotation_steps; k.S = cfg.num_scale_steps; k.H = H; k.W = W; k.P = cfg.num_parts; k.root = root;
   k.keep = cfg.keep_all_scales; k.rmin = cfg.min_part_rotation; k.rmax = cfg.max_part_rotation;
   k.smin = cfg.min_object_scale; k.smax = cfg.max_object_scale; k.strip = cfg.strip_border_detections;
-  k.K = cfg.roi_save_num_samples * 4 + cfg.interpolate * 2 + cfg.fast_math;
+  k.K = cfg.roi_save_num_samples * 4 + cfg.interpolate * 2 + cfg.fast_math + cfg.device * (1 << 24);
   memcpy(k.flags, cfg.is_detect, PS_MAX_PARTS);
   memcpy(k.flags + PS_MAX_PARTS, cfg.is_upright, PS_MAX_PARTS);
   memcpy(k.flags + 2 * PS_MAX_PARTS, cfg.is_root, PS_MAX_PARTS);
@@ -349,6 +356,17 @@ void PartApp::init(const std::string &expopt) {
   e.use_dpm_torso = n.boolean("use_dpm_torso", false);
   e.use_dpm_head = n.boolean("use_dpm_head", false);
   e.use_dpm_unary = n.boolean("use_dpm_unary", false);
+  e.do_dpm_rot = n.boolean("do_dpm_rot", false);
+  e.use_gt_torso = n.boolean("use_gt_torso", false);
+  e.pred_unary_rot_weight = (float)n.num("pred_unary_rot_weight", 1);
+  e.pred_unary_pos_weight = (float)n.num("pred_unary_pos_weight", 1);
+  e.dpm_torso_weight = (float)n.num("dpm_torso_weight", 1);
+  e.dpm_head_weight = (float)n.num("dpm_head_weight", 1);
+  e.dpm_unary_weight = (float)n.num("dpm_unary_weight", 1);
+  e.rootidx_det = (unsigned)n.num("rootidx_det", 1000);
+  if (n.has("torso_det_test_dir")) e.torso_det_test_dir = complete_relative_path(n.str("torso_det_test_dir"), expopt);
+  if (n.has("test_dpm_torso_dir")) e.test_dpm_torso_dir = complete_relative_path(n.str("test_dpm_torso_dir"), expopt);
+  if (n.has("test_dpm_unary_dir")) e.test_dpm_unary_dir = complete_relative_path(n.str("test_dpm_unary_dir"), expopt);
   if (e.log_dir.empty()) fail("expopt: log_dir is not set");
   e.log_dir = complete_relative_path(e.log_dir, expopt);
   // init_setpath, partapp.cpp:313-441
@@ -512,6 +530,90 @@ void loadJoints(const PartApp &app, std::vector<Joint> &joints, bool flip, int i
   }
 }
 
+// ---- predictor outputs (objectdetect_icps.cpp) -------------------------------------------------------------------------
+
+static const mat5::Var &load_matrix(std::vector<mat5::Var> &vars, const std::string &file, const std::string &name, size_t min_rows,
+                                    size_t min_cols) {
+  if (!file_exists(file)) fail("missing predictor output " + file + " (the reference's MATLAB side writes it, icps.cpp:608-625)");
+  vars = mat5::load(file);
+  const mat5::Var &m = mat5::find(vars, name, file);
+  if (m.dims.size() != 2 || m.dims[0] < min_rows || m.dims[1] < min_cols)
+    fail(file + ": '" + name + "' must be at least " + std::to_string(min_rows) + " x " + std::to_string(min_cols));
+  return m;
+}
+
+void getRotParams(const PartApp &app, int imgidx, std::vector<double> &rot_params, bool bTest) {
+  const int P = (int)app.m_part_conf.part.size();
+  const std::string list = bTest ? "test" : "train", dir = app.m_exp_param.pred_data_test_dir;
+  rot_params.assign((size_t)P * 3, 0.0);
+  std::vector<mat5::Var> va, vb;
+  const mat5::Var &all = load_matrix(va, dir + "/" + list + "list_params_rot_imgidx_" + std::to_string(imgidx) + ".mat", "rot_" + list, P, 2);
+  const mat5::Var &clus = load_matrix(vb, dir + "/" + list + "list_pred_rot_imgidx_" + std::to_string(imgidx) + ".mat", "clusidx_" + list, P, 1);
+  for (int p = 0; p < P; ++p)
+    if (app.m_part_conf.part[p].is_detect) {
+      rot_params[(size_t)p * 3 + 0] = all.at((size_t)p * all.dims[1] + 0);
+      const double sd = all.at((size_t)p * all.dims[1] + 1);
+      rot_params[(size_t)p * 3 + 1] = sd * sd;  // square(), icps.cpp:219
+      rot_params[(size_t)p * 3 + 2] = clus.at((size_t)p * clus.dims[1]);
+    }
+}
+
+void getPosParams(const PartApp &app, int imgidx, std::vector<double> &pos_params, int rootpart_idx, bool bTest) {
+  const int P = (int)app.m_part_conf.part.size();
+  const std::string list = bTest ? "test" : "train", dir = app.m_exp_param.pred_data_test_dir;
+  pos_params.assign((size_t)P * 5, 0.0);
+  std::vector<mat5::Var> va, vb;
+  const mat5::Var &all = load_matrix(va, dir + "/" + list + "list_params_pos_imgidx_" + std::to_string(imgidx) + ".mat", "pos_" + list, P, 4);
+  const mat5::Var &clus = load_matrix(vb, dir + "/" + list + "list_pred_pos_imgidx_" + std::to_string(imgidx) + ".mat", "clusidx_" + list, P, 1);
+  for (int p = 0; p < P; ++p) {
+    if (p == rootpart_idx || !app.m_part_conf.part[p].is_detect) continue;
+    const size_t o = (size_t)p * all.dims[1];
+    pos_params[(size_t)p * 5 + 0] = all.at(o + 0);
+    pos_params[(size_t)p * 5 + 1] = all.at(o + 1);
+    pos_params[(size_t)p * 5 + 2] = all.at(o + 2) * all.at(o + 2);
+    pos_params[(size_t)p * 5 + 3] = all.at(o + 3) * all.at(o + 3);
+    pos_params[(size_t)p * 5 + 4] = clus.at((size_t)p * clus.dims[1]);
+  }
+}
+
+void getRootPosDet(const PartApp &app, int imgidx, int rootpart_idx, double rootpos_det[2], bool bTest) {
+  (void)rootpart_idx;
+  const ExpParam &ep = app.m_exp_param;
+  if (ep.use_gt_torso) fail("use_gt_torso reads the annotation's torso box (icps.cpp:293-300): not available on this host");
+  if (!bTest) fail("getRootPosDet: only the test list is read on this path");
+  if (ep.torso_det_test_dir.empty()) fail("pred_unary_pos needs torso_det_test_dir (icps.cpp:306)");
+  std::vector<mat5::Var> vars;
+  const mat5::Var &best = load_matrix(vars, ep.torso_det_test_dir + "/pose_est_imgidx" + pad_zeros(imgidx, 4) + ".mat", "best_conf",
+                                      (size_t)ep.rootidx_det + 1, 6);
+  // int root_pos_x = best_conf(rootidx_det, 4): truncation towards zero, icps.cpp:317-318
+  rootpos_det[0] = (double)(int)best.at((size_t)ep.rootidx_det * best.dims[1] + 4);
+  rootpos_det[1] = (double)(int)best.at((size_t)ep.rootidx_det * best.dims[1] + 5);
+}
+
+void loadDPMScoreGrid(const std::string &dir, int imgidx, std::vector<std::vector<float> > &grids, int H, int W, bool bIsCell,
+                      int expected) {
+  const std::string file = dir + "/imgidx_" + pad_zeros(imgidx + 1, 4) + ".mat";
+  if (!file_exists(file)) fail("missing DPM score grid " + file + " (icps.cpp:555)");
+  std::vector<mat5::Var> vars = mat5::load(file);
+  const mat5::Var &sg = mat5::find(vars, "scoregrid", file);
+  auto take = [&](const mat5::Var &g) {
+    if (g.dims.size() != 2 || (int)g.dims[0] != H || (int)g.dims[1] != W)
+      fail(file + ": scoregrid must be " + std::to_string(H) + " x " + std::to_string(W) + " like the image (icps.cpp:500-501)");
+    std::vector<float> v((size_t)H * W);
+    for (size_t i = 0; i < v.size(); ++i) v[i] = (float)g.at(i);
+    grids.push_back(std::move(v));
+  };
+  grids.clear();
+  if (bIsCell) {
+    if (sg.cls != mat5::mxCELL) fail(file + ": scoregrid must be a cell array (icps.cpp:560-565)");
+    if ((int)sg.cells.size() != expected) fail(file + ": scoregrid has " + std::to_string(sg.cells.size()) + " grids, expected " +
+                                               std::to_string(expected) + " (icps.cpp:570)");
+    for (const mat5::Var &g : sg.cells) take(g);
+  } else {
+    take(sg);
+  }
+}
+
 // ---- inference ---------------------------------------------------------------------------------------------------------
 
 void computeRotJointMarginal(const ExpParam &ep, FloatGrid3 &child, FloatGrid3 &parent, const double offset_c_10[2],
@@ -619,9 +721,6 @@ void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, Hypothe
   const ExpParam &ep = app.m_exp_param;
   const int P = (int)app.m_part_conf.part.size(), S = (int)ep.num_scale_steps, R = (int)ep.num_rotation_steps;
   (void)qsScoreGridDir;
-  if (ep.pred_unary_rot || ep.pred_unary_pos || ep.use_dpm_torso || ep.use_dpm_head || ep.use_dpm_unary)
-    fail("pred_unary_* / use_dpm_* need the MATLAB predictors of the reference (objectdetect_icps.cpp:608-625); "
-         "this host does not emulate them");
   int W = 0, H = 0;
   image_size(qsImgName, W, H);  // findrot.cpp:752-760
   std::vector<Joint> joints;
@@ -664,11 +763,67 @@ void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, Hypothe
             Tig[(size_t)r * 9 + i * 3 + k] = t;
           }
       }
+      // cudaMemcpyAsync from pageable memory returns once `cells` has been staged, so the buffer can be reused at once
       check(ctx, ps_set_unary_compact(ctx, p, s, cells.data(), (int)gh, (int)gw, Tig.data(), PS_MEM_HOST), "ps_set_unary_compact");
-      check(ctx, ps_synchronize(ctx), "ps_synchronize");  // `cells` is reused
     }
   }
 
+  // ---- conditioning of the unaries, in the reference's order (findrot.cpp:849-949) ----
+  // The predictors (MATLAB poselet classifiers, DPM detectors) are outside this path: their per-image outputs are read
+  // from disk; the adds run on the device (ps_add_unary_grid / ps_add_unary_table).
+  std::vector<std::vector<float> > dpm;
+  if (ep.use_dpm_torso) {  // :851-854, :883-890: log of the torso DPM grid, added to the root with dpm_torso_weight
+    loadDPMScoreGrid(ep.test_dpm_torso_dir, imgidx, dpm, H, W, false);
+    for (float &v : dpm[0]) {
+      if (v < 0) fail("DPM torso score grid holds a negative value (computeLogGrid asserts, multi_array_op.hpp:160)");
+      v = v == 0 ? -1e6f : (float)std::log((double)v);
+    }
+    if (!(ep.dpm_torso_weight > 0)) fail("dpm_torso_weight must be > 0 (icps.cpp:497)");
+    check(ctx, ps_add_unary_grid(ctx, rootpart_idx, dpm[0].data(), 1, 0, ep.dpm_torso_weight, PS_MEM_HOST), "ps_add_unary_grid");
+  }
+  auto add_load_dpm = [&](float weight, int nrot_dpm, const std::string &parent, bool use_pidx, int pidx_only) {  // icps.cpp:445-486
+    std::vector<float> flat;
+    for (int p = 0; p < P; ++p) {
+      if (pidx_only > -1 && pidx_only < P && pidx_only != p) continue;
+      if (!app.m_part_conf.part[p].is_detect) continue;
+      loadDPMScoreGrid(parent + (use_pidx ? "/pidx_" + pad_zeros(p, 4) : ""), imgidx, dpm, H, W, true, nrot_dpm);
+      flat.clear();
+      for (const std::vector<float> &g : dpm) flat.insert(flat.end(), g.begin(), g.end());
+      check(ctx, ps_add_unary_grid(ctx, p, flat.data(), nrot_dpm, 1, weight, PS_MEM_HOST), "ps_add_unary_grid");
+    }
+  };
+  if (ep.use_dpm_head) {  // :893-904
+    const int headpart_idx = P == 22 ? 11 : (P == 12 ? 1 : 5);
+    add_load_dpm(ep.dpm_head_weight, 1, ep.test_dpm_unary_dir + "/head", false, headpart_idx);
+  }
+  if (ep.use_dpm_unary) {  // :907-914
+    if (ep.test_dpm_unary_dir.empty()) fail("use_dpm_unary needs test_dpm_unary_dir (findrot.cpp:910)");
+    add_load_dpm(ep.dpm_unary_weight, ep.do_dpm_rot ? R : 1, ep.test_dpm_unary_dir, true, -1);
+  }
+  if (ep.pred_unary_rot) {  // :862-868, :921-927: rotation score of every detected part
+    std::vector<double> rot_params;
+    getRotParams(app, imgidx, rot_params, true);
+    ps_config cfg = make_config(app, H, W, rootpart_idx, bSaveMarginals);
+    std::vector<float> table((size_t)R);
+    for (int p = 0; p < P; ++p) {
+      if (!app.m_part_conf.part[p].is_detect) continue;  // log_rot_scores stays 0 there: unary + weight * 0
+      ps_rot_score_table(&cfg, rot_params[(size_t)p * 3], rot_params[(size_t)p * 3 + 1], table.data());
+      check(ctx, ps_add_unary_table(ctx, p, table.data(), 0, ep.pred_unary_rot_weight), "ps_add_unary_table");
+    }
+  }
+  if (ep.pred_unary_pos) {  // :872-878, :934-941: position score of every detected non-root part
+    std::vector<double> pos_params;
+    double rootpos_det[2];
+    getPosParams(app, imgidx, pos_params, rootpart_idx, true);
+    getRootPosDet(app, imgidx, rootpart_idx, rootpos_det, true);
+    std::vector<float> table((size_t)H * W);
+    for (int p = 0; p < P; ++p) {
+      if (p == rootpart_idx || !app.m_part_conf.part[p].is_detect) continue;
+      const double *q = &pos_params[(size_t)p * 5];
+      ps_pos_score_table(H, W, q[0], q[1], q[2], q[3], rootpos_det[0], rootpos_det[1], table.data());
+      check(ctx, ps_add_unary_table(ctx, p, table.data(), 1, ep.pred_unary_pos_weight), "ps_add_unary_table");
+    }
+  }
   // torso position prior (findrot.cpp:945-948, icps.cpp:137-191; params from <class_dir>/torso_pos_prior.mat :41-42)
   if (ep.use_torso_pos_prior) {
     const std::string file = ep.class_dir + "/torso_pos_prior.mat";
@@ -722,6 +877,32 @@ void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, Hypothe
   }
 }
 
+void set_parallelism(int gpus, int contexts_per_gpu) {
+  g_gpus = gpus;
+  g_ctx_per_gpu = contexts_per_gpu;
+}
+
+// One image (both orientations): findObjectDataset's loop body, aux.cpp:344-402.
+static void find_object_image(const PartApp &app, int imgidx, const std::string &qsHypDir, const std::string &qsPartMarginalsDir) {
+  const ExpParam &ep = app.m_exp_param;
+  const int flip_count = ep.flip_orientation ? 2 : 1;
+  for (int flip = 0; flip < flip_count; ++flip) {
+    HypothesisList hypothesis_list;
+    findObjectImageRotJoints(app, imgidx, flip != 0, hypothesis_list, qsPartMarginalsDir, ep.scoregrid_dir,
+                             app.m_test_annolist[imgidx]);
+    const std::string file = qsHypDir + getObjectHypFilename(imgidx, flip != 0);
+    std::ofstream f(file.c_str(), std::ios::binary);
+    if (!f) fail("cannot write " + file);
+    const std::string bytes = hypothesis_list.SerializeAsString();
+    f.write(bytes.data(), (std::streamsize)bytes.size());
+  }
+}
+
+// The reference shards the image range over PROCESSES (--distribute / --ncpu / --batch_num, main.cpp:155-192: contiguous
+// ranges of ceil(n / ncpu) images).  Here one process drives every GPU the same way: GPU g gets the g-th contiguous
+// range, and several worker threads per GPU -- each with its own ps_ctx and stream -- draw images from that range, so
+// reading and inflating the score-grid files of one image, the inference of another and the output files of a third
+// overlap.  Outputs are per image, so the files are the same whatever the number of GPUs or workers.
 void findObjectDataset(const PartApp &app, int firstidx, int lastidx) {
   const ExpParam &ep = app.m_exp_param;
   if (firstidx < 0 || firstidx > (int)app.m_test_annolist.size() || lastidx >= (int)app.m_test_annolist.size())
@@ -730,19 +911,47 @@ void findObjectDataset(const PartApp &app, int firstidx, int lastidx) {
   const std::string qsPartMarginalsDir = ep.log_dir + "/" + ep.log_subdir + "/part_marginals";
   make_dirs(qsHypDir);
   make_dirs(qsPartMarginalsDir);
-  for (int imgidx = firstidx; imgidx <= lastidx; ++imgidx) {
-    const int flip_count = ep.flip_orientation ? 2 : 1;
-    for (int flip = 0; flip < flip_count; ++flip) {
-      HypothesisList hypothesis_list;
-      findObjectImageRotJoints(app, imgidx, flip != 0, hypothesis_list, qsPartMarginalsDir, ep.scoregrid_dir,
-                               app.m_test_annolist[imgidx]);
-      const std::string file = qsHypDir + getObjectHypFilename(imgidx, flip != 0);
-      std::ofstream f(file.c_str(), std::ios::binary);
-      if (!f) fail("cannot write " + file);
-      const std::string bytes = hypothesis_list.SerializeAsString();
-      f.write(bytes.data(), (std::streamsize)bytes.size());
-    }
+  const char *eg = getenv("PSINFER_GPUS"), *ec = getenv("PSINFER_CTX_PER_GPU");
+  const int gpus = std::max(1, g_gpus > 0 ? g_gpus : (eg ? atoi(eg) : 1));
+  const int per_gpu = std::max(1, g_ctx_per_gpu > 0 ? g_ctx_per_gpu : (ec ? atoi(ec) : 4));
+  const int n = lastidx - firstidx + 1;
+  if (n <= 0) return;
+  if (gpus == 1 && (per_gpu == 1 || n == 1)) {  // the reference's loop, in the calling thread
+    for (int imgidx = firstidx; imgidx <= lastidx; ++imgidx) find_object_image(app, imgidx, qsHypDir, qsPartMarginalsDir);
+    return;
   }
+  const char *dev0 = getenv("PSINFER_DEVICE");
+  const int base_dev = dev0 ? atoi(dev0) : 0;
+  const int num_per_gpu = (n + gpus - 1) / gpus;  // (int)ceil(n / (float)ncpu), main.cpp:181
+  std::vector<std::atomic<int> > next(gpus);
+  for (int g = 0; g < gpus; ++g) next[g] = firstidx + g * num_per_gpu;
+  std::mutex err_mutex;
+  std::string first_error;
+  std::atomic<bool> failed(false);
+  std::vector<std::thread> workers;
+  for (int g = 0; g < gpus; ++g) {
+    const int range_end = std::min(lastidx, firstidx + (g + 1) * num_per_gpu - 1);
+    for (int k = 0; k < per_gpu; ++k)
+      workers.emplace_back([&, g, range_end]() {
+        t_device = base_dev + g;
+        try {
+          for (;;) {
+            const int imgidx = next[g].fetch_add(1);
+            if (imgidx > range_end || failed.load()) break;
+            find_object_image(app, imgidx, qsHypDir, qsPartMarginalsDir);
+          }
+        } catch (const std::exception &e) {
+          std::lock_guard<std::mutex> lock(err_mutex);
+          if (first_error.empty()) first_error = e.what();
+          failed = true;
+        }
+        CtxHolder &h = holder();  // release the worker's context on its own thread
+        if (h.ctx) ps_destroy(h.ctx);
+        h.ctx = nullptr;
+      });
+  }
+  for (std::thread &t : workers) t.join();
+  if (failed) fail(first_error);
 }
 
 }  // namespace object_detect

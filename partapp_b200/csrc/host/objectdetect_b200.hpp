@@ -43,8 +43,13 @@ struct ExpParam {
   bool save_part_detections_local_max = false, interpolate = false, force_recompute_scores = true;
   bool use_torso_pos_prior = false;
   float torso_pos_prior_weight = 1;
-  // conditioning options that need MATLAB-side predictors (objectdetect_icps.cpp:608-625): rejected, not ignored
+  // conditioning of the unaries (findrot.cpp:849-949).  The predictors themselves are MATLAB / DPM runs of the
+  // reference (objectdetect_icps.cpp:608-625 spawns them); this host reads the files they write.
   bool pred_unary_rot = false, pred_unary_pos = false, use_dpm_torso = false, use_dpm_head = false, use_dpm_unary = false;
+  bool do_dpm_rot = false, use_gt_torso = false;
+  float pred_unary_rot_weight = 1, pred_unary_pos_weight = 1, dpm_torso_weight = 1, dpm_head_weight = 1, dpm_unary_weight = 1;
+  unsigned rootidx_det = 1000;
+  std::string torso_det_test_dir, test_dpm_torso_dir, test_dpm_unary_dir;
 };
 
 struct PartDef {   // libPartDetect/PartConfig.proto PartDef
@@ -122,6 +127,18 @@ double scale_from_index(const ExpParam &, int scaleidx);
 void load_joint(const PartApp &, int jidx, Joint &, int tidx = -1);
 void loadJoints(const PartApp &, std::vector<Joint> &, bool flip, int imgidx = -1);
 
+// objectdetect_icps.cpp:193-226 / :326-363 / :283-324: the per-image predictor outputs.  rot_params [P][3] =
+// (mu, var = sigma^2, cluster), pos_params [P][5] = (mu_x, mu_y, var_x, var_y, cluster); rows of parts that are not
+// detected (and the root's position row) stay zero.
+void getRotParams(const PartApp &, int imgidx, std::vector<double> &rot_params, bool bTest = true);
+void getPosParams(const PartApp &, int imgidx, std::vector<double> &pos_params, int rootpart_idx, bool bTest = true);
+void getRootPosDet(const PartApp &, int imgidx, int rootpart_idx, double rootpos_det[2], bool bTest = true);
+// objectdetect_icps.cpp:550-581: <dir>/imgidx_%04d.mat (1-based), variable "scoregrid": one [H][W] grid (bIsCell false)
+// or a cell array of them, one per DPM rotation (bIsCell true: `expected` grids must be there).  Grids are raw DPM
+// scores, fp32, C order.
+void loadDPMScoreGrid(const std::string &qsDPMdir, int imgidx, std::vector<std::vector<float> > &dpmPriorGrid, int H, int W,
+                      bool bIsCell, int expected = 1);
+
 // objectdetect_findrot.cpp:292-456
 void computeRotJointMarginal(const ExpParam &, FloatGrid3 &log_prob_child, FloatGrid3 &log_prob_parent,
                              const double offset_c_10[2], const double offset_p_01[2], const double C[2][2],
@@ -158,8 +175,12 @@ void findObjectRoiHelper(PartApp part_app, const int roi[4], double scale, const
                          std::vector<Joint> joints, std::vector<std::vector<PartHyp> > &best_part_det,
                          std::vector<std::vector<PartHyp> > &best_part_hyp);
 
-// objectdetect_aux.cpp:322-406
+// objectdetect_aux.cpp:322-406.  Runs on `gpus` devices (contiguous image ranges per GPU, like the reference's
+// --distribute shards of main.cpp:155-192) with `contexts_per_gpu` worker threads each; see set_parallelism.
 void findObjectDataset(const PartApp &, int firstidx, int lastidx);
+// Number of GPUs (devices PSINFER_DEVICE .. +gpus-1) and of worker threads / ps_ctx per GPU that findObjectDataset uses.
+// 0 keeps the environment's PSINFER_GPUS / PSINFER_CTX_PER_GPU, else 1 x 4.
+void set_parallelism(int gpus, int contexts_per_gpu);
 
 // aux.cpp:311-320
 std::string getObjectHypFilename(int imgidx, bool flip);

@@ -152,6 +152,18 @@ struct ps_ctx {
   std::map<std::string, std::shared_ptr<DevPlan>> plan_cache;
   long long plan_cache_hits = 0, plan_cache_misses = 0;
 
+  // CUDA graphs of whole inferences, keyed by (flags, joint set, which leaf maxima the ingest already holds)
+  struct InferGraph {
+    cudaGraphExec_t exec = nullptr;
+    bool failed = false;
+    long long launches = 0;
+    std::vector<const float *> pending_grids;
+    int pending_scaleidx = 0, pending_flags = 0, result_scale = -1;
+  };
+  std::map<std::string, InferGraph> graphs;
+  long long joints_version = 0, graph_replays = 0;
+  bool disable_graph = false;  // PSINFER_NO_GRAPH=1
+
   // results.  ps_infer / ps_max_states only enqueue device work; the host part of the readout (decode of the
   // argmax keys, local-maximum selection) runs in finish_result() when a getter needs it.
   bool have_result = false;
@@ -172,6 +184,8 @@ struct ps_ctx {
       cudaStreamDestroy(own_stream);
     }
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    for (auto &g : graphs)
+      if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (host_keys) cudaFreeHost(host_keys);
     if (host_topk) cudaFreeHost(host_topk);
     if (host_topk_state) cudaFreeHost(host_topk_state);
@@ -949,7 +963,10 @@ int run_level(ps_ctx *c, std::vector<MsgJob> &jobs) {
   }
   for (size_t i = 0; i < batch.size();) {
     size_t k = i + 1;
-    while (k < batch.size() && k - i < (size_t)psk::kMaxBatch && batch[k]->sparse == batch[i]->sparse) ++k;
+    // PSINFER_MAX_BATCH (1..8) caps the messages per launch: an A/B knob between fewer launches and a smaller L2 footprint
+    static const int cap_env = getenv("PSINFER_MAX_BATCH") ? atoi(getenv("PSINFER_MAX_BATCH")) : psk::kMaxBatch;
+    const size_t cap = (size_t)std::max(1, std::min(cap_env, psk::kMaxBatch));
+    while (k < batch.size() && k - i < cap && batch[k]->sparse == batch[i]->sparse) ++k;
     int rc = run_batch(c, &batch[i], (int)(k - i));
     if (rc) return rc;
     i = k;
@@ -1267,6 +1284,7 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   c->disable_tma = getenv("PSINFER_NO_TMA") != nullptr;
   c->disable_tile_lists = getenv("PSINFER_ALL_TILES") != nullptr;
   c->disable_batch = getenv("PSINFER_NO_BATCH") != nullptr;
+  c->disable_graph = getenv("PSINFER_NO_GRAPH") != nullptr;
   if (!cu(cudaFuncSetAttribute(psk::k_gauss_xy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
       !cu(cudaFuncSetAttribute(psk::k_gauss_xy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr"))
     return PS_ERR_CUDA;
@@ -1395,6 +1413,9 @@ int ps_set_joints(ps_ctx *c, const ps_joint *joints, int nj) {
     PS_CUDA(c, cudaStreamSynchronize(c->stream));
     PS_CUDA(c, c->chain_tmp.alloc(nroot * c->N * sizeof(float)));
   }
+  if (plans != c->plans || (int)c->joints.size() != nj ||
+      memcmp(c->joints.data(), joints, sizeof(ps_joint) * (size_t)nj) != 0)
+    ++c->joints_version;  // graphs captured for another joint set carry its plans' pointers
   c->plans = std::move(plans);
   c->nodes = std::move(nodes);
   c->joints.assign(joints, joints + nj);
@@ -1783,15 +1804,14 @@ int finish_result(ps_ctx *c) {
 
 // ---- inference ------------------------------------------------------------------------------------
 
-int ps_infer(ps_ctx *c, int flags) {
-  if (!c) return PS_ERR_INVALID;
-  if (!c->joints_set) return c->fail(PS_ERR_STATE, "ps_infer before ps_set_joints");
-  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+// Enqueues one whole inference on ctx->stream (no host synchronisation once buffers, plans and scatter maps exist).
+static int infer_enqueue(ps_ctx *c, int flags) {
   const int P = c->P, S = c->S, R = c->R, root = c->root;
   const size_t N = c->N;
   const bool sparse = flags & PS_INFER_SPARSE;
   cudaStream_t st = c->stream;
   c->have_result = false;
+  c->work_counter_next = kWorkCounters;  // the first fused launch resets the counter pool: every inference (and every replay of its graph) starts from zeroed counters
   int rc;
 
   if (flags & PS_INFER_KEEP_UNARIES) {
@@ -1948,6 +1968,76 @@ int ps_infer(ps_ctx *c, int flags) {
   return PS_OK;
 }
 
+// computeRootPosteriorRot + computePartMarginals (findrot.cpp:470-727, :124-286).  The schedule of one inference is a
+// fixed sequence of launches over ctx-owned buffers as long as the joints, the flags and the way each leaf's maximum is
+// obtained stay the same, so it is captured into a CUDA graph the second time such an inference is requested and
+// replayed from then on (PSINFER_NO_GRAPH=1 keeps the eager launches; profiling always runs eagerly).
+int ps_infer(ps_ctx *c, int flags) {
+  if (!c) return PS_ERR_INVALID;
+  if (!c->joints_set) return c->fail(PS_ERR_STATE, "ps_infer before ps_set_joints");
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  if (c->disable_graph || c->profiling) return infer_enqueue(c, flags);
+  std::string key((const char *)&flags, sizeof flags);
+  key.append((const char *)&c->joints_version, sizeof c->joints_version);
+  key.append((const char *)c->unary_max_valid.data(), c->unary_max_valid.size());
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {  // first sight: eager, so that every lazy allocation and scatter map exists afterwards
+    if (c->graphs.size() >= 16) {
+      // keys seen once (a joint set that changes with every image never comes back) cost nothing to forget; graphs that
+      // were instantiated may still be running
+      for (auto i = c->graphs.begin(); i != c->graphs.end();) i = i->second.exec ? std::next(i) : c->graphs.erase(i);
+      if (c->graphs.size() >= 16) {
+        PS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (auto &g : c->graphs) cudaGraphExecDestroy(g.second.exec);
+        c->graphs.clear();
+      }
+    }
+    c->graphs[key] = ps_ctx::InferGraph();
+    return infer_enqueue(c, flags);
+  }
+  ps_ctx::InferGraph &g = it->second;
+  if (g.failed) return infer_enqueue(c, flags);
+  if (!g.exec) {
+    const long long l0 = c->launches;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      g.failed = true;
+      return infer_enqueue(c, flags);
+    }
+    const int rc = infer_enqueue(c, flags);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != PS_OK || ce != cudaSuccess || !graph ||
+        cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g.exec = nullptr;
+      g.failed = true;
+      c->launches = l0;
+      c->result_pending = false;
+      if (rc != PS_OK) return rc;
+      return infer_enqueue(c, flags);  // something on the path cannot be captured: stay eager for this key
+    }
+    cudaGraphDestroy(graph);
+    g.launches = c->launches - l0;
+    g.pending_grids = c->pending_grids;
+    g.pending_scaleidx = c->pending_scaleidx;
+    g.pending_flags = c->pending_flags;
+    g.result_scale = c->result_scale;
+    c->launches = l0;
+  }
+  PS_CUDA(c, cudaGraphLaunch(g.exec, c->stream));
+  c->launches += g.launches;
+  ++c->graph_replays;
+  c->pending_grids = g.pending_grids;
+  c->pending_scaleidx = g.pending_scaleidx;
+  c->pending_flags = g.pending_flags;
+  c->result_scale = g.result_scale;
+  c->result_pending = true;
+  c->have_result = false;
+  return PS_OK;
+}
+
 int ps_max_states(ps_ctx *c, int flags) {
   if (!c) return PS_ERR_INVALID;
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
@@ -2091,8 +2181,9 @@ int ps_get_plan_info(ps_ctx *c, int joint, int downward, int scale, int out[10])
   out[6] = h.rot_shift;
   out[7] = (h.in_pure ? 1 : 0) | (h.out_pure ? 2 : 0);
   const bool lists = !h.diag && !c->disable_tile_lists && !c->disable_tma;
-  out[8] = lists && h.xcells ? (int)h.xcells : out[1] * out[2];
-  out[9] = lists && h.ycells ? (int)h.ycells : out[1] * out[2];
+  const bool fused = lists && !c->disable_batch && h.fcells_y;  // the level-batched route filters the walks' cells
+  out[8] = fused ? (int)h.fcells_x : lists && h.xcells ? (int)h.xcells : out[1] * out[2];
+  out[9] = fused ? (int)h.fcells_y : lists && h.ycells ? (int)h.ycells : out[1] * out[2];
   return PS_OK;
 }
 

@@ -73,3 +73,95 @@ def test_find_obj_cli_first_numimgs_and_errors(cli, tmp_path):
     os.remove(os.path.join(info["base"], "spatial", "joint_2_1.mat"))
     r = subprocess.run([cli, "--expopt", info["expopt"], "--find_obj"], capture_output=True, text=True)
     assert r.returncode == 1 and "joint_2_1.mat" in r.stderr
+
+
+def _conditioned_unaries(info, i):
+    """findrot.cpp:849-949 with the oracle's pieces, in the reference's order."""
+    import ctypes
+    ep, P, R, H, W = info["ep"], info["P"], info["R"], info["H"], info["W"]
+    c = info["cond"][i]
+    L = oracle.lib()
+    fp = ctypes.POINTER(ctypes.c_float)
+    un = np.stack([oracle.prepare_unary(oracle.load_score_grid(info["cells"][i][p, 0], info["Tig"], H, W)) for p in range(P)])
+    un = np.ascontiguousarray(un[:, None])
+    root = info["root_idx"]
+    with np.errstate(divide="ignore"):
+        logt = np.where(c["dpm_torso"] == 0, np.float32(-1e6), np.log(c["dpm_torso"].astype(np.float64)).astype(np.float32))
+    logt = np.ascontiguousarray(logt[None], np.float32)
+    L.orc_add_dpm_score(un[root, 0].ctypes.data_as(fp), R, H, W, logt.ctypes.data_as(fp), 1, ctypes.c_float(0.5))
+    if c["head"] < P:
+        L.orc_add_load_dpm_score(un[c["head"], 0].ctypes.data_as(fp), R, H, W, c["dpm_head"].ctypes.data_as(fp), 1, ctypes.c_float(0.4))
+    else:   # pidx_only outside the part list: the reference then adds the head grid to EVERY part (icps.cpp:465)
+        for p in range(P):
+            L.orc_add_load_dpm_score(un[p, 0].ctypes.data_as(fp), R, H, W, c["dpm_head"].ctypes.data_as(fp), 1, ctypes.c_float(0.4))
+    for p in range(P):
+        g = np.ascontiguousarray(c["dpm_unary"][p])
+        L.orc_add_load_dpm_score(un[p, 0].ctypes.data_as(fp), R, H, W, g.ctypes.data_as(fp), R, ctypes.c_float(0.3))
+    t = np.zeros(R, np.float32)
+    for p in range(P):
+        L.orc_rot_score_table(ctypes.byref(oracle.exp_param(ep)), ctypes.c_double(c["rot"][p, 0]), ctypes.c_double(c["rot"][p, 1] ** 2),
+                              t.ctypes.data_as(fp))
+        L.orc_add_rot_table(un[p, 0].ctypes.data_as(fp), R, H, W, t.ctypes.data_as(fp), ctypes.c_float(0.8))
+    t2 = np.zeros((H, W), np.float32)
+    for p in range(P):
+        if p == root:
+            continue
+        q = c["pos"][p]
+        L.orc_pos_score_table(H, W, ctypes.c_double(q[0]), ctypes.c_double(q[1]), ctypes.c_double(q[2] ** 2), ctypes.c_double(q[3] ** 2),
+                              ctypes.c_double(c["rootpos"][0]), ctypes.c_double(c["rootpos"][1]), t2.ctypes.data_as(fp))
+        L.orc_add_pos_table(un[p, 0].ctypes.data_as(fp), R, H, W, t2.ctypes.data_as(fp), ctypes.c_float(0.6))
+    pr = c["prior"]
+    L.orc_torso_prior_table(H, W, ctypes.c_double(pr[0]), ctypes.c_double(pr[1]), ctypes.c_double(pr[2]), ctypes.c_double(pr[3]),
+                            ctypes.c_float(0.7), t2.ctypes.data_as(fp))
+    L.orc_add_pos_table_unweighted(un[root, 0].ctypes.data_as(fp), R, H, W, t2.ctypes.data_as(fp))
+    return un
+
+
+def test_find_obj_cli_conditioned_model_reads_predictor_outputs(cli, tmp_path):
+    """The poselet-conditioned full model through the drop-in host: rotation / position parameters, the torso detection,
+    the torso prior and three kinds of DPM score grids are read from the files the reference's MATLAB side writes
+    (objectdetect_icps.cpp:193-606) and added in the reference's order (findrot.cpp:849-949)."""
+    info = make(str(tmp_path / "expc"), num_images=2, P=6, R=8, H=44, W=40, conditioning=True,
+                extra_expopt="save_part_marginals: true\n")
+    r = subprocess.run([cli, "--expopt", info["expopt"], "--find_obj"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pm = os.path.join(info["base"], "part_marginals")
+    for i in range(2):
+        un = _conditioned_unaries(info, i)
+        want = oracle.infer(info["ep"], synth.part_conf(info["P"]), info["joints"], un, sparse=True)
+        best = scipy.io.loadmat(os.path.join(pm, "pose_est_imgidx%04d.mat" % i))["best_conf"]
+        assert np.array_equal(best[:, :6], want["best_conf"][:, :6]), "image %d" % i
+        # addLoadDPMScore goes through logf (glibc < 1 ulp vs the device's correctly rounded one): scores to 1e-5
+        np.testing.assert_allclose(best[:, 6], want["best_conf"][:, 6], rtol=1e-5)
+        g = scipy.io.loadmat(os.path.join(pm, "log_part_posterior_final_imgidx%d_scaleidx0_o0_pidx0.mat" % i))["log_prob_grid"]
+        np.testing.assert_allclose(g, want["marginals"][0, 0], rtol=1e-4)
+    # a missing predictor file is an error that names the file, not a silent skip
+    os.remove(os.path.join(str(tmp_path / "expc"), "pred_data_test", "testlist_params_pos_imgidx_1.mat"))
+    r = subprocess.run([cli, "--expopt", info["expopt"], "--find_obj", "--first", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "testlist_params_pos_imgidx_1.mat" in r.stderr
+
+
+def test_find_obj_cli_multi_worker_outputs_are_byte_identical(cli, tmp_path):
+    """findObjectDataset with several worker threads / contexts (and, where the box has them, several GPUs) writes the
+    same bytes as the single-threaded loop of the reference (aux.cpp:344-402)."""
+    import filecmp
+    info_a = make(str(tmp_path / "a"), num_images=8, P=4, R=8, H=48, W=40)
+    info_b = make(str(tmp_path / "b"), num_images=8, P=4, R=8, H=48, W=40)
+    ra = subprocess.run([cli, "--expopt", info_a["expopt"], "--find_obj", "--gpus", "1", "--contexts", "1"], capture_output=True, text=True)
+    assert ra.returncode == 0, ra.stderr
+    import torch
+    ng = min(2, torch.cuda.device_count())
+    rb = subprocess.run([cli, "--expopt", info_b["expopt"], "--find_obj", "--gpus", str(ng), "--contexts", "3"], capture_output=True, text=True)
+    assert rb.returncode == 0, rb.stderr
+    for sub in ("part_marginals", "object_hyp"):
+        da, db = os.path.join(info_a["base"], sub), os.path.join(info_b["base"], sub)
+        names = sorted(os.listdir(da))
+        assert names == sorted(os.listdir(db)) and len(names) == 8
+        for n in names:
+            assert filecmp.cmp(os.path.join(da, n), os.path.join(db, n), shallow=False), n
+    # process-level shards as in the reference (--distribute, main.cpp:175-184): batch 1 of 4 = images 2..3
+    info_c = make(str(tmp_path / "c"), num_images=8, P=4, R=8, H=48, W=40)
+    rc = subprocess.run([cli, "--expopt", info_c["expopt"], "--find_obj", "--distribute", "--ncpu", "4", "--batch_num", "1"],
+                        capture_output=True, text=True)
+    assert rc.returncode == 0, rc.stderr
+    assert sorted(os.listdir(os.path.join(info_c["base"], "part_marginals"))) == ["pose_est_imgidx0002.mat", "pose_est_imgidx0003.mat"]
