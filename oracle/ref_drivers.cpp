@@ -65,6 +65,7 @@ void computePosJointMarginal(FloatGrid2 &log_prob_child, FloatGrid2 &log_prob_pa
 
 namespace matlab_io {
 capture_fn g_capture = 0;
+load2d_fn g_load2d = 0;  // no file provider in this library: the loaders abort
 }
 
 namespace {

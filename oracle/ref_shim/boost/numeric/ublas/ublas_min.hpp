@@ -220,6 +220,9 @@ template <class T> vector<T> operator-(const vector<T> &a, const vector<T> &b) {
 template <class T> vector<T> operator-(const vector<T> &a) { vector<T> r(a.size()); for (std::size_t i = 0; i < a.size(); ++i) r(i) = -a(i); return r; }
 template <class T> vector<T> operator*(const vector<T> &a, const T &s) { vector<T> r(a); r *= s; return r; }
 template <class T> vector<T> operator*(const T &s, const vector<T> &a) { vector<T> r(a.size()); for (std::size_t i = 0; i < a.size(); ++i) r(i) = s * a(i); return r; }
+// uBLAS promotes an int scalar against a double vector (partdef.cpp:381 multiplies by an int axis length)
+inline vector<double> operator*(int s, const vector<double> &a) { return (double)s * a; }
+inline vector<double> operator*(const vector<double> &a, int s) { return a * (double)s; }
 template <class T> vector<T> operator/(const vector<T> &a, const T &s) { vector<T> r(a); r /= s; return r; }
 template <class T>
 T inner_prod(const vector<T> &a, const vector<T> &b) {

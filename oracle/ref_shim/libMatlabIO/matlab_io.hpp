@@ -20,7 +20,22 @@ template <class A> bool mat_save_multi_array(QString file, QString var, const A 
   return true;
 }
 template <class A> bool mat_save_multi_array(MATFile *, QString, const A &) { return true; }
-template <class A> A mat_load_multi_array(QString, QString) { abort(); }
+// Loader hook (oracle/ref_eval.cpp): the evaluator reads pose_est_imgidx*.mat through mat_load_multi_array<FloatGrid2>;
+// a registered provider hands it the matrix a test supplies instead of a file.  Without a provider the loaders abort.
+typedef bool (*load2d_fn)(const char *file, const char *var, int *rows, int *cols, const float **data);
+extern load2d_fn g_load2d;
+template <class A> A mat_load_multi_array(QString file, QString var) {
+  if constexpr (A::dimensionality == 2) {
+    int rows = 0, cols = 0;
+    const float *data = 0;
+    if (!g_load2d || !g_load2d(file.toStdString().c_str(), var.toStdString().c_str(), &rows, &cols, &data)) abort();
+    A a(boost::extents[rows][cols]);
+    for (int i = 0; i < rows * cols; ++i) a.data()[i] = data[i];
+    return a;
+  } else {
+    abort();
+  }
+}
 template <class A> A mat_load_multi_array(MATFile *, QString) { abort(); }
 inline bool mat_load_double_matrix(QString, QString, boost_math::double_matrix &) { abort(); }
 inline bool mat_load_double_vector(QString, QString, boost_math::double_vector &) { abort(); }

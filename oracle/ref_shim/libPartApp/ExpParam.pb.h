@@ -67,6 +67,11 @@ class ExpParam {
   PS_FIELD(std::string, poselet_strip, "")
   PS_FIELD(std::string, part_marginals_dir, "")
   PS_FIELD(int32_t, num_pred_part_types, 1)
+  PS_FIELD(std::string, dai_samples_dir, "")
+  PS_FIELD(std::string, part_conf_eval, "")
+  PS_FIELD(std::string, roi_annolist, "")
+  PS_FIELD(std::string, scoregrid_train_dir, "")
+  PS_FIELD(bool, dai_bbox_prior, false)
 #undef PS_FIELD
   std::string validation_dataset(int) const { return std::string(); }
   int validation_dataset_size() const { return 0; }

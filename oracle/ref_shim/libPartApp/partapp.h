@@ -19,11 +19,13 @@ void bbox_from_pos(const ExpParam &exp_param, const PartWindowParam::PartParam &
                    int iy, PartBBox &bbox);
 void bbox_from_pos(const PartWindowParam::PartParam &part_param, double scale, double rot, int ix, int iy, PartBBox &bbox);
 
+QString complete_relative_path(QString qsInputFile, QString qsReferenceFile);
 namespace filesys {
 inline bool check_dir(QString) { return true; }
 inline bool create_dir(QString) { return true; }
 inline bool check_file(QString) { return false; }
 inline bool copy_file(QString, QString) { return false; }
+inline void split_filename(QString, QString &, QString &) {}
 }  // namespace filesys
 
 class PartApp {

@@ -13,6 +13,18 @@ class PartDef {
   std::vector<int> part_pos_;
   int part_pos(int i) const { return part_pos_.at((size_t)i); }
   int part_pos_size() const { return (int)part_pos_.size(); }
+  // fields the evaluator reads (libPartDetect/partdef.cpp, libPartEval/parteval.cpp)
+  std::vector<int> part_x_axis_from_, part_x_axis_to_;
+  float part_x_axis_offset_ = 0, ext_x_pos_ = 0, ext_x_neg_ = 0, ext_y_pos_ = 0, ext_y_neg_ = 0;
+  int part_x_axis_from(int i) const { return part_x_axis_from_.at((size_t)i); }
+  int part_x_axis_from_size() const { return (int)part_x_axis_from_.size(); }
+  int part_x_axis_to(int i) const { return part_x_axis_to_.at((size_t)i); }
+  int part_x_axis_to_size() const { return (int)part_x_axis_to_.size(); }
+  float part_x_axis_offset() const { return part_x_axis_offset_; }
+  float ext_x_pos() const { return ext_x_pos_; }
+  float ext_x_neg() const { return ext_x_neg_; }
+  float ext_y_pos() const { return ext_y_pos_; }
+  float ext_y_neg() const { return ext_y_neg_; }
   int num_pred_part_types() const { return 1; }
   int max_num_part_types() const { return 1; }
   bool has_mult_types() const { return false; }

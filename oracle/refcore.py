@@ -262,3 +262,79 @@ def pos_message(child, offset, Cm, scale, sparse):
         _quiet(lambda: dlib().refd_pos_message(_f(ch[d]), _f(out[d]), ch.shape[1], ch.shape[2], po, pc, float(scale),
                                                int(bool(sparse))))
     return out, ch
+
+
+# ---- the reference's evaluator (oracle/_ref/libps_ref_eval.so = libPartEval/parteval.cpp + libPartDetect/partdef.cpp) ----
+EVAL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libps_ref_eval.so")
+_elib = None
+
+
+def eval_available():
+    return os.path.exists(EVAL_PATH)
+
+
+def elib():
+    global _elib
+    if _elib is None:
+        _elib = C.CDLL(EVAL_PATH)
+        _elib.refe_bbox_endpoints.argtypes = [_dp, _dp]
+        _elib.refe_is_gt_match.argtypes = [_dp, _dp, C.c_int, C.c_float]
+        _elib.refe_bbox_merge.argtypes = [C.c_int, _dp, C.c_float, C.c_float, C.c_int, _dp]
+        _elib.refe_get_part_bbox.argtypes = [_ip, _ip, _ip, C.c_int, _ip, C.c_int, _ip, C.c_int, _ip, C.c_int, _dp, C.c_double, _dp]
+        _elib.refe_vis_eval_helper.argtypes = [C.c_char_p, _fp, C.c_int, _ip, _dp, _dp, C.c_int, C.c_float, C.c_float, C.c_int,
+                                               _dp, C.c_int]
+    return _elib
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+def eval_endpoints(bbox10):
+    b, bp = _d(bbox10)
+    out, op = _d(np.zeros(5))
+    _quiet(lambda: elib().refe_bbox_endpoints(bp, op))
+    return out
+
+
+def eval_is_gt_match(gt10, det10, factor=0.5, match_x_axis=False):
+    g, gp = _d(gt10)
+    d, dp = _d(det10)
+    return bool(_quiet(lambda: elib().refe_is_gt_match(gp, dp, int(match_x_axis), float(factor))))
+
+
+def eval_bbox_merge(kind, boxes, rot_range=(-180.0, 180.0, 48)):
+    b, bp = _d(np.concatenate([np.asarray(x, np.float64) for x in boxes]))
+    out, op = _d(np.zeros(10))
+    _quiet(lambda: elib().refe_bbox_merge(int(kind), bp, float(rot_range[0]), float(rot_range[1]), int(rot_range[2]), op))
+    return out
+
+
+def eval_get_part_bbox(points, part_pos, axis_from, axis_to, offset_and_ext, scale):
+    """points: {id: (x, y)}; offset_and_ext = (part_x_axis_offset, ext_x_pos, ext_x_neg, ext_y_pos, ext_y_neg).
+    Returns None (axis invalid), False (a point of the part is missing) or the 10 bbox numbers."""
+    ids = sorted(points)
+    _, idp = _i(ids)
+    xs, xp = _i([points[k][0] for k in ids])
+    ys, yp = _i([points[k][1] for k in ids])
+    pos, pp = _i(part_pos)
+    fr, frp = _i(axis_from if len(axis_from) else [0])
+    to, top = _i(axis_to if len(axis_to) else [0])
+    f5, f5p = _d(offset_and_ext)
+    out, op = _d(np.zeros(10))
+    rc = _quiet(lambda: elib().refe_get_part_bbox(idp, xp, yp, len(ids), pp, len(part_pos), frp, len(axis_from), top, len(axis_to),
+                                                  f5p, float(scale), op))
+    return False if rc < 0 else (None if rc == 0 else out)
+
+
+def eval_vis_eval_helper(part_conf_type, best_conf, window, ext, ext_eval, rot_range=(-180.0, 180.0, 48)):
+    """best_conf [P][7]; window [P][4] ints; ext [P][4], ext_eval [Pe][4] = (ext_x_pos, ext_x_neg, ext_y_pos, ext_y_neg)."""
+    bc = np.ascontiguousarray(best_conf, np.float32)
+    w, wp = _i(window)
+    e, ep_ = _d(ext)
+    ee, eep = _d(ext_eval)
+    out, op = _d(np.zeros(10 * 64))
+    n = _quiet(lambda: elib().refe_vis_eval_helper(part_conf_type.encode(), _f(bc), bc.shape[0], wp, ep_, eep, len(np.asarray(ext_eval)),
+                                                   float(rot_range[0]), float(rot_range[1]), int(rot_range[2]), op, 64))
+    return out[:10 * n].reshape(n, 10)

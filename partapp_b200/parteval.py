@@ -28,7 +28,8 @@ class PartParam:
 
 
 def bbox_endpoints(row, pp: PartParam):
-    scale, rot = float(row[1]), float(row[3]) / 180.0 * np.pi      # PartHyp::getPartBBox, objectdetect.h:107-113
+    # PartHyp::getPartBBox, objectdetect.h:107-113: m_rot / 180 is a float division, the product with M_PI is double
+    scale, rot = float(row[1]), float(np.float32(row[3]) / np.float32(180)) * np.pi
     pos = np.array([float(int(row[4])), float(int(row[5]))])
     x_axis = np.array([np.cos(rot), np.sin(rot)])
     y_axis = np.array([-x_axis[1], x_axis[0]])
@@ -265,7 +266,9 @@ def get_part_bbox(rect: AnnoRect, pd: PartDef, scale: float) -> Optional[PartBBo
 
 def bbox_from_hyp(row, pp: PartParam) -> PartBBox:
     """PartHyp::getPartBBox -> bbox_from_pos (objectdetect.h:107-113, partapp.cpp:59-81) for a best_conf row."""
-    scale, rot = float(row[1]), float(row[3]) / 180 * math.pi
+    # m_rot is a float and `m_rot / 180` a FLOAT division (objectdetect.h:111); only the product with M_PI is double.
+    # Pinned against the reference's compiled code by tests/test_eval_vs_ref.py.
+    scale, rot = float(row[1]), float(np.float32(row[3]) / np.float32(180)) * math.pi
     ax = np.array([math.cos(rot), math.sin(rot)])
     ay = np.array([-ax[1], ax[0]])
     mx, my = -scale * pp.pos_offset_x, -scale * pp.pos_offset_y
