@@ -204,6 +204,10 @@ def run_ours(args):
         from partapp_b200 import synth as _s
         type_tables = [_s.make_joints(P, seed=7, type_id=t) for t in range(8)]
     results = np.zeros((B, P, 7), np.float32)
+    ALL_P = [p for p in range(P) for sc in range(S)]
+    ALL_S = [sc for p in range(P) for sc in range(S)]
+    ptrs_dev = [[t[k].data_ptr() for k in range(P * S)] for t in dev_raw]
+    ptrs_pin = [[t[k].data_ptr() for k in range(P * S)] for t in pin_raw]
     # configs[3] also conditions the unaries per image (findrot.cpp:913-949): a rotation score for every part, a position
     # score for every non-root part, the torso prior for the root.  The predictors that produce the parameters are
     # outside the path (MATLAB); the tables are inputs, drawn per image from a pool of 4 per part.
@@ -243,13 +247,10 @@ def run_ours(args):
             if type_tables is not None:
                 rng = np.random.default_rng(rank * B + i)
                 c.set_joints([type_tables[int(rng.integers(0, 8))][j] for j in range(P - 1)])
+            # every (part, scale) grid of the image sits on one detector lattice: one ingest call
+            c.set_unaries_compact(ALL_P, ALL_S, None, Tig, gh, gw, pointers=ptrs_dev[i] if device_resident else ptrs_pin[i],
+                                  device=device_resident)
             for p in range(P):
-                for sc in range(S):
-                    ptr = src[p * S + sc].data_ptr()
-                    if device_resident:
-                        c.set_unary_compact(p, sc, (gh, gw), Tig, device_ptr=ptr)
-                    else:
-                        c.set_unary_compact_pinned(p, sc, ptr, gh, gw, Tig)
                 if cond is not None:
                     v = int(rng.integers(0, 4))
                     tabs = (cond["dev"] if device_resident else cond["pin"])[p][v]
@@ -314,18 +315,14 @@ def run_ours(args):
     roofline_ctx_mode = args.fast_math
 
     def feed_image0(c):
-        for p in range(P):
-            for sc in range(S):
-                c.set_unary_compact(p, sc, (gh, gw), Tig, device_ptr=dev_raw[0][p * S + sc].data_ptr())
+        c.set_unaries_compact(ALL_P, ALL_S, None, Tig, gh, gw, pointers=ptrs_dev[0], device=True)
     if rank == 0:
         peak, peak_src = read_peaks()
         # ---- instrumented pass: CUDA events around every launch of one ctx, for the per-kernel roofline ----
         c = ctxs[0]
         c.profile_enable(True)
         for i in range(min(B, 2)):
-            for p in range(P):
-                for sc in range(S):
-                    c.set_unary_compact(p, sc, (gh, gw), Tig, device_ptr=dev_raw[i][p * S + sc].data_ptr())
+            c.set_unaries_compact(ALL_P, ALL_S, None, Tig, gh, gw, pointers=ptrs_dev[i], device=True)
             c.infer_async(sparse=True)
             c.best_conf()
         prof = c.profile_read()

@@ -145,6 +145,12 @@ int ps_set_unary_compact(ps_ctx *ctx, int part, int scale, const float *cells, i
  * grid is the caller's error. */
 int ps_set_unary_compact_raw(ps_ctx *ctx, int part, int scale, const float *cells, int grid_h, int grid_w,
                              const double *Tig, int mem_kind);
+/* The same for n (part, scale) grids that share one detector lattice (gh x gw cells, one Tig[R][3][3]) -- every part of
+ * an image, typically: one fill and one scatter launch for all of them instead of two per part.  cells[i] is the
+ * compact grid [R][gh][gw] of (parts[i], scales[i]).  Falls back to n single-grid calls when the lattice is not
+ * collision-free or interpolate is set (same results either way). */
+int ps_set_unaries_compact(ps_ctx *ctx, int n, const int *parts, const int *scales, const float *const *cells, int gh,
+                           int gw, const double *Tig, int mem_kind);
 /* multi_array_op::computeLogGrid (multi_array_op.hpp:154-167) in place on the resident grid of (part, scale)
  * (objectdetect_roi.cpp:240-242). */
 int ps_log_unary(ps_ctx *ctx, int part, int scale);

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "ps_set_unary_compact_raw": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]),
     "ps_log_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     "ps_unary_local_max": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, _fp, _ip]),
+    "ps_set_unaries_compact": (C.c_int, [_ctx_p, C.c_int, _ip, _ip, C.POINTER(C.c_void_p), C.c_int, C.c_int, _dp, C.c_int]),
     "ps_get_unary": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "ps_add_unary_table": (C.c_int, [_ctx_p, C.c_int, _fp, C.c_int, C.c_float]),
     "ps_add_unary_tables": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), _ip, _fp, C.c_int]),

@@ -434,6 +434,38 @@ __global__ void __launch_bounds__(256) k_ingest_scatter_direct(IngestArgs a, con
   if (max_dst) block_max_to(m, max_dst);
 }
 
+// The collision-free scatter for several (part, scale) grids that share one lattice (same gh x gw and Tig: every part
+// of an image is evaluated on the same detector grid): blockIdx.z selects the grid.  One launch per image instead of
+// one per part.
+constexpr int kMaxIngestBatch = 32;
+struct IngestBatch {
+  const float *cells[kMaxIngestBatch];
+  float *out[kMaxIngestBatch];
+  int *max_dst[kMaxIngestBatch];
+};
+__global__ void __launch_bounds__(256) k_ingest_scatter_direct_b(IngestArgs a, const __grid_constant__ IngestBatch b,
+                                                                 const __grid_constant__ TigRows rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y, g = blockIdx.z;
+  float m = kLogZero;
+  if (i < a.gh * a.gw) {
+    const int y1 = i / a.gw, x1 = i - y1 * a.gw;
+    const float v = b.cells[g][(size_t)r * a.gh * a.gw + i];
+    if (v != 0.0f) {
+      const double *T = rows.m + r * 6;
+      const double x3 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], (double)x1), __dmul_rn(T[1], (double)y1)), T[2]);
+      const double y3 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], (double)x1), __dmul_rn(T[4], (double)y1)), T[5]);
+      const int ix = (int)floor(__dadd_rn(x3, 0.5)), iy = (int)floor(__dadd_rn(y3, 0.5));
+      if (ix >= 0 && ix < a.W && iy >= 0 && iy < a.H) {
+        const float o = prepare_cell(v);
+        b.out[g][(size_t)r * a.H * a.W + (size_t)iy * a.W + ix] = o;
+        m = fmaxf(m, o);
+      }
+    }
+  }
+  block_max_to(m, b.max_dst[g]);
+}
+
 __device__ __forceinline__ float bilinear_at(const float *__restrict__ s, int h, int w, int pitch, double x1, double y1);
 
 // ExpParam.interpolate: TM_BILINEAR gather (transform.hpp:196-238) of every image cell through T13 = inverse(Tig),

@@ -134,6 +134,7 @@ struct ps_ctx {
   psk::TopKState *host_topk_state = nullptr;
   size_t topk_slots = 0, topk_kmax = 0;
   DevBuf counters;      // unsigned [8]
+  DevBuf ingest_batch;              // ps_set_unaries_compact: compact cells of every grid of one call
   DevBuf ingest, ingest_keys;       // ps_set_unary_compact staging: Tig rows + compact cells; order keys [R][H][W]
   DevBuf table_stage, grid_stage;   // ps_add_unary_table(s) / ps_add_unary_grid: stream-ordered staging of host inputs
   DevBuf unary_max;                 // int [P][S]: encoded max of each unary as left by the ingest
@@ -1538,6 +1539,76 @@ static int set_unary_compact_impl(ps_ctx *c, int part, int scale, const float *c
     PS_LAUNCH(c, KC_PREP, psk::k_ingest_sweep<<<cdiv((c->N + 3) / 4, 256), 256, 0, c->stream>>>(a, mslot));
   }
   c->unary_max_valid[(size_t)part * c->S + scale] = raw ? 0 : 1;  // a raw grid is not what the messages read
+  return PS_OK;
+}
+
+int ps_set_unaries_compact(ps_ctx *c, int n, const int *parts, const int *scales, const float *const *cells, int gh, int gw,
+                           const double *Tig, int mem_kind) {
+  if (!c || !parts || !scales || !cells || !Tig || n < 1) return PS_ERR_INVALID;
+  if (gh < 1 || gw < 1 || (size_t)gh * gw >= ((size_t)1 << 31)) return c->fail(PS_ERR_INVALID, "compact grid size out of range");
+  for (int i = 0; i < n; ++i)
+    if (parts[i] < 0 || parts[i] >= c->P || scales[i] < 0 || scales[i] >= c->S || !cells[i])
+      return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  // the shared-lattice fast path needs the collision-free direct scatter with by-value transforms
+  bool fast = !c->cfg.interpolate && c->R <= psk::kMaxIngestRot;
+  for (int r = 0; r < c->R && fast; ++r) {
+    const double a00 = Tig[r * 9 + 0], a01 = Tig[r * 9 + 1], a10 = Tig[r * 9 + 3], a11 = Tig[r * 9 + 4];
+    const double s1 = a00 * a00 + a01 * a01 + a10 * a10 + a11 * a11, det = a00 * a11 - a01 * a10;
+    const double disc = std::sqrt(std::max(0.0, s1 * s1 - 4 * det * det));
+    fast = 0.5 * (s1 - disc) > 2.0 * 1.01;  // squared smallest singular value, as in set_unary_compact_impl
+  }
+  if (!fast) {
+    for (int i = 0; i < n; ++i)
+      if (int rc = ps_set_unary_compact(c, parts[i], scales[i], cells[i], gh, gw, Tig, mem_kind)) return rc;
+    return PS_OK;
+  }
+  PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  const size_t ncell = (size_t)c->R * gh * gw;
+  psk::TigRows rows;
+  for (int r = 0; r < c->R; ++r)
+    for (int k = 0; k < 6; ++k) rows.m[(size_t)r * 6 + k] = Tig[(size_t)r * 9 + k];
+  if (mem_kind == PS_MEM_HOST && c->ingest_batch.bytes < (size_t)n * ncell * sizeof(float)) {
+    PS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PS_CUDA(c, c->ingest_batch.alloc((size_t)n * ncell * sizeof(float)));
+  }
+  // one fill for everything when the call covers the whole unary buffer, else one per grid
+  bool whole = n == c->P * c->S;
+  if (whole) {
+    std::vector<unsigned char> seen((size_t)c->P * c->S, 0);
+    for (int i = 0; i < n; ++i) seen[(size_t)parts[i] * c->S + scales[i]] = 1;
+    for (unsigned char v : seen) whole = whole && v;
+  }
+  if (whole) {
+    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv((size_t)n * c->N, 4096), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(
+                              c->unary.as<float>(), (size_t)n * c->N, psk::kLogZero));
+    PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<cdiv(n, 128), 128, 0, c->stream>>>(c->unary_max.as<int>(), n, PS_ENC_NEG_INF));
+  }
+  psk::IngestArgs a;
+  a.cells = nullptr; a.Tig = nullptr; a.keys = nullptr; a.out = nullptr;
+  a.R = c->R; a.gh = gh; a.gw = gw; a.H = c->H; a.W = c->W;
+  a.raw = 0;
+  for (int i0 = 0; i0 < n; i0 += psk::kMaxIngestBatch) {
+    const int nb = std::min(psk::kMaxIngestBatch, n - i0);
+    psk::IngestBatch b{};
+    for (int k = 0; k < nb; ++k) {
+      const int i = i0 + k;
+      int *mslot = c->unary_max.as<int>() + (size_t)parts[i] * c->S + scales[i];
+      if (!whole)
+        PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv(c->N, 4096), (unsigned)c->num_sms * 8), 256, 0, c->stream>>>(
+                                  c->U(parts[i], scales[i]), c->N, psk::kLogZero, mslot, PS_ENC_NEG_INF));
+      const float *src = cells[i];
+      if (mem_kind == PS_MEM_HOST) {
+        float *d = c->ingest_batch.as<float>() + (size_t)i * ncell;
+        PS_CUDA(c, cudaMemcpyAsync(d, cells[i], ncell * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        src = d;
+      }
+      b.cells[k] = src;
+      b.out[k] = c->U(parts[i], scales[i]);
+      b.max_dst[k] = mslot;
+      c->unary_max_valid[(size_t)parts[i] * c->S + scales[i]] = 1;
+    }
+    PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct_b<<<dim3(cdiv((size_t)gh * gw, 256), c->R, nb), 256, 0, c->stream>>>(a, b, rows));
+  }
   return PS_OK;
 }
 

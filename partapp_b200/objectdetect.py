@@ -212,6 +212,29 @@ class PsContext:
                                                   Tig.ctypes.data_as(C.POINTER(C.c_double)), capi.PS_MEM_HOST))
         self.synchronize()
 
+    def set_unaries_compact(self, parts, scales, cells, Tig, gh=None, gw=None, pointers=None, device=False):
+        """loadScoreGrid for several (part, scale) grids on ONE lattice in one fill + one scatter launch.  `cells`: list of
+        [R][gh][gw] arrays, or -- with `pointers`, gh, gw -- raw addresses in device (device=True) or pinned host memory."""
+        Tig = np.ascontiguousarray(Tig, np.float64)
+        if Tig.shape != (self.R, 3, 3):
+            raise ValueError("Tig must be [R][3][3]")
+        n = len(parts)
+        keep = None
+        if pointers is None:
+            keep = [_f32(c) for c in cells]
+            gh, gw = keep[0].shape[1:]
+            if any(k.shape != (self.R, gh, gw) for k in keep):
+                raise ValueError("every grid must be [R][gh][gw] with the same gh, gw")
+            pointers = [k.ctypes.data for k in keep]
+        ps = (C.c_int * n)(*[int(p) for p in parts])
+        ss = (C.c_int * n)(*[int(s) for s in scales])
+        ptrs = (C.c_void_p * n)(*[int(p) for p in pointers])
+        self._check(self.lib.ps_set_unaries_compact(self.h, n, ps, ss, ptrs, int(gh), int(gw),
+                                                    Tig.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    capi.PS_MEM_DEVICE if device else capi.PS_MEM_HOST))
+        if keep is not None:
+            self.synchronize()
+
     def set_unary_compact_raw(self, part, scale, cells, Tig):
         """The same mapping stopped after clip_scores_fill (objectdetect_roi.cpp:205-215): scores, not logs."""
         Tig = np.ascontiguousarray(Tig, np.float64)

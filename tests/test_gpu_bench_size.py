@@ -196,3 +196,54 @@ def test_fast_math_argmax_identity_over_bench_size_images():
     print(json.dumps(out))
     assert rows_equal >= 0.95 * rows_total, out
     assert worst <= 1e-4, out
+
+
+def test_pcp_identity_and_argmax_exactness_over_100_bench_size_images():
+    """North star: ">= 95 % PCP-identical part estimates vs reference plus bit-exact argmax on the test set".  100
+    synthetic LSP-shape images (configs[2]: the batch workload) through the CUDA path in both arithmetic modes against
+    the CPU oracle's estimates of the same images (one oracle inference per host thread); the oracle's estimate plays the
+    ground truth of the PCP matching rule (parteval.is_gt_match, pinned to the reference's evaluator)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from partapp_b200 import parteval as pe
+    ep = ExpParam(num_rotation_steps=24)
+    P, H, W = 10, 600, 400
+    pc = synth.part_conf(P)
+    joints = synth.make_joints(P, seed=7)
+    threads = max(1, min(os.cpu_count() or 1, 32))
+    n_img = 100 if threads >= 12 else 24
+    # LSP-like part windows (window_size_x/y, pos_offset_x/y of PartWindowParam): sticks of 60-110 px
+    rng = np.random.default_rng(3)
+    pps = [pe.PartParam(int(rng.integers(30, 50)), int(rng.integers(60, 110)), int(rng.integers(15, 25)), int(rng.integers(30, 55)))
+           for _ in range(P)]
+
+    def cpu(i):
+        un = oracle.prepare_unary(synth.raw_scores(ep, H, W, P, 2000 + i))
+        return oracle.infer(ep, pc, joints, un, sparse=True, want_marginals=False)["best_conf"]
+
+    with ThreadPoolExecutor(threads) as pool:
+        futures = [pool.submit(cpu, i) for i in range(n_img)]
+        got = {"parity": [], "fast_math": []}
+        with PsContext(ep, pc, H, W) as exact, PsContext(ep, pc, H, W, fast_math=True) as fast:
+            exact.set_joints(joints)
+            fast.set_joints(joints)
+            for i in range(n_img):
+                cells, Tig = synth.compact_scores(ep, H, W, P, 2000 + i)
+                for name, ctx in (("parity", exact), ("fast_math", fast)):
+                    for p in range(P):
+                        ctx.set_unary_compact(p, 0, cells[p, 0], Tig)
+                    ctx.infer(sparse=True)
+                    got[name].append(ctx.best_conf())
+        want = [f.result() for f in futures]
+    out = {"images": n_img, "parts": P}
+    for name in ("parity", "fast_math"):
+        exact_imgs = sum(int(np.array_equal(g[:, :6], w[:, :6])) for g, w in zip(got[name], want))
+        exact_rows = sum(int((g[:, :6] == w[:, :6]).all(axis=1).sum()) for g, w in zip(got[name], want))
+        score_bits = sum(int(np.array_equal(g[:, 6], w[:, 6])) for g, w in zip(got[name], want))
+        pcp = float(np.mean([pe.pcp_identical(w, g, pps) for g, w in zip(got[name], want)]))
+        out[name] = {"images_argmax_bit_exact": exact_imgs, "part_rows_argmax_bit_exact": exact_rows,
+                     "images_best_score_bit_exact": score_bits, "pcp_identical": pcp}
+    _report("pcp_identity.json", out)
+    print(json.dumps(out))
+    assert out["parity"]["images_argmax_bit_exact"] == n_img and out["parity"]["images_best_score_bit_exact"] == n_img, out
+    assert out["parity"]["pcp_identical"] == 1.0
+    assert out["fast_math"]["pcp_identical"] >= 0.95, out

@@ -431,6 +431,40 @@ def test_compact_ingest_interpolate_matches_load_score_grid(rotated):
         assert (ctx.get_unary(1, 0) > -1e5).sum() > 100
 
 
+@pytest.mark.parametrize("rotated", [False, True], ids=["lattice", "rotated_lattice"])
+def test_compact_ingest_all_parts_in_one_call(rotated):
+    """ps_set_unaries_compact: every (part, scale) grid of an image on one lattice, one fill + one scatter launch --
+    same unaries and same folded maxima (the inference that follows must not change) as one call per grid."""
+    ep = ExpParam(num_rotation_steps=8, num_scale_steps=2, min_object_scale=0.9, max_object_scale=1.1)
+    P, H, W = 4, 44, 52
+    cells, Tig = synth.compact_scores(ep, H, W, P, 7, rotated=rotated)
+    joints = synth.make_joints(P, seed=5, max_offset=6, sigma_range=(1.5, 3))
+    pc = synth.part_conf(P)
+    with PsContext(ep, pc, H, W) as one, PsContext(ep, pc, H, W) as many:
+        many.set_joints(joints)
+        one.set_joints(joints)
+        for p in range(P):
+            for s in range(2):
+                many.set_unary_compact(p, s, cells[p, s], Tig)
+        ps_ = [p for p in range(P) for s in range(2)]
+        ss = [s for p in range(P) for s in range(2)]
+        n0 = one.launch_count()
+        one.set_unaries_compact(ps_, ss, [cells[p, s] for p, s in zip(ps_, ss)], Tig)
+        assert one.launch_count() - n0 <= 3
+        for p in range(P):
+            for s in range(2):
+                assert np.array_equal(one.get_unary(p, s), many.get_unary(p, s)), (p, s)
+        one.infer(sparse=True)
+        many.infer(sparse=True)
+        assert np.array_equal(one.best_conf(), many.best_conf())
+        assert np.array_equal(one.marginal(1), many.marginal(1))
+        # a subset of the grids (not the whole buffer) takes the per-grid fills
+        one.set_unaries_compact([2], [1], [cells[0, 0]], Tig)
+        many.set_unary_compact(2, 1, cells[0, 0], Tig)
+        assert np.array_equal(one.get_unary(2, 1), many.get_unary(2, 1))
+        assert np.array_equal(one.get_unary(2, 0), many.get_unary(2, 0))
+
+
 def test_compact_ingest_many_rotations_back_to_back():
     """R > 64: the per-rotation transforms go through a device staging buffer shared by every (part, scale) call.
     Calls issued back to back, each with its OWN transforms, must not overwrite the rows a previous call's scatter
