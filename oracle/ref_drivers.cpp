@@ -58,7 +58,13 @@ void getRootPosDet(const PartApp &, int, int, boost_math::double_vector &, bool)
 void getPosScoreGrid(const PartApp &, Grids &, int, boost_math::double_matrix &, int, boost_math::double_vector &) { abort(); }
 void setTorsoPosPrior(const PartApp &, Grids &, boost_math::double_matrix &, int) { abort(); }
 #endif
-// objectdetect_findpos.cpp defines it but declares it in no header
+// objectdetect_findpos.cpp defines these but declares them in no header this file sees
+void mergeRotations(const PartApp &part_app, const PartConfig &part_conf,
+                    const std::vector<std::vector<std::vector<FloatGrid2> > > &part_score_grid_rotation,
+                    std::vector<std::vector<FloatGrid2> > &log_part_detections);
+void computeRootPosterior(const PartApp part_app, const std::vector<std::vector<FloatGrid2> > &log_part_detections,
+                          FloatGrid3 &root_part_posterior, int rootpart_idx, std::vector<Joint> joints, bool flip,
+                          QString qsDebugDir, bool bIsSparse);
 void computePosJointMarginal(FloatGrid2 &log_prob_child, FloatGrid2 &log_prob_parent, boost_math::double_vector offset,
                              boost_math::double_matrix C, double scale, bool bIsSparse);
 }  // namespace object_detect
@@ -216,6 +222,42 @@ void refd_pos_message(float *child, float *parent, int H, int W, const double *o
   object_detect::computePosJointMarginal(gc, gp, off, Cm, scale, sparse != 0);
   memcpy(child, gc.data(), sizeof(float) * (size_t)H * W);
   memcpy(parent, gp.data(), sizeof(float) * (size_t)H * W);
+}
+
+// The legacy POS_GAUSSIAN driver (objectdetect_findpos.cpp): mergeRotations (:118-170) of log-domain unaries
+// [P][S][R][H][W], then computeRootPosterior (:172-334).  Outputs: merged [P][S][H][W], root posterior [S][H][W].
+void refd_root_posterior_pos(const double *ep, int P, const int *is_detect, int root_idx, const double *joints, int nj, int H,
+                             int W, const float *unaries, int sparse, float *merged_out, float *root_post) {
+  PartApp app;
+  app.m_exp_param = make_ep(ep);
+  const int S = (int)app.m_exp_param.num_scale_steps(), R = (int)app.m_exp_param.num_rotation_steps();
+  for (int p = 0; p < P; ++p) {
+    PartDef d;
+    d.is_detect_ = is_detect[p] != 0;
+    d.is_root_ = p == root_idx;
+    app.m_part_conf.parts_.push_back(d);
+  }
+  std::vector<Joint> js;
+  for (int j = 0; j < nj; ++j) js.push_back(joint_from_row(joints + 13 * j));
+  std::vector<std::vector<std::vector<FloatGrid2> > > rot(P);
+  for (int p = 0; p < P; ++p) {
+    if (!is_detect[p]) continue;
+    rot[p].resize(S);
+    for (int s = 0; s < S; ++s)
+      for (int r = 0; r < R; ++r) {
+        FloatGrid2 g(boost::extents[H][W]);
+        memcpy(g.data(), unaries + ((((size_t)p * S + s) * R + r) * H) * W, sizeof(float) * (size_t)H * W);
+        rot[p][s].push_back(g);
+      }
+  }
+  std::vector<std::vector<FloatGrid2> > merged(P);
+  object_detect::mergeRotations(app, app.m_part_conf, rot, merged);
+  for (int p = 0; p < P; ++p)
+    for (int s = 0; s < S; ++s)
+      memcpy(merged_out + ((size_t)p * S + s) * H * W, merged[p][s].data(), sizeof(float) * (size_t)H * W);
+  FloatGrid3 rp;
+  object_detect::computeRootPosterior(app, merged, rp, root_idx, js, false, QString("debug"), sparse != 0);
+  memcpy(root_post, rp.data(), sizeof(float) * (size_t)S * H * W);
 }
 
 // object_detect::computeRotJointMarginal (objectdetect_findrot.cpp:292-456), the reference's code

@@ -146,6 +146,7 @@ def dlib():
         L.refd_find_local_max.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
         L.refd_load_joints.argtypes = [C.c_int, _dp, C.c_int, C.c_int, _dp, _dp]
         L.refd_pos_message.argtypes = [_fp, _fp, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int]
+        L.refd_root_posterior_pos.argtypes = [_dp, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp]
         L.refd_condition.argtypes = [_dp, C.c_int, _ip, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _dp, C.c_float, C.c_int, _fp,
                                      C.c_int]
         _dlib = L
@@ -212,6 +213,22 @@ def infer(ep, part_conf, joints, unaries, sparse=True):
                                      _f(best), _f(marg), _f(hyps), cap, nh.ctypes.data_as(_ip)))
     return {"root_post": root_post, "best_conf": best, "marginals": marg,
             "part_hyps": [hyps[p, :nh[p]].copy() for p in range(P)]}
+
+
+def root_posterior_pos(ep, part_conf, joints, unaries, sparse=True):
+    """mergeRotations + computeRootPosterior (objectdetect_findpos.cpp:118-334) as the reference compiled them.
+    unaries [P][S][R][H][W] (log domain).  Returns (merged [P][S][H][W], root posterior [S][H][W])."""
+    assert unaries.dtype == np.float32 and unaries.flags.c_contiguous
+    P, S, R, H, W = unaries.shape
+    det = np.array([int(bool(v)) for v in part_conf.is_detect], np.int32)
+    roots = [p for p in range(P) if part_conf.is_detect[p] and part_conf.is_root[p]]
+    js = _joint_rows(joints)
+    merged = np.zeros((P, S, H, W), np.float32)
+    rp = np.zeros((S, H, W), np.float32)
+    e = _epv(ep)
+    _quiet(lambda: dlib().refd_root_posterior_pos(e.ctypes.data_as(_dp), P, det.ctypes.data_as(_ip), roots[0], js.ctypes.data_as(_dp),
+                                                  len(joints), H, W, _f(unaries), int(bool(sparse)), _f(merged), _f(rp)))
+    return merged, rp
 
 
 def find_local_max(grid, max_n):

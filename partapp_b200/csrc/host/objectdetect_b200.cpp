@@ -350,6 +350,7 @@ void PartApp::init(const std::string &expopt) {
   e.interpolate = n.boolean("interpolate", false);
   e.force_recompute_scores = n.boolean("force_recompute_scores", true);
   e.use_torso_pos_prior = n.boolean("use_torso_pos_prior", false);
+  e.save_root_marginal = n.boolean("save_root_marginal", false);
   e.torso_pos_prior_weight = (float)n.num("torso_pos_prior_weight", 1);
   e.pred_unary_rot = n.boolean("pred_unary_rot", false);
   e.pred_unary_pos = n.boolean("pred_unary_pos", false);
@@ -715,26 +716,11 @@ void findObjectRoiHelper(PartApp app, const int roi[4], double scale, const std:
     }
 }
 
-void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, HypothesisList &hypothesis_list,
-                              const std::string &qsPartMarginalsDir, const std::string &qsScoreGridDir,
-                              const std::string &qsImgName) {
+// loadScoreGrid (partapp.cpp:830-903) + unary prep (findrot.cpp:834-845 / findpos.cpp:377-384) of every detected part of
+// one image, on the device.
+static void load_image_unaries(const PartApp &app, ps_ctx *ctx, int imgidx, bool flip) {
   const ExpParam &ep = app.m_exp_param;
   const int P = (int)app.m_part_conf.part.size(), S = (int)ep.num_scale_steps, R = (int)ep.num_rotation_steps;
-  (void)qsScoreGridDir;
-  int W = 0, H = 0;
-  image_size(qsImgName, W, H);  // findrot.cpp:752-760
-  std::vector<Joint> joints;
-  loadJoints(app, joints, flip, imgidx);
-  for (const Joint &j : joints)
-    if (j.type != Joint::ROT_GAUSSIAN) fail("only ROT_GAUSSIAN joints are supported (findrot.cpp:766)");
-  const int rootpart_idx = app.m_rootpart_idx;
-  if (rootpart_idx < 0) fail("root part not found (findrot.cpp:831)");
-  const bool bSaveMarginals = ep.save_part_marginals;
-  ps_ctx *ctx = get_ctx(app, H, W, rootpart_idx, bSaveMarginals);
-  std::vector<ps_joint> pj = to_ps_joints(joints);
-  check(ctx, ps_set_joints(ctx, pj.data(), (int)pj.size()), "ps_set_joints");
-
-  // loadScoreGrid (partapp.cpp:830-903) + unary prep (findrot.cpp:834-845), on the device
   std::vector<float> cells;
   std::vector<double> Tig((size_t)R * 9);
   for (int p = 0; p < P; ++p) {
@@ -767,6 +753,67 @@ void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, Hypothe
       check(ctx, ps_set_unary_compact(ctx, p, s, cells.data(), (int)gh, (int)gw, Tig.data(), PS_MEM_HOST), "ps_set_unary_compact");
     }
   }
+}
+
+void findObjectImagePosJoints(const PartApp &app, int imgidx, bool flip, HypothesisList &hypothesis_list) {
+  const ExpParam &ep = app.m_exp_param;
+  const int S = (int)ep.num_scale_steps;
+  int W = 0, H = 0;
+  image_size(app.m_test_annolist[imgidx], W, H);
+  std::vector<Joint> joints;
+  loadJoints(app, joints, flip);  // no per-image joint types on this path (findpos.cpp:350)
+  for (const Joint &j : joints)
+    if (j.type != Joint::POS_GAUSSIAN) fail("findObjectImagePosJoints: POS_GAUSSIAN joints only (aux.cpp:346)");
+  const int rootpart_idx = app.m_rootpart_idx;
+  if (rootpart_idx < 0) fail("root part not found (findpos.cpp:359-362)");
+  ps_ctx *ctx = get_ctx(app, H, W, rootpart_idx, false);
+  std::vector<ps_joint> pj = to_ps_joints(joints);
+  check(ctx, ps_set_joints(ctx, pj.data(), (int)pj.size()), "ps_set_joints");
+  load_image_unaries(app, ctx, imgidx, flip);
+  check(ctx, ps_infer(ctx, PS_INFER_SPARSE | PS_INFER_ROOT_HYPS), "ps_infer");  // bIsSparse = true (:342)
+  hypothesis_list.hyp.clear();
+  std::vector<float> rows(1000 * 4);
+  int n = 0;
+  check(ctx, ps_get_root_hyps(ctx, rows.data(), 1000, &n), "ps_get_root_hyps");
+  for (int i = 0; i < n; ++i) {  // findLocalMax(exp_param, grid, hypothesis_list, n), aux.cpp:263-300
+    ObjectHypothesis h;
+    h.scale = (float)scale_from_index(ep, (int)rows[4 * i]);
+    h.x = rows[4 * i + 1];  // no bounding-box offset on this path (aux.cpp:280-281)
+    h.y = rows[4 * i + 2];
+    h.score = rows[4 * i + 3];
+    h.flip = flip;
+    hypothesis_list.hyp.push_back(h);
+  }
+  if (ep.save_root_marginal) {  // :437-451
+    const std::string dir = ep.log_dir + "/" + ep.log_subdir + "/root_part_posterior";
+    make_dirs(dir);
+    FloatGrid3 rp(S, H, W);
+    check(ctx, ps_get_root_posterior(ctx, rp.data(), PS_MEM_HOST), "ps_get_root_posterior");
+    mat5::Writer w(dir + "/root_part_posterior_imgidx" + std::to_string(imgidx) + "_o" + std::to_string((int)flip) + ".mat");
+    w.put("root_part_posterior", rp.data(), {(size_t)S, (size_t)H, (size_t)W});
+  }
+}
+
+void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, HypothesisList &hypothesis_list,
+                              const std::string &qsPartMarginalsDir, const std::string &qsScoreGridDir,
+                              const std::string &qsImgName) {
+  const ExpParam &ep = app.m_exp_param;
+  const int P = (int)app.m_part_conf.part.size(), R = (int)ep.num_rotation_steps;
+  (void)qsScoreGridDir;
+  int W = 0, H = 0;
+  image_size(qsImgName, W, H);  // findrot.cpp:752-760
+  std::vector<Joint> joints;
+  loadJoints(app, joints, flip, imgidx);
+  for (const Joint &j : joints)
+    if (j.type != Joint::ROT_GAUSSIAN) fail("only ROT_GAUSSIAN joints are supported (findrot.cpp:766)");
+  const int rootpart_idx = app.m_rootpart_idx;
+  if (rootpart_idx < 0) fail("root part not found (findrot.cpp:831)");
+  const bool bSaveMarginals = ep.save_part_marginals;
+  ps_ctx *ctx = get_ctx(app, H, W, rootpart_idx, bSaveMarginals);
+  std::vector<ps_joint> pj = to_ps_joints(joints);
+  check(ctx, ps_set_joints(ctx, pj.data(), (int)pj.size()), "ps_set_joints");
+
+  load_image_unaries(app, ctx, imgidx, flip);
 
   // ---- conditioning of the unaries, in the reference's order (findrot.cpp:849-949) ----
   // The predictors (MATLAB poselet classifiers, DPM detectors) are outside this path: their per-image outputs are read
@@ -886,10 +933,20 @@ void set_parallelism(int gpus, int contexts_per_gpu) {
 static void find_object_image(const PartApp &app, int imgidx, const std::string &qsHypDir, const std::string &qsPartMarginalsDir) {
   const ExpParam &ep = app.m_exp_param;
   const int flip_count = ep.flip_orientation ? 2 : 1;
+  // "find out what type of joints are used in the spatial model" (aux.cpp:346-359): the first joint decides
+  bool bFindObjectRot = false;
+  if (!app.m_part_conf.joint.empty()) {
+    Joint joint;
+    load_joint(app, 0, joint, app.m_part_conf.joint[0].num_joint_types > 1 ? 0 : -1);
+    bFindObjectRot = joint.type == Joint::ROT_GAUSSIAN;
+  }
   for (int flip = 0; flip < flip_count; ++flip) {
     HypothesisList hypothesis_list;
-    findObjectImageRotJoints(app, imgidx, flip != 0, hypothesis_list, qsPartMarginalsDir, ep.scoregrid_dir,
-                             app.m_test_annolist[imgidx]);
+    if (bFindObjectRot)
+      findObjectImageRotJoints(app, imgidx, flip != 0, hypothesis_list, qsPartMarginalsDir, ep.scoregrid_dir,
+                               app.m_test_annolist[imgidx]);
+    else
+      findObjectImagePosJoints(app, imgidx, flip != 0, hypothesis_list);
     const std::string file = qsHypDir + getObjectHypFilename(imgidx, flip != 0);
     std::ofstream f(file.c_str(), std::ios::binary);
     if (!f) fail("cannot write " + file);

@@ -41,7 +41,7 @@ struct ExpParam {
   float roi_save_num_samples = 1000;
   bool use_pairwise = true, save_part_marginals = false, save_part_marginals_local_max = false;
   bool save_part_detections_local_max = false, interpolate = false, force_recompute_scores = true;
-  bool use_torso_pos_prior = false;
+  bool use_torso_pos_prior = false, save_root_marginal = false;
   float torso_pos_prior_weight = 1;
   // conditioning of the unaries (findrot.cpp:849-949).  The predictors themselves are MATLAB / DPM runs of the
   // reference (objectdetect_icps.cpp:608-625 spawns them); this host reads the files they write.
@@ -154,6 +154,12 @@ void computeRootPosteriorRot(const PartApp &, std::vector<std::vector<FloatGrid3
                              FloatGrid3 &root_part_posterior, int rootpart_idx, std::vector<Joint> joints, bool flip,
                              bool bIsSparse, int imgidx, std::vector<std::vector<PartHyp> > &best_part_hyp,
                              bool bSaveMarginals);
+
+// objectdetect_findpos.cpp:336-452 (legacy POS_GAUSSIAN joints): compact score grids -> unaries on the device ->
+// mergeRotations (:118-170) -> computeRootPosterior (:172-334) -> findLocalMax(1000) into hypothesis_list; with
+// save_root_marginal also root_part_posterior/root_part_posterior_imgidx<i>_o<f>.mat (:437-451).  ps_infer runs the whole
+// chain when the joints are POS_GAUSSIAN.
+void findObjectImagePosJoints(const PartApp &, int imgidx, bool flip, HypothesisList &hypothesis_list);
 
 // objectdetect_findrot.cpp:729-1058.  Reads the compact score grids of the image straight into the device
 // (PartApp::loadScoreGrid, partapp.cpp:830-903, runs as ps_set_unary_compact) and writes the reference's outputs.

@@ -2566,6 +2566,31 @@ __global__ void k_root_marginal(const float *__restrict__ post, size_t HW, const
   rp[i] = log_f64(s);
 }
 
+// ---- legacy POS_GAUSSIAN path: mergeRotationsSum (objectdetect_findpos.cpp:92-116) ---------------------------------
+// result[y][x] = (float) log( sum_r exp(g[r][y][x]) ).  The reference accumulates in x87 long double (64-bit mantissa);
+// here the double exponentials are summed error-free (two-sum into a hi/lo pair, ~106 bits) and the logarithm is taken as
+// log(hi) + lo/hi, so the two agree except where the value sits within ~2^-52 of an fp32 rounding boundary.  A pixel
+// whose slices are all LOG_ZERO gives log(0) = -inf, as there.
+__global__ void __launch_bounds__(256) k_merge_rotations(const float *__restrict__ g, int R, size_t HW, float *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  double hi = 0.0, lo = 0.0;
+  for (int r = 0; r < R; ++r) {
+    const double e = exp((double)g[(size_t)r * HW + i]);
+    const double s = __dadd_rn(hi, e);
+    const double bb = __dsub_rn(s, hi);
+    const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(e, bb));
+    hi = s;
+    lo = __dadd_rn(lo, err);
+  }
+  out[i] = hi > 0.0 ? (float)__dadd_rn(log(hi), lo / hi) : (float)log(hi);
+}
+// addGrid2 (multi_array_op.hpp:117-130): a += b
+__global__ void __launch_bounds__(256) k_add2(float *__restrict__ a, const float *__restrict__ b, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = __fadd_rn(a[i], b[i]);
+}
+
 // ---- readout --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_argmax(const float *__restrict__ g, size_t n, unsigned long long *dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

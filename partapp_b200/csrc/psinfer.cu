@@ -141,6 +141,11 @@ struct ps_ctx {
   std::vector<unsigned char> unary_max_valid;  // [P][S]
   size_t scratch_elems = 0;
 
+  // legacy POS_GAUSSIAN model (objectdetect_findpos.cpp): 2-D grids on an internal single-slice context
+  bool pos_model = false, pending_root_only = false;
+  ps_ctx *sub = nullptr;
+  DevBuf pos_merged, pos_post, pos_msg;  // [P][HW] merged unaries | [P][HW] upward beliefs | [HW] one message
+
   // model
   bool joints_set = false;
   std::vector<ps_joint> joints;
@@ -180,6 +185,7 @@ struct ps_ctx {
   bool have_local_max = false, have_root_hyps = false;
 
   ~ps_ctx() {  // shared by ps_destroy and by the error returns of ps_create
+    if (sub) ps_destroy(sub);
     if (own_stream) {
       cudaStreamSynchronize(own_stream);
       cudaStreamDestroy(own_stream);
@@ -1356,10 +1362,13 @@ int ps_set_joints(ps_ctx *c, const ps_joint *joints, int nj) {
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   if (nj != c->P - 1) return c->fail(PS_ERR_INVALID, "need num_parts-1 = %d joints, got %d (aux.cpp:129)", c->P - 1, nj);
   std::vector<Node> nodes(c->P);
+  // "currently no models with heterogeneous joints are supported" (aux.cpp:346): all ROT_GAUSSIAN -> the
+  // computeRootPosteriorRot path, all POS_GAUSSIAN -> the legacy 2-D computeRootPosterior (findpos.cpp:172-334)
+  const bool pos_model = nj > 0 && joints[0].type == PS_JOINT_POS_GAUSSIAN;
   for (int j = 0; j < nj; ++j) {
     const ps_joint &q = joints[j];
-    if (q.type != PS_JOINT_ROT_GAUSSIAN)
-      return c->fail(PS_ERR_UNSUPPORTED, "joint %d: only ROT_GAUSSIAN joints are on this path (findrot.cpp:766)", j);
+    if (q.type != (pos_model ? PS_JOINT_POS_GAUSSIAN : PS_JOINT_ROT_GAUSSIAN))
+      return c->fail(PS_ERR_UNSUPPORTED, "joint %d: joints must be all ROT_GAUSSIAN or all POS_GAUSSIAN (aux.cpp:346, findrot.cpp:766)", j);
     if (q.child_idx < 0 || q.child_idx >= c->P || q.parent_idx < 0 || q.parent_idx >= c->P || q.child_idx == q.parent_idx)
       return c->fail(PS_ERR_INVALID, "joint %d: part index out of range (aux.cpp:126-127)", j);
     if (nodes[q.child_idx].parent >= 0) return c->fail(PS_ERR_INVALID, "part %d has two parents", q.child_idx);
@@ -1377,12 +1386,27 @@ int ps_set_joints(ps_ctx *c, const ps_joint *joints, int nj) {
       ++steps;
     }
     if (q != c->root) return c->fail(PS_ERR_INVALID, "part %d is not connected to the root", p);
-    if (p != c->root && nodes[p].children.size() > 1)
+    if (!pos_model && p != c->root && nodes[p].children.size() > 1)
       return c->fail(PS_ERR_INVALID, "part %d has %zu children; only the root may branch (findrot.cpp:210)", p,
                      nodes[p].children.size());
   }
   if ((int)nodes[c->root].children.size() > psk::kMaxRootChildren)
     return c->fail(PS_ERR_UNSUPPORTED, "root has more than %d children", psk::kMaxRootChildren);
+  if (pos_model) {  // no per-message plans up front: ps_pos_message's plan cache fills as the messages run
+    for (int j = 0; j < nj; ++j)
+      if (!(joints[j].C[0] * joints[j].C[3] - joints[j].C[1] * joints[j].C[2] > 0))
+        return c->fail(PS_ERR_INVALID, "joint %d: covariance must have a positive determinant (aux.cpp:133)", j);
+    c->plans.clear();
+    c->nodes = std::move(nodes);
+    c->joints.assign(joints, joints + nj);
+    c->joints_set = true;
+    c->pos_model = true;
+    c->have_result = false;
+    c->result_pending = false;
+    ++c->joints_version;
+    return PS_OK;
+  }
+  c->pos_model = false;
 
   std::vector<std::shared_ptr<DevPlan>> plans((size_t)nj * 2 * c->S);
   size_t need = c->N;
@@ -1838,6 +1862,16 @@ int finish_result(ps_ctx *c) {
   const int scaleidx = c->pending_scaleidx;
   c->best_conf.assign((size_t)P * PS_HYP_VEC, 0.f);
   c->part_hyps.assign(P, std::vector<float>());
+  if (c->pending_root_only) {  // POS_GAUSSIAN: computeRootPosterior has no downward pass, hence no part estimates
+    c->have_local_max = false;
+    c->have_root_hyps = false;
+    if (c->pending_flags & PS_INFER_ROOT_HYPS) {
+      decode_local_max(c, P, c->H, c->W, c->root_hyps);
+      c->have_root_hyps = true;
+    }
+    c->have_result = true;
+    return PS_OK;
+  }
   for (int p = 0; p < P; ++p) {
     unsigned long long key = c->host_keys[p];
     if (key == 0) return c->fail(PS_ERR_INVALID, "part %d: no finite maximum (findrot.cpp:273 assert)", p);
@@ -2039,6 +2073,94 @@ static int infer_enqueue(ps_ctx *c, int flags) {
   return PS_OK;
 }
 
+// The legacy POS_GAUSSIAN model: mergeRotations + computeRootPosterior (objectdetect_findpos.cpp:118-170, :172-334).
+// Rotations are summed out of every unary first, the upward pass then runs on 2-D grids with computePosJointMarginal
+// (ps_pos_message on an internal single-slice context); there is no downward pass: the result is the root posterior of
+// every scale and, with PS_INFER_ROOT_HYPS, its local maxima.
+static int infer_pos(ps_ctx *c, int flags) {
+  const int P = c->P, S = c->S, root = c->root;
+  const size_t HW = c->HW;
+  const bool sparse = flags & PS_INFER_SPARSE;
+  cudaStream_t st = c->stream;
+  c->have_result = false;
+  if (!c->sub) {
+    ps_config sc = c->cfg;
+    sc.num_parts = 2;
+    sc.num_rotation_steps = 1;
+    sc.num_scale_steps = 1;
+    sc.min_object_scale = sc.max_object_scale = 1.0f;
+    sc.root_idx = 0;
+    sc.keep_all_scales = 0;
+    memset(sc.is_detect, 0, sizeof sc.is_detect);
+    memset(sc.is_upright, 0, sizeof sc.is_upright);
+    memset(sc.is_root, 0, sizeof sc.is_root);
+    sc.is_detect[0] = sc.is_detect[1] = 1;
+    sc.is_root[0] = 1;
+    sc.strip_border_detections = 0;
+    if (ps_create(&sc, &c->sub) != PS_OK) return c->fail(PS_ERR_CUDA, "internal 2-D context: %s", ps_last_error(nullptr));
+  }
+  if (int rc = ps_set_stream(c->sub, st)) return c->fail(rc, "internal 2-D context: %s", ps_last_error(c->sub));
+  if (c->pos_merged.bytes < (size_t)P * HW * sizeof(float)) {
+    PS_CUDA(c, cudaStreamSynchronize(st));
+    PS_CUDA(c, c->pos_merged.alloc((size_t)P * HW * sizeof(float)));
+    PS_CUDA(c, c->pos_post.alloc((size_t)P * HW * sizeof(float)));
+    PS_CUDA(c, c->pos_msg.alloc(HW * sizeof(float)));
+  }
+  float *merged = c->pos_merged.as<float>(), *post = c->pos_post.as<float>(), *msg = c->pos_msg.as<float>();
+  for (int s = 0; s < S; ++s) {
+    const double scale = scale_of(c->cfg, s);
+    for (int p = 0; p < P; ++p)  // mergeRotationsSum of every detected part (:146-165)
+      if (c->cfg.is_detect[p])
+        PS_LAUNCH(c, KC_MISC, psk::k_merge_rotations<<<cdiv(HW, 256), 256, 0, st>>>(c->U(p, s), c->R, HW, merged + (size_t)p * HW));
+    PS_CUDA(c, cudaMemsetAsync(post, 0, (size_t)P * HW * sizeof(float), st));  // log_part_posterior starts at 0 (:214)
+    // post-order walk with the reference's explicit stack (:223-301): a node waits for its first uncomputed child
+    std::vector<char> uniform(P, 1), computed(P, 0);
+    std::vector<int> stack(1, root);
+    while (!stack.empty()) {
+      const int cur = stack.back();
+      stack.pop_back();
+      bool can = true;
+      for (size_t j = 0; j < c->joints.size() && can; ++j)
+        if (c->joints[j].parent_idx == cur && !computed[c->joints[j].child_idx]) {
+          can = false;
+          stack.push_back(cur);
+          stack.push_back(c->joints[j].child_idx);
+        }
+      if (!can) continue;
+      for (size_t j = 0; j < c->joints.size(); ++j) {  // children in joint order (:252-257)
+        const ps_joint &q = c->joints[j];
+        if (q.parent_idx != cur || uniform[q.child_idx]) continue;  // a branch without detected parts sends nothing (:263)
+        if (int rc = ps_pos_message(c->sub, post + (size_t)q.child_idx * HW, msg, PS_MEM_DEVICE, q.offset_p, q.C, scale, sparse ? 1 : 0))
+          return c->fail(rc, "message of joint %zu: %s", j, ps_last_error(c->sub));
+        PS_LAUNCH(c, KC_MISC, psk::k_add2<<<cdiv(HW, 256), 256, 0, st>>>(post + (size_t)cur * HW, msg, HW));
+        uniform[cur] = 0;
+      }
+      if (c->cfg.is_detect[cur]) {  // :293-296
+        PS_LAUNCH(c, KC_MISC, psk::k_add2<<<cdiv(HW, 256), 256, 0, st>>>(post + (size_t)cur * HW, merged + (size_t)cur * HW, HW));
+        uniform[cur] = 0;
+      }
+      computed[cur] = 1;
+    }
+    PS_CUDA(c, cudaMemcpyAsync(c->root_post.as<float>() + (size_t)s * HW, post + (size_t)root * HW, HW * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  c->launches += c->sub->launches;
+  c->sub->launches = 0;
+  if (flags & PS_INFER_ROOT_HYPS) {  // findLocalMax(root_part_posterior, 1000), findpos.cpp:416-417
+    int rc = ensure_topk(c, (size_t)P + 1, (size_t)std::max(c->cfg.roi_save_num_samples, 1000), std::max(c->N, (size_t)S * HW));
+    if (rc) return rc;
+    if ((rc = enqueue_local_max(c, c->root_post.as<float>(), S, c->H, c->W, 1000, P))) return rc;
+    if ((rc = fetch_local_max(c, P + 1))) return rc;
+  }
+  c->pending_grids.clear();
+  c->pending_scaleidx = S - 1;
+  c->pending_flags = flags & PS_INFER_ROOT_HYPS;
+  c->pending_root_only = true;
+  c->result_pending = true;
+  c->result_scale = S - 1;
+  return PS_OK;
+}
+
 // computeRootPosteriorRot + computePartMarginals (findrot.cpp:470-727, :124-286).  The schedule of one inference is a
 // fixed sequence of launches over ctx-owned buffers as long as the joints, the flags and the way each leaf's maximum is
 // obtained stay the same, so it is captured into a CUDA graph the second time such an inference is requested and
@@ -2047,6 +2169,8 @@ int ps_infer(ps_ctx *c, int flags) {
   if (!c) return PS_ERR_INVALID;
   if (!c->joints_set) return c->fail(PS_ERR_STATE, "ps_infer before ps_set_joints");
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  if (c->pos_model) return infer_pos(c, flags);
+  c->pending_root_only = false;
   if (c->disable_graph || c->profiling) return infer_enqueue(c, flags);
   std::string key((const char *)&flags, sizeof flags);
   key.append((const char *)&c->joints_version, sizeof c->joints_version);
@@ -2123,6 +2247,8 @@ int ps_max_states(ps_ctx *c, int flags) {
 int ps_get_best_conf(ps_ctx *c, float *out) {
   if (!c || !out) return PS_ERR_INVALID;
   if (int rc = finish_result(c)) return rc;
+  if (c->pending_root_only)
+    return c->fail(PS_ERR_STATE, "no part estimates: the POS_GAUSSIAN path has no downward pass (findpos.cpp:172-334)");
   memcpy(out, c->best_conf.data(), c->best_conf.size() * sizeof(float));
   return PS_OK;
 }
@@ -2142,6 +2268,7 @@ int ps_get_marginal(ps_ctx *c, int part, int scale, float *dst, int mem_kind) {
   if (int rc = finish_result(c)) return rc;
   if (c->result_scale < 0) return c->fail(PS_ERR_STATE, "no marginals: call ps_infer first");
   if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
+  if (c->pending_root_only) return c->fail(PS_ERR_STATE, "no marginals on the POS_GAUSSIAN path");
   if (!c->cfg.keep_all_scales && scale != c->S - 1)
     return c->fail(PS_ERR_STATE, "only the last scale is resident; create the ctx with keep_all_scales");
   PS_CUDA(c, cudaMemcpyAsync(dst, c->POST(part, scale), c->N * sizeof(float),

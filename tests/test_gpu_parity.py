@@ -5,6 +5,8 @@ The kernels are written to be bit-identical to the oracle (same fp32 summation o
 results equal glibc's for every fp32 input, profiles/r01_libm_exhaustive.txt), so the checks here demand EXACT
 equality of every cell (_cmp with max_ulp_frac = 0); the 1e-4 tolerance of the north star is never used.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -920,3 +922,36 @@ def test_gpu_conditioning_adds_equal_reference_code_output(name):
         for p in range(P):
             for s in range(S):
                 _cmp(ctx.get_unary(p, s), _DRV["cond_" + name][p, s], "%s part %d scale %d" % (name, p, s))
+
+
+# ---- legacy POS_GAUSSIAN driver (objectdetect_findpos.cpp:118-334) ---------------------------------------
+from tests.golden import ref_pos_driver_cases as _pc
+
+
+@pytest.mark.parametrize("name", sorted(_pc.cases()))
+def test_gpu_pos_gaussian_driver_equals_reference_code_output(name):
+    """ps_infer with POS_GAUSSIAN joints = mergeRotations + computeRootPosterior: the root posterior of every scale
+    against what the reference's own code returned.  The rotation sum is x87 long double there and an error-free
+    double pair here: identical except, at most, a handful of last-bit cells."""
+    ep, pc, joints, un, sparse = _pc.cases()[name]
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pos_driver.npz"))[name + "/root_post"]
+    P, S, R, H, W = un.shape
+    with PsContext(ep, pc, H, W) as ctx:
+        ctx.set_joints(joints)
+        for p in range(P):
+            for s in range(S):
+                ctx.set_unary(p, s, un[p, s])
+        ctx.infer(sparse=sparse, root_hyps=True)
+        got = ctx.root_posterior()
+        assert got.shape == want.shape
+        assert np.array_equal(np.isneginf(got), np.isneginf(want))
+        fin = np.isfinite(want)
+        neq = (got != want) & fin
+        assert neq.mean() <= 1e-4, "%d cells differ" % neq.sum()
+        np.testing.assert_allclose(got[fin], want[fin], rtol=2e-7, atol=0)
+        hyps = ctx.root_hyps()
+        lm = oracle.find_local_max(want, 1000)
+        assert len(hyps) == len(lm) or neq.any()
+        from partapp_b200 import capi
+        with pytest.raises(capi.PsInferError):
+            ctx.best_conf()       # no downward pass on this path
