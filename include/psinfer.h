@@ -52,7 +52,11 @@ enum ps_infer_flags {
   PS_INFER_SPARSE = 1,        /* bIsSparse of computeRootPosteriorRot (findrot.cpp:740 passes true) */
   PS_INFER_LOCAL_MAX = 2,     /* also extract <=K local maxima per part (findLocalMax, aux.cpp:193-261) */
   PS_INFER_ROOT_HYPS = 4,     /* also extract <=1000 local maxima of the root posterior (findrot.cpp:1037-1038) */
-  PS_INFER_KEEP_UNARIES = 8   /* restore the unaries after the call (what findrot.cpp:847,1001 does around it) */
+  PS_INFER_KEEP_UNARIES = 8,  /* restore the unaries after the call (what findrot.cpp:847,1001 does around it) */
+  PS_INFER_NO_BORDER_STRIP = 16 /* skip the root border strip: the message passing of libDiscPS's
+                                   partSampleWithPriorHelper (disc_sample_with_prior.cpp:64-330), a copy of
+                                   computeRootPosteriorRot + computePartMarginals that keeps the upright masking but has no
+                                   strip; its samples are then drawn from ps_get_marginal(part, scaleidx) */
 };
 
 /* The ExpParam / PartConfig fields the path reads:

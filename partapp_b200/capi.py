@@ -12,7 +12,7 @@ PS_HYP_VEC = 7
 PS_OK, PS_ERR_INVALID, PS_ERR_CUDA, PS_ERR_STATE, PS_ERR_UNSUPPORTED = range(5)
 PS_MEM_HOST, PS_MEM_DEVICE = 0, 1
 PS_JOINT_POS_GAUSSIAN, PS_JOINT_ROT_GAUSSIAN = 1, 2
-PS_INFER_SPARSE, PS_INFER_LOCAL_MAX, PS_INFER_ROOT_HYPS, PS_INFER_KEEP_UNARIES = 1, 2, 4, 8
+PS_INFER_SPARSE, PS_INFER_LOCAL_MAX, PS_INFER_ROOT_HYPS, PS_INFER_KEEP_UNARIES, PS_INFER_NO_BORDER_STRIP = 1, 2, 4, 8, 16
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpsinfer.so")
 

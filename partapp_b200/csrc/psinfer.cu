@@ -1940,7 +1940,7 @@ static int infer_enqueue(ps_ctx *c, int flags) {
                                                                                  c->upright_mask.as<unsigned char>()));
       }
     // border strip of the root, all scales, every iteration (findrot.cpp:528-551; idempotent)
-    if (c->cfg.strip_border_detections > 0) {
+    if (c->cfg.strip_border_detections > 0 && !(flags & PS_INFER_NO_BORDER_STRIP)) {
       int sw = (int)(c->cfg.strip_border_detections * c->W);
       if (sw > 0)
         for (int s2 = 0; s2 < S; ++s2) {

@@ -317,9 +317,10 @@ class PsContext:
         self._check(self.lib.ps_add_unary_grid(self.h, part, _ptr(g), g.shape[0], mode, weight, capi.PS_MEM_HOST))
 
     # -- inference ---------------------------------------------------------------------------------
-    def infer(self, sparse=True, local_max=False, root_hyps=False, keep_unaries=False):
+    def infer(self, sparse=True, local_max=False, root_hyps=False, keep_unaries=False, no_border_strip=False):
         flags = (capi.PS_INFER_SPARSE if sparse else 0) | (capi.PS_INFER_LOCAL_MAX if local_max else 0) | \
-                (capi.PS_INFER_ROOT_HYPS if root_hyps else 0) | (capi.PS_INFER_KEEP_UNARIES if keep_unaries else 0)
+                (capi.PS_INFER_ROOT_HYPS if root_hyps else 0) | (capi.PS_INFER_KEEP_UNARIES if keep_unaries else 0) | \
+                (capi.PS_INFER_NO_BORDER_STRIP if no_border_strip else 0)
         self._check(self.lib.ps_infer(self.h, flags))
 
     infer_async = infer  # ps_infer only enqueues device work; getters synchronise

@@ -955,3 +955,30 @@ def test_gpu_pos_gaussian_driver_equals_reference_code_output(name):
         from partapp_b200 import capi
         with pytest.raises(capi.PsInferError):
             ctx.best_conf()       # no downward pass on this path
+
+
+def test_disc_ps_message_passing_has_no_border_strip():
+    """partSampleWithPriorHelper (libDiscPS/disc_sample_with_prior.cpp:64-330) is computeRootPosteriorRot +
+    computePartMarginals with the upright masking but WITHOUT the root's border strip: PS_INFER_NO_BORDER_STRIP on a
+    context whose ExpParam asks for the strip must give what the oracle gives with strip_border_detections = 0."""
+    ep_strip = ExpParam(num_rotation_steps=8, strip_border_detections=0.2)
+    ep_plain = ExpParam(num_rotation_steps=8)
+    P, H, W = 4, 40, 44
+    un = oracle.prepare_unary(synth.raw_scores(ep_plain, H, W, P, 9))
+    joints = synth.make_joints(P, seed=2, max_offset=8, sigma_range=(1.5, 4))
+    pc = synth.part_conf(P, upright_root=True)
+    want = oracle.infer(ep_plain, pc, joints, un.copy(), sparse=True)
+    stripped = oracle.infer(ep_strip, pc, joints, un.copy(), sparse=True)
+    assert not np.array_equal(want["marginals"][0, 1], stripped["marginals"][0, 1])   # the strip matters on this input
+    with PsContext(ep_strip, pc, H, W) as ctx:
+        ctx.set_joints(joints)
+        for p in range(P):
+            ctx.set_unary(p, 0, un[p, 0])
+        ctx.infer(sparse=True, no_border_strip=True)
+        assert np.array_equal(ctx.best_conf(), want["best_conf"])
+        for p in range(P):
+            _cmp(ctx.marginal(p), want["marginals"][0, p], "no-strip marginal %d" % p)
+        for p in range(P):
+            ctx.set_unary(p, 0, un[p, 0])
+        ctx.infer(sparse=True)
+        _cmp(ctx.marginal(1), stripped["marginals"][0, 1], "stripped marginal")
