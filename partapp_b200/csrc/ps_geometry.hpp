@@ -470,10 +470,10 @@ inline MessagePlan plan_message(const Grid &g, const double off_in[2], const dou
               if (all || rect_hits(ex0 - 0.5, yor + 64 * i - ny - 0.5, ex0 + SG - 0.5, yor + 64 * i + 64 - 0.5 + ny)) m |= 1u << g;
             }
             masks.push_back((unsigned char)m);
-            if (count) {
-              int bits = 0;
-              for (int g = 0; g < 8; ++g) bits += (m >> g) & 1;
-              p.fcells_x += (long long)bits * SG * 64;
+            if (count) {  // cells inside the grid that this box filters along x
+              const long long rows_in = std::max(0, std::min(p.EH, yor + 64 * i + 64) - std::max(0, yor + 64 * i));
+              for (int g = 0; g < 8; ++g)
+                if ((m >> g) & 1) p.fcells_x += rows_in * std::max(0, std::min(SG, p.EW - (w.st * TS + g * SG)));
             }
           }
           if (count) p.fcells_y += (long long)std::min(w.ng * SG, p.EH - w.g0 * SG) * std::min(TS, p.EW - w.st * TS);

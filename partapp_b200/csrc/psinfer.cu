@@ -914,8 +914,15 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     gb.ring_rows = 64 * (lagmax + 1);
     smem = 2 * (size_t)stride + (size_t)gb.ring_rows * psk::kRingPitch * sizeof(float);
     if ((rc = take_work_counter(c, &gb.counter))) return rc;
-    // two blocks per SM when two fit beside their static shared memory, else one
-    const int bps = smem <= 108 * 1024 ? 2 : 1;
+    // Blocks per SM and shared-memory footprint decide what else fits on an SM while the taps run.  Two blocks per SM
+    // (92 registers x 288 threads each, ~100 KB of shared memory each) fill the SM: nothing of another image's
+    // memory-bound kernels co-resides, and with several images in flight the GPU then alternates between fp32-bound and
+    // memory-bound phases.  PSINFER_GAUSS_BPS (1 or 2) and PSINFER_GAUSS_SMEM (minimum dynamic shared memory in bytes;
+    // > 113.5 KB keeps a second Gaussian block of ANOTHER launch off the SM) are the A/B knobs.
+    static const int bps_env = getenv("PSINFER_GAUSS_BPS") ? atoi(getenv("PSINFER_GAUSS_BPS")) : 1;
+    static const long pad_env = getenv("PSINFER_GAUSS_SMEM") ? atol(getenv("PSINFER_GAUSS_SMEM")) : 116 * 1024;
+    const int bps = (bps_env >= 2 && smem <= 108 * 1024) ? 2 : 1;
+    if (bps == 1) smem = std::min<size_t>(std::max<size_t>(smem, (size_t)std::max(0L, pad_env)), kFusedSmemMax);
     const int grid = std::min(items, c->num_sms * bps);
     if (c->cfg.fast_math)
       PS_LAUNCH(c, KC_GAUSS_XY, psk::k_gauss_xy<true><<<grid, 288, smem, st>>>(tm, gb, PS_NEGZERO2));
