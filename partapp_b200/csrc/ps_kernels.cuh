@@ -1770,6 +1770,7 @@ struct GaussBatch {
   int nmsg, R, total_items;
   unsigned stage_stride;       // bytes between the TMA stages (the largest box of the batch, 128-byte multiple)
   int ring_rows;               // 64 * (largest lag of the batch + 1)
+  int stages;                  // TMA stages, 1 or 2
 };
 constexpr int kMaxFusedTaps = 256;
 struct alignas(64) TmapBatch {
@@ -1777,12 +1778,16 @@ struct alignas(64) TmapBatch {
 };
 __device__ __forceinline__ void bar_sync_filter() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+#ifndef PS_GAUSS_MINB
+#define PS_GAUSS_MINB 3  // register budget of k_gauss_xy: 65536 / (3 * 288) -> 72 registers (two blocks take 41 K of the 64 K)
+#endif
 template <bool FMA>
-__global__ void __launch_bounds__(288, 2) k_gauss_xy(const __grid_constant__ TmapBatch tm, const __grid_constant__ GaussBatch b, u64 nz) {
-  constexpr int T = 8, NS = 2;
+__global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_constant__ TmapBatch tm, const __grid_constant__ GaussBatch b, u64 nz) {
+  constexpr int T = 8;
+  const int NS = b.stages;  // TMA stages: 1 (the next box is requested when the x phase ends and lands during the y phase) or 2
   extern __shared__ __align__(128) unsigned char s_raw[];
-  __shared__ __align__(8) unsigned long long s_full[NS], s_empty[NS];
-  __shared__ int4 s_meta[NS][2];  // [0] = (message or -1, strip, first row, groups)  [1] = (block index, slice, mask, 0)
+  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+  __shared__ int4 s_meta[2][2];  // [0] = (message or -1, strip, first row, groups)  [1] = (block index, slice, mask, 0)
   __shared__ float s_tx[kMaxFusedTaps], s_ty[kMaxFusedTaps];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   float *ring = reinterpret_cast<float *>(s_raw + NS * b.stage_stride);
@@ -2567,16 +2572,19 @@ __global__ void k_root_marginal(const float *__restrict__ post, size_t HW, const
 }
 
 // ---- legacy POS_GAUSSIAN path: mergeRotationsSum (objectdetect_findpos.cpp:92-116) ---------------------------------
-// result[y][x] = (float) log( sum_r exp(g[r][y][x]) ).  The reference accumulates in x87 long double (64-bit mantissa);
-// here the double exponentials are summed error-free (two-sum into a hi/lo pair, ~106 bits) and the logarithm is taken as
-// log(hi) + lo/hi, so the two agree except where the value sits within ~2^-52 of an fp32 rounding boundary.  A pixel
-// whose slices are all LOG_ZERO gives log(0) = -inf, as there.
+// result[y][x] = (float) log( sum_r exp(g[r][y][x]) ).  findpos.cpp has `using namespace std`, so exp(float) is the
+// FLOAT overload there: every term is rounded to fp32 before it is added (first GPU run of this path: summing the double
+// exponentials instead moved 10 % of the root-posterior cells by an ulp or two).  The reference accumulates the terms in
+// x87 long double (64-bit mantissa) and takes logl; here the fp32 terms are summed error-free (two-sum into a hi/lo pair,
+// ~106 bits) and the logarithm is log(hi) + lo/hi, so the two agree except where the value sits within ~2^-52 of an fp32
+// rounding boundary or glibc's expf (< 1 ulp, not correctly rounded) differs from the correctly rounded exponential used
+// here.  A pixel whose slices are all LOG_ZERO gives log(0) = -inf, as there.
 __global__ void __launch_bounds__(256) k_merge_rotations(const float *__restrict__ g, int R, size_t HW, float *__restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
   double hi = 0.0, lo = 0.0;
   for (int r = 0; r < R; ++r) {
-    const double e = exp((double)g[(size_t)r * HW + i]);
+    const double e = (double)exp_f64(g[(size_t)r * HW + i]);
     const double s = __dadd_rn(hi, e);
     const double bb = __dsub_rn(s, hi);
     const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(e, bb));

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -484,16 +485,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn tensor_map_encoder() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // function-local static with an initialiser: thread-safe (several host threads create contexts at once)
+  static const EncodeTiledFn fn = []() -> EncodeTiledFn {
     void *p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
+      return (EncodeTiledFn)p;
+    return nullptr;
+  }();
   return fn;
 }
 
@@ -912,17 +912,28 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     gb.total_items = items;
     gb.stage_stride = stride;
     gb.ring_rows = 64 * (lagmax + 1);
-    smem = 2 * (size_t)stride + (size_t)gb.ring_rows * psk::kRingPitch * sizeof(float);
     if ((rc = take_work_counter(c, &gb.counter))) return rc;
-    // Blocks per SM and shared-memory footprint decide what else fits on an SM while the taps run.  Two blocks per SM
-    // (92 registers x 288 threads each, ~100 KB of shared memory each) fill the SM: nothing of another image's
-    // memory-bound kernels co-resides, and with several images in flight the GPU then alternates between fp32-bound and
-    // memory-bound phases.  PSINFER_GAUSS_BPS (1 or 2) and PSINFER_GAUSS_SMEM (minimum dynamic shared memory in bytes;
-    // > 113.5 KB keeps a second Gaussian block of ANOTHER launch off the SM) are the A/B knobs.
-    static const int bps_env = getenv("PSINFER_GAUSS_BPS") ? atoi(getenv("PSINFER_GAUSS_BPS")) : 1;
-    static const long pad_env = getenv("PSINFER_GAUSS_SMEM") ? atol(getenv("PSINFER_GAUSS_SMEM")) : 116 * 1024;
-    const int bps = (bps_env >= 2 && smem <= 108 * 1024) ? 2 : 1;
-    if (bps == 1) smem = std::min<size_t>(std::max<size_t>(smem, (size_t)std::max(0L, pad_env)), kFusedSmemMax);
+    // Footprint of the Gaussian blocks = what else fits on an SM while the taps run (A/B on the B200, cfg-2, see
+    // DESIGN.md 5).  Two blocks per SM give the tap loops four warps per scheduler; at 92 registers and two TMA stages
+    // they fill the SM and nothing of another image's memory-bound kernels co-resides; one block per SM leaves room but
+    // only two warps per scheduler to cover the FFMA2 -> FADD2 latency (fp32 pipe 62 % busy).  Shipped: two blocks of
+    // <= 72 registers with ONE TMA stage each (the next box is requested when the x phase ends and lands during the y
+    // phase) and the dynamic shared memory padded so that a third block cannot fit.
+    // PSINFER_GAUSS_BPS (1 | 2), PSINFER_GAUSS_STAGES (1 | 2), PSINFER_GAUSS_SMEM (minimum dynamic bytes) are the knobs.
+    static const int bps_env = getenv("PSINFER_GAUSS_BPS") ? atoi(getenv("PSINFER_GAUSS_BPS")) : 2;
+    static const int ns_env = getenv("PSINFER_GAUSS_STAGES") ? atoi(getenv("PSINFER_GAUSS_STAGES")) : 1;
+    static const long pad_env = getenv("PSINFER_GAUSS_SMEM") ? atol(getenv("PSINFER_GAUSS_SMEM")) : -1;
+    gb.stages = ns_env >= 2 ? 2 : 1;
+    smem = (size_t)gb.stages * stride + (size_t)gb.ring_rows * psk::kRingPitch * sizeof(float);
+    if (smem > kFusedSmemMax) {  // two stages of the widest box do not fit: one does (can_batch checked the 2-stage size per message)
+      gb.stages = 1;
+      smem = (size_t)stride + (size_t)gb.ring_rows * psk::kRingPitch * sizeof(float);
+    }
+    int bps = (bps_env >= 2 && smem <= 108 * 1024) ? 2 : 1;
+    // cap the blocks per SM at `bps` for launches of OTHER images too: (bps + 1) blocks must not fit into 227 KB
+    const size_t cap_pad = bps == 2 ? 72 * 1024 : 116 * 1024;
+    const size_t pad = pad_env >= 0 ? (size_t)pad_env : cap_pad;
+    smem = std::min<size_t>(std::max(smem, pad), kFusedSmemMax);
     const int grid = std::min(items, c->num_sms * bps);
     if (c->cfg.fast_math)
       PS_LAUNCH(c, KC_GAUSS_XY, psk::k_gauss_xy<true><<<grid, 288, smem, st>>>(tm, gb, PS_NEGZERO2));
@@ -1007,6 +1018,11 @@ int grid_max(ps_ctx *c, const float *g, size_t n, int *slot) {
 
 // Fills the device tables of exp_fast / log_fast (ps_kernels.cuh) with host-libm doubles.
 int math_tables_init(ps_ctx *c) {
+  // the tables are per device and never change: fill them once per device (other contexts' kernels may be reading them)
+  static std::mutex mu;
+  static std::vector<char> done(64, 0);
+  std::lock_guard<std::mutex> lock(mu);
+  if (c->cfg.device < (int)done.size() && done[c->cfg.device]) return PS_OK;
   double2 lt[129];
   for (int j = 0; j <= 128; ++j) {
     double F = 1.0 + j / 128.0;
@@ -1020,6 +1036,7 @@ int math_tables_init(ps_ctx *c) {
   PS_CUDA(c, cudaMemcpyToSymbol(psk::d_log_tab, lt, sizeof lt));
   PS_CUDA(c, cudaMemcpyToSymbol(psk::d_eln2_tab, et, sizeof et));
   PS_CUDA(c, cudaMemcpyToSymbol(psk::d_exp_tab, xt, sizeof xt));
+  if (c->cfg.device < (int)done.size()) done[c->cfg.device] = 1;
   return PS_OK;
 }
 
@@ -1304,16 +1321,25 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
   c->disable_tile_lists = getenv("PSINFER_ALL_TILES") != nullptr;
   c->disable_batch = getenv("PSINFER_NO_BATCH") != nullptr;
   c->disable_graph = getenv("PSINFER_NO_GRAPH") != nullptr;
-  if (!cu(cudaFuncSetAttribute(psk::k_gauss_xy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_gauss_xy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr"))
-    return PS_ERR_CUDA;
-  if (!cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_conv_rows2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
-      !cu(cudaFuncSetAttribute(psk::k_conv_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr"))
-    return PS_ERR_CUDA;
+  {
+    // kernel attributes are per device and never change: set them once per device, under a lock -- several host threads
+    // create contexts at once (findObjectDataset's workers) while others are already launching these kernels
+    static std::mutex mu;
+    static std::vector<char> done(64, 0);
+    std::lock_guard<std::mutex> lock(mu);
+    if (cfg->device >= (int)done.size() || !done[cfg->device]) {
+      if (!cu(cudaFuncSetAttribute(psk::k_gauss_xy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_gauss_xy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_conv_cols2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_conv_rows2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_conv_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget), "smem attr"))
+        return PS_ERR_CUDA;
+      if (cfg->device < (int)done.size()) done[cfg->device] = 1;
+    }
+  }
   // non-detect parts have all-zero unaries in the reference (findrot.cpp:794 resize, never loaded)
   if (!cu(cudaMemsetAsync(c->unary.p, 0, c->unary.bytes, c->stream), "memset")) return PS_ERR_CUDA;
 
