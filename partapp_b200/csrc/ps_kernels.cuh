@@ -1574,6 +1574,16 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
       "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(PS_MBAR_HINT_NS) : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_h(unsigned long long *bar, unsigned parity, unsigned hint_ns) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -1771,6 +1781,7 @@ struct GaussBatch {
   unsigned stage_stride;       // bytes between the TMA stages (the largest box of the batch, 128-byte multiple)
   int ring_rows;               // 64 * (largest lag of the batch + 1)
   int stages;                  // TMA stages, 1 or 2
+  unsigned hint_ns;            // suspend-time hint of the mbarrier waits
 };
 constexpr int kMaxFusedTaps = 256;
 struct alignas(64) TmapBatch {
@@ -1810,7 +1821,7 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
       };
       auto wait_free = [&]() {
         if (u >= 1) {
-          while (!mbar_try_wait(&s_empty[s], (unsigned)(u - 1) & 1u)) {}
+          while (!mbar_try_wait_h(&s_empty[s], (unsigned)(u - 1) & 1u, b.hint_ns)) {}
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
         }
       };
@@ -1852,7 +1863,7 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
       s = 0;
       ++u;
     }
-    while (!mbar_try_wait(&s_full[s], (unsigned)u & 1u)) {}
+    while (!mbar_try_wait_h(&s_full[s], (unsigned)u & 1u, b.hint_ns)) {}
     const int4 m0 = s_meta[s][0], m1 = s_meta[s][1];
     if (m0.x < 0) break;
     const GaussMsg &g = b.m[m0.x];

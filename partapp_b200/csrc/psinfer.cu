@@ -935,10 +935,33 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     const size_t pad = pad_env >= 0 ? (size_t)pad_env : cap_pad;
     smem = std::min<size_t>(std::max(smem, pad), kFusedSmemMax);
     const int grid = std::min(items, c->num_sms * bps);
+    static const unsigned hint_env = getenv("PSINFER_MBAR_HINT") ? (unsigned)atol(getenv("PSINFER_MBAR_HINT")) : PS_MBAR_HINT_NS;
+    gb.hint_ns = hint_env;
+    // The taps are the one fp32-bound stage; everything else is memory-bound.  With several images in flight the block
+    // scheduler should hand freed SM slots to a waiting Gaussian launch first, so that it holds its (capped) share of every
+    // SM for its whole run and the memory-bound blocks of the other images fill the rest: launch priority, not a separate
+    // stream.  PSINFER_GAUSS_PRIO=0 launches at the stream's priority (A/B).
+    static const bool prio_env = !(getenv("PSINFER_GAUSS_PRIO") && atoi(getenv("PSINFER_GAUSS_PRIO")) == 0);
+    static const int prio_hi = []() {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      return hi;
+    }();
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(288);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributePriority;
+    la[0].val.priority = prio_hi;
+    lc.attrs = la;
+    lc.numAttrs = prio_env ? 1 : 0;
+    const psk::u64 nz2 = PS_NEGZERO2;
     if (c->cfg.fast_math)
-      PS_LAUNCH(c, KC_GAUSS_XY, psk::k_gauss_xy<true><<<grid, 288, smem, st>>>(tm, gb, PS_NEGZERO2));
+      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<true>, tm, gb, nz2));
     else
-      PS_LAUNCH(c, KC_GAUSS_XY, psk::k_gauss_xy<false><<<grid, 288, smem, st>>>(tm, gb, PS_NEGZERO2));
+      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<false>, tm, gb, nz2));
   }
   // stage 4: bilinear read-back into the image frame, V[i] -> B[i]
   {

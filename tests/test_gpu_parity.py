@@ -966,7 +966,7 @@ def test_disc_ps_message_passing_has_no_border_strip():
     P, H, W = 4, 40, 44
     un = oracle.prepare_unary(synth.raw_scores(ep_plain, H, W, P, 9))
     joints = synth.make_joints(P, seed=2, max_offset=8, sigma_range=(1.5, 4))
-    pc = synth.part_conf(P, upright_root=True)
+    pc = synth.part_conf(P)
     want = oracle.infer(ep_plain, pc, joints, un.copy(), sparse=True)
     stripped = oracle.infer(ep_strip, pc, joints, un.copy(), sparse=True)
     _, root = synth.tree(P)
