@@ -32,7 +32,8 @@ WORKLOAD = dict(R=24, S=1, H=600, W=400, P=10)
 # Other BASELINE.json configs, for manual runs only (--workload); the contract line is always configs[1].
 WORKLOADS = {"cfg2": dict(R=24, S=1, H=600, W=400, P=10),
              "cfg4": dict(R=24, S=1, H=600, W=400, P=22),       # 22-part full model, joint types swapped per image
-             "cfg5": dict(R=48, S=5, H=1000, W=1000, P=10)}     # stress state space
+             "cfg5": dict(R=48, S=5, H=1000, W=1000, P=10),     # stress state space
+             "cfg2r8": dict(R=8, S=1, H=600, W=400, P=10)}      # experiment: one 8-slice group of cfg-2 (L2-resident level)
 METRIC = "ps_inference_images_per_sec"
 UNIT = "images/s"
 
@@ -43,7 +44,8 @@ WORKLOAD_TEXT = {
     "cfg4": "configs[3]: poselet-conditioned full model, 22-part tree (root 10), R=24 x S=1, 600x400 grid; per image every "
             "joint is drawn from an 8-entry type table (whole joint swapped, aux.cpp:76-99) and every part's unary is "
             "conditioned by a rotation score and a position score / the torso prior (findrot.cpp:913-949)",
-    "cfg5": "configs[4]: stress state space, 10-part tree, R=48 x S=5, 1000x1000 grid, marginals + argmax readout"}
+    "cfg5": "configs[4]: stress state space, 10-part tree, R=48 x S=5, 1000x1000 grid, marginals + argmax readout",
+    "cfg2r8": "experiment (not a BASELINE config): configs[1] with R=8"}
 WORKLOAD_NAME = ["cfg2"]
 
 
@@ -612,7 +614,7 @@ def main():
     WORKLOAD.update(WORKLOADS[args.workload])
     WORKLOAD_NAME[0] = args.workload
     if args.images <= 0:
-        args.images = {"cfg2": 32, "cfg4": 16, "cfg5": 4}[args.workload]
+        args.images = {"cfg2": 32, "cfg4": 16, "cfg5": 4, "cfg2r8": 32}[args.workload]
     args.streams = max(1, min(args.streams, args.images))
     if args.impl == "reference":
         run_reference(args)

@@ -11,6 +11,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -111,6 +112,14 @@ template <typename T>
 inline void fortran_to_c(const std::vector<T> &src, const std::vector<size_t> &dims, std::vector<T> &dst) {
   const size_t nd = dims.size(), n = src.size();
   dst.resize(n);
+  if (nd == 2 && n == dims[0] * dims[1]) {  // the common case (score grids, parameter matrices): a blocked 2-D transpose
+    const size_t R = dims[0], C = dims[1], B = 32;
+    for (size_t r0 = 0; r0 < R; r0 += B)
+      for (size_t c0 = 0; c0 < C; c0 += B)
+        for (size_t c = c0; c < std::min(C, c0 + B); ++c)
+          for (size_t r = r0; r < std::min(R, r0 + B); ++r) dst[r * C + c] = src[c * R + r];
+    return;
+  }
   std::vector<size_t> cstride(nd, 1), idx(nd, 0);
   for (size_t d = nd - 1; d-- > 0;) cstride[d] = cstride[d + 1] * dims[d + 1];
   for (size_t f = 0; f < n; ++f) {  // f walks column-major: first index fastest
@@ -174,6 +183,12 @@ inline Var parse_matrix(const uint8_t *data, uint32_t nbytes) {
   } else if (v.cls >= mxDOUBLE && v.cls <= mxUINT64) {
     if (n == 0) return v;
     read_tag(c, type, nb, d);  // real part
+    if (v.cls == mxSINGLE && type == miSINGLE && nb / 4 >= n) {  // single stored as single: no detour through double
+      std::vector<float> colf(n);
+      memcpy(colf.data(), d, n * sizeof(float));
+      fortran_to_c(colf, v.dims, v.f32);
+      return v;
+    }
     std::vector<double> col;
     numeric_to_double(type, d, nb, col);
     if (col.size() < n) throw std::runtime_error("mat5: short numeric data");

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -84,6 +85,15 @@ CtxHolder &holder() {
   static thread_local CtxHolder h;
   return h;
 }
+
+// PSINFER_HOST_TIMING=1: seconds spent per phase, summed over the worker threads, printed by findObjectDataset.
+std::atomic<long long> g_ns_load(0), g_ns_ingest(0), g_ns_infer(0), g_ns_out(0), g_ns_joints(0);
+struct PhaseTimer {
+  std::atomic<long long> &acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(std::atomic<long long> &a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~PhaseTimer() { acc += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 // Device of the calling worker thread (findObjectDataset sets it); -1: PSINFER_DEVICE or device 0.
 thread_local int t_device = -1;
@@ -726,7 +736,11 @@ static void load_image_unaries(const PartApp &app, ps_ctx *ctx, int imgidx, bool
   for (int p = 0; p < P; ++p) {
     if (!app.m_part_conf.part[p].is_detect) continue;
     const std::string file = app.getScoreGridFileName(imgidx, p, flip);
-    std::vector<mat5::Var> vars = mat5::load(file);
+    std::vector<mat5::Var> vars;
+    {
+      PhaseTimer t(g_ns_load);
+      vars = mat5::load(file);
+    }
     const mat5::Var &cg = mat5::find(vars, "cell_scoregrid", file);
     const mat5::Var &Ti2 = mat5::find(vars, "transform_Ti2", file), &T2g = mat5::find(vars, "transform_T2g", file);
     if (cg.cls != mat5::mxCELL || cg.dims.size() != 2 || (int)cg.dims[0] != S || (int)cg.dims[1] != R)
@@ -739,7 +753,10 @@ static void load_image_unaries(const PartApp &app, ps_ctx *ctx, int imgidx, bool
       for (int r = 0; r < R; ++r) {
         const mat5::Var &c = cg.cells[(size_t)s * R + r];
         if (c.dims.size() != 2 || c.dims[0] != gh || c.dims[1] != gw) fail(file + ": score grids of one scale differ in size");
-        for (size_t i = 0; i < gh * gw; ++i) cells[(size_t)r * gh * gw + i] = (float)c.at(i);
+        if (c.cls == mat5::mxSINGLE && c.f32.size() == gh * gw)
+          memcpy(&cells[(size_t)r * gh * gw], c.f32.data(), gh * gw * sizeof(float));
+        else
+          for (size_t i = 0; i < gh * gw; ++i) cells[(size_t)r * gh * gw + i] = (float)c.at(i);
         // Tig = prod(Ti2, T2g) in double (partapp.cpp:881-887; array_to_matrix widens the floats)
         const size_t o = ((size_t)s * R + r) * 9;
         for (int i = 0; i < 3; ++i)
@@ -750,6 +767,7 @@ static void load_image_unaries(const PartApp &app, ps_ctx *ctx, int imgidx, bool
           }
       }
       // cudaMemcpyAsync from pageable memory returns once `cells` has been staged, so the buffer can be reused at once
+      PhaseTimer t(g_ns_ingest);
       check(ctx, ps_set_unary_compact(ctx, p, s, cells.data(), (int)gh, (int)gw, Tig.data(), PS_MEM_HOST), "ps_set_unary_compact");
     }
   }
@@ -803,7 +821,10 @@ void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, Hypothe
   int W = 0, H = 0;
   image_size(qsImgName, W, H);  // findrot.cpp:752-760
   std::vector<Joint> joints;
-  loadJoints(app, joints, flip, imgidx);
+  {
+    PhaseTimer t(g_ns_joints);
+    loadJoints(app, joints, flip, imgidx);
+  }
   for (const Joint &j : joints)
     if (j.type != Joint::ROT_GAUSSIAN) fail("only ROT_GAUSSIAN joints are supported (findrot.cpp:766)");
   const int rootpart_idx = app.m_rootpart_idx;
@@ -884,12 +905,15 @@ void findObjectImageRotJoints(const PartApp &app, int imgidx, bool flip, Hypothe
 
   int flags = PS_INFER_SPARSE | PS_INFER_ROOT_HYPS | PS_INFER_KEEP_UNARIES;
   if (ep.save_part_marginals_local_max) flags |= PS_INFER_LOCAL_MAX;
-  if (ep.use_pairwise) check(ctx, ps_infer(ctx, flags), "ps_infer");
-  else check(ctx, ps_max_states(ctx, flags & PS_INFER_LOCAL_MAX), "ps_max_states");
-
-  make_dirs(qsPartMarginalsDir);
   std::vector<float> best_conf((size_t)P * PS_HYP_VEC);
-  check(ctx, ps_get_best_conf(ctx, best_conf.data()), "ps_get_best_conf");
+  {
+    PhaseTimer t(g_ns_infer);
+    if (ep.use_pairwise) check(ctx, ps_infer(ctx, flags), "ps_infer");
+    else check(ctx, ps_max_states(ctx, flags & PS_INFER_LOCAL_MAX), "ps_max_states");
+    check(ctx, ps_get_best_conf(ctx, best_conf.data()), "ps_get_best_conf");
+  }
+  PhaseTimer t_out(g_ns_out);
+  make_dirs(qsPartMarginalsDir);
   {  // findrot.cpp:1005-1011
     mat5::Writer w(qsPartMarginalsDir + "/pose_est_imgidx" + pad_zeros(imgidx, 4) + ".mat");
     w.put("best_conf", best_conf.data(), {(size_t)P, (size_t)PS_HYP_VEC});
@@ -1009,6 +1033,9 @@ void findObjectDataset(const PartApp &app, int firstidx, int lastidx) {
   }
   for (std::thread &t : workers) t.join();
   if (failed) fail(first_error);
+  if (getenv("PSINFER_HOST_TIMING"))
+    fprintf(stderr, "host phases, seconds summed over %d threads: joints %.2f  load+inflate %.2f  ingest calls %.2f  infer+wait %.2f  outputs %.2f\n",
+            gpus * per_gpu, g_ns_joints / 1e9, g_ns_load / 1e9, g_ns_ingest / 1e9, g_ns_infer / 1e9, g_ns_out / 1e9);
 }
 
 }  // namespace object_detect

@@ -45,12 +45,13 @@ def main():
             shutil.rmtree(os.path.join(base, sub), ignore_errors=True)
         t0 = time.time()
         r = subprocess.run([cli, "--expopt", info["expopt"], "--find_obj", "--gpus", str(gpus), "--contexts", str(args.contexts)],
-                           capture_output=True, text=True)
+                           capture_output=True, text=True, env=dict(os.environ, PSINFER_HOST_TIMING="1"))
         wall = time.time() - t0
         assert r.returncode == 0, r.stderr
         m = re.search(r"in ([0-9.]+) s \(([0-9.]+) images/s\)", r.stdout)
         run = {"gpus": gpus, "contexts_per_gpu": args.contexts, "images": args.images, "wall_s": round(wall, 2),
-               "loop_s": float(m.group(1)), "images_per_s": float(m.group(2))}
+               "loop_s": float(m.group(1)), "images_per_s": float(m.group(2)), "host_cpus": os.cpu_count(),
+               "host_phases": r.stderr.strip().splitlines()[-1] if r.stderr.strip() else None}
         keep = os.path.join(tmp, "out_%d" % gpus)
         os.makedirs(keep)
         for sub in ("part_marginals", "object_hyp"):
