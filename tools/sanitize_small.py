@@ -45,3 +45,27 @@ with PsContext(ep4, synth.part_conf(2), H2, W2) as ctx:
     for sparse in (True, False):
         out = ctx.message(child, (5.0, -3.0), (-4.0, 6.0), [[20.0, 9.0], [9.0, 14.0]], 0.2, 0.5, 1.0, sparse)
         print(sparse, float(out.max()))
+# round 2: one-call ingest, fused table add, the level-batched route replayed from its CUDA graph (second and third
+# inference with the same joints), a 10-part tree (levels of 5 and 4 messages), the POS_GAUSSIAN model
+ep8 = ExpParam(num_rotation_steps=8, roi_save_num_samples=10)
+P10, H3, W3 = 10, 72, 64
+cells, Tig = synth.compact_scores(ep8, H3, W3, P10, 4)
+joints10 = synth.make_joints(P10, seed=7, max_offset=8, sigma_range=(2, 6))
+with PsContext(ep8, synth.part_conf(P10), H3, W3) as ctx:
+    ctx.set_joints(joints10)
+    for rep in range(3):
+        ctx.set_unaries_compact(list(range(P10)), [0] * P10, [cells[p, 0] for p in range(P10)], Tig)
+        rot = ctx.rot_score_table(0.3, 0.2)
+        pos = ctx.pos_score_table(2.0, -3.0, 90.0, 60.0, W3 / 2, H3 / 2)
+        ctx.add_unary_tables(3, [rot, pos], [0, 1], [0.8, 0.6])
+        ctx.infer(sparse=True)
+        print(rep, ctx.best_conf()[:3, 2:6].tolist(), ctx.launch_count())
+for j in joints:
+    j.type = 1
+with PsContext(ep, synth.part_conf(P), H, W) as ctx:
+    ctx.set_joints(joints)
+    cells, Tig = synth.compact_scores(ep, H, W, P, 1)
+    for p in range(P):
+        ctx.set_unary_compact(p, 0, cells[p, 0], Tig)
+    ctx.infer(sparse=True, root_hyps=True)
+    print("pos model", float(np.nanmax(ctx.root_posterior())), len(ctx.root_hyps()))
