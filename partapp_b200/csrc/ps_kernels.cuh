@@ -1792,7 +1792,7 @@ __device__ __forceinline__ void bar_sync_filter() { asm volatile("bar.sync 1, 25
 #ifndef PS_GAUSS_MINB
 #define PS_GAUSS_MINB 3  // register budget of k_gauss_xy: 65536 / (3 * 288) -> 72 registers (two blocks take 41 K of the 64 K)
 #endif
-template <bool FMA>
+template <bool FMA, bool DYN>
 __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_constant__ TmapBatch tm, const __grid_constant__ GaussBatch b, u64 nz) {
   constexpr int T = 8;
   const int NS = b.stages;  // TMA stages: 1 (the next box is requested when the x phase ends and lands during the y phase) or 2
@@ -1825,8 +1825,15 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
         }
       };
+      // Work items in a fixed order, item = blockIdx.x + k * gridDim.x (messages in launch order, longest walk first,
+      // all slices of a walk adjacent: every block gets the same mix of long and short walks).  The filter warps walk
+      // the same sequence on their own, so nothing but the boxes passes from the producer to them.
+      // (DYN: items drawn from an atomic counter and published through s_meta instead -- same results, same speed;
+      // racecheck cannot see the mbarrier that orders those shared-memory records and reports them.)
+      int item = (int)blockIdx.x - (int)gridDim.x;
       for (;;) {
-        const int item = (int)atomicAdd(b.counter, 1u);
+        if (DYN) item = (int)atomicAdd(b.counter, 1u);
+        else item += (int)gridDim.x;
         if (item >= b.total_items) break;
         int mi = 0;
         while (mi + 1 < b.nmsg && item >= b.m[mi + 1].item0) ++mi;
@@ -1839,16 +1846,20 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
         const unsigned bytes = (unsigned)(64 + 2 * nx) * 64u * sizeof(float);
         for (int i = 0; i < nxb; ++i) {
           wait_free();
-          s_meta[s][0] = make_int4(mi, we.x, we.y, we.z);
-          s_meta[s][1] = make_int4(i, z, (int)g.masks[we.w + i], 0);
+          if (DYN) {
+            s_meta[s][0] = make_int4(mi, we.x, we.y, we.z);
+            s_meta[s][1] = make_int4(i, z, (int)g.masks[we.w + i], 0);
+          }
           mbar_expect_tx(&s_full[s], bytes);
           tma_load_3d(s_raw + s * b.stage_stride, &tm.t[mi], we.y - g.halo + 64 * i, we.x * 64 - nx, z, &s_full[s]);
           next_stage();
         }
       }
-      wait_free();
-      s_meta[s][0] = make_int4(-1, 0, 0, 0);
-      mbar_arrive(&s_full[s]);
+      if (DYN) {
+        wait_free();
+        s_meta[s][0] = make_int4(-1, 0, 0, 0);
+        mbar_arrive(&s_full[s]);
+      }
     }
     return;
   }
@@ -1858,14 +1869,41 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
   }
   bar_sync_filter();
   int s = -1, u = 0, cur = -1;
+  // static order: the walk this block is in (see the producer)
+  int item = (int)blockIdx.x - (int)gridDim.x, step = 0, nsteps = 0, s_mi = 0, s_z = 0, mask_cur = 0;
+  int4 s_we = make_int4(0, 0, 0, 0);
   for (;;) {
+    int4 m0, m1;
+    if (!DYN) {
+      if (step == nsteps) {
+        item += (int)gridDim.x;
+        if (item >= b.total_items) break;
+        s_mi = 0;
+        while (s_mi + 1 < b.nmsg && item >= b.m[s_mi + 1].item0) ++s_mi;
+        const GaussMsg &gg = b.m[s_mi];
+        const int local = item - gg.item0;
+        const int wk = local / b.R;
+        s_z = local - wk * b.R;
+        s_we = *reinterpret_cast<const int4 *>(gg.walks + 4 * wk);
+        nsteps = (s_we.z + 7) / 8 + gg.lag;
+        step = 0;
+        mask_cur = gg.masks[s_we.w];
+      }
+      m0 = make_int4(s_mi, s_we.x, s_we.y, s_we.z);
+      m1 = make_int4(step, s_z, mask_cur, 0);
+      ++step;
+      if (step < nsteps) mask_cur = b.m[s_mi].masks[s_we.w + step];  // the next box's mask, in flight during this step
+    }
     if (++s == NS) {
       s = 0;
       ++u;
     }
     while (!mbar_try_wait_h(&s_full[s], (unsigned)u & 1u, b.hint_ns)) {}
-    const int4 m0 = s_meta[s][0], m1 = s_meta[s][1];
-    if (m0.x < 0) break;
+    if (DYN) {
+      m0 = s_meta[s][0];
+      m1 = s_meta[s][1];
+      if (m0.x < 0) break;
+    }
     const GaussMsg &g = b.m[m0.x];
     const int nx = (g.len_x - 1) / 2, ny = (g.len_y - 1) / 2;
     const int cap = 64 * (g.lag + 1), dshift = g.halo - ny;

@@ -937,6 +937,8 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     const int grid = std::min(items, c->num_sms * bps);
     static const unsigned hint_env = getenv("PSINFER_MBAR_HINT") ? (unsigned)atol(getenv("PSINFER_MBAR_HINT")) : PS_MBAR_HINT_NS;
     gb.hint_ns = hint_env;
+    // PSINFER_GAUSS_DYNAMIC=1: work items from an atomic counter instead of the fixed interleaved order (A/B)
+    static const bool dyn_env = getenv("PSINFER_GAUSS_DYNAMIC") && atoi(getenv("PSINFER_GAUSS_DYNAMIC")) != 0;
     // The taps are the one fp32-bound stage; everything else is memory-bound.  With several images in flight the block
     // scheduler should hand freed SM slots to a waiting Gaussian launch first, so that it holds its (capped) share of every
     // SM for its whole run and the memory-bound blocks of the other images fill the rest: launch priority, not a separate
@@ -958,10 +960,14 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     lc.attrs = la;
     lc.numAttrs = prio_env ? 1 : 0;
     const psk::u64 nz2 = PS_NEGZERO2;
-    if (c->cfg.fast_math)
-      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<true>, tm, gb, nz2));
+    if (c->cfg.fast_math && dyn_env)
+      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<true, true>, tm, gb, nz2));
+    else if (c->cfg.fast_math)
+      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<true, false>, tm, gb, nz2));
+    else if (dyn_env)
+      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<false, true>, tm, gb, nz2));
     else
-      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<false>, tm, gb, nz2));
+      PS_LAUNCH(c, KC_GAUSS_XY, cudaLaunchKernelEx(&lc, psk::k_gauss_xy<false, false>, tm, gb, nz2));
   }
   // stage 4: bilinear read-back into the image frame, V[i] -> B[i]
   {
@@ -1351,8 +1357,10 @@ int ps_create(const ps_config *cfg, ps_ctx **out) {
     static std::vector<char> done(64, 0);
     std::lock_guard<std::mutex> lock(mu);
     if (cfg->device >= (int)done.size() || !done[cfg->device]) {
-      if (!cu(cudaFuncSetAttribute(psk::k_gauss_xy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
-          !cu(cudaFuncSetAttribute(psk::k_gauss_xy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
+      if (!cu(cudaFuncSetAttribute(psk::k_gauss_xy<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_gauss_xy<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_gauss_xy<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
+          !cu(cudaFuncSetAttribute(psk::k_gauss_xy<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax), "smem attr") ||
           !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
           !cu(cudaFuncSetAttribute(psk::k_conv_cols_tma2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024), "smem attr") ||
           !cu(cudaFuncSetAttribute(psk::k_conv_rows3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "smem attr") ||
