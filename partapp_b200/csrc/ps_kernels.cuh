@@ -1764,7 +1764,6 @@ __global__ void __launch_bounds__(288, PS_TMA_MINB) k_conv_cols_tma2(const __gri
 // publishes (message, walk, block, slice) next to each box and issues the TMA; the eight filter warps follow the
 // published records, hand a stage back through its `empty` mbarrier right after the x phase and meet at a named
 // barrier between the phases.
-constexpr int kMaxGaussRanks = 48;  // walks (64-column strips) per message the fixed work order can index
 constexpr int kRingPitch = 68;  // floats per ring row: 64 + 4 keeps rows 16-byte aligned and the transposed stores 2-way at worst
 struct GaussMsg {
   float *out;                  // [z][ey][ex], pitch EP, plane oplane
@@ -1783,32 +1782,12 @@ struct GaussBatch {
   int ring_rows;               // 64 * (largest lag of the batch + 1)
   int stages;                  // TMA stages, 1 or 2
   unsigned hint_ns;            // suspend-time hint of the mbarrier waits
-  // fixed work order: items sorted by walk rank first (messages are sorted by their number of walks, walks by length),
-  // rank_item0[r] = first item of rank r, nranks of them; dealt to the blocks back and forth ("snake")
-  int nranks;
-  int rank_item0[kMaxGaussRanks + 1];
 };
 constexpr int kMaxFusedTaps = 256;
 struct alignas(64) TmapBatch {
   CUtensorMap t[kMaxBatch];
 };
 __device__ __forceinline__ void bar_sync_filter() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// Fixed work order of k_gauss_xy: the j-th item of block c is global item j*G + (j odd ? G-1-c : c) of the rank-major
-// list (longest walks of every message first), i.e. the blocks are dealt items back and forth over a list of decreasing
-// length -- the static counterpart of drawing from a counter.  Returns false past the end.
-__device__ __forceinline__ bool gauss_static_item(const GaussBatch &b, int j, int &mi, int &wk, int &z) {
-  const int G = (int)gridDim.x, c = (int)blockIdx.x;
-  const int gidx = j * G + ((j & 1) ? G - 1 - c : c);
-  if (gidx >= b.total_items) return false;
-  int r = 0;
-  while (r + 1 < b.nranks && gidx >= b.rank_item0[r + 1]) ++r;
-  const int local = gidx - b.rank_item0[r];
-  mi = local / b.R;
-  z = local - mi * b.R;
-  wk = r;
-  return true;
-}
 
 #ifndef PS_GAUSS_MINB
 #define PS_GAUSS_MINB 3  // register budget of k_gauss_xy: 65536 / (3 * 288) -> 72 registers (two blocks take 41 K of the 64 K)
@@ -1846,23 +1825,21 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
         }
       };
-      // Work items in a fixed order (gauss_static_item: rank-major list dealt back and forth over the blocks).  The filter
-      // warps walk the same sequence on their own, so nothing but the boxes passes from the producer to them.
+      // Work items in a fixed order, item = blockIdx.x + k * gridDim.x (messages in launch order, longest walk first,
+      // all slices of a walk adjacent: every block gets the same mix of long and short walks).  The filter warps walk
+      // the same sequence on their own, so nothing but the boxes passes from the producer to them.
       // (DYN: items drawn from an atomic counter and published through s_meta instead -- same results, same speed;
       // racecheck cannot see the mbarrier that orders those shared-memory records and reports them.)
-      for (int j = 0;; ++j) {
-        int mi = 0, wk = 0, z = 0;
-        if (DYN) {
-          const int item = (int)atomicAdd(b.counter, 1u);
-          if (item >= b.total_items) break;
-          while (mi + 1 < b.nmsg && item >= b.m[mi + 1].item0) ++mi;
-          const int local = item - b.m[mi].item0;
-          wk = local / b.R;
-          z = local - wk * b.R;
-        } else if (!gauss_static_item(b, j, mi, wk, z)) {
-          break;
-        }
+      int item = (int)blockIdx.x - (int)gridDim.x;
+      for (;;) {
+        if (DYN) item = (int)atomicAdd(b.counter, 1u);
+        else item += (int)gridDim.x;
+        if (item >= b.total_items) break;
+        int mi = 0;
+        while (mi + 1 < b.nmsg && item >= b.m[mi + 1].item0) ++mi;
         const GaussMsg &g = b.m[mi];
+        const int local = item - g.item0;
+        const int wk = local / b.R, z = local - wk * b.R;
         const int4 we = *reinterpret_cast<const int4 *>(g.walks + 4 * wk);
         const int nxb = (we.z + 7) / 8 + g.lag;
         const int nx = (g.len_x - 1) / 2;
@@ -1893,15 +1870,20 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
   bar_sync_filter();
   int s = -1, u = 0, cur = -1;
   // static order: the walk this block is in (see the producer)
-  int item = 0, step = 0, nsteps = 0, s_mi = 0, s_z = 0, mask_cur = 0;  // item: how many walks this block has started
+  int item = (int)blockIdx.x - (int)gridDim.x, step = 0, nsteps = 0, s_mi = 0, s_z = 0, mask_cur = 0;
   int4 s_we = make_int4(0, 0, 0, 0);
   for (;;) {
     int4 m0, m1;
     if (!DYN) {
       if (step == nsteps) {
-        int wk = 0;
-        if (!gauss_static_item(b, item++, s_mi, wk, s_z)) break;
+        item += (int)gridDim.x;
+        if (item >= b.total_items) break;
+        s_mi = 0;
+        while (s_mi + 1 < b.nmsg && item >= b.m[s_mi + 1].item0) ++s_mi;
         const GaussMsg &gg = b.m[s_mi];
+        const int local = item - gg.item0;
+        const int wk = local / b.R;
+        s_z = local - wk * b.R;
         s_we = *reinterpret_cast<const int4 *>(gg.walks + 4 * wk);
         nsteps = (s_we.z + 7) / 8 + gg.lag;
         step = 0;

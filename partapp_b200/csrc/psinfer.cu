@@ -881,13 +881,8 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     size_t smem = 0;
     unsigned stride = 0;
     int lagmax = 1, items = 0;
-    // messages by decreasing number of walks: rank r of the fixed work order covers the first rank_count[r] of them
-    std::vector<int> order(n);
-    for (int i = 0; i < n; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a]->dp->nwalks > jobs[b]->dp->nwalks; });
-    for (int k = 0; k < n; ++k) {
-      const int i = k, src = order[k];  // entry k of the batch = job `src` (its slot buffers are slotU/V[src])
-      const DevPlan &dp = *jobs[src]->dp;
+    for (int i = 0; i < n; ++i) {
+      const DevPlan &dp = *jobs[i]->dp;
       const psg::MessagePlan &h = dp.host;
       const int EHP = (h.EH + 7) & ~7;
       const int nx = ((int)h.fx.size() - 1) / 2;
@@ -895,12 +890,12 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
       cuuint64_t strides[2] = {(cuuint64_t)EHP * sizeof(float), (cuuint64_t)h.EW * EHP * sizeof(float)};
       cuuint32_t box[3] = {64, (cuuint32_t)(64 + 2 * nx), 1};
       cuuint32_t estr[3] = {1, 1, 1};
-      CUresult r = tensor_map_encoder()(&tm.t[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->slotU[src].p, dims, strides, box, estr,
+      CUresult r = tensor_map_encoder()(&tm.t[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->slotU[i].p, dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return c->fail(PS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
       psk::GaussMsg &g = gb.m[i];
-      g.out = c->slotV[src].as<float>();
+      g.out = c->slotV[i].as<float>();
       g.taps_x = dp.fx(); g.taps_y = dp.fy();
       g.walks = dp.walks.as<int>();
       g.masks = (const unsigned char *)(dp.walks.as<int>() + 4 * (size_t)dp.nwalks);
@@ -915,18 +910,6 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
       lagmax = std::max(lagmax, h.lag);
     }
     gb.total_items = items;
-    {
-      const int maxw = jobs[order[0]]->dp->nwalks;
-      gb.nranks = std::min(maxw, psk::kMaxGaussRanks);
-      int acc = 0;
-      for (int r = 0; r < gb.nranks; ++r) {
-        gb.rank_item0[r] = acc;
-        int cnt = 0;
-        for (int k = 0; k < n; ++k) cnt += jobs[order[k]]->dp->nwalks > r;
-        acc += cnt * R;
-      }
-      gb.rank_item0[gb.nranks] = acc;
-    }
     gb.stage_stride = stride;
     gb.ring_rows = 64 * (lagmax + 1);
     if ((rc = take_work_counter(c, &gb.counter))) return rc;
@@ -955,8 +938,7 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     static const unsigned hint_env = getenv("PSINFER_MBAR_HINT") ? (unsigned)atol(getenv("PSINFER_MBAR_HINT")) : PS_MBAR_HINT_NS;
     gb.hint_ns = hint_env;
     // PSINFER_GAUSS_DYNAMIC=1: work items from an atomic counter instead of the fixed interleaved order (A/B)
-    static const bool dyn_flag = getenv("PSINFER_GAUSS_DYNAMIC") && atoi(getenv("PSINFER_GAUSS_DYNAMIC")) != 0;
-    const bool dyn_env = dyn_flag || jobs[order[0]]->dp->nwalks > psk::kMaxGaussRanks;  // more strips than the rank table holds
+    static const bool dyn_env = getenv("PSINFER_GAUSS_DYNAMIC") && atoi(getenv("PSINFER_GAUSS_DYNAMIC")) != 0;
     // The taps are the one fp32-bound stage; everything else is memory-bound.  With several images in flight the block
     // scheduler should hand freed SM slots to a waiting Gaussian launch first, so that it holds its (capped) share of every
     // SM for its whole run and the memory-bound blocks of the other images fill the rest: launch priority, not a separate
