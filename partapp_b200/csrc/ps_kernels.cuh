@@ -1782,6 +1782,9 @@ struct GaussBatch {
   int ring_rows;               // 64 * (largest lag of the batch + 1)
   int stages;                  // TMA stages, 1 or 2
   unsigned hint_ns;            // suspend-time hint of the mbarrier waits
+  // fixed work order: block c processes items cta_items[cta_off[c] .. cta_off[c + 1]), each (message << 24 | walk << 12 |
+  // slice); the host deals the message-major item list to the least loaded block (list scheduling on the tap counts)
+  const int *cta_off, *cta_items;
 };
 constexpr int kMaxFusedTaps = 256;
 struct alignas(64) TmapBatch {
@@ -1825,21 +1828,29 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
         }
       };
-      // Work items in a fixed order, item = blockIdx.x + k * gridDim.x (messages in launch order, longest walk first,
-      // all slices of a walk adjacent: every block gets the same mix of long and short walks).  The filter warps walk
-      // the same sequence on their own, so nothing but the boxes passes from the producer to them.
+      // Work items in a fixed order: this block's list of the table the host dealt (cta_off / cta_items).  The filter
+      // warps walk the same list on their own, so nothing but the boxes passes from the producer to them.
       // (DYN: items drawn from an atomic counter and published through s_meta instead -- same results, same speed;
       // racecheck cannot see the mbarrier that orders those shared-memory records and reports them.)
-      int item = (int)blockIdx.x - (int)gridDim.x;
+      int idx = DYN ? 0 : b.cta_off[blockIdx.x];
+      const int idx_end = DYN ? 0 : b.cta_off[blockIdx.x + 1];
       for (;;) {
-        if (DYN) item = (int)atomicAdd(b.counter, 1u);
-        else item += (int)gridDim.x;
-        if (item >= b.total_items) break;
-        int mi = 0;
-        while (mi + 1 < b.nmsg && item >= b.m[mi + 1].item0) ++mi;
+        int mi = 0, wk = 0, z = 0;
+        if (DYN) {
+          const int item = (int)atomicAdd(b.counter, 1u);
+          if (item >= b.total_items) break;
+          while (mi + 1 < b.nmsg && item >= b.m[mi + 1].item0) ++mi;
+          const int local = item - b.m[mi].item0;
+          wk = local / b.R;
+          z = local - wk * b.R;
+        } else {
+          if (idx >= idx_end) break;
+          const int it = b.cta_items[idx++];
+          mi = it >> 24;
+          wk = (it >> 12) & 0xfff;
+          z = it & 0xfff;
+        }
         const GaussMsg &g = b.m[mi];
-        const int local = item - g.item0;
-        const int wk = local / b.R, z = local - wk * b.R;
         const int4 we = *reinterpret_cast<const int4 *>(g.walks + 4 * wk);
         const int nxb = (we.z + 7) / 8 + g.lag;
         const int nx = (g.len_x - 1) / 2;
@@ -1870,20 +1881,19 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
   bar_sync_filter();
   int s = -1, u = 0, cur = -1;
   // static order: the walk this block is in (see the producer)
-  int item = (int)blockIdx.x - (int)gridDim.x, step = 0, nsteps = 0, s_mi = 0, s_z = 0, mask_cur = 0;
+  int idx = DYN ? 0 : b.cta_off[blockIdx.x], step = 0, nsteps = 0, s_mi = 0, s_z = 0, mask_cur = 0;
+  const int idx_end = DYN ? 0 : b.cta_off[blockIdx.x + 1];
   int4 s_we = make_int4(0, 0, 0, 0);
   for (;;) {
     int4 m0, m1;
     if (!DYN) {
       if (step == nsteps) {
-        item += (int)gridDim.x;
-        if (item >= b.total_items) break;
-        s_mi = 0;
-        while (s_mi + 1 < b.nmsg && item >= b.m[s_mi + 1].item0) ++s_mi;
+        if (idx >= idx_end) break;
+        const int it = b.cta_items[idx++];
+        s_mi = it >> 24;
+        const int wk = (it >> 12) & 0xfff;
+        s_z = it & 0xfff;
         const GaussMsg &gg = b.m[s_mi];
-        const int local = item - gg.item0;
-        const int wk = local / b.R;
-        s_z = local - wk * b.R;
         s_we = *reinterpret_cast<const int4 *>(gg.walks + 4 * wk);
         nsteps = (s_we.z + 7) / 8 + gg.lag;
         step = 0;

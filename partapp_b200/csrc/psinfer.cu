@@ -118,6 +118,8 @@ struct ps_ctx {
   std::vector<DevBuf> slotB, slotU, slotV;
   size_t slot_elems = 0;
   DevBuf chain_tmp;     // [n_root_children][N]: down-pass inputs of the chains (ping-pong partner of rootmsg)
+  // fixed work order of the fused Gaussian launches: per batch (plans, grid) the items of every block, dealt on the host
+  std::map<std::string, std::shared_ptr<DevBuf>> gauss_tables;
   DevBuf work_counters; // unsigned [kWorkCounters]: one zeroed work-item counter per fused Gaussian launch
   int work_counter_next = 0;
   bool disable_batch = false;  // PSINFER_NO_BATCH=1: one message per launch through the two-pass Gaussian route (A/B testing)
@@ -331,6 +333,11 @@ int get_plan(ps_ctx *c, const double off_in[2], const double off_out[2], const d
     PS_CUDA(c, cudaStreamSynchronize(c->stream));
     for (auto i = c->plan_cache.begin(); i != c->plan_cache.end();)
       i = i->second.use_count() == 1 ? c->plan_cache.erase(i) : std::next(i);
+    // work-order tables and captured graphs are keyed by / hold plan addresses, which may now be reused
+    c->gauss_tables.clear();
+    for (auto &g : c->graphs)
+      if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    c->graphs.clear();
   }
   c->plan_cache.emplace(key, dp);
   out = dp;
@@ -937,8 +944,68 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     const int grid = std::min(items, c->num_sms * bps);
     static const unsigned hint_env = getenv("PSINFER_MBAR_HINT") ? (unsigned)atol(getenv("PSINFER_MBAR_HINT")) : PS_MBAR_HINT_NS;
     gb.hint_ns = hint_env;
-    // PSINFER_GAUSS_DYNAMIC=1: work items from an atomic counter instead of the fixed interleaved order (A/B)
-    static const bool dyn_env = getenv("PSINFER_GAUSS_DYNAMIC") && atoi(getenv("PSINFER_GAUSS_DYNAMIC")) != 0;
+    // Fixed work order (default): the message-major item list -- the order that keeps a message's boxes in L2 -- dealt to
+    // the least loaded block, costs = tap-outputs of the item (list scheduling: what drawing from a counter does at run
+    // time, decided here once per batch).  Tables are cached per (plans, grid); a poselet-conditioned run whose joints
+    // change with every image fills the cache and then draws from the counter.
+    // PSINFER_GAUSS_DYNAMIC=1: work items from an atomic counter instead of the fixed order (A/B)
+    static const bool dyn_flag = getenv("PSINFER_GAUSS_DYNAMIC") && atoi(getenv("PSINFER_GAUSS_DYNAMIC")) != 0;
+    bool use_table = false;
+    if (!dyn_flag) {
+      std::string key((const char *)&grid, sizeof grid);
+      for (int i = 0; i < n; ++i) {
+        const DevPlan *p = jobs[i]->dp;
+        key.append((const char *)&p, sizeof p);
+      }
+      auto it = c->gauss_tables.find(key);
+      if (it == c->gauss_tables.end() && c->gauss_tables.size() < 256) {
+        std::vector<long long> load(grid, 0);
+        std::vector<std::vector<int>> per(grid);
+        // min-heap over (load, block)
+        std::vector<std::pair<long long, int>> heap;
+        for (int g = 0; g < grid; ++g) heap.push_back({0, g});
+        auto cmp = [](const std::pair<long long, int> &a, const std::pair<long long, int> &b) { return a > b; };
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        bool fits = R <= 0xfff;
+        for (int i = 0; i < n && fits; ++i) {
+          const psg::MessagePlan &h = jobs[i]->dp->host;
+          const std::vector<int> &wl = c->disable_tile_lists ? h.walks_all : h.walks;
+          const std::vector<unsigned char> &ml = c->disable_tile_lists ? h.xmasks_all : h.xmasks;
+          const int nw = (int)wl.size() / 4;
+          if (nw > 0xfff) fits = false;
+          for (int w = 0; w < nw && fits; ++w) {
+            const int ng = wl[4 * w + 2], moff = wl[4 * w + 3], nxb = (ng + 7) / 8 + h.lag;
+            long long cost = (long long)ng * 8 * 64 * (long long)h.fy.size();
+            for (int x = 0; x < nxb; ++x) cost += (long long)__builtin_popcount(ml[moff + x]) * 8 * 64 * (long long)h.fx.size();
+            cost += 20000LL * nxb;  // per-step overhead (barriers, stores)
+            for (int z = 0; z < R; ++z) {
+              std::pop_heap(heap.begin(), heap.end(), cmp);
+              std::pair<long long, int> &top = heap.back();
+              per[top.second].push_back((i << 24) | (w << 12) | z);
+              top.first += cost;
+              std::push_heap(heap.begin(), heap.end(), cmp);
+            }
+          }
+        }
+        if (fits) {
+          std::vector<int> flat(grid + 1, 0);
+          for (int g = 0; g < grid; ++g) flat[g + 1] = flat[g] + (int)per[g].size();
+          for (int g = 0; g < grid; ++g) flat.insert(flat.end(), per[g].begin(), per[g].end());
+          std::shared_ptr<DevBuf> tb(new DevBuf);
+          PS_CUDA(c, tb->alloc(flat.size() * sizeof(int)));
+          PS_CUDA(c, cudaMemcpyAsync(tb->p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+          PS_CUDA(c, cudaStreamSynchronize(st));  // `flat` goes out of scope; happens once per batch shape
+          it = c->gauss_tables.emplace(key, tb).first;
+        }
+      }
+      if (it != c->gauss_tables.end()) {
+        gb.cta_off = it->second->as<int>();
+        gb.cta_items = it->second->as<int>() + grid + 1;
+        use_table = true;
+      }
+    }
+    const bool dyn_env = !use_table;
+
     // The taps are the one fp32-bound stage; everything else is memory-bound.  With several images in flight the block
     // scheduler should hand freed SM slots to a waiting Gaussian launch first, so that it holds its (capped) share of every
     // SM for its whole run and the memory-bound blocks of the other images fill the rest: launch priority, not a separate
