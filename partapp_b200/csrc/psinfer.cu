@@ -170,7 +170,8 @@ struct ps_ctx {
     int pending_scaleidx = 0, pending_flags = 0, result_scale = -1;
   };
   std::map<std::string, InferGraph> graphs;
-  long long joints_version = 0, graph_replays = 0;
+  long long joints_version = 0, graph_replays = 0, last_infer_version = -1;
+  bool joints_reused = true;  // the joint set of this inference is the one of the previous inference (or there was none)
   bool disable_graph = false;  // PSINFER_NO_GRAPH=1
 
   // results.  ps_infer / ps_max_states only enqueue device work; the host part of the readout (decode of the
@@ -958,7 +959,9 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
         key.append((const char *)&p, sizeof p);
       }
       auto it = c->gauss_tables.find(key);
-      if (it == c->gauss_tables.end() && c->gauss_tables.size() < 256) {
+      // build a table only for a joint set that is being reused (or the very first one): a run that swaps joints with every
+      // image would pay a host-side build and a stream synchronisation per level for tables it never sees again
+      if (it == c->gauss_tables.end() && c->gauss_tables.size() < 256 && c->joints_reused) {
         std::vector<long long> load(grid, 0);
         std::vector<std::vector<int>> per(grid);
         // min-heap over (load, block)
@@ -2307,6 +2310,8 @@ int ps_infer(ps_ctx *c, int flags) {
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   if (c->pos_model) return infer_pos(c, flags);
   c->pending_root_only = false;
+  c->joints_reused = c->last_infer_version < 0 || c->last_infer_version == c->joints_version;
+  c->last_infer_version = c->joints_version;
   if (c->disable_graph || c->profiling) return infer_enqueue(c, flags);
   std::string key((const char *)&flags, sizeof flags);
   key.append((const char *)&c->joints_version, sizeof c->joints_version);
