@@ -483,11 +483,110 @@ def eval_segments(annolist: Sequence[Annotation], part_conf_eval: Sequence[PartD
     return SegmentEval(ratio, seg_correct, seg_total, correct, total, endpoints)
 
 
+def _image_size(path: str) -> Tuple[int, int]:
+    """(width, height) from a PNG / JPEG / PNM header (the reference loads the image for it, findrot.cpp:752-760)."""
+    import struct
+    with open(path, "rb") as f:
+        h = f.read(32)
+        if h[:4] == b"\x89PNG":
+            return struct.unpack(">II", h[16:24])
+        if h[:2] == b"\xff\xd8":
+            f.seek(2)
+            while True:
+                m = f.read(4)
+                if len(m) < 4 or m[0] != 0xFF:
+                    break
+                ln = (m[2] << 8) | m[3]
+                if 0xC0 <= m[1] <= 0xCF and m[1] not in (0xC4, 0xC8, 0xCC):
+                    s5 = f.read(5)
+                    return ((s5[3] << 8) | s5[4], (s5[1] << 8) | s5[2])
+                f.seek(ln - 2, 1)
+        if h[:1] == b"P" and h[1:2] in (b"2", b"3", b"5", b"6"):
+            f.seek(2)
+            w, hh = f.read(64).split()[:2]
+            return int(w), int(hh)
+    raise ValueError("cannot read the size of image " + path)
+
+
+# ---- the other hypothesis sources of vis_eval_helper (parteval.cpp:326-383, :495-514) --------------------------------
+def load_score_grid_direct(cells: np.ndarray, Tig: np.ndarray, height: int, width: int) -> np.ndarray:
+    """PartApp::loadScoreGrid with TM_DIRECT (partapp.cpp:830-903, multi_array_transform.hpp:167-192) in numpy: every
+    non-zero grid cell (x1 outer, y1 inner: later writers win) lands on round(Tig * (x1, y1)); unevaluated cells stay 0."""
+    R, gh, gw = cells.shape
+    out = np.zeros((R, height, width), np.float32)
+    y1, x1 = np.meshgrid(np.arange(gh), np.arange(gw), indexing="ij")
+    order = np.lexsort((y1.ravel(), x1.ravel()))               # scatter order: x1 outer, y1 inner
+    xs, ys = x1.ravel()[order].astype(np.float64), y1.ravel()[order].astype(np.float64)
+    for r in range(R):
+        T = np.asarray(Tig[r], np.float64)
+        x3 = (T[0, 0] * xs + T[0, 1] * ys) + T[0, 2]
+        y3 = (T[1, 0] * xs + T[1, 1] * ys) + T[1, 2]
+        ix, iy = np.floor(x3 + 0.5).astype(np.int64), np.floor(y3 + 0.5).astype(np.int64)
+        v = cells[r].ravel()[order]
+        ok = (v != 0) & (ix >= 0) & (ix < width) & (iy >= 0) & (iy < height)
+        out[r, iy[ok], ix[ok]] = v[ok]                          # duplicates: numpy keeps the last one = the last writer
+    return out
+
+
+def unary_best_hyp(scores: np.ndarray, scaleidx: int, scale: float, rot_range: Tuple[float, float, int]) -> np.ndarray:
+    """EVAL_TYPE_UNARIES (parteval.cpp:355-379): the first strict maximum of one part's score grids in the reference's
+    scan order -- rotation, then x, then y -- as a best_conf row."""
+    R, H, W = scores.shape
+    flat = np.transpose(scores, (0, 2, 1)).reshape(-1)          # [r][x][y]
+    k = int(np.argmax(flat))                                     # first occurrence of the maximum = strict '>' scan
+    r, rem = divmod(k, W * H)
+    x, y = divmod(rem, H)
+    rmin, rmax, n = rot_range
+    rot = rmin if rmin == rmax else rmin + (rmax - rmin) / n * (0.5 + r)
+    return np.array([scaleidx, np.float32(scale), r, np.float32(rot), x, y, flat[k]], np.float32)
+
+
+def eval_segments_roi(annolist: Sequence[Annotation], roi_counts: Sequence[int], part_conf_eval: Sequence[PartDef],
+                      window_param: Sequence[PartParam], load_best_conf_roi, firstidx: int, lastidx: int, scale: float = 1.0,
+                      part_conf: Optional[Sequence[PartDef]] = None, part_conf_type: str = "human_full",
+                      rot_range: Tuple[float, float, int] = (-180.0, 180.0, 48)) -> SegmentEval:
+    """eval_segments_roi (parteval.cpp:1779-1889): every region of interest of an image has its own pose_est file
+    (`load_best_conf_roi(imgidx, roi_idx)` = best_conf of pose_est_imgidx%04d_roi%04d.mat, :495-514); a part counts as
+    correct if it matches ANY annotated person of the image ("check all gt rectangles", first match wins).  Unlike
+    eval_segments the ground-truth box keeps its y extension here (:1845-1847)."""
+    P = len(part_conf_eval)
+    model_conf = part_conf_eval if part_conf is None else part_conf
+    correct = [0] * P
+    seg_correct = seg_total = 0
+    for imgidx in range(firstidx, lastidx + 1):
+        for roi_idx in range(roi_counts[imgidx]):
+            best_conf = np.asarray(load_best_conf_roi(imgidx, roi_idx), np.float32).reshape(-1, 7)
+            assert best_conf.shape[0] == len(model_conf)
+            dets = convert_eval_bboxes(part_conf_type, [bbox_from_hyp(best_conf[i], window_param[i]) for i in range(len(best_conf))],
+                                       [float(r[1]) for r in best_conf], part_conf_eval, model_conf, rot_range)
+            assert len(dets) == P
+            for pidx in range(P):
+                match = False
+                for rect in annolist[imgidx].rects:
+                    if not rect.points:
+                        continue
+                    gt = get_part_bbox(rect, part_conf_eval[pidx], scale)
+                    if gt is None:
+                        raise ValueError("image %d part %d: annotated axis points coincide" % (imgidx, pidx))
+                    if is_gt_match_bbox(gt, dets[pidx]):
+                        match = True
+                        break
+                seg_correct += int(match)
+                correct[pidx] += int(match)
+                seg_total += 1
+    ratio = seg_correct / float(seg_total) if seg_total else 0.0
+    per_total = seg_total // P if P else 0
+    return SegmentEval(ratio, seg_correct, seg_total, correct, [per_total] * P, {})
+
+
 def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: Optional[int] = None,
-                             save_endpoints: bool = True) -> SegmentEval:
+                             save_endpoints: bool = True, eval_type: str = "ps") -> SegmentEval:
     """`partapp --expopt X --eval_segments` for a finished `--find_obj` run (main.cpp:834-845): reads the expopt, the
     part configuration (part_conf_eval if given), window_param.txt, the test annotation list and the
-    pose_est_imgidx%04d.mat files under <log_dir>/<log_subdir>/part_marginals."""
+    pose_est_imgidx%04d.mat files under <log_dir>/<log_subdir>/part_marginals.
+    eval_type "ps" (EVAL_TYPE_PS) reads those files; "unaries" (EVAL_TYPE_UNARIES, parteval.cpp:326-383) takes every
+    part's estimate from the maximum of its detector score grids (<scoregrid_dir>/imgidx%d-pidx%d-o0-scoregrid.mat);
+    "roi" is eval_segments_roi over pose_est_imgidx%04d_roi%04d.mat and the ROI annotation list."""
     import scipy.io
     base = os.path.dirname(os.path.abspath(expopt))
     rel = lambda p: p if os.path.isabs(p) else os.path.normpath(os.path.join(base, p))  # complete_relative_path
@@ -501,8 +600,11 @@ def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: 
     conf = load_part_conf(rel(one("part_conf_eval"))) if one("part_conf_eval") else model_conf
     win = load_window_param(os.path.join(class_dir, "window_param.txt"))
     annos: List[Annotation] = []
+    anno_dir: List[str] = []                                            # convertFullPath (partapp.cpp:87-107)
     for ds in ep.get("test_dataset", []):
-        annos += load_annolist(rel(ds))
+        part = load_annolist(rel(ds))
+        annos += part
+        anno_dir += [os.path.dirname(rel(ds))] * len(part)
     n = len(annos)
     firstidx = 0 if first is None else first
     lastidx = n - 1 if numimgs is None else min(n - 1, firstidx + numimgs - 1)
@@ -512,10 +614,36 @@ def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: 
     load = lambda i: scipy.io.loadmat(os.path.join(hyp_dir, "pose_est_imgidx%04d.mat" % i))["best_conf"]
     rot_range = (float(one("min_part_rotation", -180.0)), float(one("max_part_rotation", 180.0)),
                  int(one("num_rotation_steps", 48)))                                    # ExpParam.proto defaults
+    ptype = str(one("part_conf_type", "human_full"))
+    if eval_type == "roi":
+        roi_annos = load_annolist(rel(one("roi_annolist")))
+        assert len(roi_annos) == n, "roi_annolist.size() == m_test_annolist.size() (parteval.cpp:1803)"
+        roi_dir = os.path.join(log_dir, log_subdir, "part_marginals_roi")
+        load_roi = lambda i, k: scipy.io.loadmat(os.path.join(roi_dir, "pose_est_imgidx%04d_roi%04d.mat" % (i, k)))["best_conf"]
+        return eval_segments_roi(annos, [len(a.rects) for a in roi_annos], conf, win, load_roi, firstidx, lastidx, scale,
+                                 part_conf=model_conf, part_conf_type=ptype, rot_range=rot_range)
+    if eval_type == "unaries":
+        assert len(model_conf) in (6, 10, 21), "single-scale settings only (parteval.cpp:344-346)"
+        sg_dir = rel(one("scoregrid_dir")) if one("scoregrid_dir") else os.path.join(log_dir, log_subdir, "test_scoregrid")
+        sizes = {}
+
+        def load(i):                                                     # noqa: F811 -- the unary source replaces the file reader
+            if i not in sizes:
+                sizes[i] = _image_size(annos[i].image if os.path.exists(annos[i].image) else os.path.join(anno_dir[i], annos[i].image))
+            W, H = sizes[i]
+            rows = []
+            for p in range(len(win)):
+                m = scipy.io.loadmat(os.path.join(sg_dir, "imgidx%d-pidx%d-o0-scoregrid.mat" % (i, p)))
+                cg, Ti2, T2g = m["cell_scoregrid"], m["transform_Ti2"].astype(np.float64), m["transform_T2g"].astype(np.float64)
+                R = cg.shape[1]
+                cells = np.stack([np.asarray(cg[0, r], np.float32) for r in range(R)])
+                Tig = np.stack([Ti2[0, r] @ T2g[0, r] for r in range(R)])
+                rows.append(unary_best_hyp(load_score_grid_direct(cells, Tig, H, W), 0, scale, rot_range))
+            return np.stack(rows)
+        hyp_dir = sg_dir
     return eval_segments(annos, conf, win, load, firstidx, lastidx, scale,
                          save_dir=os.path.join(hyp_dir, "seg_endpoints") if save_endpoints else None,
-                         part_conf=model_conf, part_conf_type=str(one("part_conf_type", "human_full")),
-                         rot_range=rot_range)
+                         part_conf=model_conf, part_conf_type=ptype, rot_range=rot_range)
 
 
 if __name__ == "__main__":
@@ -524,8 +652,9 @@ if __name__ == "__main__":
     ap.add_argument("--expopt", required=True)
     ap.add_argument("--first", type=int)
     ap.add_argument("--numimgs", type=int)
+    ap.add_argument("--eval-type", default="ps", choices=["ps", "unaries", "roi"])
     a = ap.parse_args()
-    r = eval_segments_experiment(a.expopt, a.first, a.numimgs)
+    r = eval_segments_experiment(a.expopt, a.first, a.numimgs, eval_type=a.eval_type)
     print("seg_correct: %d\nseg_total: %d\nratio: %g" % (r.seg_correct, r.seg_total, r.ratio))
     for i, (c, t) in enumerate(zip(r.per_part_correct, r.per_part_total)):
         print("part: %d, correct: %d, total: %d, ratio: %g" % (i, c, t, c / float(t if t else 1)))

@@ -388,3 +388,85 @@ def test_fused_gaussian_walks_cover_every_cell_the_read_back_touches(k):
     assert not (need_x & ~xcov).any(), "an x-filtered value the y pass reads is masked out"
     if min(H, W) >= 256:
         assert ycov[pad:pad + EH, :EW].sum() <= 1.5 * H * W and xcov[pad:pad + EH, :EW].sum() <= 1.9 * H * W
+
+
+def test_evaluator_unary_and_roi_hypothesis_sources(tmp_path):
+    """EVAL_TYPE_UNARIES (parteval.cpp:326-383): the estimate of a part is the first maximum of its detector score grids
+    in (rotation, x, y) scan order after the TM_DIRECT scatter of loadScoreGrid; eval_segments_roi (:1779-1889): one
+    pose_est file per region of interest, a part is correct if it matches any annotated person."""
+    import oracle
+    from partapp_b200 import ExpParam, synth
+    from partapp_b200 import parteval as pe
+    ep = ExpParam(num_rotation_steps=8)
+    H, W, P = 40, 36, 2
+    cells, Tig = synth.compact_scores(ep, H, W, P, 3, rotated=True)
+    for p in range(P):
+        want = oracle.load_score_grid(cells[p, 0], Tig, H, W)                      # the oracle's loadScoreGrid
+        got = pe.load_score_grid_direct(cells[p, 0], Tig, H, W)
+        assert np.array_equal(got, want)
+        # a tie: the same maximum at two places -> the (rotation, x, y) scan order decides, not the flat [r][y][x] order
+        g = got.copy()
+        g[:] = 0
+        g[2, 30, 5] = g[2, 4, 9] = 7.0
+        row = pe.unary_best_hyp(g, 0, 1.0, (-180.0, 180.0, 8))
+        assert (row[2], row[4], row[5], row[6]) == (2, 5, 30, 7.0)                 # x = 5 comes before x = 9
+        assert abs(row[3] - (-180 + 45 * 2.5)) < 1e-6
+    # ROI evaluation: two people annotated, two regions of interest, each estimate matches one of them
+    pd = [pe.PartDef(1, [1, 2], [1], [2], -90.0, 0, 0, 0, 0)]
+    win = [pe.PartParam(20, 40, 10, 20)]
+    person = lambda x, y: pe.AnnoRect(points={1: (x, y), 2: (x, y + 40)})
+    annos = [pe.Annotation("a.png", [person(100, 100), person(200, 120)])]
+    confs = {(0, 0): np.array([[0, 1, 0, 0, 100, 120, 1]], np.float32),   # upright stick centred on person 1
+             (0, 1): np.array([[0, 1, 0, 0, 201, 141, 1]], np.float32),   # on person 2
+             }
+    r = pe.eval_segments_roi(annos, [2], pd, win, lambda i, k: confs[(i, k)], 0, 0)
+    assert (r.seg_correct, r.seg_total) == (2, 2)
+    confs[(0, 1)] = np.array([[0, 1, 0, 0, 300, 141, 1]], np.float32)    # far from both
+    r = pe.eval_segments_roi(annos, [2], pd, win, lambda i, k: confs[(i, k)], 0, 0)
+    assert (r.seg_correct, r.seg_total) == (1, 2)
+
+
+def test_eval_segments_experiment_unary_source(tmp_path):
+    """`eval_type="unaries"` on an experiment directory in the reference's formats: the hypotheses are the maxima of the
+    score-grid files, and the annotated stick of each part is placed on that maximum, so every part is correct; moving the
+    annotation of one part away makes exactly that part wrong."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import make_experiment
+    import oracle
+    from partapp_b200 import parteval as pe
+    P, R, H, W = 6, 8, 48, 40
+    info = make_experiment.make(str(tmp_path), num_images=2, P=P, R=R, H=H, W=W)
+    win = "".join("part { window_size_x: 8 window_size_y: 16 pos_offset_x: 4 pos_offset_y: 8 }\n" for _ in range(P))
+    with open(os.path.join(info["base"], "class", "window_param.txt"), "a") as f:
+        f.write(win)
+    conf = "".join("part {\n part_id: %d\n part_pos: %d\n part_pos: %d\n part_x_axis_from: %d\n part_x_axis_to: %d\n"
+                   " part_x_axis_offset: -90\n}\n" % (p + 1, 2 * p + 1, 2 * p + 2, 2 * p + 1, 2 * p + 2) for p in range(P))
+    (tmp_path / "part_conf_eval.txt").write_text(conf)
+    with open(info["expopt"], "a") as f:
+        f.write('part_conf_eval: "part_conf_eval.txt"\n')
+
+    def write_al(shift_part=None):
+        out = "<annotationlist>\n"
+        for i in range(2):
+            pts = ""
+            for p in range(P):
+                g = oracle.load_score_grid(info["cells"][i][p, 0], info["Tig"], H, W)
+                row = pe.unary_best_hyp(g, 0, 1.0, (-180.0, 180.0, R))
+                b = pe.bbox_from_hyp(row, pe.PartParam(8, 16, 4, 8))
+                e1, e2, _ = pe.get_bbox_endpoints(b)
+                if shift_part == (i, p):
+                    e1, e2 = e1 + 30, e2 + 30
+                for k, e in enumerate((e1, e2)):
+                    pts += "<point><id>%d</id><x>%d</x><y>%d</y></point>" % (2 * p + 1 + k, round(e[0]), round(e[1]))
+            out += ("<annotation><image><name>images/im%04d.png</name></image><annorect><x1>0</x1><y1>0</y1><x2>9</x2><y2>9</y2>"
+                    "<annopoints>%s</annopoints></annorect></annotation>\n" % (i, pts))
+        (tmp_path / "test.al").write_text(out + "</annotationlist>\n")
+
+    write_al()
+    r = pe.eval_segments_experiment(info["expopt"], eval_type="unaries", save_endpoints=False)
+    assert (r.seg_correct, r.seg_total) == (2 * P, 2 * P)
+    write_al(shift_part=(1, 3))
+    r = pe.eval_segments_experiment(info["expopt"], eval_type="unaries", save_endpoints=False)
+    assert (r.seg_correct, r.seg_total) == (2 * P - 1, 2 * P) and r.per_part_correct[3] == 1
