@@ -1764,6 +1764,39 @@ __global__ void __launch_bounds__(288, PS_TMA_MINB) k_conv_cols_tma2(const __gri
 // publishes (message, walk, block, slice) next to each box and issues the TMA; the eight filter warps follow the
 // published records, hand a stage back through its `empty` mbarrier right after the x phase and meet at a named
 // barrier between the phases.
+// The last REM (= taps mod 8, odd because every filter has 2 n + 1 taps) taps of a phase as straight-line code: every
+// load of the tail is issued before its first use (ncu r02f: the per-tap branches of a predicated tail ran at half the
+// multiply-add density of the main loop).  Row 0 of the tail is at w0, rows 1.. at w1 + (row - 1) * stride: the ring
+// of the y phase may wrap between the two.
+template <bool FMA, int REM>
+__device__ __forceinline__ void gauss_tail(u64 (&acc)[8], u64 (&d)[8], const u64 *w0, const u64 *w1, int stride,
+                                           const float *taps, u64 nz) {
+  constexpr int T = 8;
+  u64 nd[REM];
+  float f[REM];
+  nd[0] = w0[0];
+#pragma unroll
+  for (int uu = 1; uu < REM; ++uu) nd[uu] = w1[(uu - 1) * stride];
+#pragma unroll
+  for (int uu = 0; uu < REM; ++uu) f[uu] = taps[uu];
+#pragma unroll
+  for (int uu = 0; uu < REM; ++uu) {
+    d[(uu + T - 1) % T] = nd[uu];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f[uu], nz);
+  }
+}
+template <bool FMA>
+__device__ __forceinline__ void gauss_tail_any(int rem, u64 (&acc)[8], u64 (&d)[8], const u64 *w0, const u64 *w1,
+                                               int stride, const float *taps, u64 nz) {
+  switch (rem) {  // warp-uniform
+    case 1: gauss_tail<FMA, 1>(acc, d, w0, w1, stride, taps, nz); break;
+    case 3: gauss_tail<FMA, 3>(acc, d, w0, w1, stride, taps, nz); break;
+    case 5: gauss_tail<FMA, 5>(acc, d, w0, w1, stride, taps, nz); break;
+    case 7: gauss_tail<FMA, 7>(acc, d, w0, w1, stride, taps, nz); break;
+    default: break;  // even tap counts never reach this kernel (can_batch)
+  }
+}
 constexpr int kRingPitch = 68;  // floats per ring row: 64 + 4 keeps rows 16-byte aligned and the transposed stores 2-way at worst
 struct GaussMsg {
   float *out;                  // [z][ey][ex], pitch EP, plane oplane
@@ -1879,7 +1912,7 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
     for (int i = tid; i < b.ring_rows * kRingPitch; i += 256) ring[i] = 0.0f;
   }
   bar_sync_filter();
-  int s = -1, u = 0, cur = -1;
+  int s = -1, u = 0, cur = -1, slot = 0;
   // static order: the walk this block is in (see the producer)
   int idx = DYN ? 0 : b.cta_off[blockIdx.x], step = 0, nsteps = 0, s_mi = 0, s_z = 0, mask_cur = 0;
   const int idx_end = DYN ? 0 : b.cta_off[blockIdx.x + 1];
@@ -1918,6 +1951,7 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
     const int nx = (g.len_x - 1) / 2, ny = (g.len_y - 1) / 2;
     const int cap = 64 * (g.lag + 1), dshift = g.halo - ny;
     const int i = m1.x, z = m1.y;
+    slot = (i == 0 || slot == g.lag) ? 0 : slot + 1;  // i mod (K + 1): a block takes the steps of a walk in order
     if (i == 0 && m0.x != cur) {  // every warp is past the previous walk's last barrier: the tap arrays are free
       cur = m0.x;
       for (int k = tid; k < g.len_x; k += 256) s_tx[k] = g.taps_x[k];
@@ -1943,19 +1977,11 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
           for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f, nz);
         }
       }
-#pragma unroll
-      for (int uu = 0; uu < T; ++uu) {
-        if (kk + uu < g.len_x) {
-          d[(uu + T - 1) % T] = wp[uu * 32];
-          const float f = s_tx[kk + uu];
-#pragma unroll
-          for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f, nz);
-        }
-      }
+      gauss_tail_any<FMA>(g.len_x - kk, acc, d, wp, wp + 32, 32, s_tx + kk, nz);
       float lo[T], hi[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) upk2(acc[t], lo[t], hi[t]);
-      int q0 = 64 * (i % (g.lag + 1)) + 2 * lane - dshift;  // ring row of ey column 2*lane of this box
+      int q0 = 64 * slot + 2 * lane - dshift;  // ring row of ey column 2*lane of this box (slot = i mod (K + 1))
       if (q0 < 0) q0 += cap;
       int q1 = q0 + 1;
       if (q1 == cap) q1 = 0;
@@ -1974,7 +2000,8 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
     if (ob >= 0) {
       const int row0 = m0.z + 64 * ob + w * T;
       if (w < m0.w - 8 * ob && row0 < g.EH) {  // warp-uniform
-        int q = (64 * ob + w * T) % cap;  // multiple of 8; rows q .. q + 7 + 2 ny (mod cap) hold the window
+        // (64 ob + 8 w) mod cap without a division: ob = i - K is congruent to slot + 1 modulo K + 1
+        int q = 64 * (slot == g.lag ? 0 : slot + 1) + w * T;  // multiple of 8; rows q .. q + 7 + 2 ny (mod cap) hold the window
         const u64 *rbase = reinterpret_cast<const u64 *>(ring) + lane;
         u64 acc[T], d[T];
 #pragma unroll
@@ -2002,29 +2029,34 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
           }
           q += T - 1;  // q % 8 == 7 again (never reaches cap: cap % 8 == 0)
         }
-#pragma unroll
-        for (int uu = 0; uu < T; ++uu) {
-          if (kk + uu < g.len_y) {
-            d[(uu + T - 1) % T] = rbase[q * (kRingPitch / 2)];
-            q = q + 1 == cap ? 0 : q + 1;
-            const float f = s_ty[kk + uu];
-#pragma unroll
-            for (int t = 0; t < T; ++t) acc[t] = tap2<FMA>(acc[t], d[(uu + t) % T], f, nz);
-          }
+        {
+          const int q1 = q + 1 == cap ? 0 : q + 1;  // q % 8 == 7: at most one wrap, right after the tail's first row
+          gauss_tail_any<FMA>(g.len_y - kk, acc, d, rbase + q * (kRingPitch / 2), rbase + q1 * (kRingPitch / 2),
+                              kRingPitch / 2, s_ty + kk, nz);
         }
         const int x = m0.y * 64 + lane * 2;
         if (x < g.EW) {
           const bool in1 = x + 1 < g.EW;
           float *dst = g.out + (size_t)z * g.oplane + x;
+          if (in1 && row0 + T <= g.EH) {  // all eight rows and both columns inside: one running pointer, no tests
+            float *o = dst + (size_t)row0 * g.EP;
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const int y = row0 + t;
-            if (y < g.EH) {
+            for (int t = 0; t < T; ++t, o += g.EP) {
               float lo, hi;
               upk2(acc[t], lo, hi);
-              float *o = dst + (size_t)y * g.EP;
-              if (in1) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
-              else o[0] = lo;
+              *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const int y = row0 + t;
+              if (y < g.EH) {
+                float lo, hi;
+                upk2(acc[t], lo, hi);
+                float *o = dst + (size_t)y * g.EP;
+                if (in1) *reinterpret_cast<float2 *>(o) = make_float2(lo, hi);
+                else o[0] = lo;
+              }
             }
           }
         }

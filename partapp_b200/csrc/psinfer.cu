@@ -775,6 +775,7 @@ bool can_batch(const ps_ctx *c, const MsgJob &j) {
   if (c->disable_batch || c->disable_tma || h.diag || !tensor_map_encoder()) return false;
   if (c->R % PS_RG != 0 || c->W % 4 != 0 || !h.in_pure || !h.out_pure || j.dp->nwalks == 0) return false;
   if ((int)h.fx.size() > 193 || (int)h.fy.size() > psk::kMaxFusedTaps) return false;
+  if (h.fx.size() % 2 == 0 || h.fy.size() % 2 == 0) return false;  // k_gauss_xy's tail code takes 2 n + 1 taps
   unsigned stage;
   if (fused_smem_bytes(h, stage) > kFusedSmemMax) return false;
   const Sink &k = j.sink;
