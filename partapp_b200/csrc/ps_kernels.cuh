@@ -443,6 +443,9 @@ struct IngestBatch {
   float *out[kMaxIngestBatch];
   int *max_dst[kMaxIngestBatch];
 };
+// ALL: the destination already holds "fill + this lattice" (the image before used the same transforms): unevaluated
+// cells write LOG_ZERO over whatever the last image left on their lattice point, and no fill pass is needed.
+template <bool ALL>
 __global__ void __launch_bounds__(256) k_ingest_scatter_direct_b(IngestArgs a, const __grid_constant__ IngestBatch b,
                                                                  const __grid_constant__ TigRows rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,13 +454,13 @@ __global__ void __launch_bounds__(256) k_ingest_scatter_direct_b(IngestArgs a, c
   if (i < a.gh * a.gw) {
     const int y1 = i / a.gw, x1 = i - y1 * a.gw;
     const float v = b.cells[g][(size_t)r * a.gh * a.gw + i];
-    if (v != 0.0f) {
+    if (ALL || v != 0.0f) {
       const double *T = rows.m + r * 6;
       const double x3 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], (double)x1), __dmul_rn(T[1], (double)y1)), T[2]);
       const double y3 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], (double)x1), __dmul_rn(T[4], (double)y1)), T[5]);
       const int ix = (int)floor(__dadd_rn(x3, 0.5)), iy = (int)floor(__dadd_rn(y3, 0.5));
       if (ix >= 0 && ix < a.W && iy >= 0 && iy < a.H) {
-        const float o = prepare_cell(v);
+        const float o = (!ALL || v != 0.0f) ? prepare_cell(v) : kLogZero;
         b.out[g][(size_t)r * a.H * a.W + (size_t)iy * a.W + ix] = o;
         m = fmaxf(m, o);
       }

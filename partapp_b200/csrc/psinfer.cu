@@ -138,6 +138,12 @@ struct ps_ctx {
   size_t topk_slots = 0, topk_kmax = 0;
   DevBuf counters;      // unsigned [8]
   DevBuf ingest_batch;              // ps_set_unaries_compact: compact cells of every grid of one call
+  // ps_set_unaries_compact: when the whole unary buffer holds nothing but a LOG_ZERO fill plus the collision-free
+  // scatter of one lattice (these transforms, this compact grid size), the next image on the same lattice overwrites
+  // every lattice cell (LOG_ZERO where its score is 0) and the fill is skipped.  Every other writer of the unaries
+  // clears the flag.
+  bool lattice_clean = false;
+  std::vector<double> lattice_sig;
   DevBuf ingest, ingest_keys;       // ps_set_unary_compact staging: Tig rows + compact cells; order keys [R][H][W]
   DevBuf table_stage, grid_stage;   // ps_add_unary_table(s) / ps_add_unary_grid: stream-ordered staging of host inputs
   DevBuf unary_max;                 // int [P][S]: encoded max of each unary as left by the ingest
@@ -1597,6 +1603,7 @@ int ps_set_unary(ps_ctx *c, int part, int scale, const float *src, int mem_kind,
   if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   float *dst = c->U(part, scale);
+  c->lattice_clean = false;
   c->unary_max_valid[(size_t)part * c->S + scale] = 0;
   PS_CUDA(c, cudaMemcpyAsync(dst, src, c->N * sizeof(float),
                              mem_kind == PS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
@@ -1621,6 +1628,7 @@ int ps_log_unary(ps_ctx *c, int part, int scale) {
   if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
   int *mslot = c->unary_max.as<int>() + (size_t)part * c->S + scale;
+  c->lattice_clean = false;
   PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<1, 32, 0, c->stream>>>(mslot, 1, PS_ENC_NEG_INF));
   PS_LAUNCH(c, KC_PREP, psk::k_prepare_unary<<<std::min(cdiv(c->N / 4 + 1, 256), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(
                             c->U(part, scale), c->N, mslot));
@@ -1633,6 +1641,7 @@ static int set_unary_compact_impl(ps_ctx *c, int part, int scale, const float *c
   if (part < 0 || part >= c->P || scale < 0 || scale >= c->S) return c->fail(PS_ERR_INVALID, "part/scale out of range");
   if (gh < 1 || gw < 1 || (size_t)gh * gw >= ((size_t)1 << 31)) return c->fail(PS_ERR_INVALID, "compact grid size out of range");
   PS_CUDA(c, cudaSetDevice(c->cfg.device));
+  c->lattice_clean = false;
   const size_t ncell = (size_t)c->R * gh * gw;
   // staging: cells | Tig rows (doubles first for alignment)
   const size_t need = (size_t)c->R * 6 * sizeof(double) + ncell * sizeof(float);
@@ -1742,9 +1751,20 @@ int ps_set_unaries_compact(ps_ctx *c, int n, const int *parts, const int *scales
     for (int i = 0; i < n; ++i) seen[(size_t)parts[i] * c->S + scales[i]] = 1;
     for (unsigned char v : seen) whole = whole && v;
   }
+  // Same lattice as the image before and nothing else has written the unaries since: every lattice cell is overwritten
+  // (LOG_ZERO where the score is 0), every other cell still holds the fill -- the 4 P S R H W-byte fill is skipped.
+  std::vector<double> sig((size_t)c->R * 6 + 2);
+  for (size_t k = 0; k < (size_t)c->R * 6; ++k) sig[k] = rows.m[k];
+  sig[(size_t)c->R * 6] = gh;
+  sig[(size_t)c->R * 6 + 1] = gw;
+  static const bool no_skip = getenv("PSINFER_ALWAYS_FILL") != nullptr;  // A/B switch
+  const bool overwrite = whole && c->lattice_clean && !no_skip && sig.size() == c->lattice_sig.size() &&
+                         memcmp(sig.data(), c->lattice_sig.data(), sig.size() * sizeof(double)) == 0;
+  c->lattice_clean = false;  // until every launch below has been issued
   if (whole) {
-    PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv((size_t)n * c->N, 4096), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(
-                              c->unary.as<float>(), (size_t)n * c->N, psk::kLogZero));
+    if (!overwrite)
+      PS_LAUNCH(c, KC_PREP, psk::k_fill<<<std::min(cdiv((size_t)n * c->N, 4096), (unsigned)c->num_sms * 16), 256, 0, c->stream>>>(
+                                c->unary.as<float>(), (size_t)n * c->N, psk::kLogZero));
     PS_LAUNCH(c, KC_MISC, psk::k_set_int<<<cdiv(n, 128), 128, 0, c->stream>>>(c->unary_max.as<int>(), n, PS_ENC_NEG_INF));
   }
   psk::IngestArgs a;
@@ -1771,7 +1791,14 @@ int ps_set_unaries_compact(ps_ctx *c, int n, const int *parts, const int *scales
       b.max_dst[k] = mslot;
       c->unary_max_valid[(size_t)parts[i] * c->S + scales[i]] = 1;
     }
-    PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct_b<<<dim3(cdiv((size_t)gh * gw, 256), c->R, nb), 256, 0, c->stream>>>(a, b, rows));
+    if (overwrite)
+      PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct_b<true><<<dim3(cdiv((size_t)gh * gw, 256), c->R, nb), 256, 0, c->stream>>>(a, b, rows));
+    else
+      PS_LAUNCH(c, KC_PREP, psk::k_ingest_scatter_direct_b<false><<<dim3(cdiv((size_t)gh * gw, 256), c->R, nb), 256, 0, c->stream>>>(a, b, rows));
+  }
+  if (whole) {
+    c->lattice_sig.swap(sig);
+    c->lattice_clean = true;
   }
   return PS_OK;
 }
@@ -1810,6 +1837,7 @@ int ps_add_unary_tables(ps_ctx *c, int part, int n, const float *const *tables, 
     need += kinds[k] == 0 ? (size_t)c->R : c->HW;
   }
   for (int s2 = 0; s2 < c->S; ++s2) c->unary_max_valid[(size_t)part * c->S + s2] = 0;
+  c->lattice_clean = false;
   psk::TableArgs a{};
   a.n = n;
   if (mem_kind == PS_MEM_HOST && c->table_stage.bytes < need * sizeof(float)) {
@@ -2063,6 +2091,14 @@ static int infer_enqueue(ps_ctx *c, int flags) {
     if (c->unary_backup.bytes < c->unary.bytes) PS_CUDA(c, c->unary_backup.alloc(c->unary.bytes));
     PS_CUDA(c, cudaMemcpyAsync(c->unary_backup.p, c->unary.p, c->unary.bytes, cudaMemcpyDeviceToDevice, st));
   }
+  // upright masks and the border strip rewrite unary cells in place: the buffer is "fill + one lattice" again only if
+  // it is restored at the end (see lattice_clean)
+  const bool lattice_was_clean = c->lattice_clean;
+  {
+    bool masks = c->cfg.strip_border_detections > 0 && !(flags & PS_INFER_NO_BORDER_STRIP);
+    for (int p = 0; p < P; ++p) masks = masks || c->cfg.is_upright[p];
+    if (masks) c->lattice_clean = false;
+  }
 
   const Node &rn = c->nodes[root];
   const int nrc = (int)rn.children.size();
@@ -2208,8 +2244,10 @@ static int infer_enqueue(ps_ctx *c, int flags) {
   for (int p = 0; p < P; ++p) grids[p] = c->POST(p, S - 1);
   if ((rc = enqueue_readout(c, grids, S - 1, flags, /*keys_ready=*/true))) return rc;
   c->result_scale = S - 1;
-  if (flags & PS_INFER_KEEP_UNARIES)
+  if (flags & PS_INFER_KEEP_UNARIES) {
     PS_CUDA(c, cudaMemcpyAsync(c->unary.p, c->unary_backup.p, c->unary.bytes, cudaMemcpyDeviceToDevice, st));
+    c->lattice_clean = lattice_was_clean;
+  }
   return PS_OK;
 }
 

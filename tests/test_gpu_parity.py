@@ -467,6 +467,72 @@ def test_compact_ingest_all_parts_in_one_call(rotated):
         assert np.array_equal(one.get_unary(2, 0), many.get_unary(2, 0))
 
 
+@pytest.mark.parametrize("rotated", [False, True], ids=["lattice", "rotated_lattice"])
+def test_compact_ingest_image_after_image_without_the_fill(rotated):
+    """A second image on the same lattice overwrites every lattice cell instead of refilling the buffer (LOG_ZERO where
+    its own score is 0 and the previous image's was not); any other writer of the unaries, a different lattice, or an
+    inference that masks them in place brings the fill back.  Every step is compared with loadScoreGrid + the unary
+    prep of the oracle for exactly that image."""
+    ep = ExpParam(num_rotation_steps=8, num_scale_steps=2, min_object_scale=0.9, max_object_scale=1.1)
+    P, H, W = 3, 44, 52
+    ps_ = [p for p in range(P) for s in range(2)]
+    ss = [s for p in range(P) for s in range(2)]
+
+    def image(k, rot=rotated, stride=4):
+        cells, Tig = synth.compact_scores(ep, H, W, P, 20 + k, rotated=rot, stride=stride)
+        rng = np.random.default_rng(50 + k)
+        cells = cells.copy()
+        cells[rng.random(cells.shape) < 0.4] = 0.0       # a different set of unevaluated cells in every image
+        return cells, Tig
+
+    def check(ctx, cells, Tig, what):
+        for p in range(P):
+            for s in range(2):
+                want = oracle.prepare_unary(oracle.load_score_grid(cells[p, s], Tig, H, W))
+                _cmp(ctx.get_unary(p, s), want, "%s part %d scale %d" % (what, p, s))
+
+    def ingest(ctx, cells, Tig):
+        n0 = ctx.launch_count()
+        ctx.set_unaries_compact(ps_, ss, [cells[p, s] for p, s in zip(ps_, ss)], Tig)
+        return ctx.launch_count() - n0
+
+    upright = synth.part_conf(P)
+    upright.is_upright[1] = True
+    with PsContext(ep, synth.part_conf(P), H, W) as ctx, PsContext(ep, upright, H, W) as up:
+        ctx.set_joints(synth.make_joints(P, seed=5, max_offset=6, sigma_range=(1.5, 3)))
+        up.set_joints(synth.make_joints(P, seed=5, max_offset=6, sigma_range=(1.5, 3)))
+        c0, T0 = image(0)
+        assert ingest(ctx, c0, T0) == 3                   # fill, max reset, scatter
+        check(ctx, c0, T0, "first image")
+        c1, T1 = image(1)
+        assert ingest(ctx, c1, T1) == 2                   # same lattice: no fill
+        check(ctx, c1, T1, "second image, fill skipped")
+        ctx.infer(sparse=True)                            # reads the unaries, writes none of them
+        c2, T2 = image(2)
+        assert ingest(ctx, c2, T2) == 2
+        check(ctx, c2, T2, "third image after an inference")
+        ctx.add_unary_table(1, np.linspace(-1, 0, 8).astype(np.float32), kind=0, weight=0.5)   # another writer
+        c3, T3 = image(3)
+        assert ingest(ctx, c3, T3) == 3
+        check(ctx, c3, T3, "image after a conditioning add")
+        ctx.set_unary_compact(0, 1, c2[0, 1], T2)         # single-grid call: also another writer
+        assert ingest(ctx, c3, T3) == 3
+        c4, T4 = image(4, rot=not rotated)                # a different lattice
+        assert ingest(ctx, c4, T4) == 3
+        check(ctx, c4, T4, "image on another lattice")
+        c5, T5 = image(5, rot=not rotated)
+        assert ingest(ctx, c5, T5) == 2
+        check(ctx, c5, T5, "second image on the other lattice")
+        # upright masking rewrites unary slices in place (findrot.cpp:509-523): without keep_unaries the fill returns
+        assert ingest(up, c0, T0) == 3 and ingest(up, c1, T1) == 2
+        up.infer(sparse=True, keep_unaries=True)
+        assert ingest(up, c2, T2) == 2
+        check(up, c2, T2, "after an inference that restored the unaries")
+        up.infer(sparse=True)
+        assert ingest(up, c3, T3) == 3
+        check(up, c3, T3, "after an inference that masked the unaries in place")
+
+
 def test_compact_ingest_many_rotations_back_to_back():
     """R > 64: the per-rotation transforms go through a device staging buffer shared by every (part, scale) call.
     Calls issued back to back, each with its OWN transforms, must not overwrite the rows a previous call's scatter
