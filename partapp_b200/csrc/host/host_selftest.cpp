@@ -70,6 +70,12 @@ int main(int argc, char **argv) {
         object_detect::image_size(im, w, h);
         printf("image %s %d %d\n", im.c_str(), w, h);
       }
+      if (e.use_gt_torso)
+        for (size_t i = 0; i < app.m_test_annolist.size(); ++i) {
+          double rp[2];
+          object_detect::getRootPosDet(app, (int)i, app.m_rootpart_idx, rp, true);
+          printf("gt_torso %zu %g %g\n", i, rp[0], rp[1]);
+        }
       if (argc >= 4) {
         std::vector<object_detect::Joint> joints;
         object_detect::loadJoints(app, joints, atoi(argv[3]) != 0, -1);

@@ -400,6 +400,7 @@ void PartApp::init(const std::string &expopt) {
     d.is_root = p.boolean("is_root", false);
     d.is_detect = p.boolean("is_detect", true);
     d.is_upright = p.boolean("is_upright", false);
+    for (size_t k = 0; k < p.count("part_pos"); ++k) d.part_pos.push_back(atoi(p.get("part_pos", k).scalar.c_str()));
     m_part_conf.part.push_back(d);
   }
   for (size_t i = 0; i < pc.count("joint"); ++i) {
@@ -437,13 +438,47 @@ void PartApp::init(const std::string &expopt) {
     ss << f.rdbuf();
     const std::string text = ss.str();
     std::vector<std::string> names;
+    std::vector<std::vector<AnnoPoint> > points;
     if (text.find("<name>") != std::string::npos) {
+      // <annotation><image><name>..</name></image><annorect>..<annopoints><point><id/><x/><y/></point>..
+      auto element = [](const std::string &t, const char *tag, size_t from, size_t to, size_t &next) -> std::string {
+        const std::string open = std::string("<") + tag + ">", close = std::string("</") + tag + ">";
+        const size_t a = t.find(open, from);
+        if (a == std::string::npos || a >= to) return next = std::string::npos, std::string();
+        const size_t b = t.find(close, a);
+        if (b == std::string::npos || b > to) return next = std::string::npos, std::string();
+        next = b + close.size();
+        return t.substr(a + open.size(), b - a - open.size());
+      };
       size_t pos = 0;
       while ((pos = text.find("<name>", pos)) != std::string::npos) {
         size_t end = text.find("</name>", pos);
         if (end == std::string::npos) break;
         names.push_back(text.substr(pos + 6, end - pos - 6));
         pos = end + 7;
+        // the first annorect of this annotation, up to the next image name
+        size_t stop = text.find("<name>", pos);
+        if (stop == std::string::npos) stop = text.size();
+        std::vector<AnnoPoint> pts;
+        size_t nx;
+        const size_t r0 = text.find("<annorect>", pos);
+        if (r0 != std::string::npos && r0 < stop) {
+          size_t r1 = text.find("</annorect>", r0);
+          if (r1 == std::string::npos || r1 > stop) r1 = stop;
+          size_t q = r0;
+          for (;;) {
+            const std::string pt = element(text, "point", q, r1, nx);
+            if (nx == std::string::npos) break;
+            q = nx;
+            size_t dummy;
+            AnnoPoint ap;  // getElementDataInt: atoi of the element text
+            ap.id = atoi(element(pt, "id", 0, pt.size(), dummy).c_str());
+            ap.x = atoi(element(pt, "x", 0, pt.size(), dummy).c_str());
+            ap.y = atoi(element(pt, "y", 0, pt.size(), dummy).c_str());
+            pts.push_back(ap);
+          }
+        }
+        points.push_back(pts);
       }
     } else {
       std::istringstream ls(text);
@@ -453,10 +488,13 @@ void PartApp::init(const std::string &expopt) {
         if (b != std::string::npos) names.push_back(line.substr(a + 1, b - a - 1));
       }
     }
-    for (std::string nm : names) {  // convertFullPath, partapp.cpp:87-107
+    points.resize(names.size());
+    for (size_t k = 0; k < names.size(); ++k) {  // convertFullPath, partapp.cpp:87-107
+      std::string nm = names[k];
       if (!file_exists(nm)) nm = dirname_of(path) + "/" + nm;
       if (!file_exists(nm)) fail("image file not found: " + nm);
       m_test_annolist.push_back(nm);
+      m_test_annopoints.push_back(points[k]);
     }
   }
 }
@@ -588,9 +626,40 @@ void getPosParams(const PartApp &app, int imgidx, std::vector<double> &pos_param
 }
 
 void getRootPosDet(const PartApp &app, int imgidx, int rootpart_idx, double rootpos_det[2], bool bTest) {
-  (void)rootpart_idx;
   const ExpParam &ep = app.m_exp_param;
-  if (ep.use_gt_torso) fail("use_gt_torso reads the annotation's torso box (icps.cpp:293-300): not available on this host");
+  if (ep.use_gt_torso) {
+    // icps.cpp:292-300: part_pos of get_part_bbox(m_test_annolist[imgidx][0], part(rootpart_idx)); the return value (an
+    // invalid x axis) is ignored and part_pos is assigned before the axis either way (partdef.cpp:249, :315).
+    // < 3 points: (sum of the points) * (1.0 / n) (partdef.cpp:140-158); else the centre of their bounding box
+    // (:128-138).  `int root_pos_x = part_pos(0)`: truncation towards zero.
+    const std::vector<int> &ids = app.m_part_conf.part.at((size_t)rootpart_idx).part_pos;
+    if (ids.empty()) fail("use_gt_torso: the root part has no part_pos in part_conf");
+    if ((size_t)imgidx >= app.m_test_annopoints.size()) fail("use_gt_torso: no annotation for image " + std::to_string(imgidx));
+    const std::vector<AnnoPoint> &pts = app.m_test_annopoints[(size_t)imgidx];
+    double sx = 0, sy = 0, x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+    for (int id : ids) {
+      const AnnoPoint *p = nullptr;
+      for (const AnnoPoint &q : pts)
+        if (q.id == id) {
+          p = &q;
+          break;
+        }
+      if (!p) fail("use_gt_torso: image " + std::to_string(imgidx) + " has no annopoint " + std::to_string(id) + " (partdef.cpp:146)");
+      sx += p->x; sy += p->y;
+      x0 = std::min(x0, (double)p->x); x1 = std::max(x1, (double)p->x);
+      y0 = std::min(y0, (double)p->y); y1 = std::max(y1, (double)p->y);
+    }
+    double px, py;
+    if (ids.size() < 3) {
+      const double inv = 1.0 / (double)ids.size();
+      px = sx * inv; py = sy * inv;
+    } else {
+      px = 0.5 * (x0 + x1); py = 0.5 * (y0 + y1);
+    }
+    rootpos_det[0] = (double)(int)px;
+    rootpos_det[1] = (double)(int)py;
+    return;
+  }
   if (!bTest) fail("getRootPosDet: only the test list is read on this path");
   if (ep.torso_det_test_dir.empty()) fail("pred_unary_pos needs torso_det_test_dir (icps.cpp:306)");
   std::vector<mat5::Var> vars;

@@ -55,6 +55,11 @@ struct ExpParam {
 struct PartDef {   // libPartDetect/PartConfig.proto PartDef
   int part_id = 0;
   bool is_root = false, is_detect = true, is_upright = false;
+  std::vector<int> part_pos;  // annopoint ids that define the part's position (read by use_gt_torso only)
+};
+// The annopoints of an image's FIRST annotated rectangle (libAnnotation AnnoRect::get_annopoint_by_id: first match wins)
+struct AnnoPoint {
+  int id = 0, x = 0, y = 0;
 };
 struct JointDef {  // PartConfig.proto Joint
   int child_idx = 0, parent_idx = 0;
@@ -75,6 +80,7 @@ struct PartApp {
   PartConfig m_part_conf;
   PartWindowParam m_window_param;
   std::vector<std::string> m_test_annolist;  // image file names (AnnotationList::imageName())
+  std::vector<std::vector<AnnoPoint> > m_test_annopoints;  // per image: m_test_annolist[imgidx][0].m_vAnnoPoints (.al lists only)
   int m_rootpart_idx = -1;
   // PartApp::init (partapp.cpp:141) + init_setpath (:294): parse the expopt, resolve relative paths against it,
   // fill default directories, load part_conf, window_param.txt (if present) and the test image list.

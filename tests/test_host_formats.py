@@ -135,3 +135,53 @@ def test_expopt_part_conf_joints(tool, tmp_path):
         vals = [float(v) for v in row]
         assert vals[3] == -j.offset_c[0] and vals[4] == j.offset_c[1] and vals[11] == -j.rot_mean
         assert vals[8] == -np.asarray(j.C)[0, 1]
+
+
+@pytest.mark.parametrize("npos", [1, 2, 4])
+def test_use_gt_torso_reads_the_annotated_root_position(tool, tmp_path, npos):
+    """ExpParam.use_gt_torso (objectdetect_icps.cpp:292-300): the root position prior is centred on part_pos of
+    get_part_bbox(first annotated rectangle, root part), truncated to int -- checked against parteval.get_part_bbox, the
+    Python mirror that tests/test_eval_vs_ref.py pins to the reference's own partdef.cpp."""
+    from partapp_b200 import parteval as pe
+    from tests.make_experiment import make
+    info = make(str(tmp_path / "exp"), num_images=3, extra_expopt="use_gt_torso: true\n")
+    root = info["root_idx"]
+    ids = [11, 12, 13, 14][:npos]
+    pts = [[(17, 9), (30, 41), (3, 22), (25, 25)], [(5, 5), (8, 12), (39, 1), (20, 47)], [(1, 2), (2, 1), (0, 0), (7, 7)]]
+    conf = ""
+    for p in range(info["P"]):
+        conf += "part {\n  part_id: %d\n  is_detect: true\n  is_root: %s\n" % (p + 1, "true" if p == root else "false")
+        if p == root:
+            conf += "".join("  part_pos: %d\n" % i for i in ids) + "  part_x_axis_from: 11\n  part_x_axis_to: 11\n"
+        conf += "}\n"
+    edges = [(j.child_idx, j.parent_idx) for j in info["joints"]]
+    conf += "".join('joint {\n  child_idx: %d\n  parent_idx: %d\n  type: "RotGaussian"\n}\n' % (c + 1, q + 1) for c, q in edges)
+    (tmp_path / "exp" / "part_conf.txt").write_text(conf)
+    al = "<annotationlist>\n"
+    for i in range(3):
+        point = lambda k, xy: "<point><id>%d</id><x>%d</x><y>%d</y></point>" % (k, xy[0], xy[1])
+        first = "".join(point(11 + k, pts[i][k]) for k in (2, 0, 3, 1)) + point(11, (99, 99))   # a duplicate id: first wins
+        second = "".join(point(11 + k, (50, 50)) for k in range(4))                                # another person: ignored
+        al += ("<annotation><image><name>images/im%04d.png</name></image><annorect><x1>1</x1><y1>1</y1><x2>9</x2><y2>9</y2>"
+               "<annopoints>%s</annopoints></annorect><annorect><annopoints>%s</annopoints></annorect></annotation>\n"
+               % (i, first, second))
+    (tmp_path / "exp" / "test.al").write_text(al + "</annotationlist>\n")
+    out = run(tool, "expopt-dump", info["expopt"])
+    got = [l.split()[1:] for l in out.split("\n") if l.startswith("gt_torso")]
+    assert len(got) == 3
+    pd = pe.PartDef(root + 1, ids, [11], [11])      # coinciding axis points: the axis is invalid, part_pos is still used
+    for i in range(3):
+        rect = pe.load_annolist(str(tmp_path / "exp" / "test.al"))[i].rects[0]
+        if npos < 3:
+            want = np.mean([rect.points[k] for k in ids], axis=0) if npos == 1 else \
+                (np.sum([rect.points[k] for k in ids], axis=0) * (1.0 / npos))
+        else:
+            xs, ys = [rect.points[k][0] for k in ids], [rect.points[k][1] for k in ids]
+            want = np.array([0.5 * (min(xs) + max(xs)), 0.5 * (min(ys) + max(ys))])
+        assert [float(v) for v in got[i][1:]] == [float(int(want[0])), float(int(want[1]))], (i, got[i], want)
+    # the same numbers from the pinned Python mirror where its axis is valid
+    pd2 = pe.PartDef(root + 1, ids, [11], [12]) if npos >= 2 else None
+    if pd2:
+        rect = pe.load_annolist(str(tmp_path / "exp" / "test.al"))[0].rects[0]
+        bb = pe.get_part_bbox(rect, pd2, 1.0)
+        assert [float(v) for v in got[0][1:]] == [float(int(bb.part_pos[0])), float(int(bb.part_pos[1]))]
