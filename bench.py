@@ -398,7 +398,9 @@ def run_ours(args):
                     "note": "bit-exact (parity) arithmetic keeps both roundings of every tap, which costs two fp32 pipe "
                             "slots per tap-output: the Gaussian taps are bound by the fp32 pipe, not by HBM (DESIGN.md 5)"}
         cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline and cond is None:
+        # the CPU leg is one full image on one thread: ~20 s at cfg-2, a quarter of an hour at cfg-5 -- off by default for
+        # the other workloads (a box-minute of a GPU node per CPU-minute), --cpu-baseline turns it on
+        if world == 1 and not args.no_cpu_baseline and cond is None and (WORKLOAD_NAME[0] in ("cfg2", "cfg2r8") or args.cpu_baseline):
             from partapp_b200 import synth as _synth
             cpu_baseline, cpu_result = run_cpu_sample(ep, pc, joints, _synth.raw_scores(ep, w["H"], w["W"], P, 0), threads=1)
             parity_check = {ARITH_KEY[bool(args.fast_math)]: parity_against_cpu(ctxs[0], cpu_result, feed_image0)}
@@ -599,6 +601,7 @@ def main():
     ap.add_argument("--streams", type=int, default=8, help="contexts/streams per GPU (one image in flight on each)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true", help="run the CPU leg for workloads other than cfg2 too (minutes)")
     ap.add_argument("--fast-math", action="store_true",
                     help="headline in ps_config.fast_math (fused multiply-add taps, marginals within the north star's "
                          "1e-4) instead of the default bit-exact parity arithmetic")

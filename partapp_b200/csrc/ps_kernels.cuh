@@ -1358,6 +1358,22 @@ __global__ void __launch_bounds__(256) k_rotconv3(RotArgs a, u64 nz) {
 // Here the exp tile is stored circularly EXTENDED (row i = A[(i - npad) mod R], i < R + L - 1), so a thread's window
 // is OUT + L - 1 loads at compile-time offsets from one address; the per-rotation shift records live in shared
 // memory; a pixel's (x, y) comes from one FastDiv; exp runs branch-free behind one warp vote per cell.
+// The filter of k_rotconv4 over the centred LE of the L staged taps (LE, L odd, LE <= L).
+template <int LE, int L, int OUT, int NPAIR, bool FMA>
+__device__ __forceinline__ void rot_filter(const u64 *col, const float *s_taps, u64 nz, float (&lo)[OUT], float (&hi)[OUT]) {
+  constexpr int K0 = (L - (LE < L ? LE : L)) / 2, K1 = K0 + (LE < L ? LE : L);
+  u64 acc[OUT];
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) acc[o] = pk2(0.0f, 0.0f);
+#pragma unroll
+  for (int k = K0; k < K1; ++k) {
+    const float f = s_taps[k];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) acc[o] = tap2<FMA>(acc[o], col[(o + k) * NPAIR], f, nz);
+  }
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) upk2(acc[o], lo[o], hi[o]);
+}
 template <int R, int L, int PX, int OUT, bool FMA>
 __global__ void __launch_bounds__(256) k_rotconv4(const __grid_constant__ RotBatch rb, FastDiv Wdiv, u64 nz) {
   static_assert(R % OUT == 0 && PX % 2 == 0 && 256 % PX == 0 && PX >= 32, "tiling");
@@ -1435,17 +1451,14 @@ __global__ void __launch_bounds__(256) k_rotconv4(const __grid_constant__ RotBat
     const u64 *col = reinterpret_cast<const u64 *>(&s_e[0][0]) + (i0 * NPAIR + pp);
     float lo[OUT], hi[OUT];
     if (a.mode == 1) {
-      u64 acc[OUT];
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) acc[o] = pk2(0.0f, 0.0f);
-#pragma unroll
-      for (int k = 0; k < L; ++k) {
-        const float f = s_taps[k];
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) acc[o] = tap2<FMA>(acc[o], col[(o + k) * NPAIR], f, nz);
-      }
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) upk2(acc[o], lo[o], hi[o]);
+      // L is the longest filter of the launch.  With many rotations (R = 48: up to 47 taps) a message whose own filter
+      // is shorter runs only the centred LE <= L taps that can be non-zero -- the skipped ones are exactly 0 and add +0
+      // to a non-negative sum.  Block-uniform.  (At R = 24 the extra code costs more than the taps it saves: measured.)
+      if (R > 24 && L > 15 && a.len <= 15) rot_filter<15, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
+      else if (R > 24 && L > 23 && a.len <= 23) rot_filter<23, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
+      else if (R > 24 && L > 31 && a.len <= 31) rot_filter<31, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
+      else if (R > 24 && L > 39 && a.len <= 39) rot_filter<39, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
+      else rot_filter<L, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
     } else {
 #pragma unroll
       for (int o = 0; o < OUT; ++o) {

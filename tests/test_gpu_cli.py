@@ -135,6 +135,32 @@ def test_find_obj_cli_conditioned_model_reads_predictor_outputs(cli, tmp_path):
         np.testing.assert_allclose(best[:, 6], want["best_conf"][:, 6], rtol=1e-5)
         g = scipy.io.loadmat(os.path.join(pm, "log_part_posterior_final_imgidx%d_scaleidx0_o0_pidx0.mat" % i))["log_prob_grid"]
         np.testing.assert_allclose(g, want["marginals"][0, 0], rtol=1e-4)
+    # use_gt_torso (icps.cpp:292-300): the position tables are centred on the annotated root part instead of the torso
+    # detection -- part_pos of the first annotated rectangle, two points -> their mean, truncated to int
+    root = info["root_idx"]
+    exp_dir = str(tmp_path / "expc")
+    conf = open(os.path.join(exp_dir, "part_conf.txt")).read()
+    marker = "part_id: %d\n" % (root + 1)
+    assert conf.count(marker) == 1
+    open(os.path.join(exp_dir, "part_conf.txt"), "w").write(conf.replace(marker, marker + "  part_pos: 3\n  part_pos: 7\n"))
+    gt = [((11, 20), (18, 25)), ((30, 9), (21, 14))]
+    with open(os.path.join(exp_dir, "test.al"), "w") as f:
+        f.write("<annotationlist>\n")
+        for i in range(2):
+            pts = "".join("<point><id>%d</id><x>%d</x><y>%d</y></point>" % (k, x, y) for k, (x, y) in zip((3, 7), gt[i]))
+            f.write("<annotation><image><name>images/im%04d.png</name></image><annorect><annopoints>%s</annopoints></annorect>"
+                    "</annotation>\n" % (i, pts))
+        f.write("</annotationlist>\n")
+    with open(info["expopt"], "a") as f:
+        f.write("use_gt_torso: true\n")
+    r = subprocess.run([cli, "--expopt", info["expopt"], "--find_obj"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for i in range(2):
+        info["cond"][i]["rootpos"] = (int((gt[i][0][0] + gt[i][1][0]) * 0.5), int((gt[i][0][1] + gt[i][1][1]) * 0.5))
+        want = oracle.infer(info["ep"], synth.part_conf(info["P"]), info["joints"], _conditioned_unaries(info, i), sparse=True)
+        best = scipy.io.loadmat(os.path.join(pm, "pose_est_imgidx%04d.mat" % i))["best_conf"]
+        assert np.array_equal(best[:, :6], want["best_conf"][:, :6]), "use_gt_torso image %d" % i
+        np.testing.assert_allclose(best[:, 6], want["best_conf"][:, 6], rtol=1e-5)
     # a missing predictor file is an error that names the file, not a silent skip
     os.remove(os.path.join(str(tmp_path / "expc"), "pred_data_test", "testlist_params_pos_imgidx_1.mat"))
     r = subprocess.run([cli, "--expopt", info["expopt"], "--find_obj", "--first", "1"], capture_output=True, text=True)

@@ -90,13 +90,15 @@ def traffic(path, n_messages):
 
 
 def lastimage(path):
-    """Prints "<launches in the list> <launches of the last image>": the last image starts at the k_fill of its ingest."""
+    """Prints "<launches in the list> <launches of the last image>": the last image starts at the first launch of its ingest."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     ix = {h: i for i, h in enumerate(rows[0])}
     names = [r[ix['Kernel Name']] for r in rows[1:] if r[ix['Metric Name']] == 'gpu__time_duration.sum']
     last_scatter = max(i for i, n in enumerate(names) if 'k_ingest' in n)
+    # the ingest of an image is [k_fill] k_set_int k_ingest_*: the fill is skipped from the second image on the same
+    # lattice on, so walk back over whichever of the two are there
     start = last_scatter
-    while start > 0 and 'k_fill' not in names[start]:
+    while start > 0 and ('k_fill' in names[start - 1] or 'k_set_int' in names[start - 1]):
         start -= 1
     print(len(names), len(names) - start)
 
