@@ -1453,7 +1453,7 @@ __global__ void __launch_bounds__(256) k_rotconv4(const __grid_constant__ RotBat
     if (a.mode == 1) {
       // L is the longest filter of the launch.  With many rotations (R = 48: up to 47 taps) a message whose own filter
       // is shorter runs only the centred LE <= L taps that can be non-zero -- the skipped ones are exactly 0 and add +0
-      // to a non-negative sum.  Block-uniform.  (At R = 24 the extra code costs more than the taps it saves: measured.)
+      // to a non-negative sum.  Block-uniform.  (At R = 24 the gather + exp phase bounds the kernel: the same dispatch moved it by 1.5 %, measured.)
       if (R > 24 && L > 15 && a.len <= 15) rot_filter<15, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
       else if (R > 24 && L > 23 && a.len <= 23) rot_filter<23, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
       else if (R > 24 && L > 31 && a.len <= 31) rot_filter<31, L, OUT, NPAIR, FMA>(col, s_taps, nz, lo, hi);
