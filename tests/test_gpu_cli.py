@@ -140,9 +140,10 @@ def test_find_obj_cli_conditioned_model_reads_predictor_outputs(cli, tmp_path):
     root = info["root_idx"]
     exp_dir = str(tmp_path / "expc")
     conf = open(os.path.join(exp_dir, "part_conf.txt")).read()
-    marker = "part_id: %d\n" % (root + 1)
+    marker = "part_id: %d\n  part_pos: %d\n" % (root + 1, root)
     assert conf.count(marker) == 1
-    open(os.path.join(exp_dir, "part_conf.txt"), "w").write(conf.replace(marker, marker + "  part_pos: 3\n  part_pos: 7\n"))
+    open(os.path.join(exp_dir, "part_conf.txt"), "w").write(
+        conf.replace(marker, "part_id: %d\n  part_pos: 3\n  part_pos: 7\n" % (root + 1)))
     gt = [((11, 20), (18, 25)), ((30, 9), (21, 14))]
     with open(os.path.join(exp_dir, "test.al"), "w") as f:
         f.write("<annotationlist>\n")

@@ -14,10 +14,10 @@ import oracle  # noqa: E402  (test infrastructure: the checker)
 from partapp_b200 import ExpParam, PsContext, synth  # noqa: E402
 
 
-def main():
-    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-    maxdim = int(sys.argv[3]) if len(sys.argv) > 3 else 150
+def main(cases=None, seed=None, maxdim=None):
+    cases = cases if cases is not None else int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    seed = seed if seed is not None else int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    maxdim = maxdim if maxdim is not None else int(sys.argv[3]) if len(sys.argv) > 3 else 150
     rng = np.random.default_rng(seed)
     bad = 0
     lines = []
