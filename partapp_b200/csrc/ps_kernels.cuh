@@ -1841,11 +1841,21 @@ struct alignas(64) TmapBatch {
 };
 __device__ __forceinline__ void bar_sync_filter() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-#ifndef PS_GAUSS_MINB
-#define PS_GAUSS_MINB 3  // register budget of k_gauss_xy: 65536 / (3 * 288) -> 72 registers (two blocks take 41 K of the 64 K)
+// Register budget of k_gauss_xy: 64 per thread.  Two blocks of the fixed-order kernel (8 warps) then hold exactly half of
+// the SM's 64 K registers and four 256-thread blocks of the 32-register kernels around it fit beside them (72 registers
+// and a producer warp left room for two: A/B 464 -> 469 images/s at 64 registers although the kernel alone is 3 %
+// slower; 56 registers spill 40 bytes and lose: 455).  PS_GAUSS_MINB (a __launch_bounds__ minimum) selects a budget for
+// A/B builds instead.
+#ifndef PS_GAUSS_MAXREG
+#define PS_GAUSS_MAXREG 64
 #endif
 template <bool FMA, bool DYN>
-__global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_constant__ TmapBatch tm, const __grid_constant__ GaussBatch b, u64 nz) {
+#ifndef PS_GAUSS_MINB
+__global__ void __maxnreg__(PS_GAUSS_MAXREG) k_gauss_xy(
+#else
+__global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(
+#endif
+    const __grid_constant__ TmapBatch tm, const __grid_constant__ GaussBatch b, u64 nz) {
   constexpr int T = 8;
   const int NS = b.stages;  // TMA stages: 1 (the next box is requested when the x phase ends and lands during the y phase) or 2
   extern __shared__ __align__(128) unsigned char s_raw[];
@@ -1862,7 +1872,37 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (w == 8) {  // producer
+  // Static order (DYN = false): 256 threads, no producer warp.  Thread 0 requests the block's boxes itself -- NS of them
+  // up front, the next one each time the barrier behind an x phase says that every warp is done reading a stage -- from a
+  // cursor over the block's item list that lives in shared memory (registers are the scarce resource of this kernel: 64
+  // per thread, so that two blocks leave half of the register file to the other kernels of the image).
+  __shared__ int s_pc[8];  // idx, step, steps of the walk, message, slice, strip, first row, stage
+  auto issue_next_box = [&]() {  // thread 0 only
+    int idx = s_pc[0], step = s_pc[1], nsteps = s_pc[2];
+    if (step == nsteps) {
+      if (idx >= b.cta_off[blockIdx.x + 1]) return;
+      const int it = b.cta_items[idx++];
+      const int mi = it >> 24;
+      const GaussMsg &gg = b.m[mi];
+      const int4 we = *reinterpret_cast<const int4 *>(gg.walks + 4 * ((it >> 12) & 0xfff));
+      nsteps = (we.z + 7) / 8 + gg.lag;
+      step = 0;
+      s_pc[0] = idx; s_pc[2] = nsteps; s_pc[3] = mi; s_pc[4] = it & 0xfff; s_pc[5] = we.x; s_pc[6] = we.y;
+    }
+    const int mi = s_pc[3], st = s_pc[7];
+    const GaussMsg &g = b.m[mi];
+    const int nx = (g.len_x - 1) / 2;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage -> async write
+    mbar_expect_tx(&s_full[st], (unsigned)(64 + 2 * nx) * 64u * sizeof(float));
+    tma_load_3d(s_raw + st * b.stage_stride, &tm.t[mi], s_pc[6] - g.halo + 64 * step, s_pc[5] * 64 - nx, s_pc[4], &s_full[st]);
+    s_pc[1] = step + 1;
+    s_pc[7] = st + 1 == NS ? 0 : st + 1;
+  };
+  if (!DYN && tid == 0) {
+    s_pc[0] = b.cta_off[blockIdx.x]; s_pc[1] = 0; s_pc[2] = 0; s_pc[7] = 0;
+    for (int i = 0; i < NS; ++i) issue_next_box();
+  }
+  if (DYN && w == 8) {  // producer warp of the counter-drawn order (288 threads)
     if (lane == 0) {
       int s = 0, u = 0;
       auto next_stage = [&]() {
@@ -2008,9 +2048,12 @@ __global__ void __launch_bounds__(288, PS_GAUSS_MINB) k_gauss_xy(const __grid_co
       r1[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
       r1[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);  // the box is consumed: the producer may refill the stage
+    if (DYN) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);  // the box is consumed: the producer may refill the stage
+    }
     bar_sync_filter();
+    if (!DYN && tid == 0) issue_next_box();  // every warp is past its reads of this stage: refill it during the y phase
     // ---- Y(i - K): filter along ey from the ring ----
     const int ob = i - g.lag;
     if (ob >= 0) {

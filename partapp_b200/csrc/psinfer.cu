@@ -1028,7 +1028,7 @@ int run_batch(ps_ctx *c, MsgJob *const *jobs, int n) {
     }();
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(288);
+    lc.blockDim = dim3(dyn_env ? 288 : 256);  // the counter-drawn order keeps its producer warp, the fixed order has none
     lc.dynamicSmemBytes = smem;
     lc.stream = st;
     cudaLaunchAttribute la[1];
