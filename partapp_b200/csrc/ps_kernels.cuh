@@ -1776,10 +1776,13 @@ __global__ void __launch_bounds__(288, PS_TMA_MINB) k_conv_cols_tma2(const __gri
 //         window never straddles the wrap.  Warps whose 8 ex-rows no y output of the rectangle can reach (xmask) skip.
 //   Y(i - K): 64 output rows (8 per warp) filtered along ey from the ring, stored to out[z][ey][ex].
 // Arithmetic per output is the same ascending-tap RN(acc + RN(x f)) chain as the two-kernel route: bit-identical.
-// Warp 8 is the producer: it draws work items from an atomic counter (messages in launch order, longest walk first),
-// publishes (message, walk, block, slice) next to each box and issues the TMA; the eight filter warps follow the
-// published records, hand a stage back through its `empty` mbarrier right after the x phase and meet at a named
-// barrier between the phases.
+// Two work orders.  Fixed (DYN = false, the default): eight filter warps, 256 threads; every block walks its own list of
+// the table the host dealt, and thread 0 requests the next box right behind the barrier that closes an x phase.
+// Counter-drawn (DYN = true): a ninth warp is the producer -- it draws work items from an atomic counter (messages in
+// launch order, longest walk first), publishes (message, walk, block, slice) next to each box and issues the TMA; the
+// filter warps follow the published records and hand a stage back through its `empty` mbarrier right after the x phase.
+// In both, the filter warps meet at a named barrier between the phases.
+
 // The last REM (= taps mod 8, odd because every filter has 2 n + 1 taps) taps of a phase as straight-line code: every
 // load of the tail is issued before its first use (ncu r02f: the per-tap branches of a predicated tail ran at half the
 // multiply-add density of the main loop).  Row 0 of the tail is at w0, rows 1.. at w1 + (row - 1) * stride: the ring
