@@ -541,6 +541,31 @@ def unary_best_hyp(scores: np.ndarray, scaleidx: int, scale: float, rot_range: T
     return np.array([scaleidx, np.float32(scale), r, np.float32(rot), x, y, flat[k]], np.float32)
 
 
+def disc_ps_best_hyp(vect_scale_idx, vect_rot_idx, vect_iy, vect_ix, posterior, scale_range: Tuple[float, float, int],
+                     rot_range: Tuple[float, float, int], vect_didx=None, didx: int = -1) -> np.ndarray:
+    """EVAL_TYPE_DISC_PS (parteval.cpp:384-493): a part's estimate is the sample with the first strictly largest
+    posterior among the samples libDiscPS drew for it (`samples_pidx<p>.mat`: vect_scale_idx / vect_rot_idx / vect_iy /
+    vect_ix [/ vect_didx], `samples_imgidx%04d_post.mat`: samples_post_part<p>); with `didx` >= 0 only the samples of that
+    subject compete (:441-482).  Returns the PartHyp of the winner as a best_conf row (objectdetect.h:91-97, :139-160)."""
+    post = np.asarray(posterior, np.float64).reshape(-1)
+    cols = [np.asarray(v).reshape(-1) for v in (vect_scale_idx, vect_rot_idx, vect_iy, vect_ix)]
+    assert post.size > 0 and all(c.size == post.size for c in cols), "sample vectors and posterior differ in length (:451-455)"
+    if didx == -1 or vect_didx is None:
+        k = int(np.argmax(post))                     # boost_math::get_max: first index of the maximum
+    else:
+        d = np.asarray(vect_didx).reshape(-1)
+        assert d.size == post.size
+        idx = np.flatnonzero(d == didx)
+        assert idx.size > 0, "maxidx >= 0 (:485)"
+        k = int(idx[np.argmax(post[idx])])
+    si, ri, iy, ix = (int(c[k]) for c in cols)
+    smin, smax, ns = scale_range
+    rmin, rmax, nr = rot_range
+    scale = smin if smin == smax else smin + (smax - smin) / ns * (0.5 + si)
+    rot = rmin if rmin == rmax else rmin + (rmax - rmin) / nr * (0.5 + ri)
+    return np.array([si, np.float32(scale), ri, np.float32(rot), ix, iy, np.float32(post[k])], np.float32)
+
+
 def eval_segments_roi(annolist: Sequence[Annotation], roi_counts: Sequence[int], part_conf_eval: Sequence[PartDef],
                       window_param: Sequence[PartParam], load_best_conf_roi, firstidx: int, lastidx: int, scale: float = 1.0,
                       part_conf: Optional[Sequence[PartDef]] = None, part_conf_type: str = "human_full",
@@ -580,13 +605,15 @@ def eval_segments_roi(annolist: Sequence[Annotation], roi_counts: Sequence[int],
 
 
 def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: Optional[int] = None,
-                             save_endpoints: bool = True, eval_type: str = "ps") -> SegmentEval:
+                             save_endpoints: bool = True, eval_type: str = "ps", eval_didx: int = -1) -> SegmentEval:
     """`partapp --expopt X --eval_segments` for a finished `--find_obj` run (main.cpp:834-845): reads the expopt, the
     part configuration (part_conf_eval if given), window_param.txt, the test annotation list and the
     pose_est_imgidx%04d.mat files under <log_dir>/<log_subdir>/part_marginals.
     eval_type "ps" (EVAL_TYPE_PS) reads those files; "unaries" (EVAL_TYPE_UNARIES, parteval.cpp:326-383) takes every
     part's estimate from the maximum of its detector score grids (<scoregrid_dir>/imgidx%d-pidx%d-o0-scoregrid.mat);
-    "roi" is eval_segments_roi over pose_est_imgidx%04d_roi%04d.mat and the ROI annotation list."""
+    "roi" is eval_segments_roi over pose_est_imgidx%04d_roi%04d.mat and the ROI annotation list; "disc_ps"
+    (EVAL_TYPE_DISC_PS, :384-493) takes the best of the samples libDiscPS drew and scored (`eval_didx` >= 0: the samples
+    and the annotated rectangle of that subject)."""
     import scipy.io
     base = os.path.dirname(os.path.abspath(expopt))
     rel = lambda p: p if os.path.isabs(p) else os.path.normpath(os.path.join(base, p))  # complete_relative_path
@@ -622,6 +649,25 @@ def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: 
         load_roi = lambda i, k: scipy.io.loadmat(os.path.join(roi_dir, "pose_est_imgidx%04d_roi%04d.mat" % (i, k)))["best_conf"]
         return eval_segments_roi(annos, [len(a.rects) for a in roi_annos], conf, win, load_roi, firstidx, lastidx, scale,
                                  part_conf=model_conf, part_conf_type=ptype, rot_range=rot_range)
+    if eval_type == "disc_ps":
+        # parteval.cpp:401-426 and :1210-1238: samples under dai_samples_dir, their posteriors under
+        # <log_dir>/<log_subdir>/<part_marginals_samples|test_scoregrid_samples>_post, endpoints saved next to them
+        sdir = rel(one("dai_samples_dir"))
+        kind = os.path.basename(sdir.rstrip("/"))
+        assert kind in ("part_marginals_samples", "test_scoregrid_samples"), "unknown part samples type (:421)"
+        post_dir = os.path.join(log_dir, log_subdir, kind + "_post")
+        srange = (smin, smax, ns)
+
+        def load(i):                                                     # noqa: F811
+            post = scipy.io.loadmat(os.path.join(post_dir, "samples_imgidx%04d_post.mat" % i))
+            rows = []
+            for p in range(len(model_conf)):
+                m = scipy.io.loadmat(os.path.join(sdir, "samples_imgidx%04d" % i, "samples_pidx%d.mat" % p))
+                rows.append(disc_ps_best_hyp(m["vect_scale_idx"], m["vect_rot_idx"], m["vect_iy"], m["vect_ix"],
+                                             post["samples_post_part%d" % p], srange, rot_range,
+                                             m.get("vect_didx") if eval_didx >= 0 else None, eval_didx))
+            return np.stack(rows)
+        hyp_dir = post_dir
     if eval_type == "unaries":
         assert len(model_conf) in (6, 10, 21), "single-scale settings only (parteval.cpp:344-346)"
         sg_dir = rel(one("scoregrid_dir")) if one("scoregrid_dir") else os.path.join(log_dir, log_subdir, "test_scoregrid")
@@ -641,7 +687,7 @@ def eval_segments_experiment(expopt: str, first: Optional[int] = None, numimgs: 
                 rows.append(unary_best_hyp(load_score_grid_direct(cells, Tig, H, W), 0, scale, rot_range))
             return np.stack(rows)
         hyp_dir = sg_dir
-    return eval_segments(annos, conf, win, load, firstidx, lastidx, scale,
+    return eval_segments(annos, conf, win, load, firstidx, lastidx, scale, eval_didx=eval_didx,
                          save_dir=os.path.join(hyp_dir, "seg_endpoints") if save_endpoints else None,
                          part_conf=model_conf, part_conf_type=ptype, rot_range=rot_range)
 
@@ -652,9 +698,10 @@ if __name__ == "__main__":
     ap.add_argument("--expopt", required=True)
     ap.add_argument("--first", type=int)
     ap.add_argument("--numimgs", type=int)
-    ap.add_argument("--eval-type", default="ps", choices=["ps", "unaries", "roi"])
+    ap.add_argument("--eval-type", default="ps", choices=["ps", "unaries", "roi", "disc_ps"])
+    ap.add_argument("--eval-didx", type=int, default=-1, help="subject (annotated rectangle) to evaluate, disc_ps only")
     a = ap.parse_args()
-    r = eval_segments_experiment(a.expopt, a.first, a.numimgs, eval_type=a.eval_type)
+    r = eval_segments_experiment(a.expopt, a.first, a.numimgs, eval_type=a.eval_type, eval_didx=a.eval_didx)
     print("seg_correct: %d\nseg_total: %d\nratio: %g" % (r.seg_correct, r.seg_total, r.ratio))
     for i, (c, t) in enumerate(zip(r.per_part_correct, r.per_part_total)):
         print("part: %d, correct: %d, total: %d, ratio: %g" % (i, c, t, c / float(t if t else 1)))

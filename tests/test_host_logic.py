@@ -470,3 +470,62 @@ def test_eval_segments_experiment_unary_source(tmp_path):
     write_al(shift_part=(1, 3))
     r = pe.eval_segments_experiment(info["expopt"], eval_type="unaries", save_endpoints=False)
     assert (r.seg_correct, r.seg_total) == (2 * P - 1, 2 * P) and r.per_part_correct[3] == 1
+
+
+def test_eval_segments_experiment_disc_ps_source(tmp_path):
+    """EVAL_TYPE_DISC_PS (parteval.cpp:384-493): per part the sample with the first strictly largest posterior -- among
+    all samples, or among those of one subject (vect_didx) -- becomes the PartHyp that is evaluated; files and
+    directories as libDiscPS leaves them."""
+    import scipy.io
+    from partapp_b200 import parteval as pe
+    (tmp_path / "part_conf.txt").write_text(_PART_CONF)
+    (tmp_path / "test.al").write_text(_ANNOLIST)
+    sub = tmp_path / "logs" / "exp-dps"
+    (sub / "class").mkdir(parents=True)
+    (sub / "class" / "window_param.txt").write_text("train_object_height: 200\n" + _WINDOW_PARAM)
+    sdir = tmp_path / "dai" / "part_marginals_samples"
+    post_dir = sub / "part_marginals_samples_post"
+    post_dir.mkdir(parents=True)
+    (tmp_path / "exp-dps.txt").write_text('test_dataset: "test.al"\nlog_dir: "./logs"\npart_conf: "part_conf.txt"\n'
+                                          'num_rotation_steps: 24\ndai_samples_dir: "./dai/part_marginals_samples"\n')
+    rot = lambda r: -180.0 + 360.0 / 24 * (0.5 + r)
+    # image 0, part 0: three samples, the second and third tie on the posterior -> the second (first maximum) wins;
+    # rotation index 11 is 0 +- 7.5 degrees: the upright stick at (100, 100) matches the annotation
+    samples = {(0, 0): ([0, 0, 0], [3, 11, 20], [10, 100, 100], [10, 100, 30], [0.1, 0.7, 0.7], [0, 1, 0]),
+               (0, 1): ([0, 0], [5, 17], [120, 120], [100, 100], [0.9, 0.2], [0, 1]),
+               (1, 0): ([0], [11], [100], [180], [0.5], [0]),
+               (1, 1): ([0], [11], [0], [0], [0.5], [0])}
+    for (i, p), (si, ri, iy, ix, post, didx) in samples.items():
+        d = sdir / ("samples_imgidx%04d" % i)
+        d.mkdir(parents=True, exist_ok=True)
+        scipy.io.savemat(str(d / ("samples_pidx%d.mat" % p)),
+                         {"vect_scale_idx": np.array(si, np.float64), "vect_rot_idx": np.array(ri, np.float64),
+                          "vect_iy": np.array(iy, np.float64), "vect_ix": np.array(ix, np.float64),
+                          "vect_didx": np.array(didx, np.float64)})
+    for i in range(2):
+        scipy.io.savemat(str(post_dir / ("samples_imgidx%04d_post.mat" % i)),
+                         {"samples_post_part%d" % p: np.array(samples[(i, p)][4], np.float64).reshape(-1, 1) for p in range(2)})
+    row = pe.disc_ps_best_hyp(*samples[(0, 0)][:5], (1.0, 1.0, 1), (-180.0, 180.0, 24))
+    assert row.tolist() == [0, 1, 11, np.float32(rot(11)), 100, 100, np.float32(0.7)]
+    # the same through the experiment entry, against eval_segments fed with hand-built PartHyp rows
+    annos = pe.load_annolist(str(tmp_path / "test.al"))
+    conf = pe.load_part_conf(str(tmp_path / "part_conf.txt"))
+    win = pe.load_window_param(str(sub / "class" / "window_param.txt"))
+    hand = {0: np.array([[0, 1, 11, rot(11), 100, 100, 0.7], [0, 1, 5, rot(5), 100, 120, 0.9]], np.float32),
+            1: np.array([[0, 1, 11, rot(11), 180, 100, 0.5], [0, 1, 11, rot(11), 0, 0, 0.5]], np.float32)}
+    want = pe.eval_segments(annos, conf, win, lambda i: hand[i], 0, 1, 1.0, rot_range=(-180.0, 180.0, 24))
+    got = pe.eval_segments_experiment(str(tmp_path / "exp-dps.txt"), eval_type="disc_ps")
+    assert (got.seg_correct, got.seg_total, got.per_part_correct) == (want.seg_correct, want.seg_total, want.per_part_correct)
+    assert got.seg_correct >= 1                                        # the upright stick of image 0 is found
+    assert (post_dir / "seg_endpoints" / "endpoints_0000.mat").exists()
+    # one subject only (vect_didx): subject 1 of part 1 is its second sample; subject 0 of part 0 are samples 0 and 2
+    row1 = pe.disc_ps_best_hyp(*samples[(0, 1)][:5], (1.0, 1.0, 1), (-180.0, 180.0, 24), samples[(0, 1)][5], 1)
+    assert row1[2] == 17 and row1[6] == np.float32(0.2)
+    row0 = pe.disc_ps_best_hyp(*samples[(0, 0)][:5], (1.0, 1.0, 1), (-180.0, 180.0, 24), samples[(0, 0)][5], 0)
+    assert row0[2] == 20 and row0[6] == np.float32(0.7) and (row0[4], row0[5]) == (30, 100)
+    hand0 = {0: np.array([[0, 1, 20, rot(20), 30, 100, 0.7], [0, 1, 5, rot(5), 100, 120, 0.9]], np.float32)}
+    want0 = pe.eval_segments(annos, conf, win, lambda i: hand0[i], 0, 0, 1.0, eval_didx=0, rot_range=(-180.0, 180.0, 24))
+    got0 = pe.eval_segments_experiment(str(tmp_path / "exp-dps.txt"), first=0, numimgs=1, eval_type="disc_ps", eval_didx=0,
+                                       save_endpoints=False)
+    assert (got0.seg_correct, got0.seg_total, got0.per_part_correct) == (want0.seg_correct, want0.seg_total, want0.per_part_correct)
+    assert got0.per_part_correct[0] == 0                               # the sample at x = 30 misses the stick at x = 100
